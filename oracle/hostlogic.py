@@ -1,0 +1,367 @@
+"""
+TEST INFRASTRUCTURE ONLY -- plain-Python restatement of the host-side logic of the reference's callLoops path.
+Each function cites the reference lines (path:line under /root/reference) it follows.  Small-case loops on
+purpose: this is the checker, not the product (the product's host code is cloops2_b200/*.py, vectorised and
+driven by the CUDA library).
+"""
+import numpy as np
+from scipy.stats import hypergeom, binom, poisson
+
+
+class OLoop(object):
+    """Field-for-field stand-in for cLoops2/ds.py:245-281 (Loop)."""
+    __slots__ = ["chromX", "chromY", "x_start", "x_end", "x_center", "ra", "y_start", "y_end", "y_center", "rb",
+                 "rab", "cis", "distance", "density", "ES", "P2LL", "FDR", "hypergeometric_p_value",
+                 "poisson_p_value", "binomial_p_value", "x_peak_poisson_p_value", "x_peak_es",
+                 "y_peak_poisson_p_value", "y_peak_es", "significant"]
+
+    def coords(self):
+        return (self.chromX, self.x_start, self.x_end, self.chromY, self.y_start, self.y_end)
+
+
+def parse_ixy_filter(xy, cut=0, mcut=-1):
+    """cLoops2/io.py:274-291 (parseIxy) on an in-memory int64[N,2] array."""
+    xy = np.asarray(xy, dtype=np.int64)
+    if cut > 0:
+        xy = xy[(xy[:, 1] - xy[:, 0]) >= cut]
+    if mcut > 0:
+        xy = xy[(xy[:, 1] - xy[:, 0]) <= mcut]
+    return xy
+
+
+def _bbox_loops(key, xy, labels, ncl, cis):
+    from . import cluster_bbox
+    bbox, size = cluster_bbox(xy, labels, ncl)
+    out = []
+    for c in range(ncl):
+        if size[c] == 0:
+            continue
+        x0, x1, y0, y1 = (int(v) for v in bbox[c])
+        if x0 == x1 or y0 == y1:                      # callCisLoops.py:97-99
+            continue
+        lp = OLoop()
+        lp.rab = int(size[c])
+        lp.chromX, lp.chromY = key[0], key[1]
+        lp.x_start, lp.x_end = x0, x1
+        lp.x_center = (x0 + x1) / 2
+        lp.y_start, lp.y_end = y0, y1
+        lp.y_center = (y0 + y1) / 2
+        lp.cis = cis
+        out.append(lp)
+    return out
+
+
+def cis_candidates(key, xy, eps, minPts, cut=0, hic=False):
+    """callCisLoops.py:58-124 (runCisDBSCANLoops) after parseIxy; `xy` is already cut/mcut filtered."""
+    from . import block_dbscan, cdbscan2
+    if key[0] != key[1]:
+        return None
+    if cut > 0:                                       # :75-79 (idempotent second filter)
+        xy = xy[(xy[:, 1] - xy[:, 0]) >= cut]
+    if len(xy) == 0:
+        return None
+    labels, ncl = (cdbscan2 if hic else block_dbscan)(xy, eps, minPts)
+    loops = []
+    for lp in _bbox_loops(key, xy, labels, ncl, True):
+        lp.distance = abs(lp.y_center - lp.x_center)
+        if lp.x_end - lp.x_start + lp.y_end - lp.y_start < 200:     # :114
+            continue
+        if lp.x_end < lp.y_start:                                   # :116
+            loops.append(lp)
+    return "-".join(key), loops
+
+
+def trans_candidates(key, xy, eps, minPts):
+    """callTransLoops.py:33-84 (runTransDBSCANLoops): blockDBSCAN only, no anchor-size / order filters."""
+    from . import block_dbscan
+    labels, ncl = block_dbscan(xy, eps, minPts)
+    loops = _bbox_loops(key, xy, labels, ncl, False)
+    for lp in loops:
+        lp.distance = -1
+    return "-".join(key), loops
+
+
+def combine_loops(loops, loops_2):
+    """geo.py:90-112."""
+    for key in loops_2.keys():
+        if key not in loops:
+            loops[key] = loops_2[key]
+        else:
+            seen = set(lp.coords() for lp in loops[key])
+            for lp in loops_2[key]:
+                if lp.coords() not in seen:
+                    loops[key].append(lp)
+    return loops
+
+
+def filter_by_dis(loops, cut):
+    """callCisLoops.py:146-156."""
+    return {k: [lp for lp in v if lp.distance > cut] for k, v in loops.items()}
+
+
+def filter_dup(loops):
+    """callCisLoops.py:159-169: first position, last object."""
+    out = {}
+    for k, v in loops.items():
+        d = {}
+        for lp in v:
+            d[lp.coords()] = lp
+        out[k] = list(d.values())
+    return out
+
+
+def _anchor_sig(N, span, count, wide):
+    """callCisLoops.py:226-247 (estAnchorSig) given the two counts; span = max(ys) - min(xs)."""
+    pass
+
+
+def est_loop_sig_cis(key, loops, xy, tot, minPts=5, pseudo=1, peakPcut=1e-5, win=5, countDiffCut=20, hic=False):
+    """callCisLoops.py:250-354 (estLoopSig); `xy` is the cut/mcut-filtered array (ixy2pet, io.py:294-300)."""
+    from . import XYIndex
+    if len(loops) == 0:
+        return key, []
+    idx = XYIndex(xy)
+    N = idx.n
+    span = float(np.max(xy[:, 1]) - np.min(xy[:, 0]))
+    rpb = float(N) / span
+    arr = np.array([[lp.x_start, lp.x_end, lp.y_start, lp.y_end] for lp in loops], dtype=np.int64)
+    core, na, nb, nab, anc = idx.loop_counts(arr, win=win, mode=0)
+    out = []
+    for i, lp in enumerate(loops):
+        la, lb = lp.x_end - lp.x_start, lp.y_end - lp.y_start
+        if la / lb > countDiffCut or lb / la > countDiffCut:        # :282-286
+            continue
+        ra, rb, rab, lower = (int(v) for v in core[i])
+        if rab < minPts:                                            # :290
+            continue
+        if ra == rab or rb == rab:                                  # :293
+            continue
+        if ra / float(rb) > countDiffCut or rb / float(ra) > countDiffCut:   # :296
+            continue
+        lp.ra, lp.rb, lp.rab = ra, rb, rab
+        lp.P2LL = float(rab) / max(lower, pseudo)                   # :306
+        if hic and lp.P2LL < 1:
+            continue
+        hyp = max([1e-300, hypergeom.sf(rab - 1.0, N, ra, rb)])     # :310
+        if hyp > 1e-2:
+            continue
+        rabs, nbps = [], []                                          # :207-223
+        for a in range(2 * win):
+            nac = float(na[i, a])
+            for b in range(2 * win):
+                nbc = float(nb[i, b])
+                nrab = float(nab[i, a * 2 * win + b])
+                if nrab > 0:
+                    rabs.append(nrab)
+                    nbps.append(nrab / (nac * nbc))
+                else:
+                    rabs.append(0)
+                    nbps.append(0.0)
+        rabs, nbps = np.array(rabs), np.array(nbps)
+        mrabs = float(np.median(rabs))
+        mbps = np.median(nbps)
+        fdr = len(rabs[rabs > rab]) / float(len(rabs)) if len(rabs) > 0 else 0.0
+        if mrabs >= rab or fdr >= 0.1:                              # :322
+            continue
+        es = rab / max(mrabs, pseudo)
+        if es < 1:
+            continue
+        pop = max([1e-300, poisson.sf(rab - 1.0, mrabs)])
+        nbp = max([1e-300, binom.sf(rab - 1.0, ra * rb - rab, mbps)])
+        lp.FDR, lp.ES = fdr, es
+        lp.density = float(rab) / (la + lb) / tot * 10.0**9
+        lp.hypergeometric_p_value, lp.poisson_p_value, lp.binomial_p_value = hyp, pop, nbp
+        res = []
+        for a, (left, right) in enumerate(((lp.x_start, lp.x_end), (lp.y_start, lp.y_end))):   # :226-247
+            length = right - left
+            count = int(anc[i, 2 * a])
+            r = (int(anc[i, 2 * a + 1]) - count) / 5 / 2
+            c = float(max([r, rpb * length, 1]))
+            res.append((max([1e-300, poisson.sf(count - 1.0, c)]), count / c))
+        (px, esx), (py, esy) = res
+        if hic is False and not (px < peakPcut and py < peakPcut):  # :347
+            continue
+        lp.x_peak_poisson_p_value, lp.x_peak_es = px, esx
+        lp.y_peak_poisson_p_value, lp.y_peak_es = py, esy
+        out.append(lp)
+    return key, out
+
+
+def est_loop_sig_trans(key, loops, xy, minPts=5, pseudo=1, countDiffCut=10, win=5):
+    """callTransLoops.py:106-193 (trans estLoopSig)."""
+    from . import XYIndex
+    if len(loops) == 0:
+        return key, []
+    idx = XYIndex(xy)
+    N = idx.n
+    span = float(np.max(xy[:, 1]) - np.min(xy[:, 0]))
+    rpb = float(N) / span
+    arr = np.array([[lp.x_start, lp.x_end, lp.y_start, lp.y_end] for lp in loops], dtype=np.int64)
+    core, na, nb, nab, anc = idx.loop_counts(arr, win=win, mode=1)
+    out = []
+    for i, lp in enumerate(loops):
+        ra, rb, rab, lower = (int(v) for v in core[i])
+        if rab < minPts:
+            continue
+        lp.ra, lp.rb, lp.rab = ra, rb, rab
+        if ra / float(rb) > countDiffCut or rb / float(ra) > countDiffCut:
+            continue
+        la, lb = lp.x_end - lp.x_start, lp.y_end - lp.y_start
+        if la / lb > countDiffCut or lb / la > countDiffCut:
+            continue
+        lp.P2LL = float(rab) / max(lower, pseudo)
+        res = []
+        for a, (left, right) in enumerate(((lp.x_start, lp.x_end), (lp.y_start, lp.y_end))):
+            length = right - left
+            count = int(anc[i, 2 * a])
+            r = (int(anc[i, 2 * a + 1]) - count) / 5 / 2
+            c = float(max([r, rpb * length, 1]))
+            res.append((max([1e-300, poisson.sf(count - 1.0, c)]), count / c))
+        (lp.x_peak_poisson_p_value, lp.x_peak_es), (lp.y_peak_poisson_p_value, lp.y_peak_es) = res
+        hyp = max([1e-300, hypergeom.sf(rab - 1.0, N, ra, rb)])
+        rabs, nbps = [], []
+        for a in range(2 * win):
+            nac = float(na[i, a])
+            for b in range(2 * win):
+                nbc = float(nb[i, b])
+                nrab = float(nab[i, a * 2 * win + b])
+                rabs.append(nrab)
+                if nac > 0 and nbc > 0:
+                    nbps.append(nrab / (nac * nbc))
+                else:
+                    nbps.append(0.0)
+        rabs, nbps = np.array(rabs), np.array(nbps)
+        mrabs = float(np.mean(rabs))
+        mbps = np.mean(nbps)
+        fdr = len(rabs[rabs > rab]) / float(len(rabs))
+        es = rab / max(mrabs, pseudo)
+        pop = max([1e-300, poisson.sf(rab - 1.0, mrabs)])
+        nbp = max([1e-300, binom.sf(rab - 1.0, ra * rb, mbps)])
+        lp.FDR, lp.ES = fdr, es
+        lp.density = float(rab) / (la + lb) / N * 10.0**9
+        lp.hypergeometric_p_value, lp.poisson_p_value, lp.binomial_p_value = hyp, pop, nbp
+        out.append(lp)
+    return key, out
+
+
+def mark_sig_cis(loops, hic=False):
+    """callCisLoops.py:357-376."""
+    for lp in loops:
+        sig = lp.FDR <= 0.05 and lp.ES >= 2 and lp.hypergeometric_p_value <= 1e-5 and lp.poisson_p_value <= 1e-5
+        if sig:
+            lp.significant = 1 if lp.binomial_p_value < (1e-3 if hic else 1e-1) else 0
+        else:
+            lp.significant = 0
+    return loops
+
+
+def mark_sig_trans(loops):
+    """callTransLoops.py:196-206.  The reference's lambda reads `loop.ES` from the enclosing loop variable,
+    which at call time is the loop being tested, so it is the plain three-way test."""
+    for lp in loops:
+        lp.significant = 1 if (lp.binomial_p_value <= 1e-10 and lp.FDR <= 0.05 and lp.ES >= 2) else 0
+    return loops
+
+
+def _anchor_ov(xa, xb, ya, yb):
+    """geo.py:65-73."""
+    if (ya <= xa <= yb) or (ya <= xb <= yb) or (ya <= xa <= xb <= yb):
+        return True
+    if (xa <= ya <= xb) or (xa <= yb <= xb) or (xa <= ya <= yb <= xb):
+        return True
+    return False
+
+
+def _loop_ov(a, b):
+    """geo.py:76-87."""
+    if a.chromX != b.chromX or a.chromY != b.chromY:
+        return False
+    return _anchor_ov(a.x_start, a.x_end, b.x_start, b.x_end) and _anchor_ov(a.y_start, a.y_end, b.y_start, b.y_end)
+
+
+def sel_sig_loops(loops):
+    """callCisLoops.py:379-422."""
+    loops = [lp for lp in loops if lp.significant > 0]
+    groups, skips = [], set()
+    for i in range(len(loops)):
+        if i in skips:
+            continue
+        n = [loops[i]]
+        for j in range(i + 1, len(loops)):
+            for p in n:
+                if _loop_ov(p, loops[j]):
+                    n.append(loops[j])
+                    skips.add(j)
+                    break
+        groups.append(n)
+    reps = []
+    for n in groups:
+        if len(n) == 1:
+            reps.append(n[0])
+        else:
+            for i in range(len(n) - 1):
+                for j in range(i + 1, len(n)):
+                    if n[i].ES < n[j].ES:
+                        n[i], n[j] = n[j], n[i]
+            reps.append(n[0])
+    for la in loops:
+        if not any(_loop_ov(la, lb) for lb in reps):
+            reps.append(la)
+    return reps
+
+
+def call_cis_loops(files, tot, eps, minPts, cut=0, mcut=-1, hic=False, emPair=False):
+    """callCisLoops.py:471-599 on in-memory inputs.  files: ordered dict "chrA-chrA" -> int64[N,2]."""
+    loops = {}
+    pairs = list(zip(eps, minPts)) if emPair else [(e, m) for e in eps for m in minPts]
+    filt = {k: parse_ixy_filter(v, cut, mcut) for k, v in files.items()}
+    for ep, mp in pairs:
+        cur = {}
+        for k in files:
+            r = cis_candidates(tuple(k.split("-")), filt[k], ep, mp, cut=cut, hic=hic)
+            if r is not None and len(r[1]) > 0:
+                cur[r[0]] = r[1]
+        loops = combine_loops(loops, cur)
+    loops = filter_dup(filter_by_dis(loops, cut))
+    mm = min(minPts) if emPair else max(minPts)
+    final = []
+    per_key = {}
+    for k in loops:
+        _, ls = est_loop_sig_cis(k, loops[k], filt[k], tot, minPts=mm, hic=hic)
+        ls = mark_sig_cis(ls, hic=hic)
+        ls = sel_sig_loops(sel_sig_loops(ls))
+        per_key[k] = ls
+        final.extend(ls)
+    return final, per_key
+
+
+def call_trans_loops(files, eps, minPts):
+    """callTransLoops.py:209-275 on in-memory inputs.  files: ordered dict "chrA-chrB" -> int64[N,2]."""
+    loops = {}
+    for ep in eps:
+        for mp in minPts:
+            cur = {}
+            for k in files:
+                r = trans_candidates(tuple(k.split("-")), np.asarray(files[k], dtype=np.int64), ep, mp)
+                if len(r[1]) > 0:
+                    cur[r[0]] = r[1]
+            loops = combine_loops(loops, cur)
+    final = []
+    for k in loops:
+        _, ls = est_loop_sig_trans(k, loops[k], np.asarray(files[k], dtype=np.int64), minPts=max(minPts))
+        ls = mark_sig_trans(ls)
+        ls = sel_sig_loops(sel_sig_loops(ls))
+        final.extend(ls)
+    return final
+
+
+def loops_to_rows(loops):
+    """Rows of io.py:517-561 (loops2txt) as lists of str, header excluded."""
+    rows = []
+    for i, lp in enumerate(loops):
+        line = ["loop_%s-%s-%s" % (lp.chromX, lp.chromY, i), lp.chromX, lp.x_start, lp.x_end, lp.chromY, lp.y_start,
+                lp.y_end, lp.distance, lp.x_center, lp.y_center, lp.ra, lp.rb, lp.cis, lp.rab, lp.density, lp.ES,
+                lp.P2LL, lp.FDR, lp.binomial_p_value, lp.hypergeometric_p_value, lp.poisson_p_value,
+                lp.x_peak_poisson_p_value, lp.y_peak_poisson_p_value, lp.significant]
+        rows.append(list(map(str, line)))
+    return rows
