@@ -1,0 +1,330 @@
+"""
+ctypes binding of libcl2.so (include/cl2.h) -- the only compute path of this package.
+
+There is deliberately NO CPU fallback: if the CUDA library is missing or no GPU is visible, every entry point
+raises (Cl2Error / OSError).  The library is built in-tree by `build()` (nvcc, sm_100a) so it travels with the
+repository snapshot to the GPU box.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+SO_PATH = os.path.join(_HERE, "libcl2.so")
+SOURCES = ["cl2_api.cu", "cl2_sort.cu", "cl2_block.cu", "cl2_cdbscan.cu", "cl2_count.cu", "cl2_host.cu"]
+HEADERS = ["cl2_common.cuh", "cl2_points.cuh", os.path.join("..", "..", "include", "cl2.h")]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
+              "-Xcompiler", "-fPIC"]
+
+MODE_CIS, MODE_TRANS = 0, 1
+
+
+class Cl2Error(RuntimeError):
+    pass
+
+
+def _stale():
+    if not os.path.exists(SO_PATH):
+        return True
+    t = os.path.getmtime(SO_PATH)
+    for f in SOURCES + HEADERS:
+        p = os.path.join(_CSRC, f)
+        if os.path.exists(p) and os.path.getmtime(p) > t:
+            return True
+    return False
+
+
+def build(force=False, verbose=False):
+    """Compile libcl2.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    if not force and not _stale():
+        return SO_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    objs = []
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(_CSRC, src.replace(".cu", ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + ["-c", "-o", obj, os.path.join(_CSRC, src)]
+        if verbose:
+            print(" ".join(cmd))
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+        objs.append(obj)
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise Cl2Error("nvcc failed: %s\n%s" % (" ".join(cmd), out.decode(errors="replace")))
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO_PATH] + objs + ["-lcudart"]
+    subprocess.check_call(cmd)
+    return SO_PATH
+
+
+_i64p = ctypes.POINTER(ctypes.c_int64)
+_i32p = ctypes.POINTER(ctypes.c_int32)
+_u8p = ctypes.POINTER(ctypes.c_uint8)
+_f64p = ctypes.POINTER(ctypes.c_double)
+_vp = ctypes.c_void_p
+
+# name -> (restype, argtypes); mirrors include/cl2.h one to one (tests/test_abi.py checks the two agree)
+SIGNATURES = {
+    "cl2_version": (ctypes.c_char_p, []),
+    "cl2_ctx_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_vp)]),
+    "cl2_ctx_destroy": (None, [_vp]),
+    "cl2_last_error": (ctypes.c_char_p, [_vp]),
+    "cl2_ctx_sync": (ctypes.c_int, [_vp]),
+    "cl2_host_alloc": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.POINTER(_vp)]),
+    "cl2_host_free": (None, [_vp, _vp]),
+    "cl2_points_upload": (ctypes.c_int, [_vp, _i64p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(_vp)]),
+    "cl2_points_count": (ctypes.c_int64, [_vp]),
+    "cl2_points_extent": (ctypes.c_int, [_vp, _vp, _i64p]),
+    "cl2_points_download": (ctypes.c_int, [_vp, _vp, _i64p]),
+    "cl2_points_free": (None, [_vp, _vp]),
+    "cl2_block_dbscan": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _i32p, _i32p]),
+    "cl2_cdbscan2": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _i32p, _i32p]),
+    "cl2_cluster_bbox": (ctypes.c_int, [_vp, _vp, _i64p, _i64p]),
+    "cl2_block_noise": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _u8p]),
+    "cl2_index_build": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(_vp)]),
+    "cl2_index_free": (None, [_vp, _vp]),
+    "cl2_loop_counts": (ctypes.c_int, [_vp, _vp, _i64p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
+                                       _i64p, _i64p, _i64p, _i64p, _i64p]),
+    "cl2_sel_sig_loops": (ctypes.c_int, [_i64p, _f64p, ctypes.c_int64, _i64p, _i64p]),
+    "cl2_launch_count": (ctypes.c_int64, [_vp]),
+    "cl2_launch_count_reset": (None, [_vp]),
+    "cl2_timing_enable": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "cl2_transfer_bytes": (None, [_vp, _i64p, _i64p]),
+    "cl2_timing_read": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_char_p, _f64p, _i64p, _f64p]),
+    "cl2_timing_reset": (None, [_vp]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen libcl2.so and set the prototypes.  Raises if the library has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise Cl2Error("libcl2.so not built (%s); run `python -c 'import __graft_entry__ as g; g.build()'`" % SO_PATH)
+        L = ctypes.CDLL(SO_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            f = getattr(L, name)
+            f.restype = res
+            f.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _ptr(a, t):
+    return None if a is None else a.ctypes.data_as(t)
+
+
+class Context:
+    """One GPU (cl2_ctx): stream, scratch pool, kernel timers."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = _vp()
+        rc = self.lib.cl2_ctx_create(int(device), ctypes.byref(h))
+        if rc != 0 or not h:
+            raise Cl2Error("cl2_ctx_create(device=%d) failed rc=%d (no CUDA device visible?)" % (device, rc))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cl2_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc, what):
+        if rc != 0:
+            msg = self.lib.cl2_last_error(self.h)
+            raise Cl2Error("%s failed rc=%d: %s" % (what, rc, msg.decode(errors="replace") if msg else ""))
+
+    def sync(self):
+        self.check(self.lib.cl2_ctx_sync(self.h), "cl2_ctx_sync")
+
+    # ---- pinned host staging
+    def pinned_empty(self, shape, dtype=np.int64):
+        """numpy array backed by page-locked memory (freed with the returned array's owner)."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) if len(np.shape(shape)) else int(shape)
+        nbytes = max(1, n * dtype.itemsize)
+        p = _vp()
+        self.check(self.lib.cl2_host_alloc(self.h, nbytes, ctypes.byref(p)), "cl2_host_alloc")
+        buf = (ctypes.c_char * nbytes).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+        owner = _PinnedOwner(self, p)
+        arr = arr.view(_PinnedArray)
+        arr._owner = owner
+        return arr
+
+    # ---- measurement
+    def launch_count(self):
+        return int(self.lib.cl2_launch_count(self.h))
+
+    def launch_count_reset(self):
+        self.lib.cl2_launch_count_reset(self.h)
+
+    def transfer_bytes(self):
+        a, b = ctypes.c_int64(0), ctypes.c_int64(0)
+        self.lib.cl2_transfer_bytes(self.h, ctypes.byref(a), ctypes.byref(b))
+        return a.value, b.value
+
+    def timing_enable(self, on=True):
+        self.check(self.lib.cl2_timing_enable(self.h, 1 if on else 0), "cl2_timing_enable")
+
+    def timing_reset(self):
+        self.lib.cl2_timing_reset(self.h)
+
+    def timing_read(self):
+        k = 32
+        names = ctypes.create_string_buffer(32 * k)
+        ms = (ctypes.c_double * k)()
+        ln = (ctypes.c_int64 * k)()
+        by = (ctypes.c_double * k)()
+        m = self.lib.cl2_timing_read(self.h, k, names, ms, ln, by)
+        out = {}
+        for i in range(m):
+            nm = names.raw[32 * i:32 * i + 32].split(b"\0")[0].decode()
+            out[nm] = {"ms": ms[i], "launches": int(ln[i]), "bytes": by[i]}
+        return out
+
+
+class _PinnedOwner:
+    def __init__(self, ctx, p):
+        self.ctx, self.p = ctx, p
+
+    def __del__(self):
+        try:
+            if self.p and self.ctx.h:
+                self.ctx.lib.cl2_host_free(self.ctx.h, self.p)
+        except Exception:
+            pass
+        self.p = None
+
+
+class _PinnedArray(np.ndarray):
+    _owner = None
+
+    def __array_finalize__(self, obj):
+        if obj is not None and getattr(obj, "_owner", None) is not None:
+            self._owner = obj._owner
+
+
+class Points:
+    """One .ixy matrix resident in HBM (cl2_points); the reference's `mat` after parseIxy (io.py:274-291)."""
+
+    def __init__(self, ctx, xy, cut=0, mcut=-1):
+        self.ctx = ctx
+        xy = np.ascontiguousarray(xy, dtype=np.int64)
+        if xy.ndim != 2 or xy.shape[1] != 2:
+            raise ValueError("xy must be int64[N,2]")
+        h = _vp()
+        ctx.check(ctx.lib.cl2_points_upload(ctx.h, _ptr(xy, _i64p), xy.shape[0], int(cut), int(mcut), ctypes.byref(h)),
+                  "cl2_points_upload")
+        self.h = h
+        self.n = int(ctx.lib.cl2_points_count(h))
+        self.ncl = 0
+
+    def close(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            self.ctx.lib.cl2_points_free(self.ctx.h, self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def extent(self):
+        ext = np.zeros(4, dtype=np.int64)
+        self.ctx.check(self.ctx.lib.cl2_points_extent(self.ctx.h, self.h, _ptr(ext, _i64p)), "cl2_points_extent")
+        return ext
+
+    def download(self):
+        out = np.empty((self.n, 2), dtype=np.int64)
+        self.ctx.check(self.ctx.lib.cl2_points_download(self.ctx.h, self.h, _ptr(out, _i64p)), "cl2_points_download")
+        return out
+
+    def _dbscan(self, fn, name, eps, minPts, want_labels):
+        labels = np.empty(self.n, dtype=np.int32) if want_labels else None
+        ncl = ctypes.c_int32(0)
+        self.ctx.check(fn(self.ctx.h, self.h, int(eps), int(minPts), _ptr(labels, _i32p), ctypes.byref(ncl)), name)
+        self.ncl = ncl.value
+        return labels, ncl.value
+
+    def block_dbscan(self, eps, minPts, want_labels=True):
+        return self._dbscan(self.ctx.lib.cl2_block_dbscan, "cl2_block_dbscan", eps, minPts, want_labels)
+
+    def cdbscan2(self, eps, minPts, want_labels=True):
+        return self._dbscan(self.ctx.lib.cl2_cdbscan2, "cl2_cdbscan2", eps, minPts, want_labels)
+
+    def cluster_bbox(self):
+        bbox = np.empty((self.ncl, 4), dtype=np.int64)
+        size = np.empty(self.ncl, dtype=np.int64)
+        if self.ncl:
+            self.ctx.check(self.ctx.lib.cl2_cluster_bbox(self.ctx.h, self.h, _ptr(bbox, _i64p), _ptr(size, _i64p)),
+                           "cl2_cluster_bbox")
+        return bbox, size
+
+    def block_noise_keep(self, eps, minPts):
+        keep = np.zeros(self.n, dtype=np.uint8)
+        self.ctx.check(self.ctx.lib.cl2_block_noise(self.ctx.h, self.h, int(eps), int(minPts), _ptr(keep, _u8p)),
+                       "cl2_block_noise")
+        return keep.astype(bool)
+
+
+class Index:
+    """Device XY index (cl2_index) = cLoops2/ds.py:141-198."""
+
+    def __init__(self, pts):
+        self.ctx = pts.ctx
+        self.n = pts.n
+        h = _vp()
+        self.ctx.check(self.ctx.lib.cl2_index_build(self.ctx.h, pts.h, ctypes.byref(h)), "cl2_index_build")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            self.ctx.lib.cl2_index_free(self.ctx.h, self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def loop_counts(self, loops, win=5, mode=MODE_CIS, core=True, windows=True, anchors=True):
+        loops = np.ascontiguousarray(loops, dtype=np.int64).reshape(-1, 4)
+        L = loops.shape[0]
+        W = 2 * win
+        o_core = np.zeros((L, 4), dtype=np.int64) if core else None
+        o_na = np.zeros((L, W), dtype=np.int64) if windows else None
+        o_nb = np.zeros((L, W), dtype=np.int64) if windows else None
+        o_nab = np.zeros((L, W * W), dtype=np.int64) if windows else None
+        o_anc = np.zeros((L, 4), dtype=np.int64) if anchors else None
+        self.ctx.check(self.ctx.lib.cl2_loop_counts(self.ctx.h, self.h, _ptr(loops, _i64p), L, win, mode,
+                                                    _ptr(o_core, _i64p), _ptr(o_na, _i64p), _ptr(o_nb, _i64p),
+                                                    _ptr(o_nab, _i64p), _ptr(o_anc, _i64p)), "cl2_loop_counts")
+        return o_core, o_na, o_nb, o_nab, o_anc
+
+
+_default_ctx = {}
+
+
+def default_context(device=None):
+    """Process-wide context for `device` (LOCAL_RANK when launched by torchrun, else 0)."""
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]

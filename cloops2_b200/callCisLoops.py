@@ -1,0 +1,289 @@
+"""
+Intra-chromosomal loop calling on B200 -- drop-in for cLoops2/callCisLoops.py on the `callLoops` path.
+
+Same public functions and argument meaning as the reference (runCisDBSCANLoops :58, estLoopSig :250, markSigLoops
+:357, selSigLoops :379, callCisLoops :471), but the work is organised around the device: each chromosome file is
+uploaded ONCE (pinned staging -> int32 coordinates in HBM), stays resident across the whole eps x minPts sweep
+(clustering + candidate boxes per pass), then the XY index is built on the device and the candidates are counted by
+the rectangle-count kernel; only candidate boxes and per-loop counts cross PCIe.  The reference's joblib fan-out
+over chromosomes (:134, :561) becomes chromosome sharding over ranks (one process per GPU, cloops2_b200/shard.py).
+"""
+import json
+import os
+from glob import glob
+
+import numpy as np
+
+from . import _lib, hostops, shard
+from .ds import Loop
+from .io import (ixyKey, loadIxy, parseIxy, updateJson, loops2txt, loops2ucscTxt, loops2juiceTxt, loops2washuTxt,
+                 loops2NewWashuTxt)
+
+logger = None
+
+
+def _log(msg):
+    if logger is not None:
+        logger.info(msg)
+
+
+def _sweep(eps, minPts, emPair):
+    """Order of clustering runs (callCisLoops.py:529-551): eps-major, or zipped pairs with -emPair."""
+    return list(zip(eps, minPts)) if emPair else [(e, m) for e in eps for m in minPts]
+
+
+# ---------------------------------------------------------------------------------------------- device passes
+def cluster_pass(pts, eps, minPts, hic=False, cis=True):
+    """One DBSCAN run on resident points + candidate filters.  Returns (cands int64[C,4], sizes int64[C]) in
+    ascending cluster id, which is the order the reference collects them in (callCisLoops.py:92-120)."""
+    if hic:
+        pts.cdbscan2(eps, minPts, want_labels=False)
+    else:
+        pts.block_dbscan(eps, minPts, want_labels=False)
+    bbox, size = pts.cluster_bbox()
+    ok = hostops.cis_candidate_mask(bbox) if cis else hostops.trans_candidate_mask(bbox)
+    return bbox[ok], size[ok]
+
+
+def cis_chromosome(ctx, key, xy, tot, eps, minPts, cut=0, mcut=-1, hic=False, emPair=False, pts=None):
+    """Whole per-chromosome path: sweep -> combine -> count -> test -> mark -> select.
+    xy: host int64[N,2] (ignored when a resident `pts` is passed).  Returns (final cols, stats dict)."""
+    own = pts is None
+    if own:
+        pts = _lib.Points(ctx, xy, cut=cut, mcut=mcut)
+    try:
+        stats = {"pets": pts.n, "candidates": 0, "tested": 0, "loops": 0}
+        if pts.n == 0:
+            return hostops._empty_cols(), stats
+        per_pass = []
+        for ep, mp in _sweep(eps, minPts, emPair):
+            _log("Clustering %s and %s using eps %s, minPts %s,pre-set distance cutoff > %s" % (key[0], key[1], ep, mp, cut))
+            c, s = cluster_pass(pts, ep, mp, hic=hic, cis=True)
+            _log("Clustering %s and %s finished. Estimated %s candidate loops with %s PETs." % (key[0], key[1], len(c), int(s.sum())))
+            per_pass.append(c)
+        cands = hostops.combine_unique(per_pass)
+        if cands.shape[0]:
+            cands = cands[hostops.cis_distance(cands) > cut]                         # filterLoopsByDis :146-156
+        stats["candidates"] = int(cands.shape[0])
+        if cands.shape[0] == 0:
+            return hostops._empty_cols(), stats
+        mm = min(minPts) if emPair else max(minPts)                                 # :557-560
+        ext = pts.extent()
+        span = float(int(ext[3]) - int(ext[0]))
+        index = _lib.Index(pts)
+        try:
+            _log("Estimate significance for %s candidate interactions in %s with %s PETs distance > =%s and <=%s,requiring minPts >=%s."
+                 % (cands.shape[0], "-".join(key), pts.n, cut, mcut, mm))
+            cols = hostops.est_cis(index, cands, pts.n, span, tot, mm, hic=hic)
+        finally:
+            index.close()
+        stats["tested"] = int(cols["coords"].shape[0])
+        sig = hostops.mark_sig_cis(cols, hic=hic)
+        final = hostops.select_twice(cols, sig)
+        stats["loops"] = int(final["coords"].shape[0])
+        return final, stats
+    finally:
+        if own:
+            pts.close()
+
+
+def cols_to_loops(key, cols, cis=True):
+    """Column arrays -> Loop objects (cLoops2/ds.py:245-281), Python scalars so str() prints as the reference's."""
+    out = []
+    c = cols["coords"]
+    for i in range(c.shape[0]):
+        lp = Loop()
+        lp.chromX, lp.chromY = key[0], key[1]
+        lp.x_start, lp.x_end, lp.y_start, lp.y_end = (int(v) for v in c[i])
+        lp.x_center = (lp.x_start + lp.x_end) / 2
+        lp.y_center = (lp.y_start + lp.y_end) / 2
+        lp.cis = cis
+        lp.distance = abs(lp.y_center - lp.x_center) if cis else -1
+        lp.ra, lp.rb, lp.rab = int(cols["ra"][i]), int(cols["rb"][i]), int(cols["rab"][i])
+        lp.P2LL, lp.FDR, lp.ES, lp.density = (float(cols[k][i]) for k in ("P2LL", "FDR", "ES", "density"))
+        lp.hypergeometric_p_value = float(cols["hyp"][i])
+        lp.poisson_p_value = float(cols["pop"][i])
+        lp.binomial_p_value = float(cols["nbp"][i])
+        lp.x_peak_poisson_p_value, lp.x_peak_es = float(cols["px"][i]), float(cols["esx"][i])
+        lp.y_peak_poisson_p_value, lp.y_peak_es = float(cols["py"][i]), float(cols["esy"][i])
+        lp.significant = 1
+        out.append(lp)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- reference API
+def runCisDBSCANLoops(fixy, eps, minPts, cut=0, mcut=-1, hic=False):
+    """Drop-in for callCisLoops.py:58-124: ("chrA-chrA", [Loop]) or None.  (`hic` selects cDBSCAN2, which the
+    reference does through the module-global DBSCAN, :498-504.)"""
+    key = ixyKey(fixy)
+    if key[0] != key[1]:
+        return None
+    ctx = _lib.default_context()
+    pts = _lib.Points(ctx, loadIxy(fixy), cut=cut, mcut=mcut)
+    try:
+        if pts.n == 0:
+            _log("No PETs found in %s, maybe due to cut > %s" % (fixy, cut))
+            return None
+        c, s = cluster_pass(pts, eps, minPts, hic=hic, cis=True)
+    finally:
+        pts.close()
+    loops = []
+    for i in range(c.shape[0]):
+        lp = Loop()
+        lp.rab = int(s[i])
+        lp.chromX, lp.chromY = key
+        lp.x_start, lp.x_end, lp.y_start, lp.y_end = (int(v) for v in c[i])
+        lp.x_center = (lp.x_start + lp.x_end) / 2
+        lp.y_center = (lp.y_start + lp.y_end) / 2
+        lp.cis = True
+        lp.distance = abs(lp.y_center - lp.x_center)
+        loops.append(lp)
+    return "-".join(key), loops
+
+
+def _loops_to_cands(loops):
+    return np.array([[lp.x_start, lp.x_end, lp.y_start, lp.y_end] for lp in loops], dtype=np.int64).reshape(-1, 4)
+
+
+def estLoopSig(key, loops, fixy, tot, minPts=5, pseudo=1, cut=0, mcut=-1, peakPcut=1e-5, win=5, countDiffCut=20,
+               hic=False):
+    """Drop-in for callCisLoops.py:250-354: (key, [Loop]) with the surviving loops annotated."""
+    ctx = _lib.default_context()
+    pts = _lib.Points(ctx, loadIxy(fixy), cut=cut, mcut=mcut)
+    try:
+        ext = pts.extent()
+        index = _lib.Index(pts)
+        try:
+            cols = hostops.est_cis(index, _loops_to_cands(loops), pts.n, float(int(ext[3]) - int(ext[0])), tot, minPts,
+                                   hic=hic, pseudo=pseudo, peakPcut=peakPcut, win=win, countDiffCut=countDiffCut)
+        finally:
+            index.close()
+    finally:
+        pts.close()
+    out = cols_to_loops(tuple(key.split("-")), cols, cis=True)
+    for lp in out:
+        del lp.significant
+    return key, out
+
+
+def markSigLoops(key, loops, hic=False):
+    """Drop-in for callCisLoops.py:357-376."""
+    for lp in loops:
+        sig = lp.FDR <= 0.05 and lp.ES >= 2 and lp.hypergeometric_p_value <= 1e-5 and lp.poisson_p_value <= 1e-5
+        lp.significant = 1 if (sig and lp.binomial_p_value < (1e-3 if hic else 1e-1)) else 0
+    return key, loops
+
+
+def selSigLoops(key, loops):
+    """Drop-in for callCisLoops.py:379-422 (native selection in libcl2.so)."""
+    loops = [lp for lp in loops if lp.significant > 0]
+    if not loops:
+        return key, []
+    pick = hostops.sel_sig(_loops_to_cands(loops), np.array([lp.ES for lp in loops], dtype=np.float64))
+    return key, [loops[i] for i in pick]
+
+
+def filterPETs(key, predir, fixy, loops, margin=1):
+    """-filter (callCisLoops.py:425-468): keep PETs with an end inside any merged anchor."""
+    _log("Filtering PETs of %s with %s loops." % (key, len(loops)))
+    if not loops:
+        return
+    iv = []
+    for lp in loops:
+        iv.append((lp.x_start, lp.x_end))
+        iv.append((lp.y_start, lp.y_end))
+    iv.sort()
+    # getAllAnchors (:425-447): covered base pairs merged while the gap between consecutive covered positions is
+    # <= margin; the reference's loop drops the final covered position of the last anchor.
+    merged = []
+    for s, e in iv:
+        if merged and s - merged[-1][1] <= margin:
+            merged[-1][1] = max(merged[-1][1], e)
+        else:
+            merged.append([s, e])
+    if merged:
+        if merged[-1][1] > merged[-1][0]:
+            merged[-1][1] -= 1
+        elif len(merged) > 1:
+            merged.pop()
+    key2, mat = parseIxy(fixy)
+    rs = set()
+    xs, ys = mat[:, 0], mat[:, 1]
+    for s, e in merged:
+        hit = np.nonzero(((xs >= s) & (xs <= e)) | ((ys >= s) & (ys <= e)))[0]
+        rs.update(hit.tolist())
+    rs = list(rs)
+    if len(rs) == 0:
+        return
+    import joblib
+    joblib.dump(mat[rs, ], predir + "/" + "-".join(key2) + ".ixy")
+
+
+def callCisLoops(predir, fout, log, eps=[2000, 5000], minPts=[5, 10], cpu=1, cut=0, mcut=-1, plot=False,
+                 max_cut=False, hic=False, filter=False, ucsc=False, juicebox=False, washU=False, emPair=False):
+    """Drop-in for callCisLoops.py:471-628.  `cpu` is accepted for compatibility; parallelism is one process per GPU
+    (launch under torchrun for more than one), chromosomes sharded by PET count."""
+    global logger
+    logger = log
+    if hic:
+        _log("-hic option selected, cDBSCAN2 is used instead of blockDBSCAN.")
+    if emPair and len(eps) != len(minPts):
+        _log("-emPair option selected, number of eps not equal to minPts, return.")
+        return
+    meta = json.loads(open(predir + "/petMeta.json").read())
+    tot = meta["Unique PETs"]
+    rank, world = shard.rank_world()
+    fdir = fout + "_filtered"
+    if filter and rank == 0:
+        _log("-filter option chosed, will filter raw PETs based on called loops, for any PET that any end overlaps loop anchors will be kept. ")
+        if not os.path.exists(fdir):
+            os.mkdir(fdir)
+        elif len(os.listdir(fdir)) > 0:
+            if logger is not None:
+                logger.error("working directory %s exists and not empty." % fdir)
+            return
+    keys = list(meta["data"]["cis"].keys())
+    files = {k: meta["data"]["cis"][k]["ixy"] for k in keys}
+    mine = shard.assign(keys, [shard.ixy_rows(files[k]) for k in keys], world)[rank]
+    ctx = _lib.default_context()
+    results = {}
+    stats = np.zeros(4, dtype=np.int64)
+    for k in mine:
+        xy = loadIxy(files[k])
+        final, st = cis_chromosome(ctx, tuple(k.split("-")), xy, tot, eps, minPts, cut=cut, mcut=mcut, hic=hic,
+                                   emPair=emPair)
+        stats += np.array([st["pets"], st["candidates"], st["tested"], st["loops"]], dtype=np.int64)
+        if st["tested"] > 0:
+            results[k] = final
+    stats = shard.allreduce_stats(stats)
+    gathered = shard.gather_results(results)
+    if rank != 0:
+        return
+    _log("Estimating loop statstical significance.")
+    _log("Selecting the most significant loops of overlapped ones. ")
+    per_key = {}
+    loops = []
+    for k in keys:                                   # meta key order, as the reference's dicts (:137, :572, :597-599)
+        if k in gathered:
+            per_key[k] = cols_to_loops(tuple(k.split("-")), gathered[k], cis=True)
+            loops.extend(per_key[k])
+    _log("Output %s loops to %s_loops.txt" % (len(loops), fout))
+    loops2txt(loops, fout + "_loops.txt")
+    if ucsc:
+        loops2ucscTxt(loops, fout + "_loops_ucsc.interact")
+    if juicebox:
+        loops2juiceTxt(loops, fout + "_loops_juicebox.txt")
+    if washU:
+        loops2washuTxt(loops, fout + "_loops_legacyWashU.txt")
+        loops2NewWashuTxt(loops, fout + "_loops_newWashU.txt")
+    if filter:
+        for k in per_key:
+            filterPETs(k, fdir, files[k], per_key[k], margin=max(eps))
+        ixyfs = glob(fdir + "/*.ixy")
+        n = 0
+        for f in ixyfs:
+            n += loadIxy(f).shape[0]
+        with open(fdir + "/petMeta.json", "w") as fo:
+            json.dump({"Unique PETs": n}, fo)
+        updateJson(ixyfs, fdir + "/petMeta.json")
+    return stats

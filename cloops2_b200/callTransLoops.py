@@ -1,0 +1,147 @@
+"""
+Inter-chromosomal loop calling on B200 -- drop-in for cLoops2/callTransLoops.py (runTransDBSCANLoops :33,
+estLoopSig :106, markSigLoops :196, callTransLoops :209).  Same device-resident organisation as the cis path; the
+differences the reference has are kept: blockDBSCAN only (:29), no cut / anchor-size / order filters (:58-79),
+distance = -1 (:78), P2LL window lower-left in both axes (:142-145), mean instead of median background (:171-172),
+binomial n = ra*rb (:181), density over the file's own PET count (:185-187), no early-exit filters, and the
+significance rule binomial <= 1e-10, FDR <= 0.05, ES >= 2 (:200).
+"""
+import json
+
+import numpy as np
+
+from . import _lib, hostops, shard
+from .ds import Loop
+from .io import ixyKey, loadIxy, loops2txt, loops2juiceTxt, loops2washuTxt
+from .callCisLoops import cluster_pass, cols_to_loops, selSigLoops, _loops_to_cands  # noqa: F401
+
+
+def trans_pair(ctx, key, xy, eps, minPts, pts=None):
+    """Whole per-pair path (sweep -> combine -> count -> test -> mark -> select); returns (final cols, stats)."""
+    own = pts is None
+    if own:
+        pts = _lib.Points(ctx, xy, cut=0, mcut=-1)
+    try:
+        stats = {"pets": pts.n, "candidates": 0, "tested": 0, "loops": 0}
+        if pts.n == 0:
+            return hostops._empty_cols(), stats
+        per_pass = []
+        for ep in eps:
+            for mp in minPts:
+                c, _ = cluster_pass(pts, ep, mp, hic=False, cis=False)
+                per_pass.append(c)
+        # combineLoops only (callTransLoops.py:230-234): coordinates unseen in EARLIER passes are appended; clusters of
+        # one pass never share a bounding box with another cluster of the same pass unless their boxes coincide, in
+        # which case the reference keeps both -- reproduce by de-duplicating across passes only.
+        cands = _combine_across_passes(per_pass)
+        stats["candidates"] = int(cands.shape[0])
+        if cands.shape[0] == 0:
+            return hostops._empty_cols(), stats
+        ext = pts.extent()
+        index = _lib.Index(pts)
+        try:
+            cols = hostops.est_trans(index, cands, pts.n, float(int(ext[3]) - int(ext[0])), max(minPts))
+        finally:
+            index.close()
+        stats["tested"] = int(cols["coords"].shape[0])
+        final = hostops.select_twice(cols, hostops.mark_sig_trans(cols))
+        stats["loops"] = int(final["coords"].shape[0])
+        return final, stats
+    finally:
+        if own:
+            pts.close()
+
+
+def _combine_across_passes(per_pass):
+    seen = set()
+    out = []
+    for c in per_pass:
+        rows = [tuple(r) for r in c.tolist()]
+        out.extend(r for r in rows if r not in seen)
+        seen.update(rows)
+    return np.array(out, dtype=np.int64).reshape(-1, 4)
+
+
+def runTransDBSCANLoops(fixy, eps, minPts):
+    """Drop-in for callTransLoops.py:33-84."""
+    key = ixyKey(fixy)
+    ctx = _lib.default_context()
+    pts = _lib.Points(ctx, loadIxy(fixy))
+    try:
+        c, s = cluster_pass(pts, eps, minPts, hic=False, cis=False) if pts.n else (np.zeros((0, 4), np.int64), np.zeros(0, np.int64))
+    finally:
+        pts.close()
+    loops = []
+    for i in range(c.shape[0]):
+        lp = Loop()
+        lp.rab = int(s[i])
+        lp.chromX, lp.chromY = key
+        lp.x_start, lp.x_end, lp.y_start, lp.y_end = (int(v) for v in c[i])
+        lp.x_center = (lp.x_start + lp.x_end) / 2
+        lp.y_center = (lp.y_start + lp.y_end) / 2
+        lp.distance = -1
+        lp.cis = False
+        loops.append(lp)
+    return "-".join(key), loops
+
+
+def estLoopSig(key, loops, fixy, minPts=5, pseudo=1, peakPcut=1e-5, peakFccut=2, countDiffCut=10):
+    """Drop-in for callTransLoops.py:106-193."""
+    ctx = _lib.default_context()
+    pts = _lib.Points(ctx, loadIxy(fixy))
+    try:
+        ext = pts.extent()
+        index = _lib.Index(pts)
+        try:
+            cols = hostops.est_trans(index, _loops_to_cands(loops), pts.n, float(int(ext[3]) - int(ext[0])), minPts,
+                                     pseudo=pseudo, countDiffCut=countDiffCut)
+        finally:
+            index.close()
+    finally:
+        pts.close()
+    out = cols_to_loops(tuple(key.split("-")), cols, cis=False)
+    for lp in out:
+        del lp.significant
+    return key, out
+
+
+def markSigLoops(key, loops):
+    """Drop-in for callTransLoops.py:196-206."""
+    for lp in loops:
+        lp.significant = 1 if (lp.binomial_p_value <= 1e-10 and lp.FDR <= 0.05 and lp.ES >= 2) else 0
+    return key, loops
+
+
+def callTransLoops(predir, fout, logger, eps=[2000, 5000], minPts=[5, 10], cpu=1, filter=False, washU=False,
+                   juicebox=False):
+    """Drop-in for callTransLoops.py:209-275; chromosome pairs sharded over ranks by PET count."""
+    meta = json.loads(open(predir + "/petMeta.json").read())
+    keys = list(meta["data"]["trans"].keys())
+    files = {k: meta["data"]["trans"][k]["ixy"] for k in keys}
+    rank, world = shard.rank_world()
+    mine = shard.assign(keys, [shard.ixy_rows(files[k]) for k in keys], world)[rank]
+    ctx = _lib.default_context()
+    results = {}
+    stats = np.zeros(4, dtype=np.int64)
+    for k in mine:
+        final, st = trans_pair(ctx, tuple(k.split("-")), loadIxy(files[k]), eps, minPts)
+        stats += np.array([st["pets"], st["candidates"], st["tested"], st["loops"]], dtype=np.int64)
+        if st["candidates"] > 0:
+            results[k] = final
+    stats = shard.allreduce_stats(stats)
+    gathered = shard.gather_results(results)
+    if rank != 0:
+        return
+    logger.info("Estimating loop statstical significance.")
+    logger.info("Selecting the most significant loops of overlapped ones. ")
+    loops = []
+    for k in keys:
+        if k in gathered:
+            loops.extend(cols_to_loops(tuple(k.split("-")), gathered[k], cis=False))
+    logger.info("Output %s loops to %s_loops.txt" % (len(loops), fout))
+    loops2txt(loops, fout + "_trans_loops.txt")
+    if washU:
+        loops2washuTxt(loops, fout + "_trans_loops_washU.txt")
+    if juicebox:
+        loops2juiceTxt(loops, fout + "_trans_loops_juicebox.txt")
+    return stats

@@ -1,0 +1,113 @@
+"""
+`cLoops2 callLoops` command line (cLoops2/cLoops2.py:1431-1548 parser, :3639-3734 dispatch, :60-85 eps / minPts
+parsing) for the B200 path.  Flags, defaults, ordering rules and log messages follow the reference; the other 21
+sub-commands of cLoops2 are out of scope.  Run as `python -m cloops2_b200.cli callLoops -d DIR -o OUT -eps ... -minPts ...`
+(under torchrun for several GPUs).
+"""
+import argparse
+import logging
+import os
+import sys
+from datetime import datetime
+
+from . import shard
+
+
+def parseEps(eps, emPair=False):
+    """cLoops2.py:60-71: comma list -> ints, ascending unless -emPair."""
+    eps = list(map(int, eps.split(","))) if "," in str(eps) else [int(eps)]
+    if not emPair:
+        eps.sort()
+    return eps
+
+
+def parseMinpts(minPts, emPair=False):
+    """cLoops2.py:74-85: comma list -> ints, descending unless -emPair."""
+    minPts = list(map(int, minPts.split(","))) if "," in str(minPts) else [int(minPts)]
+    if not emPair:
+        minPts.sort(reverse=True)
+    return minPts
+
+
+def getLogger(fn="cLoops2.log"):
+    """File + stdout logger like cLoops2/utils.py:71-99."""
+    log = logging.getLogger("cLoops2")
+    if not log.handlers:
+        log.setLevel(logging.INFO)
+        fmt = logging.Formatter("%(asctime)s %(name)-6s %(levelname)-8s %(message)s", datefmt="%Y-%m-%d %H:%M:%S")
+        for h in (logging.FileHandler(fn), logging.StreamHandler(sys.stdout)):
+            h.setFormatter(fmt)
+            log.addHandler(h)
+    return log
+
+
+def buildParser():
+    p = argparse.ArgumentParser(prog="cLoops2", description="cLoops2 callLoops on B200 (cl2-b200)")
+    sub = p.add_subparsers(dest="cmd")
+    c = sub.add_parser("callLoops", help="Call intra- (and with -trans inter-) chromosomal loops.")
+    # shared flags, cLoops2.py:165-235
+    c.add_argument("-d", dest="predir", type=str, default="")
+    c.add_argument("-o", dest="fnOut", type=str, default="cLoops2_output")
+    c.add_argument("-p", dest="cpu", type=int, default=1)
+    c.add_argument("-cut", dest="cut", type=int, default=0)
+    c.add_argument("-mcut", dest="mcut", type=int, default=-1)
+    # callLoops flags, cLoops2.py:1439-1548
+    c.add_argument("-eps", dest="eps", default=0)
+    c.add_argument("-minPts", dest="minPts", default=0)
+    c.add_argument("-plot", dest="plot", action="store_true", default=False)
+    c.add_argument("-i", dest="ucsc", action="store_true", default=False)
+    c.add_argument("-j", dest="juicebox", action="store_true", default=False)
+    c.add_argument("-w", dest="washU", action="store_true", default=False)
+    c.add_argument("-max_cut", dest="max_cut", action="store_true", default=False)
+    c.add_argument("-hic", dest="hic", action="store_true", default=False)
+    c.add_argument("-filter", dest="filterPETs", action="store_true", default=False)
+    c.add_argument("-trans", dest="trans", action="store_true", default=False)
+    c.add_argument("-emPair", dest="emPair", action="store_true", default=False)
+    return p
+
+
+def main(argv=None):
+    from .callCisLoops import callCisLoops
+    from .callTransLoops import callTransLoops
+    op = buildParser().parse_args(argv)
+    if op.cmd != "callLoops":
+        buildParser().print_help()
+        return 1
+    rank, world = shard.init_from_env()
+    logger = getLogger() if rank == 0 else logging.getLogger("cLoops2.rank%d" % rank)
+    start = datetime.now()
+    logger.info("Command: cLoops2 {} -d {} -eps {} -minPts {} -p {} -o {} -cut {} -mcut {} -filter {} -i {} -j {} -w {} -hic {} -max_cut {} -trans {} -emPair {}".format(
+        op.cmd, op.predir, op.eps, op.minPts, op.cpu, op.fnOut, op.cut, op.mcut, op.filterPETs, op.ucsc, op.juicebox,
+        op.washU, op.hic, op.max_cut, op.trans, op.emPair))
+    if op.predir == "":
+        logger.error("No -d assigned! Return.")
+        return 1
+    if not os.path.exists(op.predir):
+        logger.error("%s not exists! Return." % op.predir)
+        return 1
+    eps = parseEps(op.eps, op.emPair)
+    if len(eps) == 1 and eps[0] == 0:
+        logger.error("Input eps is 0. Return.")
+        return 1
+    minPts = parseMinpts(op.minPts, op.emPair)
+    if len(minPts) == 1 and minPts[0] == 0:
+        logger.error("Input minPts is 0. Return.")
+        return 1
+    if os.path.isfile(op.fnOut + "_loop.txt"):          # the reference checks this name (cLoops2.py:3683)
+        logger.error("Output file %s exists, return." % (op.fnOut + "_loop.txt"))
+        return 1
+    callCisLoops(op.predir, op.fnOut, logger, eps=eps, minPts=minPts, cpu=op.cpu, cut=op.cut, mcut=op.mcut,
+                 plot=op.plot, max_cut=op.max_cut, hic=op.hic, filter=op.filterPETs, ucsc=op.ucsc,
+                 juicebox=op.juicebox, washU=op.washU, emPair=op.emPair)
+    if op.trans:
+        if os.path.isfile(op.fnOut + "_trans_loop.txt"):
+            logger.error("Output file %s exists, return." % (op.fnOut + "_trans_loop.txt"))
+            return 1
+        callTransLoops(op.predir, op.fnOut, logger, eps=eps, minPts=minPts, cpu=op.cpu, filter=op.filterPETs,
+                       washU=op.washU, juicebox=op.juicebox)
+    logger.info("cLoops2 %s finished. Used time: %s." % (op.cmd, datetime.now() - start) + "\n" * 3)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,803 @@
+// cl2_block.cu -- blockDBSCAN (cLoops2/blockDBSCAN.py:13-234) as an order-independent, data-parallel pipeline.
+//
+// The reference is a sequence of Python dict passes whose result depends on dict insertion order (= .ixy row order).
+// The restatement used here (re-verified against the reference through oracle/) makes every
+// order-dependent rule an explicit key:
+//   cells      = segments of the points sorted by packed cell key (stable sort => first element of a segment carries
+//                the smallest row id = the cell's dict position `first`)
+//   noise      = cell removed iff its 3x3 population < minPts and the same holds for every existing neighbour
+//   adjacency  = centroid L1 <= eps (fp64, exactly the reference's expression) or some cross pair with L1 <= eps
+//   core cell  = cnt + sum(cnt of adjacent kept cells) >= minPts
+//   clusters   = connected components of core cells (lock-free union-find), numbered by the rank of their first
+//                cell in the stable sort by (-cnt, first)
+//   border     = kept non-core cell: largest cluster whose START cell is adjacent, else smallest adjacent cluster
+#include "cl2_points.cuh"
+
+#define NOT_FOUND (-1)
+
+__constant__ int c_dx[8] = {0, 0, -1, 1, -1, -1, 1, 1};
+__constant__ int c_dy[8] = {-1, 1, 0, 0, -1, 1, -1, 1};
+// opposite direction index
+__constant__ int c_opp[8] = {1, 0, 3, 2, 7, 6, 5, 4};
+
+// ------------------------------------------------------------------------------------------------ K1 keygen
+__global__ void __launch_bounds__(256) k_block_keygen(const int2 *__restrict__ xy, uint64_t *__restrict__ key,
+                                                       int64_t n, int minx, int miny, unsigned eps, int by) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int2 p = xy[i];
+    unsigned gx = (unsigned)(p.x - minx) / eps;   // == int((X-minX)/eps) of blockDBSCAN.py:81 for non-negative ints
+    unsigned gy = (unsigned)(p.y - miny) / eps;
+    key[i] = ((uint64_t)gx << by) | (uint64_t)gy;
+}
+
+// ------------------------------------------------------------------------------------------------ K3 gather
+__global__ void __launch_bounds__(256) k_gather_xy(const int2 *__restrict__ xy, const uint32_t *__restrict__ row,
+                                                    int2 *__restrict__ sxy, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) sxy[i] = __ldg(&xy[row[i]]);
+}
+
+// ------------------------------------------------------------------------------------------------ K4 cells
+__global__ void __launch_bounds__(256) k_head_flags(const uint64_t *__restrict__ key, int32_t *__restrict__ flag,
+                                                     int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    flag[i] = (i == 0 || key[i] != key[i - 1]) ? 1 : 0;
+}
+
+// cid holds the exclusive scan of the head flags on entry; on exit the cell id of every sorted position.
+__global__ void __launch_bounds__(256) k_cell_table(const uint64_t *__restrict__ key, int32_t *__restrict__ cid,
+                                                     int32_t *__restrict__ cstart, uint64_t *__restrict__ ckey,
+                                                     int64_t n, int32_t ncells) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t k = key[i];
+    bool head = (i == 0 || k != key[i - 1]);
+    int32_t c = cid[i] + (head ? 1 : 0) - 1;
+    cid[i] = c;
+    if (head) {
+        cstart[c] = (int32_t)i;
+        ckey[c] = k;
+    }
+    if (i == n - 1) cstart[ncells] = (int32_t)n;
+}
+
+// ------------------------------------------------------------------------------------------------ K6 neighbours
+// first index >= target, searching forward from c (exclusive) by galloping: rows of the grid are short, so the
+// answer is almost always within a few cells of c.
+__device__ __forceinline__ int lb_forward(const uint64_t *__restrict__ ckey, int ncells, int c, uint64_t target) {
+    int lo = c + 1, hi = c + 1, step = 1;
+    while (hi < ncells && ckey[hi] < target) {
+        lo = hi + 1;
+        hi += step;
+        step <<= 1;
+    }
+    if (hi > ncells) hi = ncells;
+    while (lo < hi) {
+        int m = (lo + hi) >> 1;
+        if (ckey[m] < target) lo = m + 1; else hi = m;
+    }
+    return lo;
+}
+// first index >= target, target < ckey[c], searching backward from c
+__device__ __forceinline__ int lb_backward(const uint64_t *__restrict__ ckey, int c, uint64_t target) {
+    int hi = c, lo = c - 1, step = 1;
+    while (lo >= 0 && ckey[lo] >= target) {
+        hi = lo;
+        lo -= step;
+        step <<= 1;
+    }
+    int l = (lo < 0 ? -1 : lo) + 1, h = hi;
+    while (l < h) {
+        int m = (l + h) >> 1;
+        if (ckey[m] < target) l = m + 1; else h = m;
+    }
+    return l;
+}
+
+__global__ void __launch_bounds__(256) k_block_nbr(const uint64_t *__restrict__ ckey,
+                                                    const int32_t *__restrict__ cstart, int32_t *__restrict__ nbr,
+                                                    int32_t *__restrict__ s3, int32_t *__restrict__ maxcnt,
+                                                    int32_t ncells, int by) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    int mycnt = 0;
+    if (c < ncells) {
+        const uint64_t k = ckey[c];
+        const uint64_t ymask = (1ull << by) - 1;
+        const long long gx = (long long)(k >> by), gy = (long long)(k & ymask);
+        int out[8];
+#pragma unroll
+        for (int d = 0; d < 8; d++) out[d] = NOT_FOUND;
+        // same row
+        if (gy > 0 && c > 0 && ckey[c - 1] == k - 1) out[0] = c - 1;
+        if (gy < (long long)ymask && c + 1 < ncells && ckey[c + 1] == k + 1) out[1] = c + 1;
+        // row gx+1: wanted keys (gx+1, gy-1..gy+1)
+        {
+            long long y0 = gy > 0 ? gy - 1 : 0;
+            uint64_t t0 = ((uint64_t)(gx + 1) << by) | (uint64_t)y0;
+            int p = lb_forward(ckey, ncells, c, t0);
+            for (int q = p; q < ncells && q < p + 3; q++) {
+                uint64_t kk = ckey[q];
+                if ((long long)(kk >> by) != gx + 1) break;
+                long long yy = (long long)(kk & ymask);
+                if (yy == gy - 1) out[6] = q;
+                else if (yy == gy) out[3] = q;
+                else if (yy == gy + 1) out[7] = q;
+                else break;
+            }
+        }
+        if (gx > 0) {
+            long long y0 = gy > 0 ? gy - 1 : 0;
+            uint64_t t0 = ((uint64_t)(gx - 1) << by) | (uint64_t)y0;
+            int p = lb_backward(ckey, c, t0);
+            for (int q = p; q < c && q < p + 3; q++) {
+                uint64_t kk = ckey[q];
+                if ((long long)(kk >> by) != gx - 1) break;
+                long long yy = (long long)(kk & ymask);
+                if (yy == gy - 1) out[4] = q;
+                else if (yy == gy) out[2] = q;
+                else if (yy == gy + 1) out[5] = q;
+                else break;
+            }
+        }
+        mycnt = cstart[c + 1] - cstart[c];
+        int s = mycnt;
+#pragma unroll
+        for (int d = 0; d < 8; d++) {
+            if (out[d] >= 0) s += cstart[out[d] + 1] - cstart[out[d]];
+        }
+        int4 *o = reinterpret_cast<int4 *>(nbr + 8 * (int64_t)c);
+        o[0] = make_int4(out[0], out[1], out[2], out[3]);
+        o[1] = make_int4(out[4], out[5], out[6], out[7]);
+        s3[c] = s;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mycnt = max(mycnt, __shfl_xor_sync(0xffffffffu, mycnt, o));
+    if ((threadIdx.x & 31) == 0 && mycnt > 0) atomicMax(maxcnt, mycnt);
+}
+
+// ------------------------------------------------------------------------------------------------ K7 noise
+// keep[c] = 0 iff s3[c] < minPts and every existing neighbour has s3 < minPts (blockDBSCAN.py:101-122)
+__global__ void __launch_bounds__(256) k_block_noise(const int32_t *__restrict__ nbr, const int32_t *__restrict__ s3,
+                                                      uint8_t *__restrict__ keep, int32_t ncells, int minPts) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    bool k = true;
+    if (s3[c] < minPts) {
+        k = false;
+        const int4 *o = reinterpret_cast<const int4 *>(nbr + 8 * (int64_t)c);
+        int4 a = o[0], b = o[1];
+        int nb[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int d = 0; d < 8; d++)
+            if (nb[d] >= 0 && s3[nb[d]] >= minPts) k = true;
+    }
+    keep[c] = k ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) k_keep_points(const int32_t *__restrict__ cid, const uint32_t *__restrict__ row,
+                                                      const uint8_t *__restrict__ keep, uint8_t *__restrict__ out,
+                                                      int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[row[i]] = keep[cid[i]];
+}
+
+// ------------------------------------------------------------------------------------------------ K8 cell stats
+struct CellStat {
+    long long sx, sy;        // coordinate sums (centroid = sum / cnt in fp64, blockDBSCAN.py:131-137)
+    int xmin, xmax, ymin, ymax;
+};
+
+// compact list of kept cells (so later kernels launch one unit per kept cell)
+__global__ void __launch_bounds__(256) k_keep_flags_i32(const uint8_t *__restrict__ keep, int32_t *__restrict__ f,
+                                                         int32_t ncells) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < ncells) f[c] = keep[c];
+}
+__global__ void __launch_bounds__(256) k_keep_list(const uint8_t *__restrict__ keep, const int32_t *__restrict__ pos,
+                                                    int32_t *__restrict__ list, int32_t ncells) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < ncells && keep[c]) list[pos[c]] = c;
+}
+__global__ void __launch_bounds__(256) k_block_cellstat_list(const int2 *__restrict__ sxy,
+                                                              const int32_t *__restrict__ cstart,
+                                                              const int32_t *__restrict__ list,
+                                                              CellStat *__restrict__ st, int32_t nkept) {
+    int k = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    int lane = threadIdx.x & 31;
+    if (k >= nkept) return;
+    int c = list[k];
+    int b = cstart[c], e = cstart[c + 1];
+    long long sx = 0, sy = 0;
+    int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
+    for (int i = b + lane; i < e; i += 32) {
+        int2 p = sxy[i];
+        sx += p.x; sy += p.y;
+        xmin = min(xmin, p.x); xmax = max(xmax, p.x);
+        ymin = min(ymin, p.y); ymax = max(ymax, p.y);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, o);
+        sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+        xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+        ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+        ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+    }
+    if (lane == 0) {
+        CellStat s;
+        s.sx = sx; s.sy = sy; s.xmin = xmin; s.xmax = xmax; s.ymin = ymin; s.ymax = ymax;
+        st[c] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K9 adjacency
+#define ADJ_LIGHT_MAX 2048   // |a|*|b| up to this is tested by one thread; larger pairs go to the block-per-pair kernel
+
+__device__ __forceinline__ bool centroid_close(const CellStat &a, int na, const CellStat &b, int nb, double eps) {
+    // blockDBSCAN.py:136-137 (x / len) and :46,:227 (abs(dx)+abs(dy) <= eps), fp64, no contraction possible
+    double ax = (double)a.sx / (double)na, ay = (double)a.sy / (double)na;
+    double bx = (double)b.sx / (double)nb, by = (double)b.sy / (double)nb;
+    return fabs(ax - bx) + fabs(ay - by) <= eps;
+}
+
+// forward directions (neighbour index > own index in key order): (0,+1)=1, (+1,-1)=6, (+1,0)=3, (+1,+1)=7
+__global__ void __launch_bounds__(128) k_block_adj(const int2 *__restrict__ sxy, const int32_t *__restrict__ cstart,
+                                                    const int32_t *__restrict__ nbr, const uint8_t *__restrict__ keep,
+                                                    const CellStat *__restrict__ st, const int32_t *__restrict__ list,
+                                                    int32_t nkept, unsigned *__restrict__ adj, int64_t eps,
+                                                    int2 *__restrict__ heavy, int32_t *__restrict__ nheavy) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int k = (int)(t >> 2);
+    if (k >= nkept) return;
+    const int fdir[4] = {1, 6, 3, 7};
+    int d = fdir[t & 3];
+    int a = list[k];
+    int b = nbr[8 * (int64_t)a + d];
+    if (b < 0 || !keep[b]) return;
+    int a0 = cstart[a], a1 = cstart[a + 1], b0 = cstart[b], b1 = cstart[b + 1];
+    int na = a1 - a0, nb = b1 - b0;
+    bool close = centroid_close(st[a], na, st[b], nb, (double)eps);
+    if (!close) {
+        // bounding boxes further apart than eps in L1 can hold no close pair
+        const CellStat &A = st[a], &B = st[b];
+        long long gx = max(0, max(A.xmin - B.xmax, B.xmin - A.xmax));
+        long long gy = max(0, max(A.ymin - B.ymax, B.ymin - A.ymax));
+        if (gx + gy > eps) return;
+        if ((long long)na * nb > ADJ_LIGHT_MAX) {
+            int slot = atomicAdd(nheavy, 1);
+            heavy[slot] = make_int2(a, d);
+            return;
+        }
+        for (int i = a0; i < a1 && !close; i++) {
+            int2 p = sxy[i];
+            for (int j = b0; j < b1; j++) {
+                int2 q = sxy[j];
+                long long dist = (long long)abs(p.x - q.x) + (long long)abs(p.y - q.y);
+                if (dist <= eps) { close = true; break; }
+            }
+        }
+    }
+    if (close) {
+        atomicOr(&adj[a], 1u << d);
+        atomicOr(&adj[b], 1u << c_opp[d]);
+    }
+}
+
+// one block per heavy pair: tile b's points through shared memory, all threads scan a's points against the tile
+#define HEAVY_THREADS 256
+#define HEAVY_TILE 1024
+__global__ void __launch_bounds__(HEAVY_THREADS) k_block_adj_heavy(const int2 *__restrict__ sxy,
+                                                                    const int32_t *__restrict__ cstart,
+                                                                    const int32_t *__restrict__ nbr,
+                                                                    const int2 *__restrict__ heavy,
+                                                                    unsigned *__restrict__ adj, int64_t eps) {
+    __shared__ int2 tile[HEAVY_TILE];
+    __shared__ int found;
+    int2 h = heavy[blockIdx.x];
+    int a = h.x, d = h.y;
+    int b = nbr[8 * (int64_t)a + d];
+    int a0 = cstart[a], a1 = cstart[a + 1], b0 = cstart[b], b1 = cstart[b + 1];
+    if (threadIdx.x == 0) found = 0;
+    __syncthreads();
+    for (int tb = b0; tb < b1; tb += HEAVY_TILE) {
+        int tn = min(HEAVY_TILE, b1 - tb);
+        for (int j = threadIdx.x; j < tn; j += HEAVY_THREADS) tile[j] = sxy[tb + j];
+        __syncthreads();
+        for (int i = a0 + threadIdx.x; i < a1; i += HEAVY_THREADS) {
+            int2 p = sxy[i];
+            bool hit = false;
+            for (int j = 0; j < tn; j++) {
+                int2 q = tile[j];
+                long long dist = (long long)abs(p.x - q.x) + (long long)abs(p.y - q.y);
+                if (dist <= eps) { hit = true; break; }
+            }
+            if (hit) { found = 1; break; }
+            if (found) break;   // another thread already found a pair (only shortens this thread's scan)
+        }
+        __syncthreads();
+        int f = found;          // uniform: written only between the two barriers above
+        if (f) break;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && found) {
+        atomicOr(&adj[a], 1u << d);
+        atomicOr(&adj[b], 1u << c_opp[d]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K10 core
+// near = cnt + sum of adjacent kept cells' cnt; core iff near >= minPts (blockDBSCAN.py:179-189).
+// okey orders cells like the stable sort by -cnt of blockDBSCAN.py:147 (ties: dict position = first row id).
+__global__ void __launch_bounds__(256) k_block_core(const int32_t *__restrict__ cstart, const int32_t *__restrict__ nbr,
+                                                     const unsigned *__restrict__ adj, const uint32_t *__restrict__ row,
+                                                     const int32_t *__restrict__ list, int32_t nkept, int minPts,
+                                                     int32_t maxcnt, uint8_t *__restrict__ core,
+                                                     uint64_t *__restrict__ okey, int32_t *__restrict__ parent,
+                                                     uint64_t *__restrict__ minkey) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nkept) return;
+    int c = list[k];
+    int cnt = cstart[c + 1] - cstart[c];
+    long long near = cnt;
+    unsigned m = adj[c];
+    while (m) {
+        int d = __ffs(m) - 1;
+        m &= m - 1;
+        int b = nbr[8 * (int64_t)c + d];
+        near += cstart[b + 1] - cstart[b];
+    }
+    core[c] = near >= minPts ? 1 : 0;
+    okey[c] = ((uint64_t)(uint32_t)(maxcnt - cnt) << 32) | (uint64_t)row[cstart[c]];
+    parent[c] = c;
+    minkey[c] = ~0ull;
+}
+
+// ------------------------------------------------------------------------------------------------ K11 union-find
+__device__ __forceinline__ int uf_find(int32_t *parent, int x) {
+    int p = parent[x];
+    while (p != x) {
+        int gp = parent[p];
+        if (gp != p) parent[x] = gp;   // path halving; benign race (only ever moves a node closer to its root)
+        x = p;
+        p = gp;
+    }
+    return x;
+}
+__device__ __forceinline__ void uf_unite(int32_t *parent, int a, int b) {
+    while (true) {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b) return;
+        if (a > b) { int t = a; a = b; b = t; }
+        int old = atomicCAS(&parent[b], b, a);   // hook the larger root under the smaller one
+        if (old == b) return;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_block_union(const int32_t *__restrict__ nbr, const unsigned *__restrict__ adj,
+                                                      const uint8_t *__restrict__ core, const int32_t *__restrict__ list,
+                                                      int32_t nkept, int32_t *__restrict__ parent) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nkept) return;
+    int c = list[k];
+    if (!core[c]) return;
+    unsigned m = adj[c] & ((1u << 1) | (1u << 6) | (1u << 3) | (1u << 7));
+    while (m) {
+        int d = __ffs(m) - 1;
+        m &= m - 1;
+        int b = nbr[8 * (int64_t)c + d];
+        if (core[b]) uf_unite(parent, c, b);
+    }
+}
+
+// root of every core cell + per-root minimum order key (the component's start cell, blockDBSCAN.py:146-152)
+__global__ void __launch_bounds__(256) k_block_roots(const uint8_t *__restrict__ core, const int32_t *__restrict__ list,
+                                                      int32_t nkept, int32_t *__restrict__ parent,
+                                                      const uint64_t *__restrict__ okey, uint64_t *__restrict__ minkey,
+                                                      int32_t *__restrict__ root) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nkept) return;
+    int c = list[k];
+    if (!core[c]) { root[c] = -1; return; }
+    int r = uf_find(parent, c);
+    root[c] = r;
+    atomicMin((unsigned long long *)&minkey[r], (unsigned long long)okey[c]);
+}
+
+__global__ void __launch_bounds__(256) k_block_rootflags(const uint8_t *__restrict__ core,
+                                                          const int32_t *__restrict__ root,
+                                                          const int32_t *__restrict__ list, int32_t nkept,
+                                                          int32_t *__restrict__ flag) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nkept) return;
+    int c = list[k];
+    flag[k] = (core[c] && root[c] == c) ? 1 : 0;
+}
+__global__ void __launch_bounds__(256) k_block_rootlist(const uint8_t *__restrict__ core,
+                                                         const int32_t *__restrict__ root,
+                                                         const int32_t *__restrict__ list, int32_t nkept,
+                                                         const int32_t *__restrict__ pos,
+                                                         const uint64_t *__restrict__ minkey,
+                                                         uint64_t *__restrict__ ckeys, uint32_t *__restrict__ croots) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nkept) return;
+    int c = list[k];
+    if (core[c] && root[c] == c) {
+        ckeys[pos[k]] = minkey[c];
+        croots[pos[k]] = (uint32_t)c;
+    }
+}
+// ------------------------------------------------------------------------------------------------ K14 labels
+__global__ void __launch_bounds__(256) k_block_celllabel(const int32_t *__restrict__ nbr,
+                                                          const unsigned *__restrict__ adj,
+                                                          const uint8_t *__restrict__ core,
+                                                          const int32_t *__restrict__ root,
+                                                          const int32_t *__restrict__ compid,
+                                                          const uint64_t *__restrict__ okey,
+                                                          const uint64_t *__restrict__ minkey,
+                                                          const int32_t *__restrict__ list, int32_t nkept,
+                                                          int32_t *__restrict__ clabel) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nkept) return;
+    int c = list[k];
+    int lab = -1;
+    if (core[c]) {
+        lab = compid[root[c]];
+    } else {
+        int maxstart = -1, minany = INT_MAX;
+        unsigned m = adj[c];
+        while (m) {
+            int d = __ffs(m) - 1;
+            m &= m - 1;
+            int b = nbr[8 * (int64_t)c + d];
+            if (!core[b]) continue;
+            int r = root[b];
+            int id = compid[r];
+            if (okey[b] == minkey[r]) maxstart = max(maxstart, id);   // unconditional overwrite, blockDBSCAN.py:184-185
+            minany = min(minany, id);                                  // first claim wins, blockDBSCAN.py:193-195
+        }
+        lab = maxstart >= 0 ? maxstart : (minany != INT_MAX ? minany : -1);
+    }
+    clabel[c] = lab;
+}
+
+__global__ void __launch_bounds__(256) k_point_labels(const int32_t *__restrict__ cid, const uint32_t *__restrict__ row,
+                                                       const int32_t *__restrict__ clabel,
+                                                       int32_t *__restrict__ labels, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) labels[row[i]] = clabel[cid[i]];
+}
+
+// ------------------------------------------------------------------------------------------------ K16 bbox
+struct ClusterBox {
+    int xmin, xmax, ymin, ymax;
+    unsigned size;
+};
+__global__ void __launch_bounds__(256) k_box_init(ClusterBox *__restrict__ box, int32_t ncl) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ncl) {
+        ClusterBox b;
+        b.xmin = INT_MAX; b.xmax = INT_MIN; b.ymin = INT_MAX; b.ymax = INT_MIN; b.size = 0;
+        box[i] = b;
+    }
+}
+__global__ void __launch_bounds__(256) k_block_bbox(const int32_t *__restrict__ cstart,
+                                                     const CellStat *__restrict__ st,
+                                                     const int32_t *__restrict__ clabel,
+                                                     const int32_t *__restrict__ list, int32_t nkept,
+                                                     ClusterBox *__restrict__ box) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nkept) return;
+    int c = list[k];
+    int lab = clabel[c];
+    if (lab < 0) return;
+    const CellStat s = st[c];
+    ClusterBox *b = &box[lab];
+    atomicMin(&b->xmin, s.xmin);
+    atomicMax(&b->xmax, s.xmax);
+    atomicMin(&b->ymin, s.ymin);
+    atomicMax(&b->ymax, s.ymax);
+    atomicAdd(&b->size, (unsigned)(cstart[c + 1] - cstart[c]));
+}
+
+__global__ void __launch_bounds__(256) k_fill_i32(int32_t *__restrict__ p, int32_t v, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+__global__ void __launch_bounds__(256) k_block_compid_indirect(const uint32_t *__restrict__ order,
+                                                                const uint32_t *__restrict__ croots, int32_t ncomp,
+                                                                int32_t *__restrict__ compid) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ncomp) compid[croots[order[i]]] = i;
+}
+
+// ================================================================================================ host driver
+static int read_i64(cl2_ctx *ctx, const int64_t *d, int64_t *out) {
+    CL2_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, d, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CL2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = *(int64_t *)ctx->h_scratch;
+    return CL2_OK;
+}
+static int read_i32(cl2_ctx *ctx, const int32_t *d, int32_t *out) {
+    CL2_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, d, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CL2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = *(int32_t *)ctx->h_scratch;
+    return CL2_OK;
+}
+
+// Build (or reuse) the eps grid: keygen -> radix sort -> gather -> cell table -> neighbours + 3x3 sums.
+static int block_grid_build(cl2_ctx *ctx, cl2_points *pts, int64_t eps) {
+    cl2_grid_cache &g = pts->grid;
+    if (g.valid && g.kind == 0 && g.eps == eps && g.n == pts->n) return CL2_OK;
+    cl2_grid_free(ctx, g);
+    const int64_t n = pts->n;
+    unsigned e32 = eps >= (int64_t)INT32_MAX ? (unsigned)INT32_MAX : (unsigned)eps;
+    uint64_t gxmax = (uint64_t)(pts->ext[1] - pts->ext[0]) / e32, gymax = (uint64_t)(pts->ext[3] - pts->ext[2]) / e32;
+    int bx = bits_for(gxmax), by = bits_for(gymax);
+    Scratch sc(ctx);
+    uint64_t *k0, *k1, *ks;
+    uint32_t *v0, *v1, *vs;
+    CL2_TRY(sc.get(&k0, (size_t)n));
+    CL2_TRY(sc.get(&k1, (size_t)n));
+    CL2_TRY(sc.get(&v0, (size_t)n));
+    CL2_TRY(sc.get(&v1, (size_t)n));
+    {
+        FamTimer t(ctx, FAM_KEYGEN, 16.0 * (double)n);
+        k_block_keygen<<<cl2_grid(n, 256), 256, 0, ctx->stream>>>(pts->xy, k0, n, (int)pts->ext[0], (int)pts->ext[2],
+                                                                   e32, by);
+    }
+    CL2_TRY(cl2_radix_sort_pairs(ctx, k0, k1, v0, v1, n, bx + by, &ks, &vs));
+    // keep the sorted row ids (take ownership of whichever buffer holds them)
+    sc.release(vs);
+    g.row = vs;
+    CL2_TRY(cl2_dev_alloc(ctx, &g.sxy, (size_t)n));
+    CL2_TRY(cl2_dev_alloc(ctx, &g.cid, (size_t)n));
+    {
+        FamTimer t(ctx, FAM_GATHER, 20.0 * (double)n);
+        k_gather_xy<<<cl2_grid(n, 256), 256, 0, ctx->stream>>>(pts->xy, g.row, g.sxy, n);
+    }
+    int64_t *d_total;
+    CL2_TRY(sc.get(&d_total, 1));
+    {
+        FamTimer t(ctx, FAM_CELLS, 12.0 * (double)n);
+        k_head_flags<<<cl2_grid(n, 256), 256, 0, ctx->stream>>>(ks, g.cid, n);
+    }
+    CL2_TRY(cl2_exclusive_scan_i32(ctx, g.cid, n, d_total));
+    int64_t ncells64 = 0;
+    CL2_TRY(read_i64(ctx, d_total, &ncells64));
+    int32_t ncells = (int32_t)ncells64;
+    CL2_TRY(cl2_dev_alloc(ctx, &g.cstart, (size_t)ncells + 1));
+    CL2_TRY(cl2_dev_alloc(ctx, &g.ckey, (size_t)ncells));
+    CL2_TRY(cl2_dev_alloc(ctx, &g.nbr, (size_t)ncells * 8));
+    CL2_TRY(cl2_dev_alloc(ctx, &g.s3, (size_t)ncells));
+    {
+        FamTimer t(ctx, FAM_CELLS, 16.0 * (double)n);
+        k_cell_table<<<cl2_grid(n, 256), 256, 0, ctx->stream>>>(ks, g.cid, g.cstart, g.ckey, n, ncells);
+    }
+    int32_t *d_max;
+    CL2_TRY(sc.get(&d_max, 1));
+    CL2_CUDA(ctx, cudaMemsetAsync(d_max, 0, 4, ctx->stream));
+    {
+        FamTimer t(ctx, FAM_NBR, 52.0 * (double)ncells);
+        k_block_nbr<<<cl2_grid(ncells, 256), 256, 0, ctx->stream>>>(g.ckey, g.cstart, g.nbr, g.s3, d_max, ncells, by);
+    }
+    CL2_TRY(read_i32(ctx, d_max, &g.maxcnt));
+    CL2_CUDA(ctx, cudaGetLastError());
+    g.valid = true;
+    g.kind = 0;
+    g.eps = eps;
+    g.n = n;
+    g.ncells = ncells;
+    g.by = by;
+    return CL2_OK;
+}
+
+static int block_check_args(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int32_t minPts) {
+    if (!ctx || !pts) return CL2_ERR_ARG;
+    if (eps <= 0) return cl2_fail(ctx, CL2_ERR_ARG, "eps must be > 0");
+    (void)minPts;
+    return CL2_OK;
+}
+
+extern "C" int cl2_block_noise(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int32_t minPts, uint8_t *keep_out) {
+    CL2_TRY(block_check_args(ctx, pts, eps, minPts));
+    if (pts->n == 0) return CL2_OK;
+    if (!keep_out) return CL2_ERR_ARG;
+    CL2_CUDA(ctx, cudaSetDevice(ctx->device));
+    CL2_TRY(block_grid_build(ctx, pts, eps));
+    cl2_grid_cache &g = pts->grid;
+    Scratch sc(ctx);
+    uint8_t *keep, *pk;
+    CL2_TRY(sc.get(&keep, (size_t)g.ncells));
+    CL2_TRY(sc.get(&pk, (size_t)pts->n));
+    {
+        FamTimer t(ctx, FAM_NOISE, 37.0 * (double)g.ncells);
+        k_block_noise<<<cl2_grid(g.ncells, 256), 256, 0, ctx->stream>>>(g.nbr, g.s3, keep, g.ncells, minPts);
+    }
+    k_keep_points<<<cl2_grid(pts->n, 256), 256, 0, ctx->stream>>>(g.cid, g.row, keep, pk, pts->n);
+    ctx->launches++;
+    CL2_CUDA(ctx, cudaMemcpyAsync(keep_out, pk, (size_t)pts->n, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->d2h_bytes += pts->n;
+    CL2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return CL2_OK;
+}
+
+extern "C" int cl2_block_dbscan(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int32_t minPts, int32_t *labels_out,
+                                int32_t *n_clusters) {
+    CL2_TRY(block_check_args(ctx, pts, eps, minPts));
+    if (n_clusters) *n_clusters = 0;
+    pts->ncl = 0;
+    pts->bbox.clear();
+    pts->size.clear();
+    const int64_t n = pts->n;
+    if (n == 0) return CL2_OK;
+    CL2_CUDA(ctx, cudaSetDevice(ctx->device));
+    CL2_TRY(block_grid_build(ctx, pts, eps));
+    cl2_grid_cache &g = pts->grid;
+    const int32_t ncells = g.ncells;
+    cudaStream_t s = ctx->stream;
+    Scratch sc(ctx);
+
+    // noise pruning + compact list of kept cells
+    uint8_t *keep;
+    int32_t *kpos, *list;
+    int64_t *d_total;
+    CL2_TRY(sc.get(&keep, (size_t)ncells));
+    CL2_TRY(sc.get(&kpos, (size_t)ncells));
+    CL2_TRY(sc.get(&d_total, 1));
+    {
+        FamTimer t(ctx, FAM_NOISE, 41.0 * (double)ncells, 2);
+        k_block_noise<<<cl2_grid(ncells, 256), 256, 0, s>>>(g.nbr, g.s3, keep, ncells, minPts);
+        k_keep_flags_i32<<<cl2_grid(ncells, 256), 256, 0, s>>>(keep, kpos, ncells);
+    }
+    CL2_TRY(cl2_exclusive_scan_i32(ctx, kpos, ncells, d_total));
+    int64_t nkept64 = 0;
+    CL2_TRY(read_i64(ctx, d_total, &nkept64));
+    const int32_t nkept = (int32_t)nkept64;
+
+    int32_t *clabel;
+    CL2_TRY(sc.get(&clabel, (size_t)ncells));
+    int32_t ncomp = 0;
+    ClusterBox *box = nullptr;
+
+    if (nkept > 0) {
+        CL2_TRY(sc.get(&list, (size_t)nkept));
+        {
+            FamTimer t(ctx, FAM_NOISE, 9.0 * (double)ncells);
+            k_keep_list<<<cl2_grid(ncells, 256), 256, 0, s>>>(keep, kpos, list, ncells);
+        }
+        CellStat *st;
+        unsigned *adj;
+        uint8_t *core;
+        uint64_t *okey, *minkey;
+        int32_t *parent, *root, *compid, *nheavy;
+        int2 *heavy;
+        // cell-indexed arrays are sized by ncells but only touched at kept cells
+        CL2_TRY(sc.get(&st, (size_t)ncells));
+        CL2_TRY(sc.get(&adj, (size_t)ncells));
+        CL2_TRY(sc.get(&core, (size_t)ncells));
+        CL2_TRY(sc.get(&okey, (size_t)ncells));
+        CL2_TRY(sc.get(&minkey, (size_t)ncells));
+        CL2_TRY(sc.get(&parent, (size_t)ncells));
+        CL2_TRY(sc.get(&root, (size_t)ncells));
+        CL2_TRY(sc.get(&compid, (size_t)ncells));
+        CL2_TRY(sc.get(&heavy, (size_t)nkept * 4));
+        CL2_TRY(sc.get(&nheavy, 1));
+        CL2_CUDA(ctx, cudaMemsetAsync(adj, 0, (size_t)ncells * 4, s));
+        CL2_CUDA(ctx, cudaMemsetAsync(core, 0, (size_t)ncells, s));
+        CL2_CUDA(ctx, cudaMemsetAsync(nheavy, 0, 4, s));
+        {
+            FamTimer t(ctx, FAM_CELLSTAT, 8.0 * (double)n);
+            k_block_cellstat_list<<<cl2_grid((int64_t)nkept * 32, 256), 256, 0, s>>>(g.sxy, g.cstart, list, st, nkept);
+        }
+        {
+            FamTimer t(ctx, FAM_ADJ, 8.0 * (double)n);
+            k_block_adj<<<cl2_grid((int64_t)nkept * 4, 128), 128, 0, s>>>(g.sxy, g.cstart, g.nbr, keep, st, list, nkept,
+                                                                           adj, eps, heavy, nheavy);
+        }
+        int32_t nh = 0;
+        CL2_TRY(read_i32(ctx, nheavy, &nh));
+        if (nh > 0) {
+            FamTimer t(ctx, FAM_ADJ, 0.0);
+            k_block_adj_heavy<<<nh, HEAVY_THREADS, 0, s>>>(g.sxy, g.cstart, g.nbr, heavy, adj, eps);
+        }
+        {
+            FamTimer t(ctx, FAM_CORE, 64.0 * (double)nkept);
+            k_block_core<<<cl2_grid(nkept, 256), 256, 0, s>>>(g.cstart, g.nbr, adj, g.row, list, nkept, minPts, g.maxcnt,
+                                                               core, okey, parent, minkey);
+        }
+        {
+            FamTimer t(ctx, FAM_UNION, 48.0 * (double)nkept, 2);
+            k_block_union<<<cl2_grid(nkept, 256), 256, 0, s>>>(g.nbr, adj, core, list, nkept, parent);
+            k_block_roots<<<cl2_grid(nkept, 256), 256, 0, s>>>(core, list, nkept, parent, okey, minkey, root);
+        }
+        // component list -> sort by start-cell order key -> cluster ids
+        int32_t *rflag;
+        CL2_TRY(sc.get(&rflag, (size_t)nkept));
+        {
+            FamTimer t(ctx, FAM_COMP, 16.0 * (double)nkept);
+            k_block_rootflags<<<cl2_grid(nkept, 256), 256, 0, s>>>(core, root, list, nkept, rflag);
+        }
+        CL2_TRY(cl2_exclusive_scan_i32(ctx, rflag, nkept, d_total));
+        int64_t ncomp64 = 0;
+        CL2_TRY(read_i64(ctx, d_total, &ncomp64));
+        ncomp = (int32_t)ncomp64;
+        if (ncomp > 0) {
+            uint64_t *ck0, *ck1, *cks;
+            uint32_t *cr0, *o0, *o1, *os;
+            CL2_TRY(sc.get(&ck0, (size_t)ncomp));
+            CL2_TRY(sc.get(&ck1, (size_t)ncomp));
+            CL2_TRY(sc.get(&cr0, (size_t)ncomp));
+            CL2_TRY(sc.get(&o0, (size_t)ncomp));
+            CL2_TRY(sc.get(&o1, (size_t)ncomp));
+            {
+                FamTimer t(ctx, FAM_COMP, 24.0 * (double)nkept);
+                k_block_rootlist<<<cl2_grid(nkept, 256), 256, 0, s>>>(core, root, list, nkept, rflag, minkey, ck0, cr0);
+            }
+            // sort (start-cell order key, position in the component list); the sort's first pass generates the positions
+            CL2_TRY(cl2_radix_sort_pairs(ctx, ck0, ck1, o0, o1, ncomp, 32 + bits_for((uint64_t)g.maxcnt), &cks, &os));
+            (void)cks;
+            {
+                FamTimer t(ctx, FAM_COMP, 12.0 * (double)ncomp);
+                k_block_compid_indirect<<<cl2_grid(ncomp, 256), 256, 0, s>>>(os, cr0, ncomp, compid);
+            }
+        }
+        {
+            FamTimer t(ctx, FAM_BORDER, 64.0 * (double)nkept);
+            k_fill_i32<<<cl2_grid(ncells, 256), 256, 0, s>>>(clabel, -1, ncells);
+            k_block_celllabel<<<cl2_grid(nkept, 256), 256, 0, s>>>(g.nbr, adj, core, root, compid, okey, minkey, list,
+                                                                   nkept, clabel);
+            ctx->launches++;
+        }
+        if (ncomp > 0) {
+            CL2_TRY(sc.get(&box, (size_t)ncomp));
+            FamTimer t(ctx, FAM_BBOX, 40.0 * (double)nkept, 2);
+            k_box_init<<<cl2_grid(ncomp, 256), 256, 0, s>>>(box, ncomp);
+            k_block_bbox<<<cl2_grid(nkept, 256), 256, 0, s>>>(g.cstart, st, clabel, list, nkept, box);
+        }
+    } else {
+        k_fill_i32<<<cl2_grid(ncells, 256), 256, 0, s>>>(clabel, -1, ncells);
+        ctx->launches++;
+    }
+
+    if (labels_out) {
+        int32_t *dl;
+        CL2_TRY(sc.get(&dl, (size_t)n));
+        {
+            FamTimer t(ctx, FAM_LABEL, 12.0 * (double)n);
+            k_point_labels<<<cl2_grid(n, 256), 256, 0, s>>>(g.cid, g.row, clabel, dl, n);
+        }
+        CL2_CUDA(ctx, cudaMemcpyAsync(labels_out, dl, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+        ctx->d2h_bytes += n * 4;
+    }
+    std::vector<ClusterBox> hb((size_t)ncomp);
+    if (ncomp > 0) CL2_CUDA(ctx, cudaMemcpyAsync(hb.data(), box, (size_t)ncomp * sizeof(ClusterBox), cudaMemcpyDeviceToHost, s));
+    ctx->d2h_bytes += (int64_t)ncomp * (int64_t)sizeof(ClusterBox);
+    CL2_CUDA(ctx, cudaStreamSynchronize(s));
+    CL2_CUDA(ctx, cudaGetLastError());
+    pts->ncl = ncomp;
+    pts->bbox.resize((size_t)ncomp * 4);
+    pts->size.resize((size_t)ncomp);
+    for (int32_t i = 0; i < ncomp; i++) {
+        pts->bbox[4 * (size_t)i] = hb[i].xmin;
+        pts->bbox[4 * (size_t)i + 1] = hb[i].xmax;
+        pts->bbox[4 * (size_t)i + 2] = hb[i].ymin;
+        pts->bbox[4 * (size_t)i + 3] = hb[i].ymax;
+        pts->size[i] = hb[i].size;
+    }
+    if (n_clusters) *n_clusters = ncomp;
+    return CL2_OK;
+}
+
+extern "C" int cl2_cluster_bbox(cl2_ctx *ctx, cl2_points *pts, int64_t *bbox_out, int64_t *size_out) {
+    if (!ctx || !pts) return CL2_ERR_ARG;
+    if (pts->ncl > 0) {
+        if (bbox_out) memcpy(bbox_out, pts->bbox.data(), (size_t)pts->ncl * 4 * sizeof(int64_t));
+        if (size_out) memcpy(size_out, pts->size.data(), (size_t)pts->ncl * sizeof(int64_t));
+    }
+    return CL2_OK;
+}

@@ -1,0 +1,186 @@
+// cl2_common.cuh -- context, stream-ordered scratch memory, error handling, per-kernel timing.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+#include <string>
+#include "../../include/cl2.h"
+
+#define CL2_NFAM 32
+
+enum cl2_family {
+    FAM_CONVERT = 0,   // int64 -> int32 narrowing + extent reduction + cut/mcut compaction
+    FAM_KEYGEN,        // cell key generation
+    FAM_SORT_HIST,     // radix sort: per-tile digit histogram (upsweep)
+    FAM_SORT_SCATTER,  // radix sort: stable scatter (downsweep)
+    FAM_SCAN,          // exclusive scans
+    FAM_GATHER,        // sorted-order coordinate gather
+    FAM_CELLS,         // segment heads -> cell table
+    FAM_NBR,           // neighbour cell lookup + 3x3 sums
+    FAM_NOISE,         // noise-cell pruning
+    FAM_CELLSTAT,      // per-cell sums / bbox (centroids)
+    FAM_ADJ,           // cell adjacency (centroid test + min-pair L1)
+    FAM_CORE,          // near sums / core flags / neighbour counts
+    FAM_UNION,         // lock-free union-find + pointer jumping
+    FAM_COMP,          // component ordering / numbering
+    FAM_BORDER,        // border assignment
+    FAM_LABEL,         // per-point label scatter
+    FAM_BBOX,          // cluster bounding boxes
+    FAM_INDEX,         // XY index build (two sorts + gathers)
+    FAM_COUNT,         // rectangle / window counting
+    FAM_MISC,
+    FAM_COUNT_
+};
+
+static const char *const CL2_FAM_NAMES[] = {
+    "convert", "keygen", "sort_hist", "sort_scatter", "scan", "gather", "cells", "nbr", "noise", "cellstat",
+    "adj", "core", "union", "comp", "border", "label", "bbox", "index", "count", "misc"};
+
+struct cl2_evpair {
+    cudaEvent_t a, b;
+    int fam;
+};
+
+struct cl2_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaMemPool_t pool = nullptr;
+    char err[512] = {0};
+    int64_t launches = 0;
+    int64_t h2d_bytes = 0, d2h_bytes = 0;
+    int timing = 0;
+    double fam_ms[CL2_NFAM] = {0};
+    int64_t fam_launch[CL2_NFAM] = {0};
+    double fam_bytes[CL2_NFAM] = {0};
+    std::vector<cl2_evpair> pending;
+    std::vector<cudaEvent_t> evpool;
+    int sm_count = 148;
+    void *h_scratch = nullptr;  // small pinned buffer for scalar read-backs
+};
+
+inline int cl2_fail(cl2_ctx *ctx, int code, const char *fmt, const char *a = "", const char *b = "") {
+    if (ctx) snprintf(ctx->err, sizeof(ctx->err), fmt, a, b);
+    return code;
+}
+
+#define CL2_CUDA(ctx, call)                                                                          \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) {                                                                     \
+            if (ctx) snprintf((ctx)->err, sizeof((ctx)->err), "%s failed: %s (%s:%d)", #call,        \
+                              cudaGetErrorString(e_), __FILE__, __LINE__);                           \
+            return CL2_ERR_CUDA;                                                                     \
+        }                                                                                            \
+    } while (0)
+
+#define CL2_TRY(call)            \
+    do {                         \
+        int rc_ = (call);        \
+        if (rc_ != CL2_OK) return rc_; \
+    } while (0)
+
+// Stream-ordered scratch allocations released when the scope ends (cudaMallocAsync on the context's pool; the pool
+// keeps freed blocks, so steady-state calls do not touch the driver allocator).
+struct Scratch {
+    cl2_ctx *ctx;
+    std::vector<void *> ptrs;
+    explicit Scratch(cl2_ctx *c) : ctx(c) {}
+    ~Scratch() {
+        for (void *p : ptrs) cudaFreeAsync(p, ctx->stream);
+    }
+    template <typename T>
+    int get(T **out, size_t count) {
+        void *p = nullptr;
+        size_t bytes = (count ? count : 1) * sizeof(T);
+        cudaError_t e = cudaMallocAsync(&p, bytes, ctx->stream);
+        if (e != cudaSuccess) {
+            snprintf(ctx->err, sizeof(ctx->err), "cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+            *out = nullptr;
+            return CL2_ERR_NOMEM;
+        }
+        ptrs.push_back(p);
+        *out = (T *)p;
+        return CL2_OK;
+    }
+    // hand ownership to the caller (long-lived buffers)
+    void release(void *p) {
+        for (size_t i = 0; i < ptrs.size(); i++)
+            if (ptrs[i] == p) {
+                ptrs.erase(ptrs.begin() + i);
+                return;
+            }
+    }
+};
+
+template <typename T>
+inline int cl2_dev_alloc(cl2_ctx *ctx, T **out, size_t count) {
+    void *p = nullptr;
+    size_t bytes = (count ? count : 1) * sizeof(T);
+    cudaError_t e = cudaMallocAsync(&p, bytes, ctx->stream);
+    if (e != cudaSuccess) {
+        snprintf(ctx->err, sizeof(ctx->err), "cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        *out = nullptr;
+        return CL2_ERR_NOMEM;
+    }
+    *out = (T *)p;
+    return CL2_OK;
+}
+inline void cl2_dev_free(cl2_ctx *ctx, void *p) {
+    if (p) cudaFreeAsync(p, ctx->stream);
+}
+
+// RAII timing scope: records an event pair around the launches of one kernel family when timing is on.
+struct FamTimer {
+    cl2_ctx *ctx;
+    int fam;
+    cudaEvent_t a = nullptr, b = nullptr;
+    FamTimer(cl2_ctx *c, int f, double bytes, int nlaunch = 1) : ctx(c), fam(f) {
+        ctx->launches += nlaunch;
+        if (!ctx->timing) return;
+        ctx->fam_launch[f] += nlaunch;
+        ctx->fam_bytes[f] += bytes;
+        a = take();
+        b = take();
+        cudaEventRecord(a, ctx->stream);
+    }
+    ~FamTimer() {
+        if (!a) return;
+        cudaEventRecord(b, ctx->stream);
+        ctx->pending.push_back({a, b, fam});
+    }
+    cudaEvent_t take() {
+        cudaEvent_t e;
+        if (!ctx->evpool.empty()) {
+            e = ctx->evpool.back();
+            ctx->evpool.pop_back();
+        } else {
+            cudaEventCreate(&e);
+        }
+        return e;
+    }
+};
+
+inline void cl2_timing_drain(cl2_ctx *ctx) {
+    if (ctx->pending.empty()) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &p : ctx->pending) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, p.a, p.b);
+        ctx->fam_ms[p.fam] += ms;
+        ctx->evpool.push_back(p.a);
+        ctx->evpool.push_back(p.b);
+    }
+    ctx->pending.clear();
+}
+
+static inline int cl2_grid(int64_t n, int block) { return (int)((n + block - 1) / block); }
+
+// ---- shared device-side primitives (cl2_sort.cu) ----
+// Stable LSD radix sort of (uint64 key, uint32 val) pairs on bits [0, nbits).  keys/vals are double buffers;
+// on return *kout / *vout point at the buffer holding the sorted data.
+int cl2_radix_sort_pairs(cl2_ctx *ctx, uint64_t *keys0, uint64_t *keys1, uint32_t *vals0, uint32_t *vals1, int64_t n,
+                         int nbits, uint64_t **kout, uint32_t **vout);
+// Exclusive prefix sum of int32 in place (n up to 2^31-1); total written to *d_total (device int64) when non-null.
+int cl2_exclusive_scan_i32(cl2_ctx *ctx, int32_t *d, int64_t n, int64_t *d_total);

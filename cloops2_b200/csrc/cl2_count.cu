@@ -1,0 +1,331 @@
+// cl2_count.cu -- device form of cLoops2/ds.py:141-198 (XY) and the per-candidate counting behind estLoopSig
+// (callCisLoops.py:173-354, callTransLoops.py:106-193).
+//
+// XY keeps sorted xs / ys plus value->row dicts and answers queryPeak(l,r) = {rows with l<=X<=r or l<=Y<=r} as Python
+// sets.  Here the index is two arrays, (x,y) sorted by x and (y,x) sorted by y, and every set size the reference takes
+// becomes a binary-search range plus a warp-strided scan of the range members:
+//     |P(I)|            = |Xrange(I)| + #{j in Yrange(I) : x_j not in I}
+//     |P(I1) & P(I2)|   = #{members of P(I1) that have an end in I2}
+// The reference's window bounds are multiples of 0.25 evaluated in fp64 (exact); they are carried here as integers
+// scaled by 4, so l <= X <= r is decided in exact integer arithmetic.  One warp per candidate loop.
+#include "cl2_points.cuh"
+
+// ------------------------------------------------------------------------------------------------ index build
+__global__ void __launch_bounds__(256) k_index_keys(const int2 *__restrict__ xy, uint64_t *__restrict__ key, int64_t n,
+                                                     int which) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int2 p = xy[i];
+    key[i] = (uint64_t)(uint32_t)(which == 0 ? p.x : p.y);
+}
+__global__ void __launch_bounds__(256) k_index_gather(const int2 *__restrict__ xy, const uint32_t *__restrict__ row,
+                                                       int2 *__restrict__ out, int64_t n, int which) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int2 p = __ldg(&xy[row[i]]);
+    out[i] = which == 0 ? p : make_int2(p.y, p.x);
+}
+
+extern "C" int cl2_index_build(cl2_ctx *ctx, cl2_points *pts, cl2_index **out) {
+    if (!ctx || !pts || !out) return CL2_ERR_ARG;
+    *out = nullptr;
+    CL2_CUDA(ctx, cudaSetDevice(ctx->device));
+    cl2_index *ix = new (std::nothrow) cl2_index();
+    if (!ix) return CL2_ERR_NOMEM;
+    const int64_t n = pts->n;
+    ix->n = n;
+    int rc = CL2_OK;
+    if (n > 0) {
+        Scratch sc(ctx);
+        uint64_t *k0 = nullptr, *k1 = nullptr, *ks;
+        uint32_t *v0 = nullptr, *v1 = nullptr, *vs;
+        do {
+            if ((rc = sc.get(&k0, (size_t)n)) || (rc = sc.get(&k1, (size_t)n)) || (rc = sc.get(&v0, (size_t)n)) ||
+                (rc = sc.get(&v1, (size_t)n)))
+                break;
+            if ((rc = cl2_dev_alloc(ctx, &ix->byx, (size_t)n)) || (rc = cl2_dev_alloc(ctx, &ix->byy, (size_t)n))) break;
+            for (int which = 0; which < 2 && rc == CL2_OK; which++) {
+                int64_t hi = which == 0 ? pts->ext[1] : pts->ext[3];
+                {
+                    FamTimer t(ctx, FAM_INDEX, 16.0 * (double)n);
+                    k_index_keys<<<cl2_grid(n, 256), 256, 0, ctx->stream>>>(pts->xy, k0, n, which);
+                }
+                rc = cl2_radix_sort_pairs(ctx, k0, k1, v0, v1, n, bits_for((uint64_t)hi), &ks, &vs);
+                if (rc) break;
+                FamTimer t(ctx, FAM_INDEX, 20.0 * (double)n);
+                k_index_gather<<<cl2_grid(n, 256), 256, 0, ctx->stream>>>(pts->xy, vs, which == 0 ? ix->byx : ix->byy, n,
+                                                                           which);
+            }
+            if (rc) break;
+            if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+                rc = cl2_fail(ctx, CL2_ERR_CUDA, "cl2_index_build: kernel failure");
+            }
+        } while (0);
+    }
+    if (rc != CL2_OK) {
+        cl2_dev_free(ctx, ix->byx);
+        cl2_dev_free(ctx, ix->byy);
+        delete ix;
+        return rc;
+    }
+    *out = ix;
+    return CL2_OK;
+}
+
+extern "C" void cl2_index_free(cl2_ctx *ctx, cl2_index *idx) {
+    if (!ctx || !idx) return;
+    cudaSetDevice(ctx->device);
+    cl2_dev_free(ctx, idx->byx);
+    cl2_dev_free(ctx, idx->byy);
+    delete idx;
+}
+
+// ------------------------------------------------------------------------------------------------ counting
+#define CNT_WARPS 8
+#define CNT_MAXW 16   // 2*win <= 16
+
+struct Iv {           // closed integer interval; empty when lo > hi
+    long long lo, hi;
+};
+__device__ __forceinline__ long long floordiv4(long long a) { return a >> 2; }              // arithmetic shift = floor
+__device__ __forceinline__ long long ceildiv4(long long a) { return -((-a) >> 2); }
+// interval with bounds given scaled by 4: {v integer : lo4 <= 4v <= hi4}
+__device__ __forceinline__ Iv iv4(long long lo4, long long hi4) {
+    Iv r;
+    r.lo = ceildiv4(lo4);
+    r.hi = floordiv4(hi4);
+    return r;
+}
+__device__ __forceinline__ bool in_iv(const Iv &I, int v) { return (long long)v >= I.lo && (long long)v <= I.hi; }
+
+// first index with first-coordinate >= v (np.searchsorted side="left", ds.py:170)
+__device__ __forceinline__ int64_t lower_first(const int2 *__restrict__ a, int64_t n, long long v) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        int64_t m = (lo + hi) >> 1;
+        if ((long long)a[m].x < v) lo = m + 1; else hi = m;
+    }
+    return lo;
+}
+struct Range {
+    int64_t b, e;
+};
+__device__ __forceinline__ Range range_of(const int2 *__restrict__ a, int64_t n, const Iv &I) {
+    Range r;
+    if (I.lo > I.hi) { r.b = r.e = 0; return r; }
+    r.b = lower_first(a, n, I.lo);
+    r.e = lower_first(a, n, I.hi + 1);   // side="right" on integers
+    return r;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// |P(I)|  (queryPeak, ds.py:176-182)
+__device__ int64_t count_peak(const int2 *__restrict__ byx, const int2 *__restrict__ byy, int64_t n, const Iv &I,
+                              int lane) {
+    Range rx = range_of(byx, n, I), ry = range_of(byy, n, I);
+    int c = 0;
+    for (int64_t j = ry.b + lane; j < ry.e; j += 32) {
+        int2 p = byy[j];                      // (y, x)
+        if (!in_iv(I, p.y)) c++;
+    }
+    return (rx.e - rx.b) + (int64_t)warp_sum(c);
+}
+
+// |P(I1)| and |P(I1) & P(I2)|  (queryLoop, ds.py:184-190)
+__device__ void count_pair(const int2 *__restrict__ byx, const int2 *__restrict__ byy, int64_t n, const Iv &I1,
+                           const Iv &I2, int lane, int64_t *n1, int64_t *n12) {
+    Range rx = range_of(byx, n, I1), ry = range_of(byy, n, I1);
+    int c1 = 0, c12 = 0;
+    for (int64_t i = rx.b + lane; i < rx.e; i += 32) {
+        int2 p = byx[i];                      // (x, y)
+        if (in_iv(I2, p.x) || in_iv(I2, p.y)) c12++;
+    }
+    for (int64_t j = ry.b + lane; j < ry.e; j += 32) {
+        int2 p = byy[j];                      // (y, x)
+        if (!in_iv(I1, p.y)) {
+            c1++;
+            if (in_iv(I2, p.y) || in_iv(I2, p.x)) c12++;
+        }
+    }
+    *n1 = (rx.e - rx.b) + (int64_t)warp_sum(c1);
+    *n12 = (int64_t)warp_sum(c12);
+}
+
+struct WarpAcc {
+    int na[CNT_MAXW];
+    int nb[CNT_MAXW];
+    int nab[CNT_MAXW * CNT_MAXW];
+    long long alo[CNT_MAXW], ahi[CNT_MAXW], blo[CNT_MAXW], bhi[CNT_MAXW];
+};
+
+// membership masks of one PET against the 2*win a-windows and b-windows (getPerRegions, callCisLoops.py:191-198)
+__device__ __forceinline__ void window_masks(const WarpAcc &A, int W, int x, int y, unsigned *ma, unsigned *mb) {
+    unsigned a = 0, b = 0;
+    for (int t = 0; t < W; t++) {
+        bool ia = ((long long)x >= A.alo[t] && (long long)x <= A.ahi[t]) || ((long long)y >= A.alo[t] && (long long)y <= A.ahi[t]);
+        bool ib = ((long long)x >= A.blo[t] && (long long)x <= A.bhi[t]) || ((long long)y >= A.blo[t] && (long long)y <= A.bhi[t]);
+        a |= (ia ? 1u : 0u) << t;
+        b |= (ib ? 1u : 0u) << t;
+    }
+    *ma = a;
+    *mb = b;
+}
+
+__device__ __forceinline__ void window_accumulate(WarpAcc &A, int W, unsigned ma, unsigned mb, int lane) {
+    for (int t = 0; t < W; t++) {
+        unsigned va = __ballot_sync(0xffffffffu, (ma >> t) & 1u);
+        unsigned vb = __ballot_sync(0xffffffffu, (mb >> t) & 1u);
+        if (lane == 0) {
+            A.na[t] += __popc(va);
+            A.nb[t] += __popc(vb);
+        }
+    }
+    if (ma && mb) {
+        unsigned a = ma;
+        while (a) {
+            int i = __ffs(a) - 1;
+            a &= a - 1;
+            unsigned b = mb;
+            while (b) {
+                int j = __ffs(b) - 1;
+                b &= b - 1;
+                atomicAdd(&A.nab[i * W + j], 1);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(CNT_WARPS * 32) k_loop_counts(const int2 *__restrict__ byx, const int2 *__restrict__ byy,
+                                                                 int64_t n, const longlong4 *__restrict__ loops, int64_t L,
+                                                                 int win, int mode, long long *__restrict__ core,
+                                                                 long long *__restrict__ na_out, long long *__restrict__ nb_out,
+                                                                 long long *__restrict__ nab_out,
+                                                                 long long *__restrict__ anchors) {
+    __shared__ WarpAcc acc[CNT_WARPS];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t k = (int64_t)blockIdx.x * CNT_WARPS + w;
+    if (k >= L) return;
+    const longlong4 lp = loops[k];
+    const long long xs = lp.x, xe = lp.y, ys = lp.z, ye = lp.w;
+    const Iv A = {xs, xe}, B = {ys, ye};
+
+    if (core) {
+        int64_t ra, rab, rb;
+        count_pair(byx, byy, n, A, B, lane, &ra, &rab);
+        rb = count_peak(byx, byy, n, B, lane);
+        // P2LL window: cis callCisLoops.py:302-305, trans callTransLoops.py:142-144
+        Iv A2, B2;
+        if (mode == CL2_MODE_CIS) { A2.lo = xe; A2.hi = xe + (xe - xs); }
+        else { A2.lo = xs - (xe - xs); A2.hi = xs; }
+        B2.lo = ys - (ye - ys); B2.hi = ys;
+        int64_t t1, lower;
+        count_pair(byx, byy, n, A2, B2, lane, &t1, &lower);
+        if (lane == 0) {
+            core[4 * k] = ra; core[4 * k + 1] = rb; core[4 * k + 2] = rab; core[4 * k + 3] = lower;
+        }
+    }
+
+    if (anchors) {
+        // estAnchorSig, callCisLoops.py:226-247: count = |P(l,r)|, wide = |P(max(0, m-5len), m+5len)|
+        for (int a = 0; a < 2; a++) {
+            long long l = a == 0 ? xs : ys, r = a == 0 ? xe : ye;
+            long long m4 = 2 * (l + r), len = r - l;
+            long long s4 = m4 - 20 * len;
+            if (s4 < 0) s4 = 0;
+            Iv I = {l, r};
+            Iv Wd = iv4(s4, m4 + 20 * len);
+            int64_t c = count_peak(byx, byy, n, I, lane);
+            int64_t wd = count_peak(byx, byy, n, Wd, lane);
+            if (lane == 0) { anchors[4 * k + 2 * a] = c; anchors[4 * k + 2 * a + 1] = wd; }
+        }
+    }
+
+    if (na_out || nb_out || nab_out) {
+        const int W = 2 * win;
+        WarpAcc &S = acc[w];
+        for (int t = lane; t < W * W; t += 32) S.nab[t] = 0;
+        if (lane < W) {
+            S.na[lane] = 0; S.nb[lane] = 0;
+            // windows i = -win..-1, 1..win (callCisLoops.py:191-198), all bounds scaled by 4
+            int i = lane < win ? lane - win : lane - win + 1;
+            long long ca4 = 2 * (xs + xe), cb4 = 2 * (ys + ye), sa4 = 2 * (xe - xs), sb4 = 2 * (ye - ys);
+            long long step4 = (xe - xs) + (ye - ys);
+            long long al = ca4 + i * step4 - sa4, ah = ca4 + i * step4 + sa4;
+            long long bl = cb4 + i * step4 - sb4, bh = cb4 + i * step4 + sb4;
+            if (al < 0) al = 0;
+            if (ah < 0) ah = 0;
+            if (bl < 0) bl = 0;
+            if (bh < 0) bh = 0;
+            Iv a = iv4(al, ah), b = iv4(bl, bh);
+            S.alo[lane] = a.lo; S.ahi[lane] = a.hi; S.blo[lane] = b.lo; S.bhi[lane] = b.hi;
+        }
+        __syncwarp();
+        // spans covering all a-windows / all b-windows (window centres are monotone in i)
+        Iv SA = {S.alo[0], S.ahi[W - 1]}, SB = {S.blo[0], S.bhi[W - 1]};
+        Range rxa = range_of(byx, n, SA), rya = range_of(byy, n, SA);
+        Range rxb = range_of(byx, n, SB), ryb = range_of(byy, n, SB);
+        // four lists; a PET is handled by the first list that contains it
+        for (int pass = 0; pass < 4; pass++) {
+            const int2 *arr = (pass & 1) ? byy : byx;
+            Range r = pass == 0 ? rxa : pass == 1 ? rya : pass == 2 ? rxb : ryb;
+            for (int64_t i0 = r.b; i0 < r.e; i0 += 32) {
+                int64_t i = i0 + lane;
+                unsigned ma = 0, mb = 0;
+                if (i < r.e) {
+                    int2 p = arr[i];
+                    int x = (pass & 1) ? p.y : p.x, y = (pass & 1) ? p.x : p.y;
+                    bool dup = false;
+                    if (pass >= 1 && in_iv(SA, x)) dup = true;                       // seen in list 0
+                    if (pass >= 2 && in_iv(SA, y)) dup = true;                       // seen in list 1
+                    if (pass == 3 && in_iv(SB, x)) dup = true;                       // seen in list 2
+                    if (!dup) window_masks(S, W, x, y, &ma, &mb);
+                }
+                if (__any_sync(0xffffffffu, (ma | mb) != 0)) window_accumulate(S, W, ma, mb, lane);
+            }
+        }
+        __syncwarp();
+        if (na_out && lane < W) na_out[(int64_t)W * k + lane] = S.na[lane];
+        if (nb_out && lane < W) nb_out[(int64_t)W * k + lane] = S.nb[lane];
+        if (nab_out)
+            for (int t = lane; t < W * W; t += 32) nab_out[(int64_t)W * W * k + t] = S.nab[t];
+    }
+}
+
+extern "C" int cl2_loop_counts(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops, int64_t L, int32_t win, int32_t mode,
+                               int64_t *core, int64_t *na, int64_t *nb, int64_t *nab, int64_t *anchors) {
+    if (!ctx || !idx || L < 0 || (L > 0 && !loops)) return cl2_fail(ctx, CL2_ERR_ARG, "cl2_loop_counts: bad argument");
+    if (win < 1 || 2 * win > CNT_MAXW) return cl2_fail(ctx, CL2_ERR_ARG, "cl2_loop_counts: win must be in 1..8");
+    if (mode != CL2_MODE_CIS && mode != CL2_MODE_TRANS) return cl2_fail(ctx, CL2_ERR_ARG, "cl2_loop_counts: bad mode");
+    if (L == 0) return CL2_OK;
+    CL2_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int W = 2 * win;
+    Scratch sc(ctx);
+    longlong4 *d_loops;
+    long long *d_core = nullptr, *d_na = nullptr, *d_nb = nullptr, *d_nab = nullptr, *d_anc = nullptr;
+    CL2_TRY(sc.get(&d_loops, (size_t)L));
+    if (core) CL2_TRY(sc.get(&d_core, (size_t)L * 4));
+    if (na) CL2_TRY(sc.get(&d_na, (size_t)L * W));
+    if (nb) CL2_TRY(sc.get(&d_nb, (size_t)L * W));
+    if (nab) CL2_TRY(sc.get(&d_nab, (size_t)L * W * W));
+    if (anchors) CL2_TRY(sc.get(&d_anc, (size_t)L * 4));
+    CL2_CUDA(ctx, cudaMemcpyAsync(d_loops, loops, (size_t)L * 32, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        FamTimer t(ctx, FAM_COUNT, 0.0);
+        k_loop_counts<<<cl2_grid(L, CNT_WARPS), CNT_WARPS * 32, 0, ctx->stream>>>(idx->byx, idx->byy, idx->n, d_loops, L, win,
+                                                                                  mode, d_core, d_na, d_nb, d_nab, d_anc);
+    }
+    if (core) CL2_CUDA(ctx, cudaMemcpyAsync(core, d_core, (size_t)L * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    if (na) CL2_CUDA(ctx, cudaMemcpyAsync(na, d_na, (size_t)L * W * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nb) CL2_CUDA(ctx, cudaMemcpyAsync(nb, d_nb, (size_t)L * W * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nab) CL2_CUDA(ctx, cudaMemcpyAsync(nab, d_nab, (size_t)L * W * W * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (anchors) CL2_CUDA(ctx, cudaMemcpyAsync(anchors, d_anc, (size_t)L * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->h2d_bytes += L * 32;
+    ctx->d2h_bytes += L * 8 * ((core ? 4 : 0) + (na ? W : 0) + (nb ? W : 0) + (nab ? W * W : 0) + (anchors ? 4 : 0));
+    CL2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CL2_CUDA(ctx, cudaGetLastError());
+    return CL2_OK;
+}

@@ -1,0 +1,50 @@
+// cl2_points.cuh -- device-resident form of one .ixy file and the cached eps-grid built on it.
+#pragma once
+#include "cl2_common.cuh"
+
+// Binning of the points into eps-sized cells, sorted by packed cell key; depends on (eps, grid kind) only, so it is
+// kept across the minPts values of a sweep (the reference loops eps-major, callCisLoops.py:541-551).
+struct cl2_grid_cache {
+    bool valid = false;
+    int kind = 0;             // 0 = blockDBSCAN grid (min-anchored, axis aligned), 1 = cDBSCAN2 grid (rotated)
+    int64_t eps = 0;
+    int64_t n = 0;
+    int32_t ncells = 0;
+    int by = 0;               // bits of the low (gy) field of the packed key
+    int32_t maxcnt = 0;       // largest cell population
+    uint32_t *row = nullptr;  // [n]   original row id of sorted position i
+    int2 *sxy = nullptr;      // [n]   (x,y) of sorted position i   (cDBSCAN2 grid: (u,v) rotated, int64 pairs in suv)
+    int32_t *cid = nullptr;   // [n]   cell id of sorted position i
+    int32_t *cstart = nullptr;  // [ncells+1]
+    uint64_t *ckey = nullptr;   // [ncells]
+    int32_t *nbr = nullptr;     // [ncells*8] neighbour cell id or -1, order of blockDBSCAN.py:54-55
+    int32_t *s3 = nullptr;      // [ncells]  population of the 3x3 block
+};
+
+struct cl2_points {
+    int64_t n = 0;
+    int2 *xy = nullptr;      // [n] int32 coordinates, file order after the cut/mcut filter
+    int64_t ext[4] = {0, 0, 0, 0};  // minX, maxX, minY, maxY
+    cl2_grid_cache grid;
+    // result of the last clustering run
+    int32_t ncl = 0;
+    std::vector<int64_t> bbox;  // [ncl*4]
+    std::vector<int64_t> size;  // [ncl]
+};
+
+struct cl2_index {
+    int64_t n = 0;
+    int2 *byx = nullptr;  // [n] (x, y) sorted by x
+    int2 *byy = nullptr;  // [n] (y, x) sorted by y
+};
+
+void cl2_grid_free(cl2_ctx *ctx, cl2_grid_cache &g);
+
+static inline int bits_for(uint64_t v) {  // number of bits needed to represent values 0..v
+    int b = 0;
+    while (v) {
+        b++;
+        v >>= 1;
+    }
+    return b < 1 ? 1 : b;
+}

@@ -1,0 +1,277 @@
+// cl2_sort.cu -- hand-written device primitives for the binning stage: a stable LSD radix sort of
+// (uint64 cell key, uint32 row id) pairs and an int32 exclusive scan.  sm_100a.
+//
+// Radix pass = upsweep (per-tile digit histogram, 8 B/PET read) + scan of the [256][ntiles] table + downsweep
+// (stable ranking with __match_any_sync, shared-memory reorder so each digit run leaves the SM as a contiguous,
+// coalesced store; 12 B read + 12 B written per PET).  Only ceil(nbits/8) passes are run, nbits being the number
+// of significant bits of the packed cell key for this chromosome and eps.
+#include "cl2_common.cuh"
+
+// ------------------------------------------------------------------------------------------------ scan
+#define SCAN_THREADS 256
+#define SCAN_IPT 8
+#define SCAN_TILE (SCAN_THREADS * SCAN_IPT)
+
+__device__ __forceinline__ int warp_incl_scan(int v) {
+    int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// block-wide exclusive scan of one value per thread; returns exclusive prefix, *total = block sum
+template <int THREADS>
+__device__ __forceinline__ int block_excl_scan(int v, int *total) {
+    __shared__ int wsum[THREADS / 32];
+    __shared__ int tot;
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = warp_incl_scan(v);
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int s = lane < THREADS / 32 ? wsum[lane] : 0;
+        int si = warp_incl_scan(s);
+        if (lane < THREADS / 32) wsum[lane] = si - s;
+        if (lane == THREADS / 32 - 1) tot = si;
+    }
+    __syncthreads();
+    int r = inc - v + wsum[w];
+    *total = tot;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const int32_t *__restrict__ d, int64_t n,
+                                                               int32_t *__restrict__ sums) {
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_IPT;
+    int s = 0;
+    if (base + SCAN_IPT <= n) {
+        const int4 *p = reinterpret_cast<const int4 *>(d + base);
+        int4 a = p[0], b = p[1];
+        s = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+    } else {
+        for (int k = 0; k < SCAN_IPT; k++)
+            if (base + k < n) s += d[base + k];
+    }
+    int tot;
+    block_excl_scan<SCAN_THREADS>(s, &tot);
+    if (threadIdx.x == 0) sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(int32_t *__restrict__ d, int64_t n,
+                                                              const int32_t *__restrict__ sums,
+                                                              int64_t *__restrict__ total) {
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_IPT;
+    int v[SCAN_IPT];
+    bool full = base + SCAN_IPT <= n;
+    if (full) {
+        const int4 *p = reinterpret_cast<const int4 *>(d + base);
+        int4 a = p[0], b = p[1];
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_IPT; k++) v[k] = (base + k < n) ? d[base + k] : 0;
+    }
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_IPT; k++) s += v[k];
+    int tot;
+    int ex = block_excl_scan<SCAN_THREADS>(s, &tot);
+    int off = (sums ? sums[blockIdx.x] : 0) + ex;
+    if (total && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *total = (int64_t)(sums ? sums[blockIdx.x] : 0) + tot;
+    int o[SCAN_IPT];
+#pragma unroll
+    for (int k = 0; k < SCAN_IPT; k++) {
+        o[k] = off;
+        off += v[k];
+    }
+    if (full) {
+        int4 *p = reinterpret_cast<int4 *>(d + base);
+        p[0] = make_int4(o[0], o[1], o[2], o[3]);
+        p[1] = make_int4(o[4], o[5], o[6], o[7]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_IPT; k++)
+            if (base + k < n) d[base + k] = o[k];
+    }
+}
+
+static int scan_rec(cl2_ctx *ctx, Scratch &sc, int32_t *d, int64_t n, int64_t *d_total) {
+    int64_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (nb <= 1) {
+        k_scan_apply<<<1, SCAN_THREADS, 0, ctx->stream>>>(d, n, nullptr, d_total);
+        ctx->launches++;
+        return CL2_OK;
+    }
+    int32_t *sums;
+    CL2_TRY(sc.get(&sums, (size_t)nb));
+    k_scan_reduce<<<(int)nb, SCAN_THREADS, 0, ctx->stream>>>(d, n, sums);
+    CL2_TRY(scan_rec(ctx, sc, sums, nb, nullptr));
+    k_scan_apply<<<(int)nb, SCAN_THREADS, 0, ctx->stream>>>(d, n, sums, d_total);
+    ctx->launches += 2;
+    return CL2_OK;
+}
+
+int cl2_exclusive_scan_i32(cl2_ctx *ctx, int32_t *d, int64_t n, int64_t *d_total) {
+    if (n <= 0) {
+        if (d_total) CL2_CUDA(ctx, cudaMemsetAsync(d_total, 0, sizeof(int64_t), ctx->stream));
+        return CL2_OK;
+    }
+    Scratch sc(ctx);
+    FamTimer t(ctx, FAM_SCAN, 8.0 * (double)n, 0);
+    CL2_TRY(scan_rec(ctx, sc, d, n, d_total));
+    CL2_CUDA(ctx, cudaGetLastError());
+    return CL2_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ radix sort
+#define RS_THREADS 256
+#define RS_WARPS (RS_THREADS / 32)
+#define RS_IPT 16
+#define RS_TILE (RS_THREADS * RS_IPT)
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_upsweep(const uint64_t *__restrict__ keys, int64_t n, int shift,
+                                                            int ntiles, int32_t *__restrict__ tilehist) {
+    __shared__ int hist[RS_WARPS][256];
+    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&hist[0][0])[i] = 0;
+    __syncthreads();
+    int w = threadIdx.x >> 5;
+    int64_t base = (int64_t)blockIdx.x * RS_TILE;
+#pragma unroll 4
+    for (int r = 0; r < RS_IPT; r++) {
+        int64_t i = base + (int64_t)r * RS_THREADS + threadIdx.x;
+        if (i < n) {
+            int d = (int)((keys[i] >> shift) & 255);
+            atomicAdd(&hist[w][d], 1);
+        }
+    }
+    __syncthreads();
+    int d = threadIdx.x;
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < RS_WARPS; k++) s += hist[k][d];
+    tilehist[(int64_t)d * ntiles + blockIdx.x] = s;
+}
+
+struct RsSmem {
+    uint64_t keys[RS_TILE];
+    uint32_t vals[RS_TILE];
+    int warp_cnt[RS_WARPS][256];
+    int dprefix[256];
+    int gbase[256];
+};
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_downsweep(const uint64_t *__restrict__ kin,
+                                                              const uint32_t *__restrict__ vin,
+                                                              uint64_t *__restrict__ kout, uint32_t *__restrict__ vout,
+                                                              int64_t n, int shift, int ntiles,
+                                                              const int32_t *__restrict__ tilebase, int iota) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RsSmem &S = *reinterpret_cast<RsSmem *>(smem_raw);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&S.warp_cnt[0][0])[i] = 0;
+    __syncthreads();
+    const int64_t tbase = (int64_t)blockIdx.x * RS_TILE;
+    const int64_t wbase = tbase + (int64_t)w * (32 * RS_IPT);
+    uint64_t key[RS_IPT];
+    unsigned short rank[RS_IPT];
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < RS_IPT; r++) {
+        int64_t i = wbase + r * 32 + lane;
+        key[r] = (i < n) ? kin[i] : ~0ull;
+    }
+#pragma unroll
+    for (int r = 0; r < RS_IPT; r++) {
+        int64_t i = wbase + r * 32 + lane;
+        bool valid = i < n;
+        unsigned d = valid ? (unsigned)((key[r] >> shift) & 255) : (0x10000u | lane);
+        unsigned peers = __match_any_sync(0xffffffffu, d);
+        int before = 0;
+        if (valid) before = S.warp_cnt[w][d];
+        __syncwarp();
+        rank[r] = (unsigned short)(before + __popc(peers & lt));
+        if (valid && (peers & lt) == 0) S.warp_cnt[w][d] = before + __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        // per digit: exclusive prefix over warps, then block scan over digits
+        int d = threadIdx.x;
+        int off = 0;
+#pragma unroll
+        for (int k = 0; k < RS_WARPS; k++) {
+            int c = S.warp_cnt[k][d];
+            S.warp_cnt[k][d] = off;
+            off += c;
+        }
+        int tot;
+        int ex = block_excl_scan<RS_THREADS>(off, &tot);
+        S.dprefix[d] = ex;
+        S.gbase[d] = tilebase[(int64_t)d * ntiles + blockIdx.x];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_IPT; r++) {
+        int64_t i = wbase + r * 32 + lane;
+        if (i < n) {
+            int d = (int)((key[r] >> shift) & 255);
+            int pos = S.dprefix[d] + S.warp_cnt[w][d] + rank[r];
+            S.keys[pos] = key[r];
+            S.vals[pos] = iota ? (uint32_t)i : vin[i];
+        }
+    }
+    __syncthreads();
+    int cnt = (int)((n - tbase) < RS_TILE ? (n - tbase) : RS_TILE);
+#pragma unroll 4
+    for (int j = threadIdx.x; j < cnt; j += RS_THREADS) {
+        uint64_t k = S.keys[j];
+        int d = (int)((k >> shift) & 255);
+        int64_t dst = (int64_t)S.gbase[d] + (j - S.dprefix[d]);
+        kout[dst] = k;
+        vout[dst] = S.vals[j];
+    }
+}
+
+int cl2_radix_sort_pairs(cl2_ctx *ctx, uint64_t *keys0, uint64_t *keys1, uint32_t *vals0, uint32_t *vals1, int64_t n,
+                         int nbits, uint64_t **kout, uint32_t **vout) {
+    *kout = keys0;
+    *vout = vals0;
+    if (n <= 0) return CL2_OK;
+    if (nbits < 1) nbits = 1;
+    int passes = (nbits + 7) / 8;
+    int ntiles = (int)((n + RS_TILE - 1) / RS_TILE);
+    Scratch sc(ctx);
+    int32_t *tilehist;
+    CL2_TRY(sc.get(&tilehist, (size_t)256 * ntiles));
+    static bool attr_set = false;
+    if (!attr_set) {
+        CL2_CUDA(ctx, cudaFuncSetAttribute(k_rs_downsweep, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sizeof(RsSmem)));
+        attr_set = true;
+    }
+    uint64_t *kin = keys0, *ko = keys1;
+    uint32_t *vi = vals0, *vo = vals1;
+    for (int p = 0; p < passes; p++) {
+        int shift = p * 8;
+        {
+            FamTimer t(ctx, FAM_SORT_HIST, 8.0 * (double)n);
+            k_rs_upsweep<<<ntiles, RS_THREADS, 0, ctx->stream>>>(kin, n, shift, ntiles, tilehist);
+        }
+        CL2_TRY(cl2_exclusive_scan_i32(ctx, tilehist, (int64_t)256 * ntiles, nullptr));
+        {
+            FamTimer t(ctx, FAM_SORT_SCATTER, 24.0 * (double)n);
+            k_rs_downsweep<<<ntiles, RS_THREADS, sizeof(RsSmem), ctx->stream>>>(kin, vi, ko, vo, n, shift, ntiles,
+                                                                                 tilehist, p == 0 ? 1 : 0);
+        }
+        uint64_t *tk = kin; kin = ko; ko = tk;
+        uint32_t *tv = vi; vi = vo; vo = tv;
+    }
+    CL2_CUDA(ctx, cudaGetLastError());
+    *kout = kin;
+    *vout = vi;
+    return CL2_OK;
+}

@@ -1,0 +1,110 @@
+"""
+Multi-GPU plumbing for the callLoops path: one process per GPU (torchrun), chromosome(-pair) files as the unit of
+work.  The reference fans the same units out over joblib workers (callCisLoops.py:134-137, 561-572;
+callTransLoops.py:95-97, 237-243); no data flows between units, so there is no data-path collective -- only a small
+all-reduce (NCCL over NVLink when ranks own GPUs, gloo on CPU in the tests) of the PET / candidate / loop counters,
+and a host gather of the per-chromosome loop tables to rank 0.
+"""
+import os
+
+import numpy as np
+
+
+def rank_world():
+    """(rank, world) from torch.distributed if it is initialised, else from the torchrun environment, else (0, 1)."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except Exception:
+        pass
+    return 0, 1
+
+
+def init_from_env(backend=None):
+    """Initialise torch.distributed when launched by torchrun (WORLD_SIZE > 1).  Returns (rank, world)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 0, 1
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend=backend)
+    return dist.get_rank(), dist.get_world_size()
+
+
+def ixy_rows(f):
+    """PET count of a .ixy without loading it: joblib stores the raw int64[N,2] buffer after a small pickle header
+    (~240 bytes), so rows ~= file size / 16.  Only used to balance shards."""
+    try:
+        return max(0, (os.path.getsize(f) - 240) // 16)
+    except OSError:
+        return 0
+
+
+def assign(keys, weights, world):
+    """Greedy longest-processing-time partition of `keys` by `weights` into `world` bins.  Every rank computes the
+    same assignment (deterministic tie-breaks); within a bin the original key order is kept."""
+    order = sorted(range(len(keys)), key=lambda i: (-int(weights[i]), i))
+    load = [0] * world
+    owner = [0] * len(keys)
+    for i in order:
+        r = min(range(world), key=lambda j: (load[j], j))
+        owner[i] = r
+        load[r] += int(weights[i])
+    return [[keys[i] for i in range(len(keys)) if owner[i] == r] for r in range(world)]
+
+
+def allreduce_stats(vals):
+    """Sum an int64 vector over ranks (the path's only collective)."""
+    rank, world = rank_world()
+    vals = np.asarray(vals, dtype=np.int64)
+    if world == 1:
+        return vals
+    import torch
+    import torch.distributed as dist
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.from_numpy(vals.copy()).to(dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.cpu().numpy()
+
+
+def gather_results(results):
+    """Per-chromosome result dicts of every rank merged on rank 0 (other ranks get {})."""
+    rank, world = rank_world()
+    if world == 1:
+        return results
+    import torch.distributed as dist
+    bucket = [None] * world if rank == 0 else None
+    dist.gather_object(results, bucket, dst=0)
+    if rank != 0:
+        return {}
+    merged = {}
+    for part in bucket:
+        merged.update(part)
+    return merged
+
+
+def max_over_ranks(x):
+    """max of a float over ranks (timing)."""
+    rank, world = rank_world()
+    if world == 1:
+        return float(x)
+    import torch
+    import torch.distributed as dist
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier():
+    rank, world = rank_world()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()

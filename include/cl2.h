@@ -1,0 +1,130 @@
+/*
+ * cl2.h -- C ABI of libcl2.so: the B200 (sm_100a) implementation of the cLoops2 `callLoops` hot path.
+ *
+ * The reference (cLoops2 0.0.5, pure Python) has no FFI; these entry points are what a ctypes binding inside
+ * cLoops2 would bind for this path (INTEGRATION.md shows the stub).  Each entry cites the reference interface it
+ * replaces (path:line under the cLoops2 checkout).
+ *
+ * Conventions: caller-owned host buffers, plain pointers and sizes; every call returns CL2_OK (0) or a negative
+ * error code, with a message retrievable through cl2_last_error(ctx); no exceptions cross the ABI.  One cl2_ctx
+ * per GPU; calls on one context must be serialised by the caller, independent contexts may be used from
+ * different host threads.  Labels are int32, -1 = not clustered, cluster ids numbered exactly as the reference's
+ * `.labels` dict values.
+ */
+#ifndef CL2_H
+#define CL2_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CL2_OK 0
+#define CL2_ERR_CUDA (-1)      /* a CUDA runtime call failed (message has the cudaError string) */
+#define CL2_ERR_ARG (-2)       /* bad argument (null pointer, eps <= 0, n < 0, coordinates out of range) */
+#define CL2_ERR_NOMEM (-3)     /* device or host allocation failed */
+#define CL2_ERR_RANGE (-4)     /* coordinate span does not fit the on-device int32 layout */
+
+#define CL2_MODE_CIS 0
+#define CL2_MODE_TRANS 1
+
+typedef struct cl2_ctx cl2_ctx;        /* one GPU: stream, memory pool, timers */
+typedef struct cl2_points cl2_points;  /* one .ixy file resident in HBM (kept across the eps x minPts sweep) */
+typedef struct cl2_index cl2_index;    /* device form of cLoops2/ds.py:141-198 (XY): X-sorted and Y-sorted arrays */
+
+/* version string of the library, e.g. "cl2-b200 0.1 sm_100a" */
+const char *cl2_version(void);
+
+/* ---- context ------------------------------------------------------------------------------------------ */
+int cl2_ctx_create(int device, cl2_ctx **out);
+void cl2_ctx_destroy(cl2_ctx *ctx);
+const char *cl2_last_error(cl2_ctx *ctx);
+/* blocks until all work queued on the context's stream has finished */
+int cl2_ctx_sync(cl2_ctx *ctx);
+
+/* Page-locked host staging (replaces the numpy array joblib.load returns in cLoops2/io.py:274-291). */
+int cl2_host_alloc(cl2_ctx *ctx, int64_t bytes, void **out);
+void cl2_host_free(cl2_ctx *ctx, void *p);
+
+/* ---- points ------------------------------------------------------------------------------------------- */
+/*
+ * Upload one .ixy matrix: xy = int64[n,2] row-major (x,y interleaved), the layout joblib stores
+ * (cLoops2/io.py:55-67, 274-291).  Rows failing (y-x >= cut when cut>0) or (y-x <= mcut when mcut>0) are dropped
+ * on the device, order preserved, exactly as parseIxy does (io.py:282-289); row ids are positions after the filter
+ * (callCisLoops.py:67-72).  cut=0, mcut=-1 keeps everything.
+ */
+int cl2_points_upload(cl2_ctx *ctx, const int64_t *xy, int64_t n, int64_t cut, int64_t mcut, cl2_points **out);
+/* number of rows kept after the cut/mcut filter */
+int64_t cl2_points_count(const cl2_points *pts);
+/* min X, max X, min Y, max Y of the kept rows (callCisLoops.py:231 uses max Y - min X) */
+int cl2_points_extent(cl2_ctx *ctx, const cl2_points *pts, int64_t ext[4]);
+/* kept rows back to the host as int64[n,2] (for -filter, callCisLoops.py:450-468) */
+int cl2_points_download(cl2_ctx *ctx, const cl2_points *pts, int64_t *xy_out);
+void cl2_points_free(cl2_ctx *ctx, cl2_points *pts);
+
+/* ---- clustering --------------------------------------------------------------------------------------- */
+/*
+ * blockDBSCAN(mat, eps, minPts).labels -- cLoops2/blockDBSCAN.py:13-41 (call sites callCisLoops.py:87,
+ * callTransLoops.py:53).  labels_out: int32[n] host buffer or NULL (skip the per-point label read-back).
+ */
+int cl2_block_dbscan(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int32_t minPts, int32_t *labels_out,
+                     int32_t *n_clusters);
+/* cDBSCAN(mat, eps, minPts).labels -- cLoops2/cDBSCAN2.py:13-35 (callCisLoops.py:499-502, -hic). */
+int cl2_cdbscan2(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int32_t minPts, int32_t *labels_out,
+                 int32_t *n_clusters);
+/*
+ * Per-cluster bounding box and size of the LAST clustering run on `pts` (replaces the pandas scan at
+ * callCisLoops.py:92-105 / callTransLoops.py:58-76).  bbox_out: int64[n_clusters,4] = xmin,xmax,ymin,ymax;
+ * size_out: int64[n_clusters].
+ */
+int cl2_cluster_bbox(cl2_ctx *ctx, cl2_points *pts, int64_t *bbox_out, int64_t *size_out);
+/* blockDBSCAN's noise-cell removal alone (blockDBSCAN.py:69-122; also cLoops2/filter.py:223-278):
+ * keep_out[i] = 1 iff row i survives removeNoiseGrids. */
+int cl2_block_noise(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int32_t minPts, uint8_t *keep_out);
+
+/* ---- counting ----------------------------------------------------------------------------------------- */
+/* XY(xs, ys) -- cLoops2/ds.py:146-163, built by ixy2pet (io.py:294-300). */
+int cl2_index_build(cl2_ctx *ctx, cl2_points *pts, cl2_index **out);
+void cl2_index_free(cl2_ctx *ctx, cl2_index *idx);
+/*
+ * Raw counts behind estLoopSig (callCisLoops.py:250-354; trans: callTransLoops.py:106-193) for L candidate
+ * loops, loops = int64[L,4] x_start,x_end,y_start,y_end.  Any output pointer may be NULL to skip that group.
+ *   core    int64[L,4]   ra, rb, rab (queryLoop, ds.py:184-190) and the P2LL lower-left |A' & B'|
+ *                        (cis window callCisLoops.py:302-305, trans window callTransLoops.py:142-144)
+ *   na, nb  int64[L,2*win]          |Na_i|, |Nb_j| of the shifted windows (getPerRegions, callCisLoops.py:173-198)
+ *   nab     int64[L,(2*win)^2]      |Na_i & Nb_j|, a-major (getLoopNearbyPETs, callCisLoops.py:207-223)
+ *   anchors int64[L,4]   count_x, wide_x, count_y, wide_y (estAnchorSig, callCisLoops.py:226-247, ext = 5)
+ */
+int cl2_loop_counts(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops, int64_t L, int32_t win, int32_t mode,
+                    int64_t *core, int64_t *na, int64_t *nb, int64_t *nab, int64_t *anchors);
+
+/* ---- host-side selection (native, no GPU) ----------------------------------------------------------------- */
+/*
+ * selSigLoops (callCisLoops.py:379-422) for the loops of ONE chromosome (pair), all already significant, in list
+ * order: greedy single-link overlap groups in order, per group the first loop attaining the maximum ES, then the
+ * "search again" pass.  coords = int64[L,4] x_start,x_end,y_start,y_end; es = double[L].
+ * out_idx: int64[L] receives the indices of the selected loops in output order; *out_n their number.
+ */
+int cl2_sel_sig_loops(const int64_t *coords, const double *es, int64_t L, int64_t *out_idx, int64_t *out_n);
+
+/* ---- measurement -------------------------------------------------------------------------------------- */
+/* Kernel launches issued by this context since creation (or since the last reset). */
+int64_t cl2_launch_count(cl2_ctx *ctx);
+void cl2_launch_count_reset(cl2_ctx *ctx);
+/*
+ * Per-kernel-family device time (CUDA events on the context's stream) accumulated while timing is enabled.
+ * names_out: buffer of k_max * 32 chars (NUL-terminated names), ms_out / launches_out / bytes_out: k_max entries;
+ * bytes_out is the ALGORITHMIC byte count of the launches (DESIGN.md states each kernel's per-unit figure).
+ * Returns the number of families written.
+ */
+int cl2_timing_enable(cl2_ctx *ctx, int on);
+/* Bytes this context has copied host->device and device->host since creation (or the last launch-count reset). */
+void cl2_transfer_bytes(cl2_ctx *ctx, int64_t *h2d, int64_t *d2h);
+int cl2_timing_read(cl2_ctx *ctx, int k_max, char *names_out, double *ms_out, int64_t *launches_out,
+                    double *bytes_out);
+void cl2_timing_reset(cl2_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

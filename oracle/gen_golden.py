@@ -1,0 +1,145 @@
+"""
+TEST INFRASTRUCTURE -- generates tests/golden/*.npz by running the UNMODIFIED reference (/root/reference, imported
+through oracle/ref_shim.py) in the build container.  The reference ships no golden vectors of its own
+(SURVEY.md section 4), so these are the pinned answers; the GPU box has no /root/reference and only reads the
+committed files.
+
+    python -m oracle.gen_golden            # rewrites tests/golden/
+
+Contents
+  dbscan_small.npz     120 random point sets (sparse, clustered, duplicate-heavy, X>Y rows) with the reference's
+                       blockDBSCAN and cDBSCAN `.labels` (as int32 arrays, -1 = absent from the dict)
+  cis_pipeline.npz     two synthetic chromosomes + the reference's callCisLoops `_loops.txt` (default and -hic,
+                       eps 200,500,1000 / minPts 5; plus a two-minPts, cut/mcut run)
+  trans_pipeline.npz   two synthetic chromosome pairs + the reference's callTransLoops `_trans_loops.txt`
+  estsig_cis.npz       per-candidate fields of the reference's estLoopSig on one chromosome (every attribute)
+"""
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim  # noqa: E402
+from cloops2_b200 import synth  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def ref_labels(cls, xy, eps, minPts):
+    n = len(xy)
+    mat = np.zeros((n, 3))
+    mat[:, 0] = np.arange(n)
+    mat[:, 1] = xy[:, 0]
+    mat[:, 2] = xy[:, 1]
+    mat = mat.astype("int")
+    db = cls(mat, eps, minPts)
+    lab = -np.ones(n, dtype=np.int32)
+    for k, v in db.labels.items():
+        lab[int(k)] = v
+    return lab
+
+
+def random_case(rng, it):
+    n = int(rng.integers(1, 600))
+    span = int(rng.choice([20, 50, 200, 1000, 5000]))
+    eps = int(rng.integers(1, 60))
+    minPts = int(rng.integers(2, 14))
+    kind = it % 4
+    if kind == 0:      # clustered blobs
+        k = int(rng.integers(1, 7))
+        cx = rng.integers(0, span, size=k)
+        cy = cx + rng.integers(0, span, size=k)
+        r = rng.integers(0, k, size=n)
+        s = eps * rng.uniform(0.3, 2.5)
+        x = np.abs(np.rint(rng.normal(cx[r], s))).astype(np.int64)
+        y = np.abs(np.rint(rng.normal(cy[r], s))).astype(np.int64)
+        xy = np.stack([np.minimum(x, y), np.maximum(x, y)], 1)
+    elif kind == 1:    # sparse uniform
+        x = rng.integers(0, span, size=n)
+        xy = np.stack([x, x + rng.integers(0, span, size=n)], 1)
+    elif kind == 2:    # duplicate heavy
+        x = rng.integers(0, max(2, span // 10), size=n) * 3
+        xy = np.stack([x, x + rng.integers(0, max(2, span // 10), size=n) * 2], 1)
+    else:              # unordered rows (X > Y allowed), as a trans file would have
+        xy = np.stack([rng.integers(0, span, size=n), rng.integers(0, span, size=n)], 1)
+    return xy.astype(np.int64), eps, minPts
+
+
+def gen_dbscan(ref):
+    rng = np.random.default_rng(20261019)
+    xs, offs, params, lb, lc = [], [0], [], [], []
+    for it in range(120):
+        xy, eps, minPts = random_case(rng, it)
+        xs.append(xy)
+        offs.append(offs[-1] + len(xy))
+        params.append((eps, minPts))
+        lb.append(ref_labels(ref.blockDBSCAN, xy, eps, minPts))
+        lc.append(ref_labels(ref.cDBSCAN, xy, eps, minPts))
+    np.savez_compressed(os.path.join(GOLD, "dbscan_small.npz"), xy=np.concatenate(xs), offsets=np.array(offs),
+                        params=np.array(params), labels_block=np.concatenate(lb), labels_c2=np.concatenate(lc))
+
+
+def run_ref_cis(ref, files, **kw):
+    tmp = tempfile.mkdtemp()
+    synth.write_ixy_dir(files, tmp + "/d")
+    ref.cis.callCisLoops(tmp + "/d", tmp + "/out", ref.logger, cpu=1, **kw)
+    meta = json.load(open(tmp + "/d/petMeta.json"))
+    return open(tmp + "/out_loops.txt").read(), list(meta["data"]["cis"].keys()), meta["Unique PETs"]
+
+
+def gen_cis(ref):
+    files = {"chr21-chr21": synth.cis_chrom(4_000_000, 36000, 7, "hitrac"),
+             "chr22-chr22": synth.cis_chrom(3_000_000, 24000, 8, "hitrac")}
+    out = {}
+    txt, order, tot = run_ref_cis(ref, files, eps=[200, 500, 1000], minPts=[5])
+    out["default_txt"] = txt
+    out["hic_txt"] = run_ref_cis(ref, files, eps=[200, 500, 1000], minPts=[5], hic=True)[0]
+    out["cut_txt"] = run_ref_cis(ref, files, eps=[300, 800], minPts=[8, 4], cut=2000, mcut=1500000)[0]
+    out["empair_txt"] = run_ref_cis(ref, files, eps=[800, 300], minPts=[4, 8], emPair=True)[0]
+    np.savez_compressed(os.path.join(GOLD, "cis_pipeline.npz"), order=np.array(order), tot=tot,
+                        **{k.replace("-", "_"): v for k, v in files.items()}, **out)
+    # per-candidate estLoopSig fields on one chromosome
+    tmp = tempfile.mkdtemp()
+    synth.write_ixy_dir({"chr21-chr21": files["chr21-chr21"]}, tmp + "/d")
+    fixy = tmp + "/d/chr21-chr21.ixy"
+    ref.cis.DBSCAN = ref.blockDBSCAN
+    _, cand = ref.cis.runCisDBSCANLoops(fixy, 500, 5)
+    coords = np.array([[lp.x_start, lp.x_end, lp.y_start, lp.y_end] for lp in cand], dtype=np.int64)
+    _, est = ref.cis.estLoopSig("chr21-chr21", cand, fixy, tot, minPts=5)
+    fields = ["ra", "rb", "rab", "P2LL", "FDR", "ES", "density", "hypergeometric_p_value", "poisson_p_value",
+              "binomial_p_value", "x_peak_poisson_p_value", "x_peak_es", "y_peak_poisson_p_value", "y_peak_es"]
+    kept = np.array([[lp.x_start, lp.x_end, lp.y_start, lp.y_end] for lp in est], dtype=np.int64)
+    vals = np.array([[float(getattr(lp, f)) for f in fields] for lp in est], dtype=np.float64)
+    np.savez_compressed(os.path.join(GOLD, "estsig_cis.npz"), candidates=coords, kept=kept, fields=np.array(fields),
+                        values=vals, tot=tot)
+
+
+def gen_trans(ref):
+    files = {"chr21-chr22": synth.trans_pair(2_000_000, 2_400_000, 30000, 11, sigma=800, per=1500),
+             "chr20-chr22": synth.trans_pair(1_500_000, 2_400_000, 20000, 12, sigma=800, per=1500)}
+    tmp = tempfile.mkdtemp()
+    synth.write_ixy_dir(files, tmp + "/d")
+    ref.trans.callTransLoops(tmp + "/d", tmp + "/out", ref.logger, eps=[2000, 4000], minPts=[10, 5], cpu=1)
+    meta = json.load(open(tmp + "/d/petMeta.json"))
+    np.savez_compressed(os.path.join(GOLD, "trans_pipeline.npz"), order=np.array(list(meta["data"]["trans"].keys())),
+                        trans_txt=open(tmp + "/out_trans_loops.txt").read(),
+                        **{k.replace("-", "_"): v for k, v in files.items()})
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    ref = ref_shim.load()
+    gen_dbscan(ref)
+    gen_cis(ref)
+    gen_trans(ref)
+    print("golden vectors written to", GOLD)
+
+
+if __name__ == "__main__":
+    main()

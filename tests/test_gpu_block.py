@@ -1,0 +1,125 @@
+"""blockDBSCAN on the GPU through the C ABI vs the oracle / the reference's golden labels.  Bit-exact, including
+cluster numbering."""
+import numpy as np
+import pytest
+
+import oracle
+from cloops2_b200 import _lib, synth
+from conftest import load_golden, random_case
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_block(ctx, xy, eps, minPts):
+    pts = _lib.Points(ctx, xy)
+    try:
+        if pts.n == 0:
+            return np.zeros(0, np.int32), 0, np.zeros((0, 4), np.int64), np.zeros(0, np.int64)
+        lab, ncl = pts.block_dbscan(eps, minPts)
+        bbox, size = pts.cluster_bbox()
+        return lab, ncl, bbox, size
+    finally:
+        pts.close()
+
+
+def test_golden_labels(gpu_ctx):
+    g = load_golden("dbscan_small.npz")
+    offs = g["offsets"]
+    for i, (eps, minPts) in enumerate(g["params"].tolist()):
+        xy = g["xy"][offs[i]:offs[i + 1]]
+        lab, ncl, _, _ = gpu_block(gpu_ctx, xy, eps, minPts)
+        assert np.array_equal(lab, g["labels_block"][offs[i]:offs[i + 1]]), (i, eps, minPts)
+
+
+def test_random_small_cases_labels_bbox(gpu_ctx):
+    rng = np.random.default_rng(2026)
+    for it in range(400):
+        xy, eps, minPts = random_case(rng, it)
+        want, wn = oracle.block_dbscan(xy, eps, minPts)
+        lab, ncl, bbox, size = gpu_block(gpu_ctx, xy, eps, minPts)
+        assert ncl == wn and np.array_equal(lab, want), (it, len(xy), eps, minPts)
+        wb, ws = oracle.cluster_bbox(xy, want, wn)
+        assert np.array_equal(bbox, wb) and np.array_equal(size, ws), it
+
+
+def test_noise_removal_only(gpu_ctx):
+    rng = np.random.default_rng(7)
+    for it in range(60):
+        xy, eps, minPts = random_case(rng, it)
+        pts = _lib.Points(gpu_ctx, xy)
+        try:
+            keep = pts.block_noise_keep(eps, minPts)
+        finally:
+            pts.close()
+        assert np.array_equal(keep, oracle.block_noise_keep(xy, eps, minPts)), it
+
+
+@pytest.mark.parametrize("profile,n,length,eps,minPts", [
+    ("hitrac", 300_000, 46_709_983, 200, 5), ("hitrac", 300_000, 46_709_983, 1000, 5),
+    ("hitrac", 300_000, 20_000_000, 500, 10), ("hic", 200_000, 3_000_000, 5000, 20),
+    ("hic", 200_000, 3_000_000, 10000, 50), ("chiapet", 250_000, 30_000_000, 2000, 3)])
+def test_synthetic_chromosomes(gpu_ctx, profile, n, length, eps, minPts):
+    xy = synth.cis_chrom(length, n, 1234 + eps, profile)
+    want, wn = oracle.block_dbscan(xy, eps, minPts)
+    lab, ncl, bbox, size = gpu_block(gpu_ctx, xy, eps, minPts)
+    assert ncl == wn
+    assert np.array_equal(lab, want)
+    wb, ws = oracle.cluster_bbox(xy, want, wn)
+    assert np.array_equal(bbox, wb) and np.array_equal(size, ws)
+
+
+def test_minpts_sweep_reuses_grid(gpu_ctx):
+    """eps-major sweep: the cached grid of one eps must give the same labels as a fresh build."""
+    xy = synth.cis_chrom(10_000_000, 120_000, 77, "hitrac")
+    pts = _lib.Points(gpu_ctx, xy)
+    try:
+        for eps in (300, 900):
+            for minPts in (12, 6, 3):
+                lab, ncl = pts.block_dbscan(eps, minPts)
+                want, wn = oracle.block_dbscan(xy, eps, minPts)
+                assert ncl == wn and np.array_equal(lab, want), (eps, minPts)
+    finally:
+        pts.close()
+
+
+def test_cut_mcut_filter_on_device(gpu_ctx):
+    xy = synth.cis_chrom(5_000_000, 50_000, 5, "hitrac")
+    for cut, mcut in ((0, -1), (3000, -1), (0, 500_000), (2000, 800_000)):
+        pts = _lib.Points(gpu_ctx, xy, cut=cut, mcut=mcut)
+        try:
+            want = oracle.parse_ixy_filter(xy, cut, mcut)
+            assert pts.n == len(want)
+            assert np.array_equal(pts.download(), want)
+            if pts.n:
+                ext = pts.extent()
+                assert ext.tolist() == [want[:, 0].min(), want[:, 0].max(), want[:, 1].min(), want[:, 1].max()]
+        finally:
+            pts.close()
+
+
+def test_edge_inputs(gpu_ctx):
+    for xy in (np.zeros((0, 2), np.int64), np.array([[5, 9]], np.int64), np.array([[5, 9]] * 40, np.int64),
+               np.array([[0, 0], [2**31 - 2, 2**31 - 2]], np.int64)):
+        for eps, minPts in ((10, 1), (10, 2), (1, 50), (2**31, 2)):
+            want, wn = oracle.block_dbscan(xy, eps, minPts)
+            lab, ncl, _, _ = gpu_block(gpu_ctx, xy, eps, minPts)
+            assert ncl == wn and np.array_equal(lab, want), (xy.shape, eps, minPts)
+    with pytest.raises(_lib.Cl2Error):
+        _lib.Points(gpu_ctx, np.array([[-1, 5]], np.int64))
+    with pytest.raises(_lib.Cl2Error):
+        _lib.Points(gpu_ctx, np.array([[1, 2**31]], np.int64))
+    pts = _lib.Points(gpu_ctx, np.array([[1, 2]], np.int64))
+    with pytest.raises(_lib.Cl2Error):
+        pts.block_dbscan(0, 5)
+    pts.close()
+
+
+def test_dropin_class_protocol(gpu_ctx):
+    from cloops2_b200.blockDBSCAN import blockDBSCAN
+    xy = synth.cis_chrom(2_000_000, 20_000, 9, "hitrac")
+    mat = np.zeros((len(xy), 3))
+    mat[:, 0] = np.arange(len(xy))
+    mat[:, 1:] = xy
+    db = blockDBSCAN(mat, 500, 5)          # float matrix, as callTransLoops.py:43-47 passes it
+    want, _ = oracle.block_dbscan(xy, 500, 5)
+    assert db.labels == {i: int(v) for i, v in enumerate(want.tolist()) if v >= 0}

@@ -1,0 +1,64 @@
+"""XY index + rectangle/window counting kernel vs the oracle's set-based counts (identical integers)."""
+import numpy as np
+import pytest
+
+import oracle
+from cloops2_b200 import _lib, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _cands(xy, rng, L):
+    """Candidate-like boxes around real PETs plus adversarial ones (overlapping anchors, at the origin, huge)."""
+    i = rng.integers(0, len(xy), size=L)
+    wa = rng.integers(1, 3000, size=L)
+    wb = rng.integers(1, 3000, size=L)
+    xs = np.maximum(0, xy[i, 0] - wa // 2)
+    ys = np.maximum(0, xy[i, 1] - wb // 2)
+    c = np.stack([xs, xs + wa, ys, ys + wb], 1).astype(np.int64)
+    c[0] = [0, 50, 10, 400]
+    c[1] = [0, 1, 0, 1]
+    c[2] = [100, 100000, 50000, 300000]
+    return c
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_counts_match_oracle(gpu_ctx, mode):
+    rng = np.random.default_rng(11 + mode)
+    if mode == 0:
+        xy = synth.cis_chrom(3_000_000, 80_000, 3, "hitrac")
+    else:
+        xy = synth.trans_pair(2_000_000, 2_500_000, 60_000, 4, per=1500)
+    cands = _cands(xy, rng, 300)
+    pts = _lib.Points(gpu_ctx, xy)
+    idx = _lib.Index(pts)
+    try:
+        got = idx.loop_counts(cands, win=5, mode=mode)
+    finally:
+        idx.close()
+        pts.close()
+    want = oracle.XYIndex(xy).loop_counts(cands, win=5, mode=mode)
+    for name, g, w in zip(("core", "na", "nb", "nab", "anchors"), got, want):
+        assert np.array_equal(g, w), name
+
+
+def test_counts_other_window_sizes_and_partial_outputs(gpu_ctx):
+    rng = np.random.default_rng(5)
+    xy = synth.cis_chrom(1_000_000, 30_000, 6, "hitrac")
+    cands = _cands(xy, rng, 64)
+    pts = _lib.Points(gpu_ctx, xy)
+    idx = _lib.Index(pts)
+    try:
+        for win in (1, 3, 8):
+            got = idx.loop_counts(cands, win=win)
+            want = oracle.XYIndex(xy).loop_counts(cands, win=win)
+            for g, w in zip(got, want):
+                assert np.array_equal(g, w), win
+        c, na, nb, nab, anc = idx.loop_counts(cands, windows=False, anchors=False)
+        assert na is None and anc is None and np.array_equal(c, oracle.XYIndex(xy).loop_counts(cands)[0])
+        assert idx.loop_counts(np.zeros((0, 4), np.int64))[0].shape == (0, 4)
+        with pytest.raises(_lib.Cl2Error):
+            idx.loop_counts(cands, win=9)
+    finally:
+        idx.close()
+        pts.close()

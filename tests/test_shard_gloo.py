@@ -1,0 +1,62 @@
+"""world_size-2 gloo test of the multi-rank plumbing (assignment, stats all-reduce, gather to rank 0)."""
+import os
+import socket
+
+import numpy as np
+import torch.multiprocessing as mp
+
+from cloops2_b200 import shard
+
+
+def test_lpt_assignment_is_balanced_and_deterministic():
+    from cloops2_b200.synth import HG38
+    keys = [n for n, _ in HG38]
+    w = [l for _, l in HG38]
+    for world in (1, 2, 4, 8):
+        parts = shard.assign(keys, w, world)
+        assert sorted(sum(parts, [])) == sorted(keys)
+        loads = [sum(w[keys.index(k)] for k in p) for p in parts]
+        assert max(loads) <= 1.13 * (sum(w) / world) or world == 1
+        assert parts == shard.assign(keys, w, world)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    r, w = shard.init_from_env(backend="gloo")
+    assert (r, w) == (rank, world)
+    keys = ["a", "b", "c", "d", "e"]
+    mine = shard.assign(keys, [50, 40, 30, 20, 10], world)[rank]
+    stats = shard.allreduce_stats(np.array([len(mine), rank + 1], dtype=np.int64))
+    res = shard.gather_results({k: np.full(2, rank) for k in mine})
+    t = shard.max_over_ranks(float(rank))
+    shard.barrier()
+    q.put((rank, mine, stats.tolist(), sorted(res.keys()), t))
+    import torch.distributed as dist
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_roundtrip():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, m0, s0, k0, t0), (r1, m1, s1, k1, t1) = out
+    assert sorted(m0 + m1) == ["a", "b", "c", "d", "e"] and not set(m0) & set(m1)
+    assert s0 == s1 == [5, 3]
+    assert k0 == ["a", "b", "c", "d", "e"] and k1 == []
+    assert t0 == t1 == 1.0
