@@ -516,27 +516,55 @@ __global__ void __launch_bounds__(256) k_block_compid_indirect(const uint32_t *_
 }
 
 // ================================================================================================ host driver
-static int read_i64(cl2_ctx *ctx, const int64_t *d, int64_t *out) {
+int cl2_read_i64(cl2_ctx *ctx, const int64_t *d, int64_t *out) {
     CL2_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, d, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CL2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *out = *(int64_t *)ctx->h_scratch;
     return CL2_OK;
 }
-static int read_i32(cl2_ctx *ctx, const int32_t *d, int32_t *out) {
+int cl2_read_i32(cl2_ctx *ctx, const int32_t *d, int32_t *out) {
     CL2_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, d, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CL2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *out = *(int32_t *)ctx->h_scratch;
     return CL2_OK;
 }
 
+// cDBSCAN2 grid (cDBSCAN2.py:67-70): rotate by 45 degrees, cell = truncating division (toward zero) of u = X-Y and
+// v = X+Y by eps; the indices are shifted by the truncated lower bounds so the packed fields are non-negative.
+__global__ void __launch_bounds__(256) k_rot_keygen(const int2 *__restrict__ xy, uint64_t *__restrict__ key, int64_t n,
+                                                     int eps, int gx0, unsigned gy0, int by) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int2 p = xy[i];
+    int u = p.x - p.y;
+    unsigned v = (unsigned)p.x + (unsigned)p.y;
+    unsigned gx = (unsigned)(u / eps - gx0);          // C division truncates toward zero == int(x / cw)
+    unsigned gy = v / (unsigned)eps - gy0;
+    key[i] = ((uint64_t)gx << by) | (uint64_t)gy;
+}
+
 // Build (or reuse) the eps grid: keygen -> radix sort -> gather -> cell table -> neighbours + 3x3 sums.
-static int block_grid_build(cl2_ctx *ctx, cl2_points *pts, int64_t eps) {
+// kind 0: blockDBSCAN grid anchored at (minX, minY) (blockDBSCAN.py:69-86); kind 1: cDBSCAN2 rotated grid.
+int cl2_grid_build(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int kind) {
     cl2_grid_cache &g = pts->grid;
-    if (g.valid && g.kind == 0 && g.eps == eps && g.n == pts->n) return CL2_OK;
+    if (g.valid && g.kind == kind && g.eps == eps && g.n == pts->n) return CL2_OK;
     cl2_grid_free(ctx, g);
     const int64_t n = pts->n;
     unsigned e32 = eps >= (int64_t)INT32_MAX ? (unsigned)INT32_MAX : (unsigned)eps;
-    uint64_t gxmax = (uint64_t)(pts->ext[1] - pts->ext[0]) / e32, gymax = (uint64_t)(pts->ext[3] - pts->ext[2]) / e32;
+    uint64_t gxmax, gymax;
+    int rgx0 = 0;
+    unsigned rgy0 = 0;
+    if (kind == 0) {
+        gxmax = (uint64_t)(pts->ext[1] - pts->ext[0]) / e32;
+        gymax = (uint64_t)(pts->ext[3] - pts->ext[2]) / e32;
+    } else {
+        long long ulo = pts->ext[0] - pts->ext[3], uhi = pts->ext[1] - pts->ext[2];   // bounds of X-Y
+        long long vlo = pts->ext[0] + pts->ext[2], vhi = pts->ext[1] + pts->ext[3];   // bounds of X+Y
+        rgx0 = (int)(ulo / (long long)e32);
+        rgy0 = (unsigned)(vlo / (long long)e32);
+        gxmax = (uint64_t)(uhi / (long long)e32 - ulo / (long long)e32);
+        gymax = (uint64_t)(vhi / (long long)e32 - vlo / (long long)e32);
+    }
     int bx = bits_for(gxmax), by = bits_for(gymax);
     Scratch sc(ctx);
     uint64_t *k0, *k1, *ks;
@@ -547,8 +575,11 @@ static int block_grid_build(cl2_ctx *ctx, cl2_points *pts, int64_t eps) {
     CL2_TRY(sc.get(&v1, (size_t)n));
     {
         FamTimer t(ctx, FAM_KEYGEN, 16.0 * (double)n);
-        k_block_keygen<<<cl2_grid(n, 256), 256, 0, ctx->stream>>>(pts->xy, k0, n, (int)pts->ext[0], (int)pts->ext[2],
-                                                                   e32, by);
+        if (kind == 0)
+            k_block_keygen<<<cl2_grid(n, 256), 256, 0, ctx->stream>>>(pts->xy, k0, n, (int)pts->ext[0], (int)pts->ext[2],
+                                                                       e32, by);
+        else
+            k_rot_keygen<<<cl2_grid(n, 256), 256, 0, ctx->stream>>>(pts->xy, k0, n, (int)e32, rgx0, rgy0, by);
     }
     CL2_TRY(cl2_radix_sort_pairs(ctx, k0, k1, v0, v1, n, bx + by, &ks, &vs));
     // keep the sorted row ids (take ownership of whichever buffer holds them)
@@ -568,7 +599,7 @@ static int block_grid_build(cl2_ctx *ctx, cl2_points *pts, int64_t eps) {
     }
     CL2_TRY(cl2_exclusive_scan_i32(ctx, g.cid, n, d_total));
     int64_t ncells64 = 0;
-    CL2_TRY(read_i64(ctx, d_total, &ncells64));
+    CL2_TRY(cl2_read_i64(ctx, d_total, &ncells64));
     int32_t ncells = (int32_t)ncells64;
     CL2_TRY(cl2_dev_alloc(ctx, &g.cstart, (size_t)ncells + 1));
     CL2_TRY(cl2_dev_alloc(ctx, &g.ckey, (size_t)ncells));
@@ -585,10 +616,10 @@ static int block_grid_build(cl2_ctx *ctx, cl2_points *pts, int64_t eps) {
         FamTimer t(ctx, FAM_NBR, 52.0 * (double)ncells);
         k_block_nbr<<<cl2_grid(ncells, 256), 256, 0, ctx->stream>>>(g.ckey, g.cstart, g.nbr, g.s3, d_max, ncells, by);
     }
-    CL2_TRY(read_i32(ctx, d_max, &g.maxcnt));
+    CL2_TRY(cl2_read_i32(ctx, d_max, &g.maxcnt));
     CL2_CUDA(ctx, cudaGetLastError());
     g.valid = true;
-    g.kind = 0;
+    g.kind = kind;
     g.eps = eps;
     g.n = n;
     g.ncells = ncells;
@@ -608,7 +639,7 @@ extern "C" int cl2_block_noise(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int32
     if (pts->n == 0) return CL2_OK;
     if (!keep_out) return CL2_ERR_ARG;
     CL2_CUDA(ctx, cudaSetDevice(ctx->device));
-    CL2_TRY(block_grid_build(ctx, pts, eps));
+    CL2_TRY(cl2_grid_build(ctx, pts, eps, 0));
     cl2_grid_cache &g = pts->grid;
     Scratch sc(ctx);
     uint8_t *keep, *pk;
@@ -636,7 +667,7 @@ extern "C" int cl2_block_dbscan(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int3
     const int64_t n = pts->n;
     if (n == 0) return CL2_OK;
     CL2_CUDA(ctx, cudaSetDevice(ctx->device));
-    CL2_TRY(block_grid_build(ctx, pts, eps));
+    CL2_TRY(cl2_grid_build(ctx, pts, eps, 0));
     cl2_grid_cache &g = pts->grid;
     const int32_t ncells = g.ncells;
     cudaStream_t s = ctx->stream;
@@ -656,7 +687,7 @@ extern "C" int cl2_block_dbscan(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int3
     }
     CL2_TRY(cl2_exclusive_scan_i32(ctx, kpos, ncells, d_total));
     int64_t nkept64 = 0;
-    CL2_TRY(read_i64(ctx, d_total, &nkept64));
+    CL2_TRY(cl2_read_i64(ctx, d_total, &nkept64));
     const int32_t nkept = (int32_t)nkept64;
 
     int32_t *clabel;
@@ -700,7 +731,7 @@ extern "C" int cl2_block_dbscan(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int3
                                                                            adj, eps, heavy, nheavy);
         }
         int32_t nh = 0;
-        CL2_TRY(read_i32(ctx, nheavy, &nh));
+        CL2_TRY(cl2_read_i32(ctx, nheavy, &nh));
         if (nh > 0) {
             FamTimer t(ctx, FAM_ADJ, 0.0);
             k_block_adj_heavy<<<nh, HEAVY_THREADS, 0, s>>>(g.sxy, g.cstart, g.nbr, heavy, adj, eps);
@@ -724,7 +755,7 @@ extern "C" int cl2_block_dbscan(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int3
         }
         CL2_TRY(cl2_exclusive_scan_i32(ctx, rflag, nkept, d_total));
         int64_t ncomp64 = 0;
-        CL2_TRY(read_i64(ctx, d_total, &ncomp64));
+        CL2_TRY(cl2_read_i64(ctx, d_total, &ncomp64));
         ncomp = (int32_t)ncomp64;
         if (ncomp > 0) {
             uint64_t *ck0, *ck1, *cks;

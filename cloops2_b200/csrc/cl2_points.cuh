@@ -39,6 +39,10 @@ struct cl2_index {
 };
 
 void cl2_grid_free(cl2_ctx *ctx, cl2_grid_cache &g);
+// keygen -> radix sort -> gather -> cell table -> neighbours + 3x3 sums (cl2_block.cu); cached per (eps, kind)
+int cl2_grid_build(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int kind);
+int cl2_read_i64(cl2_ctx *ctx, const int64_t *d, int64_t *out);
+int cl2_read_i32(cl2_ctx *ctx, const int32_t *d, int32_t *out);
 
 static inline int bits_for(uint64_t v) {  // number of bits needed to represent values 0..v
     int b = 0;
