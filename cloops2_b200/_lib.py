@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.path.join(_HERE, "libcl2.so")
 SOURCES = ["cl2_api.cu", "cl2_sort.cu", "cl2_block.cu", "cl2_cdbscan.cu", "cl2_count.cu", "cl2_host.cu"]
-HEADERS = ["cl2_common.cuh", "cl2_points.cuh", os.path.join("..", "..", "include", "cl2.h")]
+HEADERS = ["cl2_common.cuh", "cl2_points.cuh", "cl2_stats.cuh", os.path.join("..", "..", "include", "cl2.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC"]
 
@@ -88,7 +88,13 @@ SIGNATURES = {
     "cl2_index_free": (None, [_vp, _vp]),
     "cl2_loop_counts": (ctypes.c_int, [_vp, _vp, _i64p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
                                        _i64p, _i64p, _i64p, _i64p, _i64p]),
+    "cl2_loop_core": (ctypes.c_int, [_vp, _vp, _i64p, ctypes.c_int64, ctypes.c_int32, _i64p, _f64p]),
+    "cl2_loop_tests": (ctypes.c_int, [_vp, _vp, _i64p, _i64p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
+                                      ctypes.c_double, _f64p]),
     "cl2_sel_sig_loops": (ctypes.c_int, [_i64p, _f64p, ctypes.c_int64, _i64p, _i64p]),
+    "cl2_stat_poisson_sf": (ctypes.c_double, [ctypes.c_double, ctypes.c_double]),
+    "cl2_stat_binom_sf": (ctypes.c_double, [ctypes.c_double, ctypes.c_double, ctypes.c_double]),
+    "cl2_stat_hypergeom_sf": (ctypes.c_double, [ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double]),
     "cl2_launch_count": (ctypes.c_int64, [_vp]),
     "cl2_launch_count_reset": (None, [_vp]),
     "cl2_timing_enable": (ctypes.c_int, [_vp, ctypes.c_int]),
@@ -316,6 +322,27 @@ class Index:
                                                     _ptr(o_core, _i64p), _ptr(o_na, _i64p), _ptr(o_nb, _i64p),
                                                     _ptr(o_nab, _i64p), _ptr(o_anc, _i64p)), "cl2_loop_counts")
         return o_core, o_na, o_nb, o_nab, o_anc
+
+
+    def loop_core(self, loops, mode=MODE_CIS):
+        """(core int64[L,4], hyp float64[L]) -- phase 1 of the fused counting + statistics."""
+        loops = np.ascontiguousarray(loops, dtype=np.int64).reshape(-1, 4)
+        L = loops.shape[0]
+        core = np.zeros((L, 4), dtype=np.int64)
+        hyp = np.zeros(L, dtype=np.float64)
+        self.ctx.check(self.ctx.lib.cl2_loop_core(self.ctx.h, self.h, _ptr(loops, _i64p), L, mode, _ptr(core, _i64p),
+                                                  _ptr(hyp, _f64p)), "cl2_loop_core")
+        return core, hyp
+
+    def loop_tests(self, loops, core, rpb, win=5, mode=MODE_CIS):
+        """stats float64[L,13] -- phase 2 (see include/cl2.h)."""
+        loops = np.ascontiguousarray(loops, dtype=np.int64).reshape(-1, 4)
+        core = np.ascontiguousarray(core, dtype=np.int64).reshape(-1, 4)
+        L = loops.shape[0]
+        stats = np.zeros((L, 13), dtype=np.float64)
+        self.ctx.check(self.ctx.lib.cl2_loop_tests(self.ctx.h, self.h, _ptr(loops, _i64p), _ptr(core, _i64p), L, win, mode,
+                                                   float(rpb), _ptr(stats, _f64p)), "cl2_loop_tests")
+        return stats
 
 
 _default_ctx = {}

@@ -45,9 +45,16 @@ def cluster_pass(pts, eps, minPts, hic=False, cis=True):
     return bbox[ok], size[ok]
 
 
-def cis_chromosome(ctx, key, xy, tot, eps, minPts, cut=0, mcut=-1, hic=False, emPair=False, pts=None):
+def exact_default():
+    """Whether final loops get their tail probabilities re-evaluated by scipy (the reference's printed digits) or keep
+    the device fp64 values.  CL2_PVALUES=device|scipy overrides; the drop-in entry points default to scipy."""
+    return os.environ.get("CL2_PVALUES", "scipy").lower() != "device"
+
+
+def cis_chromosome(ctx, key, xy, tot, eps, minPts, cut=0, mcut=-1, hic=False, emPair=False, pts=None, exact=False):
     """Whole per-chromosome path: sweep -> combine -> count -> test -> mark -> select.
-    xy: host int64[N,2] (ignored when a resident `pts` is passed).  Returns (final cols, stats dict)."""
+    xy: host int64[N,2] (ignored when a resident `pts` is passed).  Returns (final cols, stats dict).
+    exact: re-evaluate the tail probabilities of the FINAL loops with scipy (hostops.scipy_pvalues)."""
     own = pts is None
     if own:
         pts = _lib.Points(ctx, xy, cut=cut, mcut=mcut)
@@ -80,6 +87,8 @@ def cis_chromosome(ctx, key, xy, tot, eps, minPts, cut=0, mcut=-1, hic=False, em
         stats["tested"] = int(cols["coords"].shape[0])
         sig = hostops.mark_sig_cis(cols, hic=hic)
         final = hostops.select_twice(cols, sig)
+        if exact:
+            final = hostops.scipy_pvalues(final, pts.n, float(pts.n) / span, cis=True)
         stats["loops"] = int(final["coords"].shape[0])
         return final, stats
     finally:
@@ -155,7 +164,8 @@ def estLoopSig(key, loops, fixy, tot, minPts=5, pseudo=1, cut=0, mcut=-1, peakPc
         index = _lib.Index(pts)
         try:
             cols = hostops.est_cis(index, _loops_to_cands(loops), pts.n, float(int(ext[3]) - int(ext[0])), tot, minPts,
-                                   hic=hic, pseudo=pseudo, peakPcut=peakPcut, win=win, countDiffCut=countDiffCut)
+                                   hic=hic, pseudo=pseudo, peakPcut=peakPcut, win=win, countDiffCut=countDiffCut,
+                                   exact=exact_default())
         finally:
             index.close()
     finally:
@@ -251,7 +261,7 @@ def callCisLoops(predir, fout, log, eps=[2000, 5000], minPts=[5, 10], cpu=1, cut
     for k in mine:
         xy = loadIxy(files[k])
         final, st = cis_chromosome(ctx, tuple(k.split("-")), xy, tot, eps, minPts, cut=cut, mcut=mcut, hic=hic,
-                                   emPair=emPair)
+                                   emPair=emPair, exact=exact_default())
         stats += np.array([st["pets"], st["candidates"], st["tested"], st["loops"]], dtype=np.int64)
         if st["tested"] > 0:
             results[k] = final

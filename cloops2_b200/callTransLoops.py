@@ -13,10 +13,10 @@ import numpy as np
 from . import _lib, hostops, shard
 from .ds import Loop
 from .io import ixyKey, loadIxy, loops2txt, loops2juiceTxt, loops2washuTxt
-from .callCisLoops import cluster_pass, cols_to_loops, selSigLoops, _loops_to_cands  # noqa: F401
+from .callCisLoops import cluster_pass, cols_to_loops, selSigLoops, _loops_to_cands, exact_default  # noqa: F401
 
 
-def trans_pair(ctx, key, xy, eps, minPts, pts=None):
+def trans_pair(ctx, key, xy, eps, minPts, pts=None, exact=False):
     """Whole per-pair path (sweep -> combine -> count -> test -> mark -> select); returns (final cols, stats)."""
     own = pts is None
     if own:
@@ -38,13 +38,16 @@ def trans_pair(ctx, key, xy, eps, minPts, pts=None):
         if cands.shape[0] == 0:
             return hostops._empty_cols(), stats
         ext = pts.extent()
+        span = float(int(ext[3]) - int(ext[0]))
         index = _lib.Index(pts)
         try:
-            cols = hostops.est_trans(index, cands, pts.n, float(int(ext[3]) - int(ext[0])), max(minPts))
+            cols = hostops.est_trans(index, cands, pts.n, span, max(minPts))
         finally:
             index.close()
         stats["tested"] = int(cols["coords"].shape[0])
         final = hostops.select_twice(cols, hostops.mark_sig_trans(cols))
+        if exact:
+            final = hostops.scipy_pvalues(final, pts.n, float(pts.n) / span, cis=False)
         stats["loops"] = int(final["coords"].shape[0])
         return final, stats
     finally:
@@ -94,7 +97,7 @@ def estLoopSig(key, loops, fixy, minPts=5, pseudo=1, peakPcut=1e-5, peakFccut=2,
         index = _lib.Index(pts)
         try:
             cols = hostops.est_trans(index, _loops_to_cands(loops), pts.n, float(int(ext[3]) - int(ext[0])), minPts,
-                                     pseudo=pseudo, countDiffCut=countDiffCut)
+                                     pseudo=pseudo, countDiffCut=countDiffCut, exact=exact_default())
         finally:
             index.close()
     finally:
@@ -124,7 +127,7 @@ def callTransLoops(predir, fout, logger, eps=[2000, 5000], minPts=[5, 10], cpu=1
     results = {}
     stats = np.zeros(4, dtype=np.int64)
     for k in mine:
-        final, st = trans_pair(ctx, tuple(k.split("-")), loadIxy(files[k]), eps, minPts)
+        final, st = trans_pair(ctx, tuple(k.split("-")), loadIxy(files[k]), eps, minPts, exact=exact_default())
         stats += np.array([st["pets"], st["candidates"], st["tested"], st["loops"]], dtype=np.int64)
         if st["candidates"] > 0:
             results[k] = final

@@ -9,6 +9,7 @@
 // The reference's window bounds are multiples of 0.25 evaluated in fp64 (exact); they are carried here as integers
 // scaled by 4, so l <= X <= r is decided in exact integer arithmetic.  One warp per candidate loop.
 #include "cl2_points.cuh"
+#include "cl2_stats.cuh"
 
 // ------------------------------------------------------------------------------------------------ index build
 __global__ void __launch_bounds__(256) k_index_keys(const int2 *__restrict__ xy, uint64_t *__restrict__ key, int64_t n,
@@ -199,6 +200,83 @@ __device__ __forceinline__ void window_accumulate(WarpAcc &A, int W, unsigned ma
     }
 }
 
+// ---- per-loop building blocks (one warp) -------------------------------------------------------------------
+// queryLoop counts + the P2LL window (cis callCisLoops.py:287-289, 302-305; trans callTransLoops.py:124-126, 142-144)
+__device__ void loop_core(const int2 *__restrict__ byx, const int2 *__restrict__ byy, int64_t n, long long xs,
+                          long long xe, long long ys, long long ye, int mode, int lane, int64_t out[4]) {
+    const Iv A = {xs, xe}, B = {ys, ye};
+    int64_t ra, rab, rb;
+    count_pair(byx, byy, n, A, B, lane, &ra, &rab);
+    rb = count_peak(byx, byy, n, B, lane);
+    Iv A2, B2;
+    if (mode == CL2_MODE_CIS) { A2.lo = xe; A2.hi = xe + (xe - xs); }
+    else { A2.lo = xs - (xe - xs); A2.hi = xs; }
+    B2.lo = ys - (ye - ys); B2.hi = ys;
+    int64_t t1, lower;
+    count_pair(byx, byy, n, A2, B2, lane, &t1, &lower);
+    out[0] = ra; out[1] = rb; out[2] = rab; out[3] = lower;
+}
+
+// estAnchorSig counts (callCisLoops.py:226-247): count = |P(l,r)|, wide = |P(max(0, m-5len), m+5len)|
+__device__ void loop_anchor(const int2 *__restrict__ byx, const int2 *__restrict__ byy, int64_t n, long long l,
+                            long long r, int lane, int64_t *count, int64_t *wide) {
+    long long m4 = 2 * (l + r), len = r - l;
+    long long s4 = m4 - 20 * len;
+    if (s4 < 0) s4 = 0;
+    Iv I = {l, r};
+    Iv Wd = iv4(s4, m4 + 20 * len);
+    *count = count_peak(byx, byy, n, I, lane);
+    *wide = count_peak(byx, byy, n, Wd, lane);
+}
+
+// getPerRegions + getLoopNearbyPETs counts into the warp's accumulator (callCisLoops.py:173-223)
+__device__ void loop_windows(const int2 *__restrict__ byx, const int2 *__restrict__ byy, int64_t n, long long xs,
+                             long long xe, long long ys, long long ye, int win, int lane, WarpAcc &S) {
+    const int W = 2 * win;
+    for (int t = lane; t < W * W; t += 32) S.nab[t] = 0;
+    if (lane < W) {
+        S.na[lane] = 0; S.nb[lane] = 0;
+        // windows i = -win..-1, 1..win (callCisLoops.py:191-198), all bounds scaled by 4
+        int i = lane < win ? lane - win : lane - win + 1;
+        long long ca4 = 2 * (xs + xe), cb4 = 2 * (ys + ye), sa4 = 2 * (xe - xs), sb4 = 2 * (ye - ys);
+        long long step4 = (xe - xs) + (ye - ys);
+        long long al = ca4 + i * step4 - sa4, ah = ca4 + i * step4 + sa4;
+        long long bl = cb4 + i * step4 - sb4, bh = cb4 + i * step4 + sb4;
+        if (al < 0) al = 0;
+        if (ah < 0) ah = 0;
+        if (bl < 0) bl = 0;
+        if (bh < 0) bh = 0;
+        Iv a = iv4(al, ah), b = iv4(bl, bh);
+        S.alo[lane] = a.lo; S.ahi[lane] = a.hi; S.blo[lane] = b.lo; S.bhi[lane] = b.hi;
+    }
+    __syncwarp();
+    // spans covering all a-windows / all b-windows (window centres are monotone in i)
+    Iv SA = {S.alo[0], S.ahi[W - 1]}, SB = {S.blo[0], S.bhi[W - 1]};
+    Range rxa = range_of(byx, n, SA), rya = range_of(byy, n, SA);
+    Range rxb = range_of(byx, n, SB), ryb = range_of(byy, n, SB);
+    // four lists; a PET is handled by the first list that contains it
+    for (int pass = 0; pass < 4; pass++) {
+        const int2 *arr = (pass & 1) ? byy : byx;
+        Range r = pass == 0 ? rxa : pass == 1 ? rya : pass == 2 ? rxb : ryb;
+        for (int64_t i0 = r.b; i0 < r.e; i0 += 32) {
+            int64_t i = i0 + lane;
+            unsigned ma = 0, mb = 0;
+            if (i < r.e) {
+                int2 p = arr[i];
+                int x = (pass & 1) ? p.y : p.x, y = (pass & 1) ? p.x : p.y;
+                bool dup = false;
+                if (pass >= 1 && in_iv(SA, x)) dup = true;                       // seen in list 0
+                if (pass >= 2 && in_iv(SA, y)) dup = true;                       // seen in list 1
+                if (pass == 3 && in_iv(SB, x)) dup = true;                       // seen in list 2
+                if (!dup) window_masks(S, W, x, y, &ma, &mb);
+            }
+            if (__any_sync(0xffffffffu, (ma | mb) != 0)) window_accumulate(S, W, ma, mb, lane);
+        }
+    }
+    __syncwarp();
+}
+
+// ---- raw counts (cl2_loop_counts) ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(CNT_WARPS * 32) k_loop_counts(const int2 *__restrict__ byx, const int2 *__restrict__ byy,
                                                                  int64_t n, const longlong4 *__restrict__ loops, int64_t L,
                                                                  int win, int mode, long long *__restrict__ core,
@@ -211,87 +289,159 @@ __global__ void __launch_bounds__(CNT_WARPS * 32) k_loop_counts(const int2 *__re
     if (k >= L) return;
     const longlong4 lp = loops[k];
     const long long xs = lp.x, xe = lp.y, ys = lp.z, ye = lp.w;
-    const Iv A = {xs, xe}, B = {ys, ye};
-
     if (core) {
-        int64_t ra, rab, rb;
-        count_pair(byx, byy, n, A, B, lane, &ra, &rab);
-        rb = count_peak(byx, byy, n, B, lane);
-        // P2LL window: cis callCisLoops.py:302-305, trans callTransLoops.py:142-144
-        Iv A2, B2;
-        if (mode == CL2_MODE_CIS) { A2.lo = xe; A2.hi = xe + (xe - xs); }
-        else { A2.lo = xs - (xe - xs); A2.hi = xs; }
-        B2.lo = ys - (ye - ys); B2.hi = ys;
-        int64_t t1, lower;
-        count_pair(byx, byy, n, A2, B2, lane, &t1, &lower);
-        if (lane == 0) {
-            core[4 * k] = ra; core[4 * k + 1] = rb; core[4 * k + 2] = rab; core[4 * k + 3] = lower;
-        }
+        int64_t c[4];
+        loop_core(byx, byy, n, xs, xe, ys, ye, mode, lane, c);
+        if (lane == 0) { core[4 * k] = c[0]; core[4 * k + 1] = c[1]; core[4 * k + 2] = c[2]; core[4 * k + 3] = c[3]; }
     }
-
     if (anchors) {
-        // estAnchorSig, callCisLoops.py:226-247: count = |P(l,r)|, wide = |P(max(0, m-5len), m+5len)|
         for (int a = 0; a < 2; a++) {
-            long long l = a == 0 ? xs : ys, r = a == 0 ? xe : ye;
-            long long m4 = 2 * (l + r), len = r - l;
-            long long s4 = m4 - 20 * len;
-            if (s4 < 0) s4 = 0;
-            Iv I = {l, r};
-            Iv Wd = iv4(s4, m4 + 20 * len);
-            int64_t c = count_peak(byx, byy, n, I, lane);
-            int64_t wd = count_peak(byx, byy, n, Wd, lane);
+            int64_t c, wd;
+            loop_anchor(byx, byy, n, a == 0 ? xs : ys, a == 0 ? xe : ye, lane, &c, &wd);
             if (lane == 0) { anchors[4 * k + 2 * a] = c; anchors[4 * k + 2 * a + 1] = wd; }
         }
     }
-
     if (na_out || nb_out || nab_out) {
         const int W = 2 * win;
         WarpAcc &S = acc[w];
-        for (int t = lane; t < W * W; t += 32) S.nab[t] = 0;
-        if (lane < W) {
-            S.na[lane] = 0; S.nb[lane] = 0;
-            // windows i = -win..-1, 1..win (callCisLoops.py:191-198), all bounds scaled by 4
-            int i = lane < win ? lane - win : lane - win + 1;
-            long long ca4 = 2 * (xs + xe), cb4 = 2 * (ys + ye), sa4 = 2 * (xe - xs), sb4 = 2 * (ye - ys);
-            long long step4 = (xe - xs) + (ye - ys);
-            long long al = ca4 + i * step4 - sa4, ah = ca4 + i * step4 + sa4;
-            long long bl = cb4 + i * step4 - sb4, bh = cb4 + i * step4 + sb4;
-            if (al < 0) al = 0;
-            if (ah < 0) ah = 0;
-            if (bl < 0) bl = 0;
-            if (bh < 0) bh = 0;
-            Iv a = iv4(al, ah), b = iv4(bl, bh);
-            S.alo[lane] = a.lo; S.ahi[lane] = a.hi; S.blo[lane] = b.lo; S.bhi[lane] = b.hi;
-        }
-        __syncwarp();
-        // spans covering all a-windows / all b-windows (window centres are monotone in i)
-        Iv SA = {S.alo[0], S.ahi[W - 1]}, SB = {S.blo[0], S.bhi[W - 1]};
-        Range rxa = range_of(byx, n, SA), rya = range_of(byy, n, SA);
-        Range rxb = range_of(byx, n, SB), ryb = range_of(byy, n, SB);
-        // four lists; a PET is handled by the first list that contains it
-        for (int pass = 0; pass < 4; pass++) {
-            const int2 *arr = (pass & 1) ? byy : byx;
-            Range r = pass == 0 ? rxa : pass == 1 ? rya : pass == 2 ? rxb : ryb;
-            for (int64_t i0 = r.b; i0 < r.e; i0 += 32) {
-                int64_t i = i0 + lane;
-                unsigned ma = 0, mb = 0;
-                if (i < r.e) {
-                    int2 p = arr[i];
-                    int x = (pass & 1) ? p.y : p.x, y = (pass & 1) ? p.x : p.y;
-                    bool dup = false;
-                    if (pass >= 1 && in_iv(SA, x)) dup = true;                       // seen in list 0
-                    if (pass >= 2 && in_iv(SA, y)) dup = true;                       // seen in list 1
-                    if (pass == 3 && in_iv(SB, x)) dup = true;                       // seen in list 2
-                    if (!dup) window_masks(S, W, x, y, &ma, &mb);
-                }
-                if (__any_sync(0xffffffffu, (ma | mb) != 0)) window_accumulate(S, W, ma, mb, lane);
-            }
-        }
-        __syncwarp();
+        loop_windows(byx, byy, n, xs, xe, ys, ye, win, lane, S);
         if (na_out && lane < W) na_out[(int64_t)W * k + lane] = S.na[lane];
         if (nb_out && lane < W) nb_out[(int64_t)W * k + lane] = S.nb[lane];
         if (nab_out)
             for (int t = lane; t < W * W; t += 32) nab_out[(int64_t)W * W * k + t] = S.nab[t];
+    }
+}
+
+// ---- fused counting + statistics ----------------------------------------------------------------------------
+// phase 1: ra, rb, rab, lower and the hypergeometric tail hypergeom.sf(rab-1, N, ra, rb) (callCisLoops.py:310)
+__global__ void __launch_bounds__(CNT_WARPS * 32) k_loop_core(const int2 *__restrict__ byx, const int2 *__restrict__ byy,
+                                                               int64_t n, const longlong4 *__restrict__ loops, int64_t L,
+                                                               int mode, long long *__restrict__ core,
+                                                               double *__restrict__ hyp) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t k = (int64_t)blockIdx.x * CNT_WARPS + w;
+    if (k >= L) return;
+    const longlong4 lp = loops[k];
+    int64_t c[4];
+    loop_core(byx, byy, n, lp.x, lp.y, lp.z, lp.w, mode, lane, c);
+    if (lane == 0) {
+        core[4 * k] = c[0]; core[4 * k + 1] = c[1]; core[4 * k + 2] = c[2]; core[4 * k + 3] = c[3];
+        hyp[k] = cl2_hypergeom_sf_ge((double)c[2], (double)n, (double)c[0], (double)c[1]);
+    }
+}
+
+// numpy's pairwise summation of a contiguous float64 vector (np.mean / np.add.reduce), n <= 256
+__device__ double np_pairwise_base(const double *a, int n) {
+    if (n < 8) {
+        double r = 0.0;
+        for (int i = 0; i < n; i++) r += a[i];
+        return r;
+    }
+    double r[8];
+    for (int j = 0; j < 8; j++) r[j] = a[j];
+    int i;
+    for (i = 8; i < n - (n % 8); i += 8)
+        for (int j = 0; j < 8; j++) r[j] += a[i + j];
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; i++) res += a[i];
+    return res;
+}
+__device__ double np_pairwise_sum(const double *a, int n) {
+    if (n <= 128) return np_pairwise_base(a, n);
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return np_pairwise_base(a, n2) + np_pairwise_base(a + n2, n - n2);
+}
+
+struct WarpVals {
+    double v[CNT_MAXW * CNT_MAXW];
+    double pick[2];
+};
+
+// median of m values held in S.v (np.median: mean of the two middle order statistics for even m), by rank counting
+__device__ double warp_median(WarpVals &S, int m, int lane) {
+    int lo = (m - 1) / 2, hi = m / 2;
+    for (int i = lane; i < m; i += 32) {
+        double x = S.v[i];
+        int rank = 0;
+        for (int j = 0; j < m; j++) {
+            double y = S.v[j];
+            rank += (y < x || (y == x && j < i)) ? 1 : 0;
+        }
+        if (rank == lo) S.pick[0] = x;
+        if (rank == hi) S.pick[1] = x;
+    }
+    __syncwarp();
+    double r = (S.pick[0] + S.pick[1]) / 2.0;
+    __syncwarp();
+    return r;
+}
+
+#define CL2_NSTAT 13
+// phase 2: permuted-window background, enrichment tests and anchor tests for loops that passed the first filters.
+// stats[k] = mrabs, mbps, fdr, poisson sf, binomial sf, px, esx, py, esy, count_x, wide_x, count_y, wide_y
+__global__ void __launch_bounds__(CNT_WARPS * 32) k_loop_tests(const int2 *__restrict__ byx, const int2 *__restrict__ byy,
+                                                                int64_t n, const longlong4 *__restrict__ loops,
+                                                                const long long *__restrict__ core, int64_t L, int win,
+                                                                int mode, double rpb, double *__restrict__ stats) {
+    __shared__ WarpAcc acc[CNT_WARPS];
+    __shared__ WarpVals vals[CNT_WARPS];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t k = (int64_t)blockIdx.x * CNT_WARPS + w;
+    if (k >= L) return;
+    const longlong4 lp = loops[k];
+    const long long xs = lp.x, xe = lp.y, ys = lp.z, ye = lp.w;
+    const double ra = (double)core[4 * k], rb = (double)core[4 * k + 1], rab = (double)core[4 * k + 2];
+    const int W = 2 * win, m = W * W;
+    WarpAcc &S = acc[w];
+    WarpVals &V = vals[w];
+    loop_windows(byx, byy, n, xs, xe, ys, ye, win, lane, S);
+    int64_t cx, wx, cy, wy;
+    loop_anchor(byx, byy, n, xs, xe, lane, &cx, &wx);
+    loop_anchor(byx, byy, n, ys, ye, lane, &cy, &wy);
+    // rabs: counts of the 4*win^2 window pairs; fdr = #{rabs > rab} / m   (callCisLoops.py:315-321)
+    int gt = 0;
+    for (int t = lane; t < m; t += 32) {
+        V.v[t] = (double)S.nab[t];
+        gt += ((double)S.nab[t] > rab) ? 1 : 0;
+    }
+    gt = warp_sum(gt);
+    __syncwarp();
+    double mrabs, mbps;
+    if (mode == CL2_MODE_CIS) {
+        mrabs = warp_median(V, m, lane);
+    } else {
+        mrabs = np_pairwise_sum(V.v, m) / (double)m;     // every lane computes the same value
+    }
+    __syncwarp();
+    // nbps: nrab / (nac * nbc), zero rule differs between cis (:213-221) and trans (callTransLoops.py:165-169)
+    for (int t = lane; t < m; t += 32) {
+        double nrab = (double)S.nab[t], nac = (double)S.na[t / W], nbc = (double)S.nb[t % W];
+        double d;
+        if (mode == CL2_MODE_CIS) d = nrab > 0 ? nrab / (nac * nbc) : 0.0;
+        else d = (nac > 0 && nbc > 0) ? nrab / (nac * nbc) : 0.0;
+        V.v[t] = d;
+    }
+    __syncwarp();
+    if (mode == CL2_MODE_CIS) mbps = warp_median(V, m, lane);
+    else mbps = np_pairwise_sum(V.v, m) / (double)m;
+    double fdr = (double)gt / (double)m;
+    double *o = stats + CL2_NSTAT * k;
+    if (lane == 0) {
+        o[0] = mrabs; o[1] = mbps; o[2] = fdr;
+        o[3] = cl2_poisson_sf_ge(rab, mrabs);                                            // :329
+        o[9] = (double)cx; o[10] = (double)wx; o[11] = (double)cy; o[12] = (double)wy;
+    } else if (lane == 1) {
+        double nn = mode == CL2_MODE_CIS ? ra * rb - rab : ra * rb;                      // :332 / callTransLoops.py:181
+        o[4] = cl2_binom_sf_ge(rab, nn, mbps);
+    } else if (lane == 2 || lane == 3) {
+        // estAnchorSig (:226-247): c = max(local mean of the +-5x window, global rate * length, 1)
+        double count = (double)(lane == 2 ? cx : cy), wide = (double)(lane == 2 ? wx : wy);
+        double len = (double)(lane == 2 ? xe - xs : ye - ys);
+        double r = (wide - count) / 5.0 / 2.0;
+        double c = fmax(fmax(r, rpb * len), 1.0);
+        o[lane == 2 ? 5 : 7] = cl2_poisson_sf_ge(count, c);
+        o[lane == 2 ? 6 : 8] = count / c;
     }
 }
 
@@ -325,6 +475,63 @@ extern "C" int cl2_loop_counts(cl2_ctx *ctx, cl2_index *idx, const int64_t *loop
     if (anchors) CL2_CUDA(ctx, cudaMemcpyAsync(anchors, d_anc, (size_t)L * 32, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->h2d_bytes += L * 32;
     ctx->d2h_bytes += L * 8 * ((core ? 4 : 0) + (na ? W : 0) + (nb ? W : 0) + (nab ? W * W : 0) + (anchors ? 4 : 0));
+    CL2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CL2_CUDA(ctx, cudaGetLastError());
+    return CL2_OK;
+}
+
+extern "C" int cl2_loop_core(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops, int64_t L, int32_t mode, int64_t *core,
+                             double *hyp) {
+    if (!ctx || !idx || L < 0 || (L > 0 && (!loops || !core || !hyp))) return cl2_fail(ctx, CL2_ERR_ARG, "cl2_loop_core: bad argument");
+    if (mode != CL2_MODE_CIS && mode != CL2_MODE_TRANS) return cl2_fail(ctx, CL2_ERR_ARG, "cl2_loop_core: bad mode");
+    if (L == 0) return CL2_OK;
+    CL2_CUDA(ctx, cudaSetDevice(ctx->device));
+    Scratch sc(ctx);
+    longlong4 *d_loops;
+    long long *d_core;
+    double *d_hyp;
+    CL2_TRY(sc.get(&d_loops, (size_t)L));
+    CL2_TRY(sc.get(&d_core, (size_t)L * 4));
+    CL2_TRY(sc.get(&d_hyp, (size_t)L));
+    CL2_CUDA(ctx, cudaMemcpyAsync(d_loops, loops, (size_t)L * 32, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        FamTimer t(ctx, FAM_COUNT, 0.0);
+        k_loop_core<<<cl2_grid(L, CNT_WARPS), CNT_WARPS * 32, 0, ctx->stream>>>(idx->byx, idx->byy, idx->n, d_loops, L, mode,
+                                                                                d_core, d_hyp);
+    }
+    CL2_CUDA(ctx, cudaMemcpyAsync(core, d_core, (size_t)L * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CL2_CUDA(ctx, cudaMemcpyAsync(hyp, d_hyp, (size_t)L * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->h2d_bytes += L * 32;
+    ctx->d2h_bytes += L * 40;
+    CL2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CL2_CUDA(ctx, cudaGetLastError());
+    return CL2_OK;
+}
+
+extern "C" int cl2_loop_tests(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops, const int64_t *core, int64_t L,
+                              int32_t win, int32_t mode, double rpb, double *stats) {
+    if (!ctx || !idx || L < 0 || (L > 0 && (!loops || !core || !stats))) return cl2_fail(ctx, CL2_ERR_ARG, "cl2_loop_tests: bad argument");
+    if (win < 1 || 2 * win > CNT_MAXW) return cl2_fail(ctx, CL2_ERR_ARG, "cl2_loop_tests: win must be in 1..8");
+    if (mode != CL2_MODE_CIS && mode != CL2_MODE_TRANS) return cl2_fail(ctx, CL2_ERR_ARG, "cl2_loop_tests: bad mode");
+    if (L == 0) return CL2_OK;
+    CL2_CUDA(ctx, cudaSetDevice(ctx->device));
+    Scratch sc(ctx);
+    longlong4 *d_loops;
+    long long *d_core;
+    double *d_stats;
+    CL2_TRY(sc.get(&d_loops, (size_t)L));
+    CL2_TRY(sc.get(&d_core, (size_t)L * 4));
+    CL2_TRY(sc.get(&d_stats, (size_t)L * CL2_NSTAT));
+    CL2_CUDA(ctx, cudaMemcpyAsync(d_loops, loops, (size_t)L * 32, cudaMemcpyHostToDevice, ctx->stream));
+    CL2_CUDA(ctx, cudaMemcpyAsync(d_core, core, (size_t)L * 32, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        FamTimer t(ctx, FAM_COUNT, 0.0);
+        k_loop_tests<<<cl2_grid(L, CNT_WARPS), CNT_WARPS * 32, 0, ctx->stream>>>(idx->byx, idx->byy, idx->n, d_loops, d_core, L,
+                                                                                 win, mode, rpb, d_stats);
+    }
+    CL2_CUDA(ctx, cudaMemcpyAsync(stats, d_stats, (size_t)L * CL2_NSTAT * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->h2d_bytes += L * 64;
+    ctx->d2h_bytes += L * CL2_NSTAT * 8;
     CL2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     CL2_CUDA(ctx, cudaGetLastError());
     return CL2_OK;

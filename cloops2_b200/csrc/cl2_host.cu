@@ -1,6 +1,7 @@
 // cl2_host.cu -- native host-side pieces of the path that are order-dependent and sequential in the reference.
 #include "cl2_common.cuh"
 #include <algorithm>
+#include "cl2_stats.cuh"
 
 static inline bool anchor_ov(int64_t xa, int64_t xb, int64_t ya, int64_t yb) {
     // geo.py:65-73, closed intervals
@@ -52,4 +53,12 @@ extern "C" int cl2_sel_sig_loops(const int64_t *coords, const double *es, int64_
     for (size_t r = 0; r < reps.size(); r++) out_idx[r] = reps[r];
     *out_n = (int64_t)reps.size();
     return CL2_OK;
+}
+
+// Host entry points to the fp64 tail functions the counting kernel evaluates on the device (same source, cl2_stats.cuh);
+// scipy-style arguments: sf(k) = P(X > k).
+extern "C" double cl2_stat_poisson_sf(double k, double mu) { return cl2_poisson_sf_ge(floor(k) + 1.0, mu); }
+extern "C" double cl2_stat_binom_sf(double k, double n, double p) { return cl2_binom_sf_ge(floor(k) + 1.0, n, p); }
+extern "C" double cl2_stat_hypergeom_sf(double k, double M, double n, double N) {
+    return cl2_hypergeom_sf_ge(floor(k) + 1.0, M, n, N);
 }

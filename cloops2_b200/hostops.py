@@ -79,9 +79,19 @@ def permuted_stats(na, nb, nab, rab, cis=True):
     return mrabs, mbps, fdr
 
 
-def est_cis(index, cands, N, span, tot, minPts, hic=False, pseudo=1, peakPcut=1e-5, win=5, countDiffCut=20):
+def _clamp(p):
+    """max([1e-300, p]) as the reference wraps every tail probability (callCisLoops.py:246,310,329,331)."""
+    return np.maximum(1e-300, p)
+
+
+def est_cis(index, cands, N, span, tot, minPts, hic=False, pseudo=1, peakPcut=1e-5, win=5, countDiffCut=20,
+            exact=False):
     """estLoopSig (callCisLoops.py:250-354) for one chromosome.  `index` is a device XY index; cands int64[L,4].
-    Returns a dict of column arrays for the loops that survive the filter cascade, in candidate order."""
+    Counting, the permuted-window statistics and the tail probabilities are computed on the device (two launches:
+    every candidate, then the survivors of the first filters); the filter cascade itself is applied here in the
+    reference's order.  Returns a dict of column arrays for the surviving loops, in candidate order.
+    exact=True re-evaluates the five tail probabilities of the surviving loops with scipy, which reproduces the
+    reference's printed digits (the device values are accurate to ~1e-14 but scipy itself is not)."""
     L = cands.shape[0]
     cols = _empty_cols()
     if L == 0:
@@ -89,10 +99,10 @@ def est_cis(index, cands, N, span, tot, minPts, hic=False, pseudo=1, peakPcut=1e
     la = (cands[:, 1] - cands[:, 0])
     lb = (cands[:, 3] - cands[:, 2])
     keep = ~((la / lb > countDiffCut) | (lb / la > countDiffCut))                    # :282-286
-    idx = np.nonzero(keep)[0]
-    if idx.size == 0:
+    c = cands[keep]
+    if c.shape[0] == 0:
         return cols
-    core, _, _, _, _ = index.loop_counts(cands[idx], win=win, mode=_lib.MODE_CIS, windows=False, anchors=False)
+    core, hyp = index.loop_core(c, mode=_lib.MODE_CIS)
     ra, rb, rab, lower = core[:, 0], core[:, 1], core[:, 2], core[:, 3]
     with np.errstate(divide="ignore", invalid="ignore"):
         k = rab >= minPts                                                             # :290
@@ -101,77 +111,87 @@ def est_cis(index, cands, N, span, tot, minPts, hic=False, pseudo=1, peakPcut=1e
     p2ll = rab.astype(np.float64) / np.maximum(lower, pseudo)                         # :306
     if hic:
         k &= ~(p2ll < 1)                                                              # :307
-    idx, ra, rb, rab, p2ll = idx[k], ra[k], rb[k], rab[k], p2ll[k]
-    if idx.size == 0:
+    hyp = _clamp(hyp)                                                                 # :310
+    k &= ~(hyp > 1e-2)                                                                # :311
+    c, core, ra, rb, rab, p2ll, hyp = c[k], core[k], ra[k], rb[k], rab[k], p2ll[k], hyp[k]
+    if c.shape[0] == 0:
         return cols
-    hyp = _floor300(hypergeom.sf(rab - 1.0, N, ra, rb))                               # :310
-    k = ~(hyp > 1e-2)
-    idx, ra, rb, rab, p2ll, hyp = idx[k], ra[k], rb[k], rab[k], p2ll[k], hyp[k]
-    if idx.size == 0:
-        return cols
-    _, na, nb, nab, anc = index.loop_counts(cands[idx], win=win, mode=_lib.MODE_CIS, core=False)
-    mrabs, mbps, fdr = permuted_stats(na, nb, nab, rab, cis=True)
+    rpb = float(N) / span                                                             # :231
+    st = index.loop_tests(c, core, rpb, win=win, mode=_lib.MODE_CIS)
+    mrabs, mbps, fdr = st[:, 0], st[:, 1], st[:, 2]
     k = ~((mrabs >= rab) | (fdr >= 0.1))                                              # :322
     es = rab / np.maximum(mrabs, pseudo)                                              # :325
     k &= ~(es < 1)
-    idx, ra, rb, rab, p2ll, hyp = idx[k], ra[k], rb[k], rab[k], p2ll[k], hyp[k]
-    mrabs, mbps, fdr, es, anc = mrabs[k], mbps[k], fdr[k], es[k], anc[k]
-    if idx.size == 0:
-        return cols
-    pop = _floor300(poisson.sf(rab - 1.0, mrabs))                                     # :329
-    nbp = _floor300(binom.sf(rab - 1.0, ra * rb - rab, mbps))                         # :331-333
-    c = cands[idx]
+    pop, nbp = _clamp(st[:, 3]), _clamp(st[:, 4])                                     # :329, :331-333
+    px, esx, py, esy = _clamp(st[:, 5]), st[:, 6], _clamp(st[:, 7]), st[:, 8]
+    if not hic:
+        k &= (px < peakPcut) & (py < peakPcut)                                        # :347
     la, lb = c[:, 1] - c[:, 0], c[:, 3] - c[:, 2]
     density = rab.astype(np.float64) / (la + lb) / tot * 10.0**9                      # :337-339
-    rpb = float(N) / span                                                             # :231
-    px, esx = anchor_sig(anc[:, 0], anc[:, 1], la, rpb)
-    py, esy = anchor_sig(anc[:, 2], anc[:, 3], lb, rpb)
-    if not hic:
-        k = (px < peakPcut) & (py < peakPcut)                                         # :347
-    else:
-        k = np.ones(idx.size, dtype=bool)
     cols = dict(coords=c[k], ra=ra[k], rb=rb[k], rab=rab[k], P2LL=p2ll[k], FDR=fdr[k], ES=es[k], density=density[k],
-                hyp=hyp[k], pop=pop[k], nbp=nbp[k], px=px[k], py=py[k], esx=esx[k], esy=esy[k])
+                hyp=hyp[k], pop=pop[k], nbp=nbp[k], px=px[k], py=py[k], esx=esx[k], esy=esy[k],
+                mrabs=mrabs[k], mbps=mbps[k], anc=st[k, 9:13])
+    if exact:
+        cols = scipy_pvalues(cols, N, rpb, cis=True)
     return cols
 
 
-def est_trans(index, cands, N, span, minPts, pseudo=1, countDiffCut=10, win=5):
+def est_trans(index, cands, N, span, minPts, pseudo=1, countDiffCut=10, win=5, exact=False):
     """trans estLoopSig (callTransLoops.py:106-193)."""
     L = cands.shape[0]
     cols = _empty_cols()
     if L == 0:
         return cols
-    core, na, nb, nab, anc = index.loop_counts(cands, win=win, mode=_lib.MODE_TRANS)
+    core, hyp = index.loop_core(cands, mode=_lib.MODE_TRANS)
     ra, rb, rab, lower = core[:, 0], core[:, 1], core[:, 2], core[:, 3]
     la, lb = cands[:, 1] - cands[:, 0], cands[:, 3] - cands[:, 2]
     with np.errstate(divide="ignore", invalid="ignore"):
         k = rab >= minPts                                                             # :127
         k &= ~((ra / rb.astype(np.float64) > countDiffCut) | (rb / ra.astype(np.float64) > countDiffCut))   # :133
         k &= ~((la / lb > countDiffCut) | (lb / la > countDiffCut))                   # :135-139
-    c, ra, rb, rab, lower, la, lb = cands[k], ra[k], rb[k], rab[k], lower[k], la[k], lb[k]
-    na, nb, nab, anc = na[k], nb[k], nab[k], anc[k]
+    c, core, ra, rb, rab, lower, la, lb, hyp = cands[k], core[k], ra[k], rb[k], rab[k], lower[k], la[k], lb[k], hyp[k]
     if c.shape[0] == 0:
         return cols
     p2ll = rab.astype(np.float64) / np.maximum(lower, pseudo)
     rpb = float(N) / span
-    px, esx = anchor_sig(anc[:, 0], anc[:, 1], la, rpb)
-    py, esy = anchor_sig(anc[:, 2], anc[:, 3], lb, rpb)
-    hyp = _floor300(hypergeom.sf(rab - 1.0, N, ra, rb))
-    mrabs, mbps, fdr = permuted_stats(na, nb, nab, rab, cis=False)
+    st = index.loop_tests(c, core, rpb, win=win, mode=_lib.MODE_TRANS)
+    mrabs, mbps, fdr = st[:, 0], st[:, 1], st[:, 2]
     es = rab / np.maximum(mrabs, pseudo)
-    pop = _floor300(poisson.sf(rab - 1.0, mrabs))
-    nbp = _floor300(binom.sf(rab - 1.0, ra * rb, mbps))                               # :181
     density = rab.astype(np.float64) / (la + lb) / N * 10.0**9                        # :185-187
-    return dict(coords=c, ra=ra, rb=rb, rab=rab, P2LL=p2ll, FDR=fdr, ES=es, density=density, hyp=hyp, pop=pop,
-                nbp=nbp, px=px, py=py, esx=esx, esy=esy)
+    cols = dict(coords=c, ra=ra, rb=rb, rab=rab, P2LL=p2ll, FDR=fdr, ES=es, density=density, hyp=_clamp(hyp),
+                pop=_clamp(st[:, 3]), nbp=_clamp(st[:, 4]), px=_clamp(st[:, 5]), py=_clamp(st[:, 7]), esx=st[:, 6],
+                esy=st[:, 8], mrabs=mrabs, mbps=mbps, anc=st[:, 9:13])
+    if exact:
+        cols = scipy_pvalues(cols, N, rpb, cis=False)
+    return cols
 
 
-COLS = ["coords", "ra", "rb", "rab", "P2LL", "FDR", "ES", "density", "hyp", "pop", "nbp", "px", "py", "esx", "esy"]
+def scipy_pvalues(cols, N, rpb, cis=True):
+    """Re-evaluate the tail probabilities of (few) surviving loops with scipy, argument for argument as the reference
+    calls it (callCisLoops.py:246,310,329,332; callTransLoops.py:153,178,181), so the printed digits are the
+    reference's.  Everything else in `cols` is already bit-identical."""
+    if cols["coords"].shape[0] == 0:
+        return cols
+    out = dict(cols)
+    ra, rb, rab = cols["ra"], cols["rb"], cols["rab"]
+    out["hyp"] = _clamp(hypergeom.sf(rab - 1.0, N, ra, rb))
+    out["pop"] = _clamp(poisson.sf(rab - 1.0, cols["mrabs"]))
+    out["nbp"] = _clamp(binom.sf(rab - 1.0, ra * rb - rab if cis else ra * rb, cols["mbps"]))
+    c = cols["coords"]
+    anc = cols["anc"]
+    out["px"], out["esx"] = anchor_sig(anc[:, 0].astype(np.int64), anc[:, 1].astype(np.int64), c[:, 1] - c[:, 0], rpb)
+    out["py"], out["esy"] = anchor_sig(anc[:, 2].astype(np.int64), anc[:, 3].astype(np.int64), c[:, 3] - c[:, 2], rpb)
+    return out
+
+
+COLS = ["coords", "ra", "rb", "rab", "P2LL", "FDR", "ES", "density", "hyp", "pop", "nbp", "px", "py", "esx", "esy",
+        "mrabs", "mbps", "anc"]
 
 
 def _empty_cols():
     d = {k: np.zeros(0) for k in COLS}
     d["coords"] = np.zeros((0, 4), dtype=np.int64)
+    d["anc"] = np.zeros((0, 4))
     for k in ("ra", "rb", "rab"):
         d[k] = np.zeros(0, dtype=np.int64)
     return d

@@ -98,6 +98,24 @@ void cl2_index_free(cl2_ctx *ctx, cl2_index *idx);
 int cl2_loop_counts(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops, int64_t L, int32_t win, int32_t mode,
                     int64_t *core, int64_t *na, int64_t *nb, int64_t *nab, int64_t *anchors);
 
+/*
+ * Fused counting + statistics, phase 1 (every candidate): core[L,4] = ra, rb, rab, lower as in cl2_loop_counts and
+ * hyp[L] = hypergeom.sf(rab - 1, N, ra, rb) with N = rows of the index (callCisLoops.py:310), NOT clamped to 1e-300.
+ */
+int cl2_loop_core(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops, int64_t L, int32_t mode, int64_t *core,
+                  double *hyp);
+/*
+ * Phase 2 (candidates that passed the first filters): permuted-window background and the remaining tests of
+ * estLoopSig (callCisLoops.py:314-346; trans callTransLoops.py:146-181).  core = the [L,4] rows phase 1 returned for
+ * these loops; rpb = PETs per bp, N / (max Y - min X) (callCisLoops.py:231).
+ * stats[L,13] = mrabs (median; mean for trans), mbps, FDR, poisson.sf(rab-1, mrabs), binom.sf(rab-1, n, mbps) with
+ * n = ra*rb-rab (trans: ra*rb), x_peak_poisson_p, x_peak_es, y_peak_poisson_p, y_peak_es, and the anchor counts
+ * count_x, wide_x, count_y, wide_y of estAnchorSig.
+ * Tail probabilities are NOT clamped to 1e-300 (the host applies max(1e-300, p) as the reference does).
+ */
+int cl2_loop_tests(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops, const int64_t *core, int64_t L, int32_t win,
+                   int32_t mode, double rpb, double *stats);
+
 /* ---- host-side selection (native, no GPU) ----------------------------------------------------------------- */
 /*
  * selSigLoops (callCisLoops.py:379-422) for the loops of ONE chromosome (pair), all already significant, in list
@@ -106,6 +124,14 @@ int cl2_loop_counts(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops, int64_t 
  * out_idx: int64[L] receives the indices of the selected loops in output order; *out_n their number.
  */
 int cl2_sel_sig_loops(const int64_t *coords, const double *es, int64_t L, int64_t *out_idx, int64_t *out_n);
+
+/*
+ * Host copies of the fp64 tail probabilities the device evaluates (scipy argument convention, sf(k) = P(X > k)):
+ * scipy.stats.poisson.sf / binom.sf / hypergeom.sf as called at callCisLoops.py:246,310,329,332.
+ */
+double cl2_stat_poisson_sf(double k, double mu);
+double cl2_stat_binom_sf(double k, double n, double p);
+double cl2_stat_hypergeom_sf(double k, double M, double n, double N);
 
 /* ---- measurement -------------------------------------------------------------------------------------- */
 /* Kernel launches issued by this context since creation (or since the last reset). */

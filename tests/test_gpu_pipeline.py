@@ -27,7 +27,7 @@ def test_cis_golden_rows(gpu_ctx, name, kw):
     g, files = golden_cis_files()
     loops = []
     for k, xy in files.items():
-        final, st = cis_chromosome(gpu_ctx, tuple(k.split("-")), xy, int(g["tot"]), **kw)
+        final, st = cis_chromosome(gpu_ctx, tuple(k.split("-")), xy, int(g["tot"]), exact=True, **kw)
         loops.extend(cols_to_loops(tuple(k.split("-")), final))
     assert _rows(loops) == txt_rows(g[name])
 
@@ -36,7 +36,7 @@ def test_trans_golden_rows(gpu_ctx):
     g, files = golden_trans_files()
     loops = []
     for k, xy in files.items():
-        final, st = trans_pair(gpu_ctx, tuple(k.split("-")), xy, [2000, 4000], [10, 5])
+        final, st = trans_pair(gpu_ctx, tuple(k.split("-")), xy, [2000, 4000], [10, 5], exact=True)
         loops.extend(cols_to_loops(tuple(k.split("-")), final, cis=False))
     assert _rows(loops) == txt_rows(g["trans_txt"])
 
@@ -72,7 +72,71 @@ def test_cis_larger_vs_oracle(gpu_ctx):
     want, _ = oracle.call_cis_loops(files, tot, [200, 500, 1000], [5])
     loops = []
     for k, xy in files.items():
-        final, st = cis_chromosome(gpu_ctx, tuple(k.split("-")), xy, tot, [200, 500, 1000], [5])
+        final, st = cis_chromosome(gpu_ctx, tuple(k.split("-")), xy, tot, [200, 500, 1000], [5], exact=True)
         loops.extend(cols_to_loops(tuple(k.split("-")), final))
     assert len(want) > 20
     assert _rows(loops) == _rows(want)
+
+
+P_COLS = (18, 19, 20, 21, 22)      # binomial, hypergeometric, poisson, peakA, peakB columns of _loops.txt
+
+
+def _assert_rows_close(got, want, rtol):
+    """Identical text except the five tail probabilities, which must agree to rtol (relative)."""
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        for j, (a, b) in enumerate(zip(g, w)):
+            if j in P_COLS:
+                fa, fb = float(a), float(b)
+                assert abs(fa - fb) <= rtol * abs(fb), (j, a, b)
+            else:
+                assert a == b, (j, a, b)
+
+
+def test_device_pvalues_within_tolerance_of_reference(gpu_ctx):
+    """Default device mode (no scipy on the path): same loops, same counts / ES / FDR / density text, tail
+    probabilities within 1e-9 relative of the reference's (north_star tolerance); tails reach 1e-300."""
+    g, files = golden_cis_files()
+    loops = []
+    for k, xy in files.items():
+        final, st = cis_chromosome(gpu_ctx, tuple(k.split("-")), xy, int(g["tot"]), [200, 500, 1000], [5])
+        loops.extend(cols_to_loops(tuple(k.split("-")), final))
+    _assert_rows_close(_rows(loops), txt_rows(g["default_txt"]), 1e-9)
+    gt, tfiles = golden_trans_files()
+    loops = []
+    for k, xy in tfiles.items():
+        final, st = trans_pair(gpu_ctx, tuple(k.split("-")), xy, [2000, 4000], [10, 5])
+        loops.extend(cols_to_loops(tuple(k.split("-")), final, cis=False))
+    _assert_rows_close(_rows(loops), txt_rows(gt["trans_txt"]), 1e-9)
+
+
+def test_fused_stats_kernels_against_oracle_counts(gpu_ctx):
+    """cl2_loop_core / cl2_loop_tests vs the same quantities derived from the oracle's set-based counts."""
+    from cloops2_b200 import hostops
+    from test_hostops import FakeIndex
+    rng = np.random.default_rng(8)
+    for mode, xy in ((0, synth.cis_chrom(3_000_000, 80_000, 3, "hitrac")),
+                     (1, synth.trans_pair(2_000_000, 2_500_000, 60_000, 4, per=1500))):
+        i = rng.integers(0, len(xy), size=200)
+        wa, wb = rng.integers(50, 3000, size=200), rng.integers(50, 3000, size=200)
+        xs, ys = np.maximum(0, xy[i, 0] - wa // 2), np.maximum(0, xy[i, 1] - wb // 2)
+        cands = np.stack([xs, xs + wa, ys, ys + wb], 1).astype(np.int64)
+        pts = _lib.Points(gpu_ctx, xy)
+        idx = _lib.Index(pts)
+        try:
+            core, hyp = idx.loop_core(cands, mode=mode)
+            rpb = len(xy) / float(xy[:, 1].max() - xy[:, 0].min())
+            st = idx.loop_tests(cands, core, rpb, mode=mode)
+        finally:
+            idx.close()
+            pts.close()
+        fk = FakeIndex(xy)
+        wcore, whyp = fk.loop_core(cands, mode=mode)
+        wst = fk.loop_tests(cands, wcore, rpb, mode=mode)
+        assert np.array_equal(core, wcore)
+        assert np.array_equal(st[:, :3], wst[:, :3])            # mrabs, mbps, FDR: bit-identical
+        assert np.array_equal(st[:, 9:], wst[:, 9:])            # anchor counts
+        assert np.array_equal(st[:, [6, 8]], wst[:, [6, 8]])    # anchor enrichment
+        for a, b in ((hyp, whyp), (st[:, 3], wst[:, 3]), (st[:, 4], wst[:, 4]), (st[:, 5], wst[:, 5]), (st[:, 7], wst[:, 7])):
+            ok = np.abs(a - b) <= 1e-12 * np.abs(b) + 1e-305     # device libm vs glibc: last-ulp differences only
+            assert ok.all(), (mode, a[~ok][:3], b[~ok][:3])

@@ -21,6 +21,34 @@ class FakeIndex:
                 anc if anchors else None)
 
 
+    def loop_core(self, loops, mode=0):
+        from cloops2_b200 import _lib
+        L = _lib.load()
+        c = self.ix.loop_counts(loops, win=5, mode=mode)[0]
+        hyp = np.array([L.cl2_stat_hypergeom_sf(float(r[2]) - 1.0, float(self.ix.n), float(r[0]), float(r[1])) for r in c])
+        return c, hyp
+
+    def loop_tests(self, loops, core, rpb, win=5, mode=0):
+        from cloops2_b200 import _lib
+        L = _lib.load()
+        _, na, nb, nab, anc = self.ix.loop_counts(loops, win=win, mode=mode)
+        rab = core[:, 2]
+        mrabs, mbps, fdr = hostops.permuted_stats(na, nb, nab, rab, cis=(mode == 0))
+        st = np.zeros((len(loops), 13))
+        st[:, 0], st[:, 1], st[:, 2] = mrabs, mbps, fdr
+        for i in range(len(loops)):
+            ra, rb, r = float(core[i, 0]), float(core[i, 1]), float(core[i, 2])
+            st[i, 3] = L.cl2_stat_poisson_sf(r - 1.0, mrabs[i])
+            st[i, 4] = L.cl2_stat_binom_sf(r - 1.0, ra * rb - r if mode == 0 else ra * rb, mbps[i])
+            for a, (lo, hi) in enumerate(((loops[i][0], loops[i][1]), (loops[i][2], loops[i][3]))):
+                count, wide = float(anc[i, 2 * a]), float(anc[i, 2 * a + 1])
+                c = max((wide - count) / 5 / 2, rpb * float(hi - lo), 1.0)
+                st[i, 5 + 2 * a] = L.cl2_stat_poisson_sf(count - 1.0, c)
+                st[i, 6 + 2 * a] = count / c
+        st[:, 9:13] = anc
+        return st
+
+
 def _rows(loops):
     return oracle.loops_to_rows(loops)
 
@@ -30,7 +58,7 @@ def test_est_cis_matches_oracle_and_reference_fields():
     _, files = golden_cis_files()
     xy = files["chr21-chr21"]
     span = float(xy[:, 1].max() - xy[:, 0].min())
-    cols = hostops.est_cis(FakeIndex(xy), e["candidates"], len(xy), span, int(e["tot"]), 5)
+    cols = hostops.est_cis(FakeIndex(xy), e["candidates"], len(xy), span, int(e["tot"]), 5, exact=True)
     assert np.array_equal(cols["coords"], e["kept"])
     names = dict(ra="ra", rb="rb", rab="rab", P2LL="P2LL", FDR="FDR", ES="ES", density="density",
                  hypergeometric_p_value="hyp", poisson_p_value="pop", binomial_p_value="nbp",
@@ -56,6 +84,7 @@ def test_full_cis_host_path_reproduces_reference_txt():
             span = float(xy[:, 1].max() - xy[:, 0].min())
             cols = hostops.est_cis(FakeIndex(xy), cands, len(xy), span, tot, max(minPts), hic=hic)
             final = hostops.select_twice(cols, hostops.mark_sig_cis(cols, hic=hic))
+            final = hostops.scipy_pvalues(final, len(xy), float(len(xy)) / span, cis=True)
             loops.extend(cols_to_loops(tuple(k.split("-")), final, cis=True))
         from conftest import txt_rows
         assert _rows(loops) == txt_rows(g[name]), name
@@ -77,6 +106,7 @@ def test_full_trans_host_path_reproduces_reference_txt():
         span = float(xy[:, 1].max() - xy[:, 0].min())
         cols = hostops.est_trans(FakeIndex(xy), cands, len(xy), span, 10)
         final = hostops.select_twice(cols, hostops.mark_sig_trans(cols))
+        final = hostops.scipy_pvalues(final, len(xy), float(len(xy)) / span, cis=False)
         loops.extend(cols_to_loops(tuple(k.split("-")), final, cis=False))
     assert _rows(loops) == txt_rows(g["trans_txt"])
 
@@ -109,3 +139,40 @@ def test_combine_unique_is_first_occurrence_order():
     out = hostops.combine_unique([a, b])
     assert out.tolist() == [[1, 2, 3, 4], [5, 6, 7, 8], [9, 9, 9, 9]]
     assert hostops.combine_unique([]).shape == (0, 4)
+
+
+def test_device_tail_functions_against_scipy_and_exact_values():
+    """fp64 tails of cl2_stats.cuh (host build of the device code).  Tolerances: 1e-9 relative against scipy where
+    scipy itself is accurate; scipy 1.18.1's hypergeom / binom drift up to ~1e-7 for populations >= 1e7 (checked
+    against exact rational arithmetic when generating the constants below), there the exact values are the bar."""
+    from scipy.stats import poisson, binom, hypergeom
+    from cloops2_b200 import _lib
+    L = _lib.load()
+    rng = np.random.default_rng(0)
+    for _ in range(3000):
+        mu = float(10 ** rng.uniform(-3, 3.5))
+        k = float(rng.integers(0, int(mu * 3 + 60)))
+        want = float(poisson.sf(k, mu))
+        if want > 1e-290:
+            assert abs(L.cl2_stat_poisson_sf(k, mu) - want) <= 1e-9 * want
+    for _ in range(3000):
+        n = float(int(10 ** rng.uniform(1, 6)))
+        p = float(10 ** rng.uniform(-6, -0.5))
+        k = float(rng.integers(0, int(min(n, n * p * 3 + 80)) + 1))
+        want = float(binom.sf(k, n, p))
+        if want > 1e-200:      # Boost's ibeta loses digits below ~1e-200 (1.9e-6 relative seen at 1e-280)
+            assert abs(L.cl2_stat_binom_sf(k, n, p) - want) <= 1e-9 * want
+    for _ in range(1500):
+        M = int(10 ** rng.uniform(3, 5.5))
+        n = int(rng.integers(1, M // 4 + 2))
+        N = int(rng.integers(1, M // 4 + 2))
+        k = float(rng.integers(0, min(n, N) + 1))
+        want = float(hypergeom.sf(k, M, n, N))
+        if want > 1e-290:
+            assert abs(L.cl2_stat_hypergeom_sf(k, M, n, N) - want) <= 1e-9 * want, (k, M, n, N)
+    # exact values (60-digit rational arithmetic) where scipy is off by 7e-8 / 2e-8
+    assert abs(L.cl2_stat_hypergeom_sf(8, 235907837, 20298, 49454) - 0.029946224828182528793) < 1e-15
+    assert abs(L.cl2_stat_binom_sf(2.0, 1106177179.0, 3.2149593661895347e-09) - 0.68944314367205768) < 1e-14
+    # degenerate arguments the path produces (median background of 0)
+    assert L.cl2_stat_poisson_sf(4.0, 0.0) == 0.0 == float(poisson.sf(4.0, 0.0))
+    assert L.cl2_stat_binom_sf(4.0, 100.0, 0.0) == 0.0 == float(binom.sf(4.0, 100.0, 0.0))
