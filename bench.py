@@ -192,7 +192,8 @@ def workload_config(args, world):
     return {"workload": "BASELINE configs[1]: synthetic Hi-TrAC-like intra-chromosomal hg38 PETs, callLoops "
                         "-eps 200,500,1000 -minPts 5 (blockDBSCAN), chromosome files sharded by PET count",
             "pets_per_gpu": int(args.pets), "files": 24 * world, "eps": EPS, "minPts": MINPTS,
-            "l2": "inputs larger than L2 (0.8 GB of resident PETs per GPU vs 126 MB)"}
+            "l2": "inputs larger than L2 (0.8 GB of resident PETs per GPU vs 126 MB)",
+            "pvalues": "device fp64 (cl2_stats.cuh; <=1e-9 relative to scipy where scipy is that accurate, DESIGN.md section 2)"}
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
@@ -259,6 +260,10 @@ def main():
             st += [s["pets"], s["candidates"], s["tested"], s["loops"]]
         counters["stats_e2e"] = st
 
+    def step_e2e_exact():
+        for k in keys:
+            cis_chromosome(ctx, tuple(k.split("-")), pinned[k], job_tot, EPS, MINPTS, exact=True)
+
     def timed(fn, warmup, steps, with_kernel_timing):
         for _ in range(warmup):
             fn()
@@ -293,6 +298,8 @@ def main():
     wall, dev_ms, clocks, fam, launches, _ = timed(step_resident, args.warmup, args.steps, True)
     wall_e, _, clocks_e, _, _, xfer = timed(step_e2e, max(1, args.warmup - 2), args.steps, False)
     xfer = shard.allreduce_stats(np.array(xfer, dtype=np.int64))
+    ex_steps = max(1, min(2, args.steps))
+    wall_x = timed(step_e2e_exact, 1, ex_steps, False)[0]
 
     stats = shard.allreduce_stats(counters["stats"])
     if rank != 0:
@@ -335,6 +342,9 @@ def main():
         "config": workload_config(args, world),
         "e2e": {"value": e2e_val, "unit": "PETs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1000.0 * wall_e / args.steps},
+        "e2e_exact_scipy": {"value": job_tot / (wall_x / ex_steps), "unit": "PETs/s", "steps": ex_steps,
+                            "note": "same call with the final loops' five tail probabilities re-evaluated by scipy on "
+                                    "the host (byte-identical _loops.txt; scipy.hypergeom.sf ~150 us per loop)"},
         "gpu_launches": int(launches),
         "clocks": clocks, "clocks_e2e": clocks_e,
         "roofline": roof, "cpu_baseline": cpu_base,
