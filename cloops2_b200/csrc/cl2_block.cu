@@ -12,6 +12,7 @@
 //                cell in the stable sort by (-cnt, first)
 //   border     = kept non-core cell: largest cluster whose START cell is adjacent, else smallest adjacent cluster
 #include "cl2_points.cuh"
+#include <algorithm>
 
 #define NOT_FOUND (-1)
 
@@ -421,13 +422,13 @@ __global__ void __launch_bounds__(256) k_block_rootlist(const uint8_t *__restric
                                                          const int32_t *__restrict__ list, int32_t nkept,
                                                          const int32_t *__restrict__ pos,
                                                          const uint64_t *__restrict__ minkey,
-                                                         uint64_t *__restrict__ ckeys, uint32_t *__restrict__ croots) {
+                                                         uint64_t *__restrict__ ckeys, int32_t *__restrict__ compid) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nkept) return;
     int c = list[k];
     if (core[c] && root[c] == c) {
-        ckeys[pos[k]] = minkey[c];
-        croots[pos[k]] = (uint32_t)c;
+        ckeys[pos[k]] = minkey[c];      // order key of the component's start cell
+        compid[c] = pos[k];             // provisional id (cell-key order); the final numbering is a host sort of ckeys
     }
 }
 // ------------------------------------------------------------------------------------------------ K14 labels
@@ -447,7 +448,9 @@ __global__ void __launch_bounds__(256) k_block_celllabel(const int32_t *__restri
     if (core[c]) {
         lab = compid[root[c]];
     } else {
-        int maxstart = -1, minany = INT_MAX;
+        // components are compared by the order key of their start cell (= the reference's cluster numbering)
+        unsigned long long maxstart = 0, minany = ~0ull;
+        int rmax = -1, rmin = -1;
         unsigned m = adj[c];
         while (m) {
             int d = __ffs(m) - 1;
@@ -455,20 +458,23 @@ __global__ void __launch_bounds__(256) k_block_celllabel(const int32_t *__restri
             int b = nbr[8 * (int64_t)c + d];
             if (!core[b]) continue;
             int r = root[b];
-            int id = compid[r];
-            if (okey[b] == minkey[r]) maxstart = max(maxstart, id);   // unconditional overwrite, blockDBSCAN.py:184-185
-            minany = min(minany, id);                                  // first claim wins, blockDBSCAN.py:193-195
+            unsigned long long key = minkey[r];
+            if (okey[b] == key && (rmax < 0 || key > maxstart)) { maxstart = key; rmax = r; }   // unconditional overwrite, blockDBSCAN.py:184-185
+            if (key < minany) { minany = key; rmin = r; }                                        // first claim wins, blockDBSCAN.py:193-195
         }
-        lab = maxstart >= 0 ? maxstart : (minany != INT_MAX ? minany : -1);
+        lab = rmax >= 0 ? compid[rmax] : (rmin >= 0 ? compid[rmin] : -1);
     }
     clabel[c] = lab;
 }
 
 __global__ void __launch_bounds__(256) k_point_labels(const int32_t *__restrict__ cid, const uint32_t *__restrict__ row,
                                                        const int32_t *__restrict__ clabel,
+                                                       const int32_t *__restrict__ final_of_prov,
                                                        int32_t *__restrict__ labels, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) labels[row[i]] = clabel[cid[i]];
+    if (i >= n) return;
+    int l = clabel[cid[i]];
+    labels[row[i]] = l >= 0 ? final_of_prov[l] : -1;
 }
 
 // ------------------------------------------------------------------------------------------------ K16 bbox
@@ -506,13 +512,6 @@ __global__ void __launch_bounds__(256) k_block_bbox(const int32_t *__restrict__ 
 __global__ void __launch_bounds__(256) k_fill_i32(int32_t *__restrict__ p, int32_t v, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
-}
-
-__global__ void __launch_bounds__(256) k_block_compid_indirect(const uint32_t *__restrict__ order,
-                                                                const uint32_t *__restrict__ croots, int32_t ncomp,
-                                                                int32_t *__restrict__ compid) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < ncomp) compid[croots[order[i]]] = i;
 }
 
 // ================================================================================================ host driver
@@ -694,6 +693,7 @@ extern "C" int cl2_block_dbscan(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int3
     CL2_TRY(sc.get(&clabel, (size_t)ncells));
     int32_t ncomp = 0;
     ClusterBox *box = nullptr;
+    uint64_t *ckeys = nullptr;
 
     if (nkept > 0) {
         CL2_TRY(sc.get(&list, (size_t)nkept));
@@ -758,24 +758,9 @@ extern "C" int cl2_block_dbscan(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int3
         CL2_TRY(cl2_read_i64(ctx, d_total, &ncomp64));
         ncomp = (int32_t)ncomp64;
         if (ncomp > 0) {
-            uint64_t *ck0, *ck1, *cks;
-            uint32_t *cr0, *o0, *o1, *os;
-            CL2_TRY(sc.get(&ck0, (size_t)ncomp));
-            CL2_TRY(sc.get(&ck1, (size_t)ncomp));
-            CL2_TRY(sc.get(&cr0, (size_t)ncomp));
-            CL2_TRY(sc.get(&o0, (size_t)ncomp));
-            CL2_TRY(sc.get(&o1, (size_t)ncomp));
-            {
-                FamTimer t(ctx, FAM_COMP, 24.0 * (double)nkept);
-                k_block_rootlist<<<cl2_grid(nkept, 256), 256, 0, s>>>(core, root, list, nkept, rflag, minkey, ck0, cr0);
-            }
-            // sort (start-cell order key, position in the component list); the sort's first pass generates the positions
-            CL2_TRY(cl2_radix_sort_pairs(ctx, ck0, ck1, o0, o1, ncomp, 32 + bits_for((uint64_t)g.maxcnt), &cks, &os));
-            (void)cks;
-            {
-                FamTimer t(ctx, FAM_COMP, 12.0 * (double)ncomp);
-                k_block_compid_indirect<<<cl2_grid(ncomp, 256), 256, 0, s>>>(os, cr0, ncomp, compid);
-            }
+            CL2_TRY(sc.get(&ckeys, (size_t)ncomp));
+            FamTimer t(ctx, FAM_COMP, 24.0 * (double)nkept);
+            k_block_rootlist<<<cl2_grid(nkept, 256), 256, 0, s>>>(core, root, list, nkept, rflag, minkey, ckeys, compid);
         }
         {
             FamTimer t(ctx, FAM_BORDER, 64.0 * (double)nkept);
@@ -795,30 +780,47 @@ extern "C" int cl2_block_dbscan(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int3
         ctx->launches++;
     }
 
-    if (labels_out) {
-        int32_t *dl;
-        CL2_TRY(sc.get(&dl, (size_t)n));
-        {
-            FamTimer t(ctx, FAM_LABEL, 12.0 * (double)n);
-            k_point_labels<<<cl2_grid(n, 256), 256, 0, s>>>(g.cid, g.row, clabel, dl, n);
-        }
-        CL2_CUDA(ctx, cudaMemcpyAsync(labels_out, dl, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
-        ctx->d2h_bytes += n * 4;
-    }
+    // Cluster numbering = rank of the components' start-cell order keys (blockDBSCAN.py:146-152).  The component
+    // count is tiny next to n, so the keys and boxes go to the host and are ordered there (no device sort).
     std::vector<ClusterBox> hb((size_t)ncomp);
-    if (ncomp > 0) CL2_CUDA(ctx, cudaMemcpyAsync(hb.data(), box, (size_t)ncomp * sizeof(ClusterBox), cudaMemcpyDeviceToHost, s));
-    ctx->d2h_bytes += (int64_t)ncomp * (int64_t)sizeof(ClusterBox);
+    std::vector<uint64_t> hk((size_t)ncomp);
+    if (ncomp > 0) {
+        CL2_CUDA(ctx, cudaMemcpyAsync(hb.data(), box, (size_t)ncomp * sizeof(ClusterBox), cudaMemcpyDeviceToHost, s));
+        CL2_CUDA(ctx, cudaMemcpyAsync(hk.data(), ckeys, (size_t)ncomp * 8, cudaMemcpyDeviceToHost, s));
+        ctx->d2h_bytes += (int64_t)ncomp * (int64_t)(sizeof(ClusterBox) + 8);
+    }
     CL2_CUDA(ctx, cudaStreamSynchronize(s));
     CL2_CUDA(ctx, cudaGetLastError());
+    std::vector<int32_t> order((size_t)ncomp);
+    for (int32_t i = 0; i < ncomp; i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return hk[a] < hk[b]; });
     pts->ncl = ncomp;
     pts->bbox.resize((size_t)ncomp * 4);
     pts->size.resize((size_t)ncomp);
     for (int32_t i = 0; i < ncomp; i++) {
-        pts->bbox[4 * (size_t)i] = hb[i].xmin;
-        pts->bbox[4 * (size_t)i + 1] = hb[i].xmax;
-        pts->bbox[4 * (size_t)i + 2] = hb[i].ymin;
-        pts->bbox[4 * (size_t)i + 3] = hb[i].ymax;
-        pts->size[i] = hb[i].size;
+        const ClusterBox &b = hb[order[i]];
+        pts->bbox[4 * (size_t)i] = b.xmin;
+        pts->bbox[4 * (size_t)i + 1] = b.xmax;
+        pts->bbox[4 * (size_t)i + 2] = b.ymin;
+        pts->bbox[4 * (size_t)i + 3] = b.ymax;
+        pts->size[i] = b.size;
+    }
+    if (labels_out) {
+        int32_t *dl, *dmap;
+        CL2_TRY(sc.get(&dl, (size_t)n));
+        CL2_TRY(sc.get(&dmap, (size_t)ncomp));
+        std::vector<int32_t> final_of_prov((size_t)ncomp);
+        for (int32_t i = 0; i < ncomp; i++) final_of_prov[order[i]] = i;
+        if (ncomp > 0) CL2_CUDA(ctx, cudaMemcpyAsync(dmap, final_of_prov.data(), (size_t)ncomp * 4, cudaMemcpyHostToDevice, s));
+        {
+            FamTimer t(ctx, FAM_LABEL, 12.0 * (double)n);
+            k_point_labels<<<cl2_grid(n, 256), 256, 0, s>>>(g.cid, g.row, clabel, dmap, dl, n);
+        }
+        CL2_CUDA(ctx, cudaMemcpyAsync(labels_out, dl, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+        ctx->d2h_bytes += n * 4;
+        ctx->h2d_bytes += (int64_t)ncomp * 4;
+        CL2_CUDA(ctx, cudaStreamSynchronize(s));
+        CL2_CUDA(ctx, cudaGetLastError());
     }
     if (n_clusters) *n_clusters = ncomp;
     return CL2_OK;

@@ -12,6 +12,7 @@
 //   release    a component whose core points + claimed border points < minPts is released (:180-183); resolved
 //              by a monotone lower/upper-bound iteration over the (few) components with < minPts core points
 #include "cl2_points.cuh"
+#include <algorithm>
 
 #define ST_UNKNOWN 0
 #define ST_ALIVE 1
@@ -374,18 +375,19 @@ __global__ void __launch_bounds__(256) k_c2_aliveflags(const int32_t *__restrict
 }
 __global__ void __launch_bounds__(256) k_c2_alivelist(const int32_t *__restrict__ root, const uint8_t *__restrict__ status,
                                                        const int32_t *__restrict__ pos, const unsigned *__restrict__ minkey,
-                                                       int32_t ncells, uint64_t *__restrict__ keys,
-                                                       uint32_t *__restrict__ roots) {
+                                                       int32_t ncells, unsigned *__restrict__ keys,
+                                                       int32_t *__restrict__ compid) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < ncells && root[c] == c && status[c] == ST_ALIVE) {
         keys[pos[c]] = minkey[c];
-        roots[pos[c]] = (uint32_t)c;
+        compid[c] = pos[c];            // provisional id; final numbering = host sort of the keys
     }
 }
-__global__ void __launch_bounds__(256) k_c2_compid(const uint32_t *__restrict__ order, const uint32_t *__restrict__ roots,
-                                                    int32_t ncomp, int32_t *__restrict__ compid) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < ncomp) compid[roots[order[i]]] = i;
+__global__ void __launch_bounds__(256) k_c2_remap(const int32_t *__restrict__ root, const uint8_t *__restrict__ status,
+                                                   const int32_t *__restrict__ final_of_prov, int32_t ncells,
+                                                   int32_t *__restrict__ compid) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < ncells && root[c] == c && status[c] == ST_ALIVE) compid[c] = final_of_prov[compid[c]];
 }
 
 struct C2Box {
@@ -561,25 +563,32 @@ extern "C" int cl2_cdbscan2(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int32_t 
     const int32_t ncomp = (int32_t)ncomp64;
     C2Box *box = nullptr;
     if (ncomp > 0) {
-        uint64_t *ck0, *ck1, *cks;
-        uint32_t *cr0, *o0, *o1, *os;
-        CL2_TRY(sc.get(&ck0, (size_t)ncomp));
-        CL2_TRY(sc.get(&ck1, (size_t)ncomp));
-        CL2_TRY(sc.get(&cr0, (size_t)ncomp));
-        CL2_TRY(sc.get(&o0, (size_t)ncomp));
-        CL2_TRY(sc.get(&o1, (size_t)ncomp));
+        unsigned *dkeys;
+        int32_t *dmap;
+        CL2_TRY(sc.get(&dkeys, (size_t)ncomp));
+        CL2_TRY(sc.get(&dmap, (size_t)ncomp));
         CL2_TRY(sc.get(&box, (size_t)ncomp));
         {
             FamTimer t(ctx, FAM_COMP, 21.0 * (double)ncells);
-            k_c2_alivelist<<<cl2_grid(ncells, 256), 256, 0, s>>>(root, status, aflag, minkey, ncells, ck0, cr0);
+            k_c2_alivelist<<<cl2_grid(ncells, 256), 256, 0, s>>>(root, status, aflag, minkey, ncells, dkeys, compid);
         }
-        CL2_TRY(cl2_radix_sort_pairs(ctx, ck0, ck1, o0, o1, ncomp, bits_for((uint64_t)n), &cks, &os));
-        (void)cks;
+        // visiting order of the components = ascending first-row key (cDBSCAN2.py:117-140); few components, host sort
+        std::vector<unsigned> hk((size_t)ncomp);
+        CL2_CUDA(ctx, cudaMemcpyAsync(hk.data(), dkeys, (size_t)ncomp * 4, cudaMemcpyDeviceToHost, s));
+        CL2_CUDA(ctx, cudaStreamSynchronize(s));
+        std::vector<int32_t> order((size_t)ncomp), fin((size_t)ncomp);
+        for (int32_t i = 0; i < ncomp; i++) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return hk[a] < hk[b]; });
+        for (int32_t i = 0; i < ncomp; i++) fin[order[i]] = i;
+        CL2_CUDA(ctx, cudaMemcpyAsync(dmap, fin.data(), (size_t)ncomp * 4, cudaMemcpyHostToDevice, s));
+        ctx->d2h_bytes += (int64_t)ncomp * 4;
+        ctx->h2d_bytes += (int64_t)ncomp * 4;
         {
-            FamTimer t(ctx, FAM_COMP, 12.0 * (double)ncomp, 2);
-            k_c2_compid<<<cl2_grid(ncomp, 256), 256, 0, s>>>(os, cr0, ncomp, compid);
+            FamTimer t(ctx, FAM_COMP, 12.0 * (double)ncells, 2);
+            k_c2_remap<<<cl2_grid(ncells, 256), 256, 0, s>>>(root, status, dmap, ncells, compid);
             k_c2_box_init<<<cl2_grid(ncomp, 256), 256, 0, s>>>(box, ncomp);
         }
+        CL2_CUDA(ctx, cudaStreamSynchronize(s));   // fin[] must outlive the copy
     }
     int32_t *dl = nullptr;
     if (labels_out) CL2_TRY(sc.get(&dl, (size_t)n));

@@ -123,3 +123,31 @@ def test_dropin_class_protocol(gpu_ctx):
     db = blockDBSCAN(mat, 500, 5)          # float matrix, as callTransLoops.py:43-47 passes it
     want, _ = oracle.block_dbscan(xy, 500, 5)
     assert db.labels == {i: int(v) for i, v in enumerate(want.tolist()) if v >= 0}
+
+
+def test_full_size_chr1_of_config2(gpu_ctx):
+    """BASELINE configs[1] at full size for its largest file: chr1 of the 100 M-PET genome (8.06 M PETs), eps 200 and
+    1000, minPts 5 -- labels and boxes equal to the oracle, plus size-independent invariants."""
+    n = int(round(100e6 * synth.HG38[0][1] / synth.HG38_TOTAL))
+    xy = synth.cis_chrom(synth.HG38[0][1], n, 20261019 + 2000, "hitrac")
+    pts = _lib.Points(gpu_ctx, xy)
+    try:
+        for eps in (200, 1000):
+            lab, ncl = pts.block_dbscan(eps, 5)
+            bbox, size = pts.cluster_bbox()
+            want, wn = oracle.block_dbscan(xy, eps, 5)
+            assert ncl == wn and np.array_equal(lab, want)
+            # invariants that do not need the oracle
+            assert lab.min() >= -1 and lab.max() == ncl - 1
+            cnt = np.bincount(lab[lab >= 0], minlength=ncl)
+            assert np.array_equal(cnt, size) and (cnt > 0).all()
+            order = np.argsort(lab, kind="stable")
+            order = order[lab[order] >= 0]
+            starts = np.concatenate([[0], np.cumsum(cnt)[:-1]])
+            assert np.array_equal(np.minimum.reduceat(xy[order, 0], starts), bbox[:, 0])
+            assert np.array_equal(np.maximum.reduceat(xy[order, 1], starts), bbox[:, 3])
+            # idempotence: a second run on the cached grid gives the same answer
+            lab2, ncl2 = pts.block_dbscan(eps, 5)
+            assert ncl2 == ncl and np.array_equal(lab2, lab)
+    finally:
+        pts.close()

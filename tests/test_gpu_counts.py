@@ -62,3 +62,31 @@ def test_counts_other_window_sizes_and_partial_outputs(gpu_ctx):
     finally:
         idx.close()
         pts.close()
+
+
+def test_full_size_counts_properties(gpu_ctx):
+    """8 M PETs (chr1 of configs[1]): counting identities that hold at any size, plus oracle equality on a sample."""
+    n = int(round(100e6 * synth.HG38[0][1] / synth.HG38_TOTAL))
+    xy = synth.cis_chrom(synth.HG38[0][1], n, 20261019 + 2000, "hitrac")
+    rng = np.random.default_rng(1)
+    cands = _cands(xy, rng, 2000)
+    pts = _lib.Points(gpu_ctx, xy)
+    idx = _lib.Index(pts)
+    try:
+        core, na, nb, nab, anc = idx.loop_counts(cands)
+    finally:
+        idx.close()
+        pts.close()
+    ra, rb, rab = core[:, 0], core[:, 1], core[:, 2]
+    assert (rab <= ra).all() and (rab <= rb).all() and (core >= 0).all()
+    assert (nab.reshape(-1, 10, 10) <= na[:, :, None]).all() and (nab.reshape(-1, 10, 10) <= nb[:, None, :]).all()
+    assert np.array_equal(anc[:, 0], ra) and np.array_equal(anc[:, 2], rb)      # estAnchorSig counts the anchor itself
+    assert (anc[:, 1] >= anc[:, 0]).all() and (anc[:, 3] >= anc[:, 2]).all()     # the +-5x window contains the anchor
+    # |P(l,r)| by brute force on numpy for a few loops
+    for i in range(0, 2000, 400):
+        l, r = cands[i, 0], cands[i, 1]
+        brute = int((((xy[:, 0] >= l) & (xy[:, 0] <= r)) | ((xy[:, 1] >= l) & (xy[:, 1] <= r))).sum())
+        assert brute == ra[i]
+    want = oracle.XYIndex(xy).loop_counts(cands[:200])
+    for g, w in zip((core[:200], na[:200], nb[:200], nab[:200], anc[:200]), want):
+        assert np.array_equal(g, w)
