@@ -248,10 +248,14 @@ def main():
 
     def step_resident():
         st = np.zeros(4, dtype=np.int64)
+        host = {}
         for k in keys:
             _, s = cis_chromosome(ctx, tuple(k.split("-")), None, job_tot, EPS, MINPTS, pts=resident[k])
             st += [s["pets"], s["candidates"], s["tested"], s["loops"]]
+            for nm, v in s.get("host_s", {}).items():
+                host[nm] = host.get(nm, 0.0) + 1e3 * v
         counters["stats"] = st
+        counters["host_ms"] = host
 
     def step_e2e():
         st = np.zeros(4, dtype=np.int64)
@@ -349,6 +353,7 @@ def main():
         "clocks": clocks, "clocks_e2e": clocks_e,
         "roofline": roof, "cpu_baseline": cpu_base,
         "kernels": kernels,
+        "stage_wall_ms_per_step": counters.get("host_ms"),
         "job": {"pets": job_tot, "candidates": int(stats[1]), "tested": int(stats[2]), "loops": int(stats[3]),
                 "device_event_ms_per_step": dev_ms / args.steps, "generate_s": gen_s},
     }

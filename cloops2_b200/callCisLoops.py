@@ -62,33 +62,46 @@ def cis_chromosome(ctx, key, xy, tot, eps, minPts, cut=0, mcut=-1, hic=False, em
         stats = {"pets": pts.n, "candidates": 0, "tested": 0, "loops": 0}
         if pts.n == 0:
             return hostops._empty_cols(), stats
+        import time
+        t0 = time.perf_counter()
         per_pass = []
         for ep, mp in _sweep(eps, minPts, emPair):
             _log("Clustering %s and %s using eps %s, minPts %s,pre-set distance cutoff > %s" % (key[0], key[1], ep, mp, cut))
             c, s = cluster_pass(pts, ep, mp, hic=hic, cis=True)
             _log("Clustering %s and %s finished. Estimated %s candidate loops with %s PETs." % (key[0], key[1], len(c), int(s.sum())))
             per_pass.append(c)
-        cands = hostops.combine_unique(per_pass)
+        t1 = time.perf_counter()
+        # The reference merges the passes (combineLoops), drops distance <= cut and duplicates, then tests.  A
+        # candidate's test result depends on its coordinates only, so the duplicates are removed AFTER the tests, on
+        # the few survivors (same loops, same order) instead of sorting ~10^5 boxes per chromosome on the host.
+        cands = np.concatenate(per_pass, axis=0) if len(per_pass) > 1 else per_pass[0]
         if cands.shape[0]:
             cands = cands[hostops.cis_distance(cands) > cut]                         # filterLoopsByDis :146-156
         stats["candidates"] = int(cands.shape[0])
+        if logger is not None and cands.shape[0]:
+            stats["candidates"] = int(hostops.combine_unique([cands]).shape[0])      # the number the reference logs
         if cands.shape[0] == 0:
             return hostops._empty_cols(), stats
         mm = min(minPts) if emPair else max(minPts)                                 # :557-560
         ext = pts.extent()
         span = float(int(ext[3]) - int(ext[0]))
         index = _lib.Index(pts)
+        t2 = time.perf_counter()
         try:
             _log("Estimate significance for %s candidate interactions in %s with %s PETs distance > =%s and <=%s,requiring minPts >=%s."
-                 % (cands.shape[0], "-".join(key), pts.n, cut, mcut, mm))
+                 % (stats["candidates"], "-".join(key), pts.n, cut, mcut, mm))
             cols = hostops.est_cis(index, cands, pts.n, span, tot, mm, hic=hic)
         finally:
             index.close()
+        cols = hostops.take(cols, hostops.first_occurrence(cols["coords"]))         # filterDupLoops :159-169
+        t3 = time.perf_counter()
         stats["tested"] = int(cols["coords"].shape[0])
         sig = hostops.mark_sig_cis(cols, hic=hic)
         final = hostops.select_twice(cols, sig)
         if exact:
             final = hostops.scipy_pvalues(final, pts.n, float(pts.n) / span, cis=True)
+        t4 = time.perf_counter()
+        stats["host_s"] = {"cluster": t1 - t0, "index": t2 - t1, "test": t3 - t2, "select": t4 - t3}
         stats["loops"] = int(final["coords"].shape[0])
         return final, stats
     finally:

@@ -30,10 +30,10 @@ def trans_pair(ctx, key, xy, eps, minPts, pts=None, exact=False):
             for mp in minPts:
                 c, _ = cluster_pass(pts, ep, mp, hic=False, cis=False)
                 per_pass.append(c)
-        # combineLoops only (callTransLoops.py:230-234): coordinates unseen in EARLIER passes are appended; clusters of
-        # one pass never share a bounding box with another cluster of the same pass unless their boxes coincide, in
-        # which case the reference keeps both -- reproduce by de-duplicating across passes only.
-        cands = _combine_across_passes(per_pass)
+        # combineLoops only (callTransLoops.py:230-234): coordinates already seen in an EARLIER pass are dropped,
+        # duplicates inside one pass survive.  As on the cis path the de-duplication is applied after the tests.
+        cands = np.concatenate(per_pass, axis=0) if len(per_pass) > 1 else per_pass[0]
+        pass_id = np.concatenate([np.full(len(c), i, dtype=np.int64) for i, c in enumerate(per_pass)])
         stats["candidates"] = int(cands.shape[0])
         if cands.shape[0] == 0:
             return hostops._empty_cols(), stats
@@ -41,9 +41,10 @@ def trans_pair(ctx, key, xy, eps, minPts, pts=None, exact=False):
         span = float(int(ext[3]) - int(ext[0]))
         index = _lib.Index(pts)
         try:
-            cols = hostops.est_trans(index, cands, pts.n, span, max(minPts))
+            cols = hostops.est_trans(index, cands, pts.n, span, max(minPts), pass_id=pass_id)
         finally:
             index.close()
+        cols = hostops.take(cols, hostops.first_occurrence(cols["coords"], cols.pop("pass_id")))
         stats["tested"] = int(cols["coords"].shape[0])
         final = hostops.select_twice(cols, hostops.mark_sig_trans(cols))
         if exact:

@@ -2,6 +2,7 @@
 // timing read-out.  C ABI declared in include/cl2.h.
 #include "cl2_points.cuh"
 #include <new>
+#include <stdlib.h>
 
 extern "C" const char *cl2_version(void) { return "cl2-b200 0.1 sm_100a"; }
 
@@ -18,6 +19,8 @@ extern "C" int cl2_ctx_create(int device, cl2_ctx **out) {
         delete ctx;
         return CL2_ERR_CUDA;
     }
+    const char *np = getenv("CL2_NO_POOL");
+    ctx->no_pool = (np && np[0] == '1') ? 1 : 0;
     cudaDeviceGetDefaultMemPool(&ctx->pool, device);
     if (ctx->pool) {
         uint64_t thr = UINT64_MAX;  // keep freed scratch in the pool: steady-state calls never reach the driver allocator

@@ -15,6 +15,7 @@
 #include <algorithm>
 
 #define NOT_FOUND (-1)
+#define CL2_HOST_SORT_MAX 4096   // component counts up to this are ordered on the host (cheaper than ~15 launches)
 
 __constant__ int c_dx[8] = {0, 0, -1, 1, -1, -1, 1, 1};
 __constant__ int c_dy[8] = {-1, 1, 0, 0, -1, 1, -1, 1};
@@ -572,15 +573,16 @@ int cl2_grid_build(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int kind) {
     CL2_TRY(sc.get(&k1, (size_t)n));
     CL2_TRY(sc.get(&v0, (size_t)n));
     CL2_TRY(sc.get(&v1, (size_t)n));
-    {
-        FamTimer t(ctx, FAM_KEYGEN, 16.0 * (double)n);
-        if (kind == 0)
-            k_block_keygen<<<cl2_grid(n, 256), 256, 0, ctx->stream>>>(pts->xy, k0, n, (int)pts->ext[0], (int)pts->ext[2],
-                                                                       e32, by);
-        else
-            k_rot_keygen<<<cl2_grid(n, 256), 256, 0, ctx->stream>>>(pts->xy, k0, n, (int)e32, rgx0, rgy0, by);
-    }
-    CL2_TRY(cl2_radix_sort_pairs(ctx, k0, k1, v0, v1, n, bx + by, &ks, &vs));
+    cl2_keygen gen;
+    gen.kind = kind == 0 ? CL2_KEY_BLOCK : CL2_KEY_ROT;
+    gen.xy = pts->xy;
+    gen.minx = (int)pts->ext[0];
+    gen.miny = (int)pts->ext[2];
+    gen.eps = e32;
+    gen.by = by;
+    gen.gx0 = rgx0;
+    gen.gy0 = rgy0;
+    CL2_TRY(cl2_radix_sort_gen(ctx, gen, k0, k1, v0, v1, n, bx + by, &ks, &vs));
     // keep the sorted row ids (take ownership of whichever buffer holds them)
     sc.release(vs);
     g.row = vs;
@@ -786,14 +788,32 @@ extern "C" int cl2_block_dbscan(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int3
     std::vector<uint64_t> hk((size_t)ncomp);
     if (ncomp > 0) {
         CL2_CUDA(ctx, cudaMemcpyAsync(hb.data(), box, (size_t)ncomp * sizeof(ClusterBox), cudaMemcpyDeviceToHost, s));
-        CL2_CUDA(ctx, cudaMemcpyAsync(hk.data(), ckeys, (size_t)ncomp * 8, cudaMemcpyDeviceToHost, s));
-        ctx->d2h_bytes += (int64_t)ncomp * (int64_t)(sizeof(ClusterBox) + 8);
+        ctx->d2h_bytes += (int64_t)ncomp * (int64_t)sizeof(ClusterBox);
+        if (ncomp <= CL2_HOST_SORT_MAX) {
+            CL2_CUDA(ctx, cudaMemcpyAsync(hk.data(), ckeys, (size_t)ncomp * 8, cudaMemcpyDeviceToHost, s));
+            ctx->d2h_bytes += (int64_t)ncomp * 8;
+        }
+    }
+    std::vector<int32_t> order((size_t)ncomp);
+    const bool device_sort = ncomp > CL2_HOST_SORT_MAX;
+    if (device_sort) {
+        // many components (large chromosomes): order the keys with the device radix sort, read back the permutation
+        uint64_t *ck1, *cks;
+        uint32_t *o0, *o1, *os;
+        CL2_TRY(sc.get(&ck1, (size_t)ncomp));
+        CL2_TRY(sc.get(&o0, (size_t)ncomp));
+        CL2_TRY(sc.get(&o1, (size_t)ncomp));
+        CL2_TRY(cl2_radix_sort_pairs(ctx, ckeys, ck1, o0, o1, ncomp, 32 + bits_for((uint64_t)g.maxcnt), &cks, &os));
+        (void)cks;
+        CL2_CUDA(ctx, cudaMemcpyAsync(order.data(), os, (size_t)ncomp * 4, cudaMemcpyDeviceToHost, s));
+        ctx->d2h_bytes += (int64_t)ncomp * 4;
     }
     CL2_CUDA(ctx, cudaStreamSynchronize(s));
     CL2_CUDA(ctx, cudaGetLastError());
-    std::vector<int32_t> order((size_t)ncomp);
-    for (int32_t i = 0; i < ncomp; i++) order[i] = i;
-    std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return hk[a] < hk[b]; });
+    if (!device_sort) {
+        for (int32_t i = 0; i < ncomp; i++) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return hk[a] < hk[b]; });
+    }
     pts->ncl = ncomp;
     pts->bbox.resize((size_t)ncomp * 4);
     pts->size.resize((size_t)ncomp);

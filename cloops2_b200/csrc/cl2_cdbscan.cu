@@ -383,6 +383,10 @@ __global__ void __launch_bounds__(256) k_c2_alivelist(const int32_t *__restrict_
         compid[c] = pos[c];            // provisional id; final numbering = host sort of the keys
     }
 }
+__global__ void __launch_bounds__(256) k_c2_widen(const unsigned *__restrict__ in, uint64_t *__restrict__ out, int32_t n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
 __global__ void __launch_bounds__(256) k_c2_remap(const int32_t *__restrict__ root, const uint8_t *__restrict__ status,
                                                    const int32_t *__restrict__ final_of_prov, int32_t ncells,
                                                    int32_t *__restrict__ compid) {
@@ -574,11 +578,27 @@ extern "C" int cl2_cdbscan2(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int32_t 
         }
         // visiting order of the components = ascending first-row key (cDBSCAN2.py:117-140); few components, host sort
         std::vector<unsigned> hk((size_t)ncomp);
-        CL2_CUDA(ctx, cudaMemcpyAsync(hk.data(), dkeys, (size_t)ncomp * 4, cudaMemcpyDeviceToHost, s));
-        CL2_CUDA(ctx, cudaStreamSynchronize(s));
         std::vector<int32_t> order((size_t)ncomp), fin((size_t)ncomp);
-        for (int32_t i = 0; i < ncomp; i++) order[i] = i;
-        std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return hk[a] < hk[b]; });
+        if (ncomp > 4096) {
+            // many components: device radix sort of (key, position), read back the permutation
+            uint64_t *k0, *k1, *cks;
+            uint32_t *o0, *o1, *os;
+            CL2_TRY(sc.get(&k0, (size_t)ncomp));
+            CL2_TRY(sc.get(&k1, (size_t)ncomp));
+            CL2_TRY(sc.get(&o0, (size_t)ncomp));
+            CL2_TRY(sc.get(&o1, (size_t)ncomp));
+            k_c2_widen<<<cl2_grid(ncomp, 256), 256, 0, s>>>(dkeys, k0, ncomp);
+            ctx->launches++;
+            CL2_TRY(cl2_radix_sort_pairs(ctx, k0, k1, o0, o1, ncomp, bits_for((uint64_t)n), &cks, &os));
+            (void)cks;
+            CL2_CUDA(ctx, cudaMemcpyAsync(order.data(), os, (size_t)ncomp * 4, cudaMemcpyDeviceToHost, s));
+            CL2_CUDA(ctx, cudaStreamSynchronize(s));
+        } else {
+            CL2_CUDA(ctx, cudaMemcpyAsync(hk.data(), dkeys, (size_t)ncomp * 4, cudaMemcpyDeviceToHost, s));
+            CL2_CUDA(ctx, cudaStreamSynchronize(s));
+            for (int32_t i = 0; i < ncomp; i++) order[i] = i;
+            std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return hk[a] < hk[b]; });
+        }
         for (int32_t i = 0; i < ncomp; i++) fin[order[i]] = i;
         CL2_CUDA(ctx, cudaMemcpyAsync(dmap, fin.data(), (size_t)ncomp * 4, cudaMemcpyHostToDevice, s));
         ctx->d2h_bytes += (int64_t)ncomp * 4;

@@ -57,6 +57,7 @@ struct cl2_ctx {
     std::vector<cl2_evpair> pending;
     std::vector<cudaEvent_t> evpool;
     int sm_count = 148;
+    int no_pool = 0;            // CL2_NO_POOL=1: plain cudaMalloc/cudaFree (used when profiling under ncu)
     void *h_scratch = nullptr;  // small pinned buffer for scalar read-backs
 };
 
@@ -88,13 +89,16 @@ struct Scratch {
     std::vector<void *> ptrs;
     explicit Scratch(cl2_ctx *c) : ctx(c) {}
     ~Scratch() {
-        for (void *p : ptrs) cudaFreeAsync(p, ctx->stream);
+        if (ctx->no_pool && !ptrs.empty()) cudaStreamSynchronize(ctx->stream);
+        for (void *p : ptrs) {
+            if (ctx->no_pool) cudaFree(p); else cudaFreeAsync(p, ctx->stream);
+        }
     }
     template <typename T>
     int get(T **out, size_t count) {
         void *p = nullptr;
         size_t bytes = (count ? count : 1) * sizeof(T);
-        cudaError_t e = cudaMallocAsync(&p, bytes, ctx->stream);
+        cudaError_t e = ctx->no_pool ? cudaMalloc(&p, bytes) : cudaMallocAsync(&p, bytes, ctx->stream);
         if (e != cudaSuccess) {
             snprintf(ctx->err, sizeof(ctx->err), "cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
             *out = nullptr;
@@ -118,7 +122,7 @@ template <typename T>
 inline int cl2_dev_alloc(cl2_ctx *ctx, T **out, size_t count) {
     void *p = nullptr;
     size_t bytes = (count ? count : 1) * sizeof(T);
-    cudaError_t e = cudaMallocAsync(&p, bytes, ctx->stream);
+    cudaError_t e = ctx->no_pool ? cudaMalloc(&p, bytes) : cudaMallocAsync(&p, bytes, ctx->stream);
     if (e != cudaSuccess) {
         snprintf(ctx->err, sizeof(ctx->err), "cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
         *out = nullptr;
@@ -128,8 +132,16 @@ inline int cl2_dev_alloc(cl2_ctx *ctx, T **out, size_t count) {
     return CL2_OK;
 }
 inline void cl2_dev_free(cl2_ctx *ctx, void *p) {
-    if (p) cudaFreeAsync(p, ctx->stream);
+    if (!p) return;
+    if (ctx->no_pool) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(p);
+    } else {
+        cudaFreeAsync(p, ctx->stream);
+    }
 }
+
+inline void cl2_timing_drain(cl2_ctx *ctx);
 
 // RAII timing scope: records an event pair around the launches of one kernel family when timing is on.
 struct FamTimer {
@@ -139,6 +151,7 @@ struct FamTimer {
     FamTimer(cl2_ctx *c, int f, double bytes, int nlaunch = 1) : ctx(c), fam(f) {
         ctx->launches += nlaunch;
         if (!ctx->timing) return;
+        if (ctx->pending.size() >= 2048) cl2_timing_drain(ctx);   // recycle events (creation is ~10 us each)
         ctx->fam_launch[f] += nlaunch;
         ctx->fam_bytes[f] += bytes;
         a = take();
@@ -178,6 +191,24 @@ inline void cl2_timing_drain(cl2_ctx *ctx) {
 static inline int cl2_grid(int64_t n, int block) { return (int)((n + block - 1) / block); }
 
 // ---- shared device-side primitives (cl2_sort.cu) ----
+// Where the sort's first pass takes its keys from: a materialised array, or generated on the fly from the resident
+// coordinates (saves the separate key-generation pass: 8 B read + 8 B written per PET).
+#define CL2_KEY_ARRAY 0
+#define CL2_KEY_BLOCK 1   // blockDBSCAN grid: ((x-minx)/eps << by) | (y-miny)/eps
+#define CL2_KEY_ROT 2     // cDBSCAN2 grid: truncating division of x-y and x+y, shifted by gx0 / gy0
+#define CL2_KEY_X 3       // x coordinate (XY index)
+#define CL2_KEY_Y 4       // y coordinate
+struct cl2_keygen {
+    int kind = CL2_KEY_ARRAY;
+    const int2 *xy = nullptr;
+    int minx = 0, miny = 0;
+    unsigned eps = 1;
+    int by = 0;
+    int gx0 = 0;
+    unsigned gy0 = 0;
+};
+int cl2_radix_sort_gen(cl2_ctx *ctx, const cl2_keygen &gen, uint64_t *keys0, uint64_t *keys1, uint32_t *vals0,
+                       uint32_t *vals1, int64_t n, int nbits, uint64_t **kout, uint32_t **vout);
 // Stable LSD radix sort of (uint64 key, uint32 val) pairs on bits [0, nbits).  keys/vals are double buffers;
 // on return *kout / *vout point at the buffer holding the sorted data.
 int cl2_radix_sort_pairs(cl2_ctx *ctx, uint64_t *keys0, uint64_t *keys1, uint32_t *vals0, uint32_t *vals1, int64_t n,

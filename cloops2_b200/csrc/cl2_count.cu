@@ -47,11 +47,10 @@ extern "C" int cl2_index_build(cl2_ctx *ctx, cl2_points *pts, cl2_index **out) {
             if ((rc = cl2_dev_alloc(ctx, &ix->byx, (size_t)n)) || (rc = cl2_dev_alloc(ctx, &ix->byy, (size_t)n))) break;
             for (int which = 0; which < 2 && rc == CL2_OK; which++) {
                 int64_t hi = which == 0 ? pts->ext[1] : pts->ext[3];
-                {
-                    FamTimer t(ctx, FAM_INDEX, 16.0 * (double)n);
-                    k_index_keys<<<cl2_grid(n, 256), 256, 0, ctx->stream>>>(pts->xy, k0, n, which);
-                }
-                rc = cl2_radix_sort_pairs(ctx, k0, k1, v0, v1, n, bits_for((uint64_t)hi), &ks, &vs);
+                cl2_keygen gen;
+                gen.kind = which == 0 ? CL2_KEY_X : CL2_KEY_Y;
+                gen.xy = pts->xy;
+                rc = cl2_radix_sort_gen(ctx, gen, k0, k1, v0, v1, n, bits_for((uint64_t)hi), &ks, &vs);
                 if (rc) break;
                 FamTimer t(ctx, FAM_INDEX, 20.0 * (double)n);
                 k_index_gather<<<cl2_grid(n, 256), 256, 0, ctx->stream>>>(pts->xy, vs, which == 0 ? ix->byx : ix->byy, n,

@@ -6,6 +6,7 @@
 // coalesced store; 12 B read + 12 B written per PET).  Only ceil(nbits/8) passes are run, nbits being the number
 // of significant bits of the packed cell key for this chromosome and eps.
 #include "cl2_common.cuh"
+#include <stdlib.h>
 
 // ------------------------------------------------------------------------------------------------ scan
 #define SCAN_THREADS 256
@@ -236,6 +237,217 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_downsweep(const uint64_t *__r
     }
 }
 
+// ------------------------------------------------------------------------------------------------ onesweep variant
+// One kernel per pass (24 B/PET): digit histograms of ALL passes are taken once up front (they do not depend on the
+// element order), tiles are claimed through an atomic ticket and obtain their per-digit base by decoupled look-back
+// over the tile descriptors (count | AGGREGATE, later inclusive | INCLUSIVE), so no per-pass upsweep read and no
+// table scan.  Tiles are ticket-ordered, so every predecessor a tile waits on is already running or finished.
+__device__ __forceinline__ uint64_t os_key(const cl2_keygen &g, const uint64_t *__restrict__ keys, int64_t i) {
+    if (g.kind == CL2_KEY_ARRAY) return keys[i];
+    int2 p = g.xy[i];
+    if (g.kind == CL2_KEY_BLOCK) {        // blockDBSCAN.py:81-82 on non-negative ints
+        unsigned gx = (unsigned)(p.x - g.minx) / g.eps, gy = (unsigned)(p.y - g.miny) / g.eps;
+        return ((uint64_t)gx << g.by) | (uint64_t)gy;
+    }
+    if (g.kind == CL2_KEY_ROT) {          // cDBSCAN2.py:67-70, truncation toward zero
+        int u = p.x - p.y;
+        unsigned v = (unsigned)p.x + (unsigned)p.y;
+        unsigned gx = (unsigned)(u / (int)g.eps - g.gx0), gy = v / g.eps - g.gy0;
+        return ((uint64_t)gx << g.by) | (uint64_t)gy;
+    }
+    return (uint64_t)(uint32_t)(g.kind == CL2_KEY_X ? p.x : p.y);
+}
+
+#define OS_AGG 0x40000000u
+#define OS_INC 0x80000000u
+#define OS_VAL 0x3FFFFFFFu
+#define OS_MAXPASS 8
+
+__global__ void __launch_bounds__(256) k_os_hist(const uint64_t *__restrict__ keys, const cl2_keygen gen, int64_t n,
+                                                  int passes, unsigned *__restrict__ ghist) {
+    __shared__ unsigned h[OS_MAXPASS][256];
+    for (int i = threadIdx.x; i < OS_MAXPASS * 256; i += 256) (&h[0][0])[i] = 0;
+    __syncthreads();
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t nround = ((n + 31) / 32) * 32;      // whole warps stay in the loop together
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+        bool valid = i < n;
+        uint64_t k = valid ? os_key(gen, keys, i) : 0;
+        unsigned act = __ballot_sync(0xffffffffu, valid);
+        for (int p = 0; p < passes; p++) {
+            unsigned d = (unsigned)((k >> (8 * p)) & 255);
+            int same;
+            __match_all_sync(0xffffffffu, valid ? d : 0x100u + (threadIdx.x & 31), &same);
+            if (same) {                      // high digits are often constant: one add per warp instead of 32 conflicts
+                if ((threadIdx.x & 31) == 0) atomicAdd(&h[p][d], (unsigned)__popc(act));
+            } else if (valid) {
+                atomicAdd(&h[p][d], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int p = 0; p < passes; p++) {
+        unsigned v = h[p][threadIdx.x];
+        if (v) atomicAdd(&ghist[p * 256 + threadIdx.x], v);
+    }
+}
+// exclusive prefix of each pass's 256-bin histogram, in place; one block per pass
+__global__ void __launch_bounds__(256) k_os_prefix(unsigned *__restrict__ ghist) {
+    int tot;
+    unsigned v = ghist[blockIdx.x * 256 + threadIdx.x];
+    int ex = block_excl_scan<256>((int)v, &tot);
+    ghist[blockIdx.x * 256 + threadIdx.x] = (unsigned)ex;
+}
+
+__global__ void __launch_bounds__(RS_THREADS) k_os_pass(const uint64_t *__restrict__ kin, const cl2_keygen gen,
+                                                         const uint32_t *__restrict__ vin,
+                                                         uint64_t *__restrict__ kout, uint32_t *__restrict__ vout,
+                                                         int64_t n, int shift, const unsigned *__restrict__ gprefix,
+                                                         unsigned *__restrict__ desc, unsigned *__restrict__ ticket,
+                                                         int iota) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RsSmem &S = *reinterpret_cast<RsSmem *>(smem_raw);
+    __shared__ unsigned s_tile;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&S.warp_cnt[0][0])[i] = 0;
+    __syncthreads();
+    const unsigned tile = s_tile;
+    const int64_t tbase = (int64_t)tile * RS_TILE;
+    const int64_t wbase = tbase + (int64_t)w * (32 * RS_IPT);
+    uint64_t key[RS_IPT];
+    unsigned short rank[RS_IPT];
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < RS_IPT; r++) {
+        int64_t i = wbase + r * 32 + lane;
+        key[r] = (i < n) ? os_key(gen, kin, i) : ~0ull;
+    }
+#pragma unroll
+    for (int r = 0; r < RS_IPT; r++) {
+        int64_t i = wbase + r * 32 + lane;
+        bool valid = i < n;
+        unsigned d = valid ? (unsigned)((key[r] >> shift) & 255) : (0x10000u | lane);
+        unsigned peers = __match_any_sync(0xffffffffu, d);
+        int before = 0;
+        if (valid) before = S.warp_cnt[w][d];
+        __syncwarp();
+        rank[r] = (unsigned short)(before + __popc(peers & lt));
+        if (valid && (peers & lt) == 0) S.warp_cnt[w][d] = before + __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        const int d = threadIdx.x;
+        int off = 0;
+#pragma unroll
+        for (int k = 0; k < RS_WARPS; k++) {
+            int c = S.warp_cnt[k][d];
+            S.warp_cnt[k][d] = off;
+            off += c;
+        }
+        // publish this tile's count for digit d, then look back for the exclusive prefix over earlier tiles
+        volatile unsigned *vd = desc;
+        vd[(size_t)tile * 256 + d] = (unsigned)off | OS_AGG;
+        unsigned excl = 0;
+        for (long long t = (long long)tile - 1; t >= 0;) {
+            unsigned v = vd[(size_t)t * 256 + d];
+            if (v & OS_INC) { excl += v & OS_VAL; break; }
+            if (v & OS_AGG) { excl += v & OS_VAL; t--; }
+            // else: predecessor has not published yet -- spin on the same descriptor
+        }
+        vd[(size_t)tile * 256 + d] = (excl + (unsigned)off) | OS_INC;
+        int tot;
+        int ex = block_excl_scan<RS_THREADS>(off, &tot);
+        S.dprefix[d] = ex;
+        S.gbase[d] = (int)(gprefix[d] + excl);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_IPT; r++) {
+        int64_t i = wbase + r * 32 + lane;
+        if (i < n) {
+            int d = (int)((key[r] >> shift) & 255);
+            int pos = S.dprefix[d] + S.warp_cnt[w][d] + rank[r];
+            S.keys[pos] = key[r];
+            S.vals[pos] = iota ? (uint32_t)i : vin[i];
+        }
+    }
+    __syncthreads();
+    int cnt = (int)((n - tbase) < RS_TILE ? (n - tbase) : RS_TILE);
+#pragma unroll 4
+    for (int j = threadIdx.x; j < cnt; j += RS_THREADS) {
+        uint64_t k = S.keys[j];
+        int d = (int)((k >> shift) & 255);
+        int64_t dst = (int64_t)S.gbase[d] + (j - S.dprefix[d]);
+        kout[dst] = k;
+        vout[dst] = S.vals[j];
+    }
+}
+
+static int radix_sort_onesweep(cl2_ctx *ctx, const cl2_keygen &gen, uint64_t *keys0, uint64_t *keys1, uint32_t *vals0,
+                               uint32_t *vals1, int64_t n, int passes, uint64_t **kout, uint32_t **vout) {
+    int ntiles = (int)((n + RS_TILE - 1) / RS_TILE);
+    Scratch sc(ctx);
+    unsigned *ghist, *desc, *ticket;
+    CL2_TRY(sc.get(&ghist, (size_t)OS_MAXPASS * 256 + OS_MAXPASS));
+    CL2_TRY(sc.get(&desc, (size_t)passes * ntiles * 256));
+    ticket = ghist + OS_MAXPASS * 256;
+    CL2_CUDA(ctx, cudaMemsetAsync(ghist, 0, ((size_t)OS_MAXPASS * 256 + OS_MAXPASS) * 4, ctx->stream));
+    CL2_CUDA(ctx, cudaMemsetAsync(desc, 0, (size_t)passes * ntiles * 256 * 4, ctx->stream));
+    static bool attr_set = false;
+    if (!attr_set) {
+        CL2_CUDA(ctx, cudaFuncSetAttribute(k_os_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
+        attr_set = true;
+    }
+    {
+        FamTimer t(ctx, FAM_SORT_HIST, 8.0 * (double)n, 2);
+        int grid = ctx->sm_count * 8;
+        int need = cl2_grid(n, 256);
+        k_os_hist<<<need < grid ? need : grid, 256, 0, ctx->stream>>>(keys0, gen, n, passes, ghist);
+        k_os_prefix<<<passes, 256, 0, ctx->stream>>>(ghist);
+    }
+    uint64_t *kin = keys0, *ko = keys1;
+    uint32_t *vi = vals0, *vo = vals1;
+    cl2_keygen none;
+    none.kind = CL2_KEY_ARRAY;
+    for (int p = 0; p < passes; p++) {
+        {
+            FamTimer t(ctx, FAM_SORT_SCATTER, 24.0 * (double)n);
+            k_os_pass<<<ntiles, RS_THREADS, sizeof(RsSmem), ctx->stream>>>(kin, p == 0 ? gen : none, vi, ko, vo, n, p * 8, ghist + p * 256,
+                                                                            desc + (size_t)p * ntiles * 256, ticket + p,
+                                                                            p == 0 ? 1 : 0);
+        }
+        uint64_t *tk = kin; kin = ko; ko = tk;
+        uint32_t *tv = vi; vi = vo; vo = tv;
+    }
+    CL2_CUDA(ctx, cudaGetLastError());
+    *kout = kin;
+    *vout = vi;
+    return CL2_OK;
+}
+
+__global__ void __launch_bounds__(256) k_os_materialise(const cl2_keygen gen, uint64_t *__restrict__ keys, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = os_key(gen, keys, i);
+}
+
+int cl2_radix_sort_gen(cl2_ctx *ctx, const cl2_keygen &gen, uint64_t *keys0, uint64_t *keys1, uint32_t *vals0,
+                       uint32_t *vals1, int64_t n, int nbits, uint64_t **kout, uint32_t **vout) {
+    *kout = keys0;
+    *vout = vals0;
+    if (n <= 0) return CL2_OK;
+    if (nbits < 1) nbits = 1;
+    int passes = (nbits + 7) / 8;
+    if (n < (int64_t)OS_VAL && passes <= OS_MAXPASS && !getenv("CL2_SORT_3KERNEL"))
+        return radix_sort_onesweep(ctx, gen, keys0, keys1, vals0, vals1, n, passes, kout, vout);
+    if (gen.kind != CL2_KEY_ARRAY) {
+        FamTimer t(ctx, FAM_KEYGEN, 16.0 * (double)n);
+        k_os_materialise<<<cl2_grid(n, 256), 256, 0, ctx->stream>>>(gen, keys0, n);
+    }
+    return cl2_radix_sort_pairs(ctx, keys0, keys1, vals0, vals1, n, nbits, kout, vout);
+}
+
 int cl2_radix_sort_pairs(cl2_ctx *ctx, uint64_t *keys0, uint64_t *keys1, uint32_t *vals0, uint32_t *vals1, int64_t n,
                          int nbits, uint64_t **kout, uint32_t **vout) {
     *kout = keys0;
@@ -243,6 +455,11 @@ int cl2_radix_sort_pairs(cl2_ctx *ctx, uint64_t *keys0, uint64_t *keys1, uint32_
     if (n <= 0) return CL2_OK;
     if (nbits < 1) nbits = 1;
     int passes = (nbits + 7) / 8;
+    if (n < (int64_t)OS_VAL && passes <= OS_MAXPASS && !getenv("CL2_SORT_3KERNEL")) {
+        cl2_keygen none;
+        none.kind = CL2_KEY_ARRAY;
+        return radix_sort_onesweep(ctx, none, keys0, keys1, vals0, vals1, n, passes, kout, vout);
+    }
     int ntiles = (int)((n + RS_TILE - 1) / RS_TILE);
     Scratch sc(ctx);
     int32_t *tilehist;

@@ -67,7 +67,13 @@ def test_est_cis_matches_oracle_and_reference_fields():
         assert np.array_equal(np.asarray(cols[names[f]], dtype=np.float64), e["values"][:, j]), f
 
 
-def test_full_cis_host_path_reproduces_reference_txt():
+import pytest
+
+
+@pytest.mark.parametrize("dedup_first", [True, False])
+def test_full_cis_host_path_reproduces_reference_txt(dedup_first):
+    """dedup_first=True is the reference's order (combine/dedup, then test); False is the product's (test every
+    candidate, drop repeated coordinates among the survivors) -- both must give the reference's rows."""
     g, files = golden_cis_files()
     tot = int(g["tot"])
     for name, eps, minPts, hic in (("default_txt", [200, 500, 1000], [5], False), ("hic_txt", [200, 500, 1000], [5], True)):
@@ -79,10 +85,12 @@ def test_full_cis_host_path_reproduces_reference_txt():
                     lab, ncl = (oracle.cdbscan2 if hic else oracle.block_dbscan)(xy, ep, mp)
                     bbox, _ = oracle.cluster_bbox(xy, lab, ncl)
                     per_pass.append(bbox[hostops.cis_candidate_mask(bbox)])
-            cands = hostops.combine_unique(per_pass)
+            cands = hostops.combine_unique(per_pass) if dedup_first else np.concatenate(per_pass)
             cands = cands[hostops.cis_distance(cands) > 0]
             span = float(xy[:, 1].max() - xy[:, 0].min())
             cols = hostops.est_cis(FakeIndex(xy), cands, len(xy), span, tot, max(minPts), hic=hic)
+            if not dedup_first:
+                cols = hostops.take(cols, hostops.first_occurrence(cols["coords"]))
             final = hostops.select_twice(cols, hostops.mark_sig_cis(cols, hic=hic))
             final = hostops.scipy_pvalues(final, len(xy), float(len(xy)) / span, cis=True)
             loops.extend(cols_to_loops(tuple(k.split("-")), final, cis=True))
@@ -105,6 +113,12 @@ def test_full_trans_host_path_reproduces_reference_txt():
         cands = _combine_across_passes(per_pass)
         span = float(xy[:, 1].max() - xy[:, 0].min())
         cols = hostops.est_trans(FakeIndex(xy), cands, len(xy), span, 10)
+        # the product's order: test everything, then drop coordinates seen in an earlier pass
+        allc = np.concatenate(per_pass)
+        pid = np.concatenate([np.full(len(c), i) for i, c in enumerate(per_pass)])
+        cols2 = hostops.est_trans(FakeIndex(xy), allc, len(xy), span, 10, pass_id=pid)
+        cols2 = hostops.take(cols2, hostops.first_occurrence(cols2["coords"], cols2.pop("pass_id")))
+        assert np.array_equal(cols2["coords"], cols["coords"]) and np.array_equal(cols2["nbp"], cols["nbp"])
         final = hostops.select_twice(cols, hostops.mark_sig_trans(cols))
         final = hostops.scipy_pvalues(final, len(xy), float(len(xy)) / span, cis=False)
         loops.extend(cols_to_loops(tuple(k.split("-")), final, cis=False))
@@ -176,3 +190,10 @@ def test_device_tail_functions_against_scipy_and_exact_values():
     # degenerate arguments the path produces (median background of 0)
     assert L.cl2_stat_poisson_sf(4.0, 0.0) == 0.0 == float(poisson.sf(4.0, 0.0))
     assert L.cl2_stat_binom_sf(4.0, 100.0, 0.0) == 0.0 == float(binom.sf(4.0, 100.0, 0.0))
+
+
+def test_first_occurrence_rules():
+    c = np.array([[1, 2, 3, 4], [5, 6, 7, 8], [1, 2, 3, 4], [1, 2, 3, 4], [9, 9, 9, 9]], dtype=np.int64)
+    assert hostops.first_occurrence(c).tolist() == [0, 1, 4]
+    # trans: duplicates inside the first pass that holds them survive, later passes are dropped
+    assert hostops.first_occurrence(c, np.array([0, 0, 0, 1, 1])).tolist() == [0, 1, 2, 4]
