@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--pets", type=float, default=100e6, help="PETs per GPU (default: the 100 M of configs[1])")
     ap.add_argument("--cpu-sample-pets", type=float, default=3.0e6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-timing", action="store_true", help="do not record per-kernel CUDA events in the timed steps")
     return ap.parse_args()
 
 
@@ -299,7 +300,7 @@ def main():
         dev_ms = ev0.elapsed_time(ev1)
         return shard.max_over_ranks(wall), dev_ms, clocks, fam, ctx.launch_count(), ctx.transfer_bytes()
 
-    wall, dev_ms, clocks, fam, launches, _ = timed(step_resident, args.warmup, args.steps, True)
+    wall, dev_ms, clocks, fam, launches, _ = timed(step_resident, args.warmup, args.steps, not args.no_kernel_timing)
     wall_e, _, clocks_e, _, _, xfer = timed(step_e2e, max(1, args.warmup - 2), args.steps, False)
     xfer = shard.allreduce_stats(np.array(xfer, dtype=np.int64))
     ex_steps = max(1, min(2, args.steps))

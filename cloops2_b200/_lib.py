@@ -80,6 +80,7 @@ SIGNATURES = {
     "cl2_points_extent": (ctypes.c_int, [_vp, _vp, _i64p]),
     "cl2_points_download": (ctypes.c_int, [_vp, _vp, _i64p]),
     "cl2_points_free": (None, [_vp, _vp]),
+    "cl2_points_drop_cache": (None, [_vp, _vp]),
     "cl2_block_dbscan": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _i32p, _i32p]),
     "cl2_cdbscan2": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _i32p, _i32p]),
     "cl2_cluster_bbox": (ctypes.c_int, [_vp, _vp, _i64p, _i64p]),
@@ -249,6 +250,11 @@ class Points:
             self.close()
         except Exception:
             pass
+
+    def drop_cache(self):
+        """Free the cached eps grid (the points stay resident)."""
+        if getattr(self, "h", None) and self.ctx.h:
+            self.ctx.lib.cl2_points_drop_cache(self.ctx.h, self.h)
 
     def extent(self):
         ext = np.zeros(4, dtype=np.int64)

@@ -70,6 +70,7 @@ def cis_chromosome(ctx, key, xy, tot, eps, minPts, cut=0, mcut=-1, hic=False, em
             c, s = cluster_pass(pts, ep, mp, hic=hic, cis=True)
             _log("Clustering %s and %s finished. Estimated %s candidate loops with %s PETs." % (key[0], key[1], len(c), int(s.sum())))
             per_pass.append(c)
+        pts.drop_cache()                      # the eps grid is only reusable inside the sweep
         t1 = time.perf_counter()
         # The reference merges the passes (combineLoops), drops distance <= cut and duplicates, then tests.  A
         # candidate's test result depends on its coordinates only, so the duplicates are removed AFTER the tests, on

@@ -30,6 +30,7 @@ def trans_pair(ctx, key, xy, eps, minPts, pts=None, exact=False):
             for mp in minPts:
                 c, _ = cluster_pass(pts, ep, mp, hic=False, cis=False)
                 per_pass.append(c)
+        pts.drop_cache()
         # combineLoops only (callTransLoops.py:230-234): coordinates already seen in an EARLIER pass are dropped,
         # duplicates inside one pass survive.  As on the cis path the de-duplication is applied after the tests.
         cands = np.concatenate(per_pass, axis=0) if len(per_pass) > 1 else per_pass[0]

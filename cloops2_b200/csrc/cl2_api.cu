@@ -276,6 +276,12 @@ void cl2_grid_free(cl2_ctx *ctx, cl2_grid_cache &g) {
     g = cl2_grid_cache();
 }
 
+extern "C" void cl2_points_drop_cache(cl2_ctx *ctx, cl2_points *pts) {
+    if (!ctx || !pts) return;
+    cudaSetDevice(ctx->device);
+    cl2_grid_free(ctx, pts->grid);
+}
+
 extern "C" void cl2_points_free(cl2_ctx *ctx, cl2_points *pts) {
     if (!ctx || !pts) return;
     cudaSetDevice(ctx->device);
