@@ -299,32 +299,52 @@ __global__ void __launch_bounds__(256) k_os_prefix(unsigned *__restrict__ ghist)
     ghist[blockIdx.x * 256 + threadIdx.x] = (unsigned)ex;
 }
 
-__global__ void __launch_bounds__(RS_THREADS) k_os_pass(const uint64_t *__restrict__ kin, const cl2_keygen gen,
-                                                         const uint32_t *__restrict__ vin,
-                                                         uint64_t *__restrict__ kout, uint32_t *__restrict__ vout,
-                                                         int64_t n, int shift, const unsigned *__restrict__ gprefix,
-                                                         unsigned *__restrict__ desc, unsigned *__restrict__ ticket,
-                                                         int iota) {
+#define OS_THREADS 512
+#define OS_WARPS (OS_THREADS / 32)
+#define OS_IPT 8
+#define OS_TILE (OS_THREADS * OS_IPT)
+
+struct OsSmem {
+    uint64_t keys[OS_TILE];
+    uint32_t vals[OS_TILE];
+    int warp_cnt[OS_WARPS][256];
+    int dprefix[256];
+    int gbase[256];
+};
+
+__global__ void __launch_bounds__(OS_THREADS, 2) k_os_pass(const uint64_t *__restrict__ kin, const cl2_keygen gen,
+                                                           const uint32_t *__restrict__ vin,
+                                                           uint64_t *__restrict__ kout, uint32_t *__restrict__ vout,
+                                                           int64_t n, int shift, const unsigned *__restrict__ gprefix,
+                                                           unsigned *__restrict__ desc, unsigned *__restrict__ ticket,
+                                                           int iota) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    RsSmem &S = *reinterpret_cast<RsSmem *>(smem_raw);
+    OsSmem &S = *reinterpret_cast<OsSmem *>(smem_raw);
     __shared__ unsigned s_tile;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&S.warp_cnt[0][0])[i] = 0;
+    for (int i = threadIdx.x; i < OS_WARPS * 256; i += OS_THREADS) (&S.warp_cnt[0][0])[i] = 0;
     __syncthreads();
     const unsigned tile = s_tile;
-    const int64_t tbase = (int64_t)tile * RS_TILE;
-    const int64_t wbase = tbase + (int64_t)w * (32 * RS_IPT);
-    uint64_t key[RS_IPT];
-    unsigned short rank[RS_IPT];
+    const int64_t tbase = (int64_t)tile * OS_TILE;
+    const int64_t wbase = tbase + (int64_t)w * (32 * OS_IPT);
+    uint64_t key[OS_IPT];
+    uint32_t val[OS_IPT];
+    unsigned short rank[OS_IPT];
     const unsigned lt = (1u << lane) - 1u;
+    // all global loads of the tile are issued up front (keys and row ids) so their latency overlaps the ranking
 #pragma unroll
-    for (int r = 0; r < RS_IPT; r++) {
+    for (int r = 0; r < OS_IPT; r++) {
         int64_t i = wbase + r * 32 + lane;
         key[r] = (i < n) ? os_key(gen, kin, i) : ~0ull;
     }
 #pragma unroll
-    for (int r = 0; r < RS_IPT; r++) {
+    for (int r = 0; r < OS_IPT; r++) {
+        int64_t i = wbase + r * 32 + lane;
+        val[r] = iota ? (uint32_t)i : ((i < n) ? vin[i] : 0u);
+    }
+#pragma unroll
+    for (int r = 0; r < OS_IPT; r++) {
         int64_t i = wbase + r * 32 + lane;
         bool valid = i < n;
         unsigned d = valid ? (unsigned)((key[r] >> shift) & 255) : (0x10000u | lane);
@@ -337,11 +357,11 @@ __global__ void __launch_bounds__(RS_THREADS) k_os_pass(const uint64_t *__restri
         __syncwarp();
     }
     __syncthreads();
-    {
+    int off = 0;
+    if (threadIdx.x < 256) {
         const int d = threadIdx.x;
-        int off = 0;
 #pragma unroll
-        for (int k = 0; k < RS_WARPS; k++) {
+        for (int k = 0; k < OS_WARPS; k++) {
             int c = S.warp_cnt[k][d];
             S.warp_cnt[k][d] = off;
             off += c;
@@ -357,26 +377,28 @@ __global__ void __launch_bounds__(RS_THREADS) k_os_pass(const uint64_t *__restri
             // else: predecessor has not published yet -- spin on the same descriptor
         }
         vd[(size_t)tile * 256 + d] = (excl + (unsigned)off) | OS_INC;
-        int tot;
-        int ex = block_excl_scan<RS_THREADS>(off, &tot);
-        S.dprefix[d] = ex;
         S.gbase[d] = (int)(gprefix[d] + excl);
+    }
+    {
+        int tot;
+        int ex = block_excl_scan<OS_THREADS>(off, &tot);
+        if (threadIdx.x < 256) S.dprefix[threadIdx.x] = ex;
     }
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < RS_IPT; r++) {
+    for (int r = 0; r < OS_IPT; r++) {
         int64_t i = wbase + r * 32 + lane;
         if (i < n) {
             int d = (int)((key[r] >> shift) & 255);
             int pos = S.dprefix[d] + S.warp_cnt[w][d] + rank[r];
             S.keys[pos] = key[r];
-            S.vals[pos] = iota ? (uint32_t)i : vin[i];
+            S.vals[pos] = val[r];
         }
     }
     __syncthreads();
-    int cnt = (int)((n - tbase) < RS_TILE ? (n - tbase) : RS_TILE);
+    int cnt = (int)((n - tbase) < OS_TILE ? (n - tbase) : OS_TILE);
 #pragma unroll 4
-    for (int j = threadIdx.x; j < cnt; j += RS_THREADS) {
+    for (int j = threadIdx.x; j < cnt; j += OS_THREADS) {
         uint64_t k = S.keys[j];
         int d = (int)((k >> shift) & 255);
         int64_t dst = (int64_t)S.gbase[d] + (j - S.dprefix[d]);
@@ -387,7 +409,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_os_pass(const uint64_t *__restri
 
 static int radix_sort_onesweep(cl2_ctx *ctx, const cl2_keygen &gen, uint64_t *keys0, uint64_t *keys1, uint32_t *vals0,
                                uint32_t *vals1, int64_t n, int passes, uint64_t **kout, uint32_t **vout) {
-    int ntiles = (int)((n + RS_TILE - 1) / RS_TILE);
+    int ntiles = (int)((n + OS_TILE - 1) / OS_TILE);
     Scratch sc(ctx);
     unsigned *ghist, *desc, *ticket;
     CL2_TRY(sc.get(&ghist, (size_t)OS_MAXPASS * 256 + OS_MAXPASS));
@@ -397,7 +419,7 @@ static int radix_sort_onesweep(cl2_ctx *ctx, const cl2_keygen &gen, uint64_t *ke
     CL2_CUDA(ctx, cudaMemsetAsync(desc, 0, (size_t)passes * ntiles * 256 * 4, ctx->stream));
     static bool attr_set = false;
     if (!attr_set) {
-        CL2_CUDA(ctx, cudaFuncSetAttribute(k_os_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
+        CL2_CUDA(ctx, cudaFuncSetAttribute(k_os_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OsSmem)));
         attr_set = true;
     }
     {
@@ -414,7 +436,7 @@ static int radix_sort_onesweep(cl2_ctx *ctx, const cl2_keygen &gen, uint64_t *ke
     for (int p = 0; p < passes; p++) {
         {
             FamTimer t(ctx, FAM_SORT_SCATTER, 24.0 * (double)n);
-            k_os_pass<<<ntiles, RS_THREADS, sizeof(RsSmem), ctx->stream>>>(kin, p == 0 ? gen : none, vi, ko, vo, n, p * 8, ghist + p * 256,
+            k_os_pass<<<ntiles, OS_THREADS, sizeof(OsSmem), ctx->stream>>>(kin, p == 0 ? gen : none, vi, ko, vo, n, p * 8, ghist + p * 256,
                                                                             desc + (size_t)p * ntiles * 256, ticket + p,
                                                                             p == 0 ? 1 : 0);
         }
