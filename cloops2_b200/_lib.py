@@ -92,6 +92,9 @@ SIGNATURES = {
     "cl2_loop_core": (ctypes.c_int, [_vp, _vp, _i64p, ctypes.c_int64, ctypes.c_int32, _i64p, _f64p]),
     "cl2_loop_tests": (ctypes.c_int, [_vp, _vp, _i64p, _i64p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
                                       ctypes.c_double, _f64p]),
+    "cl2_est_loops": (ctypes.c_int, [_vp, _vp, _i64p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                     ctypes.c_int32, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                     _i64p, _i64p, _i64p, _f64p, _f64p]),
     "cl2_sel_sig_loops": (ctypes.c_int, [_i64p, _f64p, ctypes.c_int64, _i64p, _i64p]),
     "cl2_stat_poisson_sf": (ctypes.c_double, [ctypes.c_double, ctypes.c_double]),
     "cl2_stat_binom_sf": (ctypes.c_double, [ctypes.c_double, ctypes.c_double, ctypes.c_double]),
@@ -339,6 +342,23 @@ class Index:
         self.ctx.check(self.ctx.lib.cl2_loop_core(self.ctx.h, self.h, _ptr(loops, _i64p), L, mode, _ptr(core, _i64p),
                                                   _ptr(hyp, _f64p)), "cl2_loop_core")
         return core, hyp
+
+    def est_loops(self, loops, rpb, minPts, mode=MODE_CIS, win=5, hic=False, countDiffCut=20, pseudo=1, peakPcut=1e-5):
+        """Counting + statistics + the reference's filter cascade on the device; returns only the survivors:
+        (sel int64[K] indices into loops, core int64[K,4], hyp float64[K], stats float64[K,13])."""
+        loops = np.ascontiguousarray(loops, dtype=np.int64).reshape(-1, 4)
+        L = loops.shape[0]
+        sel = np.empty(L, dtype=np.int64)
+        core = np.empty((L, 4), dtype=np.int64)
+        hyp = np.empty(L, dtype=np.float64)
+        stats = np.empty((L, 13), dtype=np.float64)
+        n = ctypes.c_int64(0)
+        self.ctx.check(self.ctx.lib.cl2_est_loops(self.ctx.h, self.h, _ptr(loops, _i64p), L, win, mode, int(minPts),
+                                                  1 if hic else 0, float(countDiffCut), float(pseudo), float(peakPcut),
+                                                  float(rpb), ctypes.byref(n), _ptr(sel, _i64p), _ptr(core, _i64p),
+                                                  _ptr(hyp, _f64p), _ptr(stats, _f64p)), "cl2_est_loops")
+        k = n.value
+        return sel[:k], core[:k], hyp[:k], stats[:k]
 
     def loop_tests(self, loops, core, rpb, win=5, mode=MODE_CIS):
         """stats float64[L,13] -- phase 2 (see include/cl2.h)."""

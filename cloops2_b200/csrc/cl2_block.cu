@@ -202,6 +202,30 @@ __global__ void __launch_bounds__(256) k_keep_list(const uint8_t *__restrict__ k
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < ncells && keep[c]) list[pos[c]] = c;
 }
+#define CELLSTAT_SERIAL_MAX 48
+// kept cells with few points (the common case): one thread per cell, consecutive threads read consecutive segments
+__global__ void __launch_bounds__(256) k_block_cellstat_small(const int2 *__restrict__ sxy,
+                                                               const int32_t *__restrict__ cstart,
+                                                               const int32_t *__restrict__ list,
+                                                               CellStat *__restrict__ st, int32_t nkept) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nkept) return;
+    int c = list[k];
+    int b = cstart[c], e = cstart[c + 1];
+    if (e - b > CELLSTAT_SERIAL_MAX) return;
+    long long sx = 0, sy = 0;
+    int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
+    for (int i = b; i < e; i++) {
+        int2 p = sxy[i];
+        sx += p.x; sy += p.y;
+        xmin = min(xmin, p.x); xmax = max(xmax, p.x);
+        ymin = min(ymin, p.y); ymax = max(ymax, p.y);
+    }
+    CellStat s;
+    s.sx = sx; s.sy = sy; s.xmin = xmin; s.xmax = xmax; s.ymin = ymin; s.ymax = ymax;
+    st[c] = s;
+}
+// crowded cells: one warp per cell
 __global__ void __launch_bounds__(256) k_block_cellstat_list(const int2 *__restrict__ sxy,
                                                               const int32_t *__restrict__ cstart,
                                                               const int32_t *__restrict__ list,
@@ -211,6 +235,7 @@ __global__ void __launch_bounds__(256) k_block_cellstat_list(const int2 *__restr
     if (k >= nkept) return;
     int c = list[k];
     int b = cstart[c], e = cstart[c + 1];
+    if (e - b <= CELLSTAT_SERIAL_MAX) return;
     long long sx = 0, sy = 0;
     int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
     for (int i = b + lane; i < e; i += 32) {
@@ -724,8 +749,10 @@ extern "C" int cl2_block_dbscan(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int3
         CL2_CUDA(ctx, cudaMemsetAsync(core, 0, (size_t)ncells, s));
         CL2_CUDA(ctx, cudaMemsetAsync(nheavy, 0, 4, s));
         {
-            FamTimer t(ctx, FAM_CELLSTAT, 8.0 * (double)n);
-            k_block_cellstat_list<<<cl2_grid((int64_t)nkept * 32, 256), 256, 0, s>>>(g.sxy, g.cstart, list, st, nkept);
+            FamTimer t(ctx, FAM_CELLSTAT, 8.0 * (double)n, 2);
+            k_block_cellstat_small<<<cl2_grid(nkept, 256), 256, 0, s>>>(g.sxy, g.cstart, list, st, nkept);
+            if (g.maxcnt > CELLSTAT_SERIAL_MAX)
+                k_block_cellstat_list<<<cl2_grid((int64_t)nkept * 32, 256), 256, 0, s>>>(g.sxy, g.cstart, list, st, nkept);
         }
         {
             FamTimer t(ctx, FAM_ADJ, 8.0 * (double)n);

@@ -135,7 +135,7 @@ __device__ __forceinline__ int warp_sum(int v) {
 }
 
 // |P(I)|  (queryPeak, ds.py:176-182)
-__device__ int64_t count_peak(const int2 *__restrict__ byx, const int2 *__restrict__ byy, int64_t n, const Iv &I,
+__device__ __noinline__ int64_t count_peak(const int2 *__restrict__ byx, const int2 *__restrict__ byy, int64_t n, const Iv &I,
                               int lane) {
     Range rx = range_of(byx, n, I), ry = range_of(byy, n, I);
     int c = 0;
@@ -147,7 +147,7 @@ __device__ int64_t count_peak(const int2 *__restrict__ byx, const int2 *__restri
 }
 
 // |P(I1)| and |P(I1) & P(I2)|  (queryLoop, ds.py:184-190)
-__device__ void count_pair(const int2 *__restrict__ byx, const int2 *__restrict__ byy, int64_t n, const Iv &I1,
+__device__ __noinline__ void count_pair(const int2 *__restrict__ byx, const int2 *__restrict__ byy, int64_t n, const Iv &I1,
                            const Iv &I2, int lane, int64_t *n1, int64_t *n12) {
     Range rx = range_of(byx, n, I1), ry = range_of(byy, n, I1);
     int c1 = 0, c12 = 0;
@@ -170,18 +170,29 @@ struct WarpAcc {
     int na[CNT_MAXW];
     int nb[CNT_MAXW];
     int nab[CNT_MAXW * CNT_MAXW];
-    long long alo[CNT_MAXW], ahi[CNT_MAXW], blo[CNT_MAXW], bhi[CNT_MAXW];
+    // window bounds as int32 (coordinates are < 2^31-1, so clamping the bounds into [0, INT_MAX] changes nothing)
+    int alo[CNT_MAXW], ahi[CNT_MAXW], blo[CNT_MAXW], bhi[CNT_MAXW];
+    int sa_lo, sa_hi, sb_lo, sb_hi;     // spans covering all a- / b-windows
 };
 
-// membership masks of one PET against the 2*win a-windows and b-windows (getPerRegions, callCisLoops.py:191-198)
+__device__ __forceinline__ int clamp_i32(long long v) { return v < 0 ? 0 : (v > (long long)INT_MAX ? INT_MAX : (int)v); }
+
+// bit t set iff lo[t] <= c <= hi[t]
+__device__ __forceinline__ unsigned coord_mask(const int *__restrict__ lo, const int *__restrict__ hi, int W, int c) {
+    unsigned m = 0;
+#pragma unroll 2
+    for (int t = 0; t < W; t++) m |= ((c >= lo[t] && c <= hi[t]) ? 1u : 0u) << t;
+    return m;
+}
+
+// membership masks of one PET against the 2*win a-windows and b-windows (getPerRegions, callCisLoops.py:191-198).
+// A coordinate outside a span cannot be in any window of that set, which skips most of the comparisons.
 __device__ __forceinline__ void window_masks(const WarpAcc &A, int W, int x, int y, unsigned *ma, unsigned *mb) {
     unsigned a = 0, b = 0;
-    for (int t = 0; t < W; t++) {
-        bool ia = ((long long)x >= A.alo[t] && (long long)x <= A.ahi[t]) || ((long long)y >= A.alo[t] && (long long)y <= A.ahi[t]);
-        bool ib = ((long long)x >= A.blo[t] && (long long)x <= A.bhi[t]) || ((long long)y >= A.blo[t] && (long long)y <= A.bhi[t]);
-        a |= (ia ? 1u : 0u) << t;
-        b |= (ib ? 1u : 0u) << t;
-    }
+    if (x >= A.sa_lo && x <= A.sa_hi) a |= coord_mask(A.alo, A.ahi, W, x);
+    if (y >= A.sa_lo && y <= A.sa_hi) a |= coord_mask(A.alo, A.ahi, W, y);
+    if (x >= A.sb_lo && x <= A.sb_hi) b |= coord_mask(A.blo, A.bhi, W, x);
+    if (y >= A.sb_lo && y <= A.sb_hi) b |= coord_mask(A.blo, A.bhi, W, y);
     *ma = a;
     *mb = b;
 }
@@ -257,10 +268,13 @@ __device__ void loop_windows(const int2 *__restrict__ byx, const int2 *__restric
         if (bl < 0) bl = 0;
         if (bh < 0) bh = 0;
         Iv a = iv4(al, ah), b = iv4(bl, bh);
-        S.alo[lane] = a.lo; S.ahi[lane] = a.hi; S.blo[lane] = b.lo; S.bhi[lane] = b.hi;
+        S.alo[lane] = clamp_i32(a.lo); S.ahi[lane] = clamp_i32(a.hi);
+        S.blo[lane] = clamp_i32(b.lo); S.bhi[lane] = clamp_i32(b.hi);
     }
     __syncwarp();
     // spans covering all a-windows / all b-windows (window centres are monotone in i)
+    if (lane == 0) { S.sa_lo = S.alo[0]; S.sa_hi = S.ahi[W - 1]; S.sb_lo = S.blo[0]; S.sb_hi = S.bhi[W - 1]; }
+    __syncwarp();
     Iv SA = {S.alo[0], S.ahi[W - 1]}, SB = {S.blo[0], S.bhi[W - 1]};
     Range rxa = range_of(byx, n, SA), rya = range_of(byy, n, SA);
     Range rxb = range_of(byx, n, SB), ryb = range_of(byy, n, SB);
@@ -388,23 +402,12 @@ __device__ double warp_median(WarpVals &S, int m, int lane) {
 }
 
 #define CL2_NSTAT 13
-// phase 2: permuted-window background, enrichment tests and anchor tests for loops that passed the first filters.
-// stats[k] = mrabs, mbps, fdr, poisson sf, binomial sf, px, esx, py, esy, count_x, wide_x, count_y, wide_y
-__global__ void __launch_bounds__(CNT_WARPS * 32) k_loop_tests(const int2 *__restrict__ byx, const int2 *__restrict__ byy,
-                                                                int64_t n, const longlong4 *__restrict__ loops,
-                                                                const long long *__restrict__ core, int64_t L, int win,
-                                                                int mode, double rpb, double *__restrict__ stats) {
-    __shared__ WarpAcc acc[CNT_WARPS];
-    __shared__ WarpVals vals[CNT_WARPS];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t k = (int64_t)blockIdx.x * CNT_WARPS + w;
-    if (k >= L) return;
-    const longlong4 lp = loops[k];
-    const long long xs = lp.x, xe = lp.y, ys = lp.z, ye = lp.w;
-    const double ra = (double)core[4 * k], rb = (double)core[4 * k + 1], rab = (double)core[4 * k + 2];
+// Permuted-window background, enrichment tests and anchor tests of one loop (one warp); results into o[13] (shared):
+// mrabs, mbps, fdr, poisson sf, binomial sf, px, esx, py, esy, count_x, wide_x, count_y, wide_y
+__device__ void loop_tests_warp(const int2 *__restrict__ byx, const int2 *__restrict__ byy, int64_t n, long long xs,
+                                long long xe, long long ys, long long ye, double ra, double rb, double rab, int win,
+                                int mode, double rpb, WarpAcc &S, WarpVals &V, int lane, double *o) {
     const int W = 2 * win, m = W * W;
-    WarpAcc &S = acc[w];
-    WarpVals &V = vals[w];
     loop_windows(byx, byy, n, xs, xe, ys, ye, win, lane, S);
     int64_t cx, wx, cy, wy;
     loop_anchor(byx, byy, n, xs, xe, lane, &cx, &wx);
@@ -436,7 +439,6 @@ __global__ void __launch_bounds__(CNT_WARPS * 32) k_loop_tests(const int2 *__res
     if (mode == CL2_MODE_CIS) mbps = warp_median(V, m, lane);
     else mbps = np_pairwise_sum(V.v, m) / (double)m;
     double fdr = (double)gt / (double)m;
-    double *o = stats + CL2_NSTAT * k;
     if (lane == 0) {
         o[0] = mrabs; o[1] = mbps; o[2] = fdr;
         o[3] = cl2_poisson_sf_ge(rab, mrabs);                                            // :329
@@ -453,6 +455,99 @@ __global__ void __launch_bounds__(CNT_WARPS * 32) k_loop_tests(const int2 *__res
         o[lane == 2 ? 5 : 7] = cl2_poisson_sf_ge(count, c);
         o[lane == 2 ? 6 : 8] = count / c;
     }
+    __syncwarp();
+}
+
+// phase 2 as a separate launch (cl2_loop_tests)
+__global__ void __launch_bounds__(CNT_WARPS * 32) k_loop_tests(const int2 *__restrict__ byx, const int2 *__restrict__ byy,
+                                                                int64_t n, const longlong4 *__restrict__ loops,
+                                                                const long long *__restrict__ core, int64_t L, int win,
+                                                                int mode, double rpb, double *__restrict__ stats) {
+    __shared__ WarpAcc acc[CNT_WARPS];
+    __shared__ WarpVals vals[CNT_WARPS];
+    __shared__ double ost[CNT_WARPS][CL2_NSTAT];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t k = (int64_t)blockIdx.x * CNT_WARPS + w;
+    if (k >= L) return;
+    const longlong4 lp = loops[k];
+    loop_tests_warp(byx, byy, n, lp.x, lp.y, lp.z, lp.w, (double)core[4 * k], (double)core[4 * k + 1],
+                    (double)core[4 * k + 2], win, mode, rpb, acc[w], vals[w], lane, ost[w]);
+    if (lane < CL2_NSTAT) stats[CL2_NSTAT * k + lane] = ost[w][lane];
+}
+
+// Whole estLoopSig arithmetic for one candidate per warp, including the reference's filter cascade
+// (cis callCisLoops.py:282-347, trans callTransLoops.py:127-139): only survivors are written, flag[k] marks them.
+__global__ void __launch_bounds__(CNT_WARPS * 32) k_est_loops(const int2 *__restrict__ byx, const int2 *__restrict__ byy,
+                                                               int64_t n, const longlong4 *__restrict__ loops, int64_t L,
+                                                               int win, int mode, int minPts, int hic, double cdc,
+                                                               double pseudo, double peakPcut, double rpb,
+                                                               long long *__restrict__ core_out,
+                                                               double *__restrict__ hyp_out,
+                                                               double *__restrict__ stats_out,
+                                                               int32_t *__restrict__ flag) {
+    __shared__ WarpAcc acc[CNT_WARPS];
+    __shared__ WarpVals vals[CNT_WARPS];
+    __shared__ double ost[CNT_WARPS][CL2_NSTAT];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t k = (int64_t)blockIdx.x * CNT_WARPS + w;
+    if (k >= L) return;
+    const longlong4 lp = loops[k];
+    const long long xs = lp.x, xe = lp.y, ys = lp.z, ye = lp.w;
+    const double la = (double)(xe - xs), lb = (double)(ye - ys);
+    const bool cis = mode == CL2_MODE_CIS;
+    bool keep = !(la / lb > cdc || lb / la > cdc);                                      // :282-286 / trans :135-139
+    if (keep) {
+        int64_t c[4];
+        loop_core(byx, byy, n, xs, xe, ys, ye, mode, lane, c);
+        const double ra = (double)c[0], rb = (double)c[1], rab = (double)c[2];
+        if (c[2] < minPts) keep = false;                                               // :290 / trans :127
+        if (cis && (c[0] == c[2] || c[1] == c[2])) keep = false;                       // :293
+        if (ra / rb > cdc || rb / ra > cdc) keep = false;                              // :296 / trans :133
+        double lower = (double)c[3];
+        double p2ll = rab / (lower > pseudo ? lower : pseudo);                         // :306
+        if (cis && hic && p2ll < 1.0) keep = false;                                    // :307
+        double hyp = 0.0;
+        if (keep) {
+            if (lane == 0) hyp = cl2_hypergeom_sf_ge(rab, (double)n, ra, rb);          // :310
+            hyp = __shfl_sync(0xffffffffu, hyp, 0);
+            if (cis && fmax(1e-300, hyp) > 1e-2) keep = false;                         // :311
+        }
+        if (keep) {
+            double *o = ost[w];
+            loop_tests_warp(byx, byy, n, xs, xe, ys, ye, ra, rb, rab, win, mode, rpb, acc[w], vals[w], lane, o);
+            if (cis) {
+                double mrabs = o[0], fdr = o[2];
+                if (mrabs >= rab || fdr >= 0.1) keep = false;                          // :322
+                double es = rab / (mrabs > pseudo ? mrabs : pseudo);                   // :325
+                if (es < 1.0) keep = false;
+                if (!hic && !(fmax(1e-300, o[5]) < peakPcut && fmax(1e-300, o[7]) < peakPcut)) keep = false;   // :347
+            }
+            if (keep) {
+                if (lane < 4) core_out[4 * k + lane] = c[lane];
+                if (lane == 0) hyp_out[k] = hyp;
+                if (lane < CL2_NSTAT) stats_out[CL2_NSTAT * k + lane] = o[lane];
+            }
+        }
+    }
+    if (lane == 0) flag[k] = keep ? 1 : 0;
+}
+
+// gather the surviving rows (flag set; pos = exclusive scan of the flags) into dense arrays, order preserved
+__global__ void __launch_bounds__(256) k_est_compact(const int32_t *__restrict__ pos, const longlong4 *__restrict__ loops,
+                                                      int64_t L, const long long *__restrict__ core,
+                                                      const double *__restrict__ hyp, const double *__restrict__ stats,
+                                                      long long *__restrict__ sel, long long *__restrict__ core_c,
+                                                      double *__restrict__ hyp_c, double *__restrict__ stats_c) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= L) return;
+    int p = pos[k];
+    bool kept = (k + 1 < L) ? (pos[k + 1] != p) : (sel[-1] != (long long)p);   // sel[-1] holds the total
+    (void)loops;
+    if (!kept) return;
+    sel[p] = k;
+    for (int j = 0; j < 4; j++) core_c[4 * (int64_t)p + j] = core[4 * k + j];
+    hyp_c[p] = hyp[k];
+    for (int j = 0; j < CL2_NSTAT; j++) stats_c[CL2_NSTAT * (int64_t)p + j] = stats[CL2_NSTAT * k + j];
 }
 
 extern "C" int cl2_loop_counts(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops, int64_t L, int32_t win, int32_t mode,
@@ -543,6 +638,66 @@ extern "C" int cl2_loop_tests(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops
     ctx->h2d_bytes += L * 64;
     ctx->d2h_bytes += L * CL2_NSTAT * 8;
     CL2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CL2_CUDA(ctx, cudaGetLastError());
+    return CL2_OK;
+}
+
+extern "C" int cl2_est_loops(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops, int64_t L, int32_t win, int32_t mode,
+                             int32_t minPts, int32_t hic, double countDiffCut, double pseudo, double peakPcut,
+                             double rpb, int64_t *n_out, int64_t *sel, int64_t *core, double *hyp, double *stats) {
+    if (!ctx || !idx || !n_out || L < 0 || (L > 0 && (!loops || !sel || !core || !hyp || !stats)))
+        return cl2_fail(ctx, CL2_ERR_ARG, "cl2_est_loops: bad argument");
+    if (win < 1 || 2 * win > CNT_MAXW) return cl2_fail(ctx, CL2_ERR_ARG, "cl2_est_loops: win must be in 1..8");
+    if (mode != CL2_MODE_CIS && mode != CL2_MODE_TRANS) return cl2_fail(ctx, CL2_ERR_ARG, "cl2_est_loops: bad mode");
+    *n_out = 0;
+    if (L == 0) return CL2_OK;
+    if (L >= (int64_t)INT32_MAX) return cl2_fail(ctx, CL2_ERR_RANGE, "cl2_est_loops: too many loops in one call");
+    CL2_CUDA(ctx, cudaSetDevice(ctx->device));
+    Scratch sc(ctx);
+    longlong4 *d_loops;
+    long long *d_core, *d_sel, *d_core_c;
+    double *d_hyp, *d_stats, *d_hyp_c, *d_stats_c;
+    int32_t *d_flag;
+    int64_t *d_total;
+    CL2_TRY(sc.get(&d_loops, (size_t)L));
+    CL2_TRY(sc.get(&d_core, (size_t)L * 4));
+    CL2_TRY(sc.get(&d_hyp, (size_t)L));
+    CL2_TRY(sc.get(&d_stats, (size_t)L * CL2_NSTAT));
+    CL2_TRY(sc.get(&d_flag, (size_t)L));
+    CL2_TRY(sc.get(&d_total, 2));
+    CL2_CUDA(ctx, cudaMemcpyAsync(d_loops, loops, (size_t)L * 32, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h2d_bytes += L * 32;
+    {
+        FamTimer t(ctx, FAM_COUNT, 0.0);
+        k_est_loops<<<cl2_grid(L, CNT_WARPS), CNT_WARPS * 32, 0, ctx->stream>>>(idx->byx, idx->byy, idx->n, d_loops, L, win, mode,
+                                                                                minPts, hic, countDiffCut, pseudo, peakPcut, rpb,
+                                                                                d_core, d_hyp, d_stats, d_flag);
+    }
+    CL2_TRY(cl2_exclusive_scan_i32(ctx, d_flag, L, d_total));
+    int64_t nk = 0;
+    CL2_TRY(cl2_read_i64(ctx, d_total, &nk));
+    *n_out = nk;
+    if (nk > 0) {
+        // d_selbuf[0] carries the total so the compaction kernel can tell whether the last row survived
+        long long *d_selbuf;
+        CL2_TRY(sc.get(&d_selbuf, (size_t)nk + 1));
+        d_sel = d_selbuf + 1;
+        CL2_TRY(sc.get(&d_core_c, (size_t)nk * 4));
+        CL2_TRY(sc.get(&d_hyp_c, (size_t)nk));
+        CL2_TRY(sc.get(&d_stats_c, (size_t)nk * CL2_NSTAT));
+        CL2_CUDA(ctx, cudaMemcpyAsync(d_selbuf, d_total, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        {
+            FamTimer t(ctx, FAM_COUNT, 0.0);
+            k_est_compact<<<cl2_grid(L, 256), 256, 0, ctx->stream>>>(d_flag, d_loops, L, d_core, d_hyp, d_stats, d_sel, d_core_c,
+                                                                     d_hyp_c, d_stats_c);
+        }
+        CL2_CUDA(ctx, cudaMemcpyAsync(sel, d_sel, (size_t)nk * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CL2_CUDA(ctx, cudaMemcpyAsync(core, d_core_c, (size_t)nk * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        CL2_CUDA(ctx, cudaMemcpyAsync(hyp, d_hyp_c, (size_t)nk * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CL2_CUDA(ctx, cudaMemcpyAsync(stats, d_stats_c, (size_t)nk * CL2_NSTAT * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->d2h_bytes += nk * (8 + 32 + 8 + CL2_NSTAT * 8);
+        CL2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     CL2_CUDA(ctx, cudaGetLastError());
     return CL2_OK;
 }

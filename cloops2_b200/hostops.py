@@ -128,6 +128,14 @@ def est_cis(index, cands, N, span, tot, minPts, hic=False, pseudo=1, peakPcut=1e
     cols = _empty_cols()
     if L == 0:
         return cols
+    if hasattr(index, "est_loops"):
+        # fused device path: counting, statistics and the filter cascade below all run in one kernel; only the
+        # survivors come back (the step-by-step path that follows is the same arithmetic, kept for small inputs)
+        rpb = float(N) / span
+        sel, core, hyp, st = index.est_loops(cands, rpb, minPts, mode=_lib.MODE_CIS, win=win, hic=hic,
+                                             countDiffCut=countDiffCut, pseudo=pseudo, peakPcut=peakPcut)
+        cols = _cols_from_stats(cands[sel], core, hyp, st, pseudo, tot)
+        return scipy_pvalues(cols, N, rpb, cis=True) if exact else cols
     la = (cands[:, 1] - cands[:, 0])
     lb = (cands[:, 3] - cands[:, 2])
     keep = ~((la / lb > countDiffCut) | (lb / la > countDiffCut))                    # :282-286
@@ -177,6 +185,14 @@ def est_trans(index, cands, N, span, minPts, pseudo=1, countDiffCut=10, win=5, e
         if pass_id is not None:
             cols["pass_id"] = np.zeros(0, dtype=np.int64)
         return cols
+    if hasattr(index, "est_loops"):
+        rpb = float(N) / span
+        sel, core, hyp, st = index.est_loops(cands, rpb, minPts, mode=_lib.MODE_TRANS, win=win,
+                                             countDiffCut=countDiffCut, pseudo=pseudo)
+        cols = _cols_from_stats(cands[sel], core, hyp, st, pseudo, N)
+        if pass_id is not None:
+            cols["pass_id"] = np.asarray(pass_id)[sel]
+        return scipy_pvalues(cols, N, rpb, cis=False) if exact else cols
     core, hyp = index.loop_core(cands, mode=_lib.MODE_TRANS)
     ra, rb, rab, lower = core[:, 0], core[:, 1], core[:, 2], core[:, 3]
     la, lb = cands[:, 1] - cands[:, 0], cands[:, 3] - cands[:, 2]
@@ -217,6 +233,20 @@ def _threaded(fn, *arrays):
     with ThreadPoolExecutor(nthr) as ex:
         parts = list(ex.map(lambda i: fn(*[a[cuts[i]:cuts[i + 1]] for a in arrays]), range(nthr)))
     return np.concatenate(parts)
+
+
+def _cols_from_stats(c, core, hyp, st, pseudo, tot):
+    """Column dict from the device outputs of the surviving loops (same expressions as the step-by-step path)."""
+    if c.shape[0] == 0:
+        return _empty_cols()
+    ra, rb, rab, lower = core[:, 0], core[:, 1], core[:, 2], core[:, 3]
+    la, lb = c[:, 1] - c[:, 0], c[:, 3] - c[:, 2]
+    mrabs = st[:, 0]
+    return dict(coords=c, ra=ra, rb=rb, rab=rab, P2LL=rab.astype(np.float64) / np.maximum(lower, pseudo),
+                FDR=st[:, 2], ES=rab / np.maximum(mrabs, pseudo),
+                density=rab.astype(np.float64) / (la + lb) / tot * 10.0**9, hyp=_clamp(hyp), pop=_clamp(st[:, 3]),
+                nbp=_clamp(st[:, 4]), px=_clamp(st[:, 5]), py=_clamp(st[:, 7]), esx=st[:, 6], esy=st[:, 8],
+                mrabs=mrabs, mbps=st[:, 1], anc=st[:, 9:13])
 
 
 def scipy_pvalues(cols, N, rpb, cis=True):

@@ -118,6 +118,17 @@ int cl2_loop_core(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops, int64_t L,
 int cl2_loop_tests(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops, const int64_t *core, int64_t L, int32_t win,
                    int32_t mode, double rpb, double *stats);
 
+/*
+ * estLoopSig in one call: counting, statistics AND the reference's filter cascade on the device (cis
+ * callCisLoops.py:282-347 with `hic` selecting the -hic rules; trans callTransLoops.py:127-139, no early exits).
+ * Only the candidates that survive are returned, in candidate order: *n_out rows, sel[i] = index of the i-th survivor
+ * in `loops`, core / hyp / stats as in cl2_loop_core and cl2_loop_tests.  All output buffers must hold L rows.
+ * countDiffCut, pseudo, peakPcut are estLoopSig's keyword arguments (20 / 1 / 1e-5 cis; 10 / 1 / - trans).
+ */
+int cl2_est_loops(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops, int64_t L, int32_t win, int32_t mode,
+                  int32_t minPts, int32_t hic, double countDiffCut, double pseudo, double peakPcut, double rpb,
+                  int64_t *n_out, int64_t *sel, int64_t *core, double *hyp, double *stats);
+
 /* ---- host-side selection (native, no GPU) ----------------------------------------------------------------- */
 /*
  * selSigLoops (callCisLoops.py:379-422) for the loops of ONE chromosome (pair), all already significant, in list

@@ -140,3 +140,37 @@ def test_fused_stats_kernels_against_oracle_counts(gpu_ctx):
         for a, b in ((hyp, whyp), (st[:, 3], wst[:, 3]), (st[:, 4], wst[:, 4]), (st[:, 5], wst[:, 5]), (st[:, 7], wst[:, 7])):
             ok = np.abs(a - b) <= 1e-12 * np.abs(b) + 1e-305     # device libm vs glibc: last-ulp differences only
             assert ok.all(), (mode, a[~ok][:3], b[~ok][:3])
+
+
+def test_fused_est_loops_equals_step_by_step(gpu_ctx):
+    """cl2_est_loops (filters on the device, survivors only) vs cl2_loop_core + cl2_loop_tests + host filters."""
+    from cloops2_b200 import hostops
+
+    class TwoPhase:            # hides est_loops so hostops takes the step-by-step path
+        def __init__(self, idx):
+            self.loop_core, self.loop_tests = idx.loop_core, idx.loop_tests
+
+    rng = np.random.default_rng(12)
+    for mode, xy in ((0, synth.cis_chrom(3_000_000, 80_000, 3, "hitrac")),
+                     (1, synth.trans_pair(2_000_000, 2_500_000, 60_000, 4, per=1500))):
+        i = rng.integers(0, len(xy), size=600)
+        wa, wb = rng.integers(20, 3000, size=600), rng.integers(20, 3000, size=600)
+        xs, ys = np.maximum(0, xy[i, 0] - wa // 2), np.maximum(0, xy[i, 1] - wb // 2)
+        cands = np.stack([xs, xs + wa, ys, ys + wb], 1).astype(np.int64)
+        span = float(xy[:, 1].max() - xy[:, 0].min())
+        pts = _lib.Points(gpu_ctx, xy)
+        idx = _lib.Index(pts)
+        try:
+            for hic in ((False, True) if mode == 0 else (False,)):
+                if mode == 0:
+                    a = hostops.est_cis(idx, cands, len(xy), span, len(xy), 3, hic=hic)
+                    b = hostops.est_cis(TwoPhase(idx), cands, len(xy), span, len(xy), 3, hic=hic)
+                else:
+                    a = hostops.est_trans(idx, cands, len(xy), span, 3)
+                    b = hostops.est_trans(TwoPhase(idx), cands, len(xy), span, 3)
+                assert a["coords"].shape[0] > 0
+                for k in hostops.COLS:
+                    assert np.array_equal(a[k], b[k]), (mode, hic, k)
+        finally:
+            idx.close()
+            pts.close()
