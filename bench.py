@@ -237,55 +237,79 @@ def main():
     tot = int(sum(len(files[k]) for k in keys))
     job_tot = int(shard.allreduce_stats(np.array([tot], dtype=np.int64))[0])
 
-    # host (pinned) copies for the e2e arm, resident points for the device arm
+    # host (pinned) copies for the e2e arm, resident points for the device arm.  A rank runs several chromosome files
+    # at once on separate streams (cloops2_b200.shard.worker_contexts), largest first.
+    ctxs = shard.worker_contexts(local)
+    keys = sorted(keys, key=lambda k: -len(files[k]))
     pinned = {}
     for k in keys:
         p = ctx.pinned_empty(files[k].shape, np.int64)
         np.copyto(p, files[k])
         pinned[k] = p
     files = None
-    resident = {k: _lib.Points(ctx, pinned[k]) for k in keys}
+    owner = {k: ctxs[i % len(ctxs)] for i, k in enumerate(keys)}
+    resident = {k: _lib.Points(owner[k], pinned[k]) for k in keys}
     counters = {}
 
-    def step_resident():
+    def _sum(results, name):
         st = np.zeros(4, dtype=np.int64)
         host = {}
-        for k in keys:
-            _, s = cis_chromosome(ctx, tuple(k.split("-")), None, job_tot, EPS, MINPTS, pts=resident[k])
+        for _, s in results:
             st += [s["pets"], s["candidates"], s["tested"], s["loops"]]
             for nm, v in s.get("host_s", {}).items():
                 host[nm] = host.get(nm, 0.0) + 1e3 * v
-        counters["stats"] = st
-        counters["host_ms"] = host
+        counters[name] = st
+        counters[name + "_host_ms"] = host
+
+    def step_resident():
+        # resident points belong to one context each; group the units by owner so every thread uses its own
+        def run(c, k):
+            return cis_chromosome(owner[k], tuple(k.split("-")), None, job_tot, EPS, MINPTS, pts=resident[k])
+        _sum(shard.map_units(ctxs, keys, run) if len(ctxs) == 1 else _owner_map(run), "stats")
+
+    def _owner_map(run):
+        import threading
+        out = {}
+
+        def work(c):
+            for k in keys:
+                if owner[k] is c:
+                    out[k] = run(c, k)
+        ths = [threading.Thread(target=work, args=(c,)) for c in ctxs]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        return [out[k] for k in keys]
 
     def step_e2e():
-        st = np.zeros(4, dtype=np.int64)
-        for k in keys:
-            _, s = cis_chromosome(ctx, tuple(k.split("-")), pinned[k], job_tot, EPS, MINPTS)
-            st += [s["pets"], s["candidates"], s["tested"], s["loops"]]
-        counters["stats_e2e"] = st
+        _sum(shard.map_units(ctxs, keys, lambda c, k: cis_chromosome(c, tuple(k.split("-")), pinned[k], job_tot, EPS, MINPTS)),
+             "stats_e2e")
 
     def step_e2e_exact():
-        for k in keys:
-            cis_chromosome(ctx, tuple(k.split("-")), pinned[k], job_tot, EPS, MINPTS, exact=True)
+        shard.map_units(ctxs, keys, lambda c, k: cis_chromosome(c, tuple(k.split("-")), pinned[k], job_tot, EPS, MINPTS,
+                                                                 exact=True))
 
     def timed(fn, warmup, steps, with_kernel_timing):
         for _ in range(warmup):
             fn()
-        ctx.sync()
+        for c in ctxs:
+            c.sync()
         shard.barrier()
         torch.cuda.synchronize()
-        if with_kernel_timing:
-            ctx.timing_reset()
-            ctx.timing_enable(True)
-        ctx.launch_count_reset()
+        for c in ctxs:
+            if with_kernel_timing:
+                c.timing_reset()
+                c.timing_enable(True)
+            c.launch_count_reset()
         sampler = ClockSampler(local)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t = time.perf_counter()
         ev0.record()
         for _ in range(steps):
             fn()
-        ctx.sync()
+        for c in ctxs:
+            c.sync()
         ev1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t
@@ -293,12 +317,19 @@ def main():
         clocks = sampler.stop()
         fam = None
         if with_kernel_timing:
-            fam = ctx.timing_read()
-            ctx.timing_enable(False)
+            fam = {}
+            for c in ctxs:
+                for nm, v in c.timing_read().items():
+                    a = fam.setdefault(nm, {"ms": 0.0, "launches": 0, "bytes": 0.0})
+                    a["ms"] += v["ms"]
+                    a["launches"] += v["launches"]
+                    a["bytes"] += v["bytes"]
+                c.timing_enable(False)
         # the step mixes device work with host-side statistics, so the step time is the host clock around the
         # synchronised region (the CUDA-event span on torch's stream is reported beside it)
         dev_ms = ev0.elapsed_time(ev1)
-        return shard.max_over_ranks(wall), dev_ms, clocks, fam, ctx.launch_count(), ctx.transfer_bytes()
+        xf = np.sum([c.transfer_bytes() for c in ctxs], axis=0)
+        return shard.max_over_ranks(wall), dev_ms, clocks, fam, sum(c.launch_count() for c in ctxs), (int(xf[0]), int(xf[1]))
 
     wall, dev_ms, clocks, fam, launches, _ = timed(step_resident, args.warmup, args.steps, not args.no_kernel_timing)
     wall_e, _, clocks_e, _, _, xfer = timed(step_e2e, max(1, args.warmup - 2), args.steps, False)
@@ -354,7 +385,8 @@ def main():
         "clocks": clocks, "clocks_e2e": clocks_e,
         "roofline": roof, "cpu_baseline": cpu_base,
         "kernels": kernels,
-        "stage_wall_ms_per_step": counters.get("host_ms"),
+        "stage_wall_ms_per_step": counters.get("stats_host_ms"),
+        "host_threads": len(ctxs),
         "job": {"pets": job_tot, "candidates": int(stats[1]), "tested": int(stats[2]), "loops": int(stats[3]),
                 "device_event_ms_per_step": dev_ms / args.steps, "generate_s": gen_s},
     }

@@ -269,13 +269,16 @@ def callCisLoops(predir, fout, log, eps=[2000, 5000], minPts=[5, 10], cpu=1, cut
     keys = list(meta["data"]["cis"].keys())
     files = {k: meta["data"]["cis"][k]["ixy"] for k in keys}
     mine = shard.assign(keys, [shard.ixy_rows(files[k]) for k in keys], world)[rank]
-    ctx = _lib.default_context()
+    ctxs = shard.worker_contexts()
+    ex = exact_default()
+
+    def one(ctx, k):
+        return cis_chromosome(ctx, tuple(k.split("-")), loadIxy(files[k]), tot, eps, minPts, cut=cut, mcut=mcut, hic=hic,
+                              emPair=emPair, exact=ex)
+
     results = {}
     stats = np.zeros(4, dtype=np.int64)
-    for k in mine:
-        xy = loadIxy(files[k])
-        final, st = cis_chromosome(ctx, tuple(k.split("-")), xy, tot, eps, minPts, cut=cut, mcut=mcut, hic=hic,
-                                   emPair=emPair, exact=exact_default())
+    for k, (final, st) in zip(mine, shard.map_units(ctxs, mine, one)):
         stats += np.array([st["pets"], st["candidates"], st["tested"], st["loops"]], dtype=np.int64)
         if st["tested"] > 0:
             results[k] = final

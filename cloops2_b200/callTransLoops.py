@@ -125,11 +125,15 @@ def callTransLoops(predir, fout, logger, eps=[2000, 5000], minPts=[5, 10], cpu=1
     files = {k: meta["data"]["trans"][k]["ixy"] for k in keys}
     rank, world = shard.rank_world()
     mine = shard.assign(keys, [shard.ixy_rows(files[k]) for k in keys], world)[rank]
-    ctx = _lib.default_context()
+    ctxs = shard.worker_contexts()
+    ex = exact_default()
+
+    def one(ctx, k):
+        return trans_pair(ctx, tuple(k.split("-")), loadIxy(files[k]), eps, minPts, exact=ex)
+
     results = {}
     stats = np.zeros(4, dtype=np.int64)
-    for k in mine:
-        final, st = trans_pair(ctx, tuple(k.split("-")), loadIxy(files[k]), eps, minPts, exact=exact_default())
+    for k, (final, st) in zip(mine, shard.map_units(ctxs, mine, one)):
         stats += np.array([st["pets"], st["candidates"], st["tested"], st["loops"]], dtype=np.int64)
         if st["candidates"] > 0:
             results[k] = final

@@ -108,3 +108,49 @@ def barrier():
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
+
+
+def worker_contexts(device=None, nthreads=None):
+    """One cl2 context (= CUDA stream + scratch) per host worker thread of this rank.  Chromosome files are
+    independent units, so a rank processes several at once: while one thread's kernels run, another thread does its
+    host-side bookkeeping (ctypes calls and numpy release the GIL).  CL2_THREADS overrides the default of 4."""
+    from . import _lib
+    if nthreads is None:
+        nthreads = int(os.environ.get("CL2_THREADS", "4"))
+    nthreads = max(1, nthreads)
+    first = _lib.default_context(device)
+    return [first] + [_lib.Context(first.device) for _ in range(nthreads - 1)]
+
+
+def map_units(ctxs, units, fn):
+    """fn(ctx, unit) for every unit, results in unit order; units are handed to the worker threads dynamically."""
+    if len(ctxs) <= 1 or len(units) <= 1:
+        return [fn(ctxs[0], u) for u in units]
+    import queue
+    import threading
+    q = queue.Queue()
+    for i, u in enumerate(units):
+        q.put((i, u))
+    out = [None] * len(units)
+    errs = []
+
+    def work(ctx):
+        while not errs:
+            try:
+                i, u = q.get_nowait()
+            except queue.Empty:
+                return
+            try:
+                out[i] = fn(ctx, u)
+            except BaseException as e:      # surface the first failure in the caller
+                errs.append(e)
+                return
+
+    ths = [threading.Thread(target=work, args=(c,)) for c in ctxs]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    if errs:
+        raise errs[0]
+    return out
