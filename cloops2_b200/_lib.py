@@ -16,7 +16,9 @@ _CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.path.join(_HERE, "libcl2.so")
 SOURCES = ["cl2_api.cu", "cl2_sort.cu", "cl2_block.cu", "cl2_cdbscan.cu", "cl2_count.cu", "cl2_host.cu"]
 HEADERS = ["cl2_common.cuh", "cl2_points.cuh", "cl2_stats.cuh", os.path.join("..", "..", "include", "cl2.h")]
-NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
+# -fmad=false: no FMA contraction, so the fp64 statistics give the same bits in every kernel they are inlined into
+# (and the same bits as the host build of cl2_stats.cuh); the path is integer / bandwidth work, nothing is lost.
+NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC"]
 
 MODE_CIS, MODE_TRANS = 0, 1

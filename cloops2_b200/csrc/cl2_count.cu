@@ -404,14 +404,13 @@ __device__ double warp_median(WarpVals &S, int m, int lane) {
 #define CL2_NSTAT 13
 // Permuted-window background, enrichment tests and anchor tests of one loop (one warp); results into o[13] (shared):
 // mrabs, mbps, fdr, poisson sf, binomial sf, px, esx, py, esy, count_x, wide_x, count_y, wide_y
-__device__ void loop_tests_warp(const int2 *__restrict__ byx, const int2 *__restrict__ byy, int64_t n, long long xs,
+// early_cut > 0 (fused cis kernel): return false right after the background statistics when the candidate fails
+// `mrabs >= rab or fdr >= 0.1` / `es < 1` (callCisLoops.py:322-327), before the anchor windows and the tails.
+__device__ bool loop_tests_warp(const int2 *__restrict__ byx, const int2 *__restrict__ byy, int64_t n, long long xs,
                                 long long xe, long long ys, long long ye, double ra, double rb, double rab, int win,
-                                int mode, double rpb, WarpAcc &S, WarpVals &V, int lane, double *o) {
+                                int mode, double rpb, WarpAcc &S, WarpVals &V, int lane, double *o, double early_cut) {
     const int W = 2 * win, m = W * W;
     loop_windows(byx, byy, n, xs, xe, ys, ye, win, lane, S);
-    int64_t cx, wx, cy, wy;
-    loop_anchor(byx, byy, n, xs, xe, lane, &cx, &wx);
-    loop_anchor(byx, byy, n, ys, ye, lane, &cy, &wy);
     // rabs: counts of the 4*win^2 window pairs; fdr = #{rabs > rab} / m   (callCisLoops.py:315-321)
     int gt = 0;
     for (int t = lane; t < m; t += 32) {
@@ -427,6 +426,11 @@ __device__ void loop_tests_warp(const int2 *__restrict__ byx, const int2 *__rest
         mrabs = np_pairwise_sum(V.v, m) / (double)m;     // every lane computes the same value
     }
     __syncwarp();
+    const double fdr = (double)gt / (double)m;
+    if (early_cut > 0) {
+        if (mrabs >= rab || fdr >= 0.1) return false;
+        if (rab / (mrabs > early_cut ? mrabs : early_cut) < 1.0) return false;
+    }
     // nbps: nrab / (nac * nbc), zero rule differs between cis (:213-221) and trans (callTransLoops.py:165-169)
     for (int t = lane; t < m; t += 32) {
         double nrab = (double)S.nab[t], nac = (double)S.na[t / W], nbc = (double)S.nb[t % W];
@@ -438,7 +442,9 @@ __device__ void loop_tests_warp(const int2 *__restrict__ byx, const int2 *__rest
     __syncwarp();
     if (mode == CL2_MODE_CIS) mbps = warp_median(V, m, lane);
     else mbps = np_pairwise_sum(V.v, m) / (double)m;
-    double fdr = (double)gt / (double)m;
+    int64_t cx, wx, cy, wy;
+    loop_anchor(byx, byy, n, xs, xe, lane, &cx, &wx);
+    loop_anchor(byx, byy, n, ys, ye, lane, &cy, &wy);
     if (lane == 0) {
         o[0] = mrabs; o[1] = mbps; o[2] = fdr;
         o[3] = cl2_poisson_sf_ge(rab, mrabs);                                            // :329
@@ -456,6 +462,7 @@ __device__ void loop_tests_warp(const int2 *__restrict__ byx, const int2 *__rest
         o[lane == 2 ? 6 : 8] = count / c;
     }
     __syncwarp();
+    return true;
 }
 
 // phase 2 as a separate launch (cl2_loop_tests)
@@ -471,7 +478,7 @@ __global__ void __launch_bounds__(CNT_WARPS * 32) k_loop_tests(const int2 *__res
     if (k >= L) return;
     const longlong4 lp = loops[k];
     loop_tests_warp(byx, byy, n, lp.x, lp.y, lp.z, lp.w, (double)core[4 * k], (double)core[4 * k + 1],
-                    (double)core[4 * k + 2], win, mode, rpb, acc[w], vals[w], lane, ost[w]);
+                    (double)core[4 * k + 2], win, mode, rpb, acc[w], vals[w], lane, ost[w], 0.0);
     if (lane < CL2_NSTAT) stats[CL2_NSTAT * k + lane] = ost[w][lane];
 }
 
@@ -514,8 +521,9 @@ __global__ void __launch_bounds__(CNT_WARPS * 32) k_est_loops(const int2 *__rest
         }
         if (keep) {
             double *o = ost[w];
-            loop_tests_warp(byx, byy, n, xs, xe, ys, ye, ra, rb, rab, win, mode, rpb, acc[w], vals[w], lane, o);
-            if (cis) {
+            keep = loop_tests_warp(byx, byy, n, xs, xe, ys, ye, ra, rb, rab, win, mode, rpb, acc[w], vals[w], lane, o,
+                                   cis ? pseudo : 0.0);
+            if (keep && cis) {
                 double mrabs = o[0], fdr = o[2];
                 if (mrabs >= rab || fdr >= 0.1) keep = false;                          // :322
                 double es = rab / (mrabs > pseudo ? mrabs : pseudo);                   // :325

@@ -308,6 +308,7 @@ struct OsSmem {
     uint64_t keys[OS_TILE];
     uint32_t vals[OS_TILE];
     int warp_cnt[OS_WARPS][256];
+    int hist[256];
     int dprefix[256];
     int gbase[256];
 };
@@ -323,7 +324,7 @@ __global__ void __launch_bounds__(OS_THREADS, 2) k_os_pass(const uint64_t *__res
     __shared__ unsigned s_tile;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-    for (int i = threadIdx.x; i < OS_WARPS * 256; i += OS_THREADS) (&S.warp_cnt[0][0])[i] = 0;
+    for (int i = threadIdx.x; i < OS_WARPS * 256 + 256; i += OS_THREADS) (&S.warp_cnt[0][0])[i] = 0;   // + hist
     __syncthreads();
     const unsigned tile = s_tile;
     const int64_t tbase = (int64_t)tile * OS_TILE;
@@ -343,6 +344,16 @@ __global__ void __launch_bounds__(OS_THREADS, 2) k_os_pass(const uint64_t *__res
         int64_t i = wbase + r * 32 + lane;
         val[r] = iota ? (uint32_t)i : ((i < n) ? vin[i] : 0u);
     }
+    // tile histogram first, so the tile's digit counts are published (AGGREGATE) before the longer ranking phase:
+    // by the time this tile looks back, its predecessors have usually published their inclusive prefixes
+#pragma unroll
+    for (int r = 0; r < OS_IPT; r++) {
+        int64_t i = wbase + r * 32 + lane;
+        if (i < n) atomicAdd(&S.hist[(key[r] >> shift) & 255], 1);
+    }
+    __syncthreads();
+    volatile unsigned *vd = desc;
+    if (threadIdx.x < 256) vd[(size_t)tile * 256 + threadIdx.x] = (unsigned)S.hist[threadIdx.x] | OS_AGG;
 #pragma unroll
     for (int r = 0; r < OS_IPT; r++) {
         int64_t i = wbase + r * 32 + lane;
@@ -366,9 +377,7 @@ __global__ void __launch_bounds__(OS_THREADS, 2) k_os_pass(const uint64_t *__res
             S.warp_cnt[k][d] = off;
             off += c;
         }
-        // publish this tile's count for digit d, then look back for the exclusive prefix over earlier tiles
-        volatile unsigned *vd = desc;
-        vd[(size_t)tile * 256 + d] = (unsigned)off | OS_AGG;
+        // look back for the exclusive prefix over earlier tiles
         unsigned excl = 0;
         for (long long t = (long long)tile - 1; t >= 0;) {
             unsigned v = vd[(size_t)t * 256 + d];
