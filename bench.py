@@ -331,8 +331,33 @@ def main():
         xf = np.sum([c.transfer_bytes() for c in ctxs], axis=0)
         return shard.max_over_ranks(wall), dev_ms, clocks, fam, sum(c.launch_count() for c in ctxs), (int(xf[0]), int(xf[1]))
 
-    wall, dev_ms, clocks, fam, launches, _ = timed(step_resident, args.warmup, args.steps, not args.no_kernel_timing)
+    wall, dev_ms, clocks, _, launches, _ = timed(step_resident, args.warmup, args.steps, False)
     wall_e, _, clocks_e, _, _, xfer = timed(step_e2e, max(1, args.warmup - 2), args.steps, False)
+    # Per-kernel roofline: the timed steps run several chromosome files concurrently on separate streams, where a
+    # CUDA-event pair around one launch also spans other streams' kernels.  The per-kernel numbers therefore come from
+    # the same resident step run once more on ONE stream at a time (same launches, same inputs), events enabled.
+    fam = None
+    if not args.no_kernel_timing:
+        def step_serial():
+            _sum([cis_chromosome(owner[k], tuple(k.split("-")), None, job_tot, EPS, MINPTS, pts=resident[k]) for k in keys],
+                 "stats")
+        for c in ctxs:
+            c.sync()
+            c.timing_reset()
+            c.timing_enable(True)
+        t_serial = time.perf_counter()
+        step_serial()
+        for c in ctxs:
+            c.sync()
+        t_serial = time.perf_counter() - t_serial
+        fam = {}
+        for c in ctxs:
+            for nm, v in c.timing_read().items():
+                a = fam.setdefault(nm, {"ms": 0.0, "launches": 0, "bytes": 0.0})
+                a["ms"] += v["ms"]
+                a["launches"] += v["launches"]
+                a["bytes"] += v["bytes"]
+            c.timing_enable(False)
     xfer = shard.allreduce_stats(np.array(xfer, dtype=np.int64))
     ex_steps = max(1, min(2, args.steps))
     wall_x = timed(step_e2e_exact, 1, ex_steps, False)[0]
@@ -355,7 +380,7 @@ def main():
     if fam:
         tot_ms = sum(v["ms"] for v in fam.values()) or 1.0
         for nm, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]):
-            kernels[nm] = {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
+            kernels[nm] = {"ms_per_step": v["ms"], "launches_per_step": v["launches"],
                            "share": v["ms"] / tot_ms,
                            "GBps": (v["bytes"] / 1e9) / (v["ms"] / 1e3) if v["ms"] > 0 and v["bytes"] > 0 else None}
         top = max(fam.items(), key=lambda kv: kv[1]["ms"])
@@ -385,6 +410,7 @@ def main():
         "clocks": clocks, "clocks_e2e": clocks_e,
         "roofline": roof, "cpu_baseline": cpu_base,
         "kernels": kernels,
+        "kernels_note": "per-kernel-family CUDA-event times of one resident step run on a single stream (see bench.py)",
         "stage_wall_ms_per_step": counters.get("stats_host_ms"),
         "host_threads": len(ctxs),
         "job": {"pets": job_tot, "candidates": int(stats[1]), "tested": int(stats[2]), "loops": int(stats[3]),
@@ -393,5 +419,17 @@ def main():
     print(json.dumps(out))
 
 
+def _shutdown():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    finally:
+        _shutdown()

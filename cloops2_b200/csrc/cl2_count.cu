@@ -135,9 +135,12 @@ __device__ __forceinline__ int warp_sum(int v) {
 }
 
 // |P(I)|  (queryPeak, ds.py:176-182)
+// g_scan: members visited by this warp so far (the counting kernel's algorithmic traffic is 16 B per member on the
+// reference layout); every lane carries the same value
 __device__ __noinline__ int64_t count_peak(const int2 *__restrict__ byx, const int2 *__restrict__ byy, int64_t n, const Iv &I,
-                              int lane) {
+                              int lane, long long *g_scan) {
     Range rx = range_of(byx, n, I), ry = range_of(byy, n, I);
+    *g_scan += ry.e - ry.b;
     int c = 0;
     for (int64_t j = ry.b + lane; j < ry.e; j += 32) {
         int2 p = byy[j];                      // (y, x)
@@ -148,8 +151,9 @@ __device__ __noinline__ int64_t count_peak(const int2 *__restrict__ byx, const i
 
 // |P(I1)| and |P(I1) & P(I2)|  (queryLoop, ds.py:184-190)
 __device__ __noinline__ void count_pair(const int2 *__restrict__ byx, const int2 *__restrict__ byy, int64_t n, const Iv &I1,
-                           const Iv &I2, int lane, int64_t *n1, int64_t *n12) {
+                           const Iv &I2, int lane, int64_t *n1, int64_t *n12, long long *g_scan) {
     Range rx = range_of(byx, n, I1), ry = range_of(byy, n, I1);
+    *g_scan += (rx.e - rx.b) + (ry.e - ry.b);
     int c1 = 0, c12 = 0;
     for (int64_t i = rx.b + lane; i < rx.e; i += 32) {
         int2 p = byx[i];                      // (x, y)
@@ -224,35 +228,37 @@ __device__ __forceinline__ void window_accumulate(WarpAcc &A, int W, unsigned ma
 // ---- per-loop building blocks (one warp) -------------------------------------------------------------------
 // queryLoop counts + the P2LL window (cis callCisLoops.py:287-289, 302-305; trans callTransLoops.py:124-126, 142-144)
 __device__ void loop_core(const int2 *__restrict__ byx, const int2 *__restrict__ byy, int64_t n, long long xs,
-                          long long xe, long long ys, long long ye, int mode, int lane, int64_t out[4]) {
+                          long long xe, long long ys, long long ye, int mode, int lane, int64_t out[4],
+                          long long *g_scan) {
     const Iv A = {xs, xe}, B = {ys, ye};
     int64_t ra, rab, rb;
-    count_pair(byx, byy, n, A, B, lane, &ra, &rab);
-    rb = count_peak(byx, byy, n, B, lane);
+    count_pair(byx, byy, n, A, B, lane, &ra, &rab, g_scan);
+    rb = count_peak(byx, byy, n, B, lane, g_scan);
     Iv A2, B2;
     if (mode == CL2_MODE_CIS) { A2.lo = xe; A2.hi = xe + (xe - xs); }
     else { A2.lo = xs - (xe - xs); A2.hi = xs; }
     B2.lo = ys - (ye - ys); B2.hi = ys;
     int64_t t1, lower;
-    count_pair(byx, byy, n, A2, B2, lane, &t1, &lower);
+    count_pair(byx, byy, n, A2, B2, lane, &t1, &lower, g_scan);
     out[0] = ra; out[1] = rb; out[2] = rab; out[3] = lower;
 }
 
 // estAnchorSig counts (callCisLoops.py:226-247): count = |P(l,r)|, wide = |P(max(0, m-5len), m+5len)|
 __device__ void loop_anchor(const int2 *__restrict__ byx, const int2 *__restrict__ byy, int64_t n, long long l,
-                            long long r, int lane, int64_t *count, int64_t *wide) {
+                            long long r, int lane, int64_t *count, int64_t *wide, long long *g_scan) {
     long long m4 = 2 * (l + r), len = r - l;
     long long s4 = m4 - 20 * len;
     if (s4 < 0) s4 = 0;
     Iv I = {l, r};
     Iv Wd = iv4(s4, m4 + 20 * len);
-    *count = count_peak(byx, byy, n, I, lane);
-    *wide = count_peak(byx, byy, n, Wd, lane);
+    *count = count_peak(byx, byy, n, I, lane, g_scan);
+    *wide = count_peak(byx, byy, n, Wd, lane, g_scan);
 }
 
 // getPerRegions + getLoopNearbyPETs counts into the warp's accumulator (callCisLoops.py:173-223)
 __device__ void loop_windows(const int2 *__restrict__ byx, const int2 *__restrict__ byy, int64_t n, long long xs,
-                             long long xe, long long ys, long long ye, int win, int lane, WarpAcc &S) {
+                             long long xe, long long ys, long long ye, int win, int lane, WarpAcc &S,
+                             long long *g_scan) {
     const int W = 2 * win;
     for (int t = lane; t < W * W; t += 32) S.nab[t] = 0;
     if (lane < W) {
@@ -278,6 +284,7 @@ __device__ void loop_windows(const int2 *__restrict__ byx, const int2 *__restric
     Iv SA = {S.alo[0], S.ahi[W - 1]}, SB = {S.blo[0], S.bhi[W - 1]};
     Range rxa = range_of(byx, n, SA), rya = range_of(byy, n, SA);
     Range rxb = range_of(byx, n, SB), ryb = range_of(byy, n, SB);
+    *g_scan += (rxa.e - rxa.b) + (rya.e - rya.b) + (rxb.e - rxb.b) + (ryb.e - ryb.b);
     // four lists; a PET is handled by the first list that contains it
     for (int pass = 0; pass < 4; pass++) {
         const int2 *arr = (pass & 1) ? byy : byx;
@@ -313,22 +320,23 @@ __global__ void __launch_bounds__(CNT_WARPS * 32) k_loop_counts(const int2 *__re
     if (k >= L) return;
     const longlong4 lp = loops[k];
     const long long xs = lp.x, xe = lp.y, ys = lp.z, ye = lp.w;
+    long long scanned = 0;
     if (core) {
         int64_t c[4];
-        loop_core(byx, byy, n, xs, xe, ys, ye, mode, lane, c);
+        loop_core(byx, byy, n, xs, xe, ys, ye, mode, lane, c, &scanned);
         if (lane == 0) { core[4 * k] = c[0]; core[4 * k + 1] = c[1]; core[4 * k + 2] = c[2]; core[4 * k + 3] = c[3]; }
     }
     if (anchors) {
         for (int a = 0; a < 2; a++) {
             int64_t c, wd;
-            loop_anchor(byx, byy, n, a == 0 ? xs : ys, a == 0 ? xe : ye, lane, &c, &wd);
+            loop_anchor(byx, byy, n, a == 0 ? xs : ys, a == 0 ? xe : ye, lane, &c, &wd, &scanned);
             if (lane == 0) { anchors[4 * k + 2 * a] = c; anchors[4 * k + 2 * a + 1] = wd; }
         }
     }
     if (na_out || nb_out || nab_out) {
         const int W = 2 * win;
         WarpAcc &S = acc[w];
-        loop_windows(byx, byy, n, xs, xe, ys, ye, win, lane, S);
+        loop_windows(byx, byy, n, xs, xe, ys, ye, win, lane, S, &scanned);
         if (na_out && lane < W) na_out[(int64_t)W * k + lane] = S.na[lane];
         if (nb_out && lane < W) nb_out[(int64_t)W * k + lane] = S.nb[lane];
         if (nab_out)
@@ -347,7 +355,8 @@ __global__ void __launch_bounds__(CNT_WARPS * 32) k_loop_core(const int2 *__rest
     if (k >= L) return;
     const longlong4 lp = loops[k];
     int64_t c[4];
-    loop_core(byx, byy, n, lp.x, lp.y, lp.z, lp.w, mode, lane, c);
+    long long scanned = 0;
+    loop_core(byx, byy, n, lp.x, lp.y, lp.z, lp.w, mode, lane, c, &scanned);
     if (lane == 0) {
         core[4 * k] = c[0]; core[4 * k + 1] = c[1]; core[4 * k + 2] = c[2]; core[4 * k + 3] = c[3];
         hyp[k] = cl2_hypergeom_sf_ge((double)c[2], (double)n, (double)c[0], (double)c[1]);
@@ -408,9 +417,10 @@ __device__ double warp_median(WarpVals &S, int m, int lane) {
 // `mrabs >= rab or fdr >= 0.1` / `es < 1` (callCisLoops.py:322-327), before the anchor windows and the tails.
 __device__ bool loop_tests_warp(const int2 *__restrict__ byx, const int2 *__restrict__ byy, int64_t n, long long xs,
                                 long long xe, long long ys, long long ye, double ra, double rb, double rab, int win,
-                                int mode, double rpb, WarpAcc &S, WarpVals &V, int lane, double *o, double early_cut) {
+                                int mode, double rpb, WarpAcc &S, WarpVals &V, int lane, double *o, double early_cut,
+                                long long *g_scan) {
     const int W = 2 * win, m = W * W;
-    loop_windows(byx, byy, n, xs, xe, ys, ye, win, lane, S);
+    loop_windows(byx, byy, n, xs, xe, ys, ye, win, lane, S, g_scan);
     // rabs: counts of the 4*win^2 window pairs; fdr = #{rabs > rab} / m   (callCisLoops.py:315-321)
     int gt = 0;
     for (int t = lane; t < m; t += 32) {
@@ -443,8 +453,8 @@ __device__ bool loop_tests_warp(const int2 *__restrict__ byx, const int2 *__rest
     if (mode == CL2_MODE_CIS) mbps = warp_median(V, m, lane);
     else mbps = np_pairwise_sum(V.v, m) / (double)m;
     int64_t cx, wx, cy, wy;
-    loop_anchor(byx, byy, n, xs, xe, lane, &cx, &wx);
-    loop_anchor(byx, byy, n, ys, ye, lane, &cy, &wy);
+    loop_anchor(byx, byy, n, xs, xe, lane, &cx, &wx, g_scan);
+    loop_anchor(byx, byy, n, ys, ye, lane, &cy, &wy, g_scan);
     if (lane == 0) {
         o[0] = mrabs; o[1] = mbps; o[2] = fdr;
         o[3] = cl2_poisson_sf_ge(rab, mrabs);                                            // :329
@@ -477,27 +487,30 @@ __global__ void __launch_bounds__(CNT_WARPS * 32) k_loop_tests(const int2 *__res
     const int64_t k = (int64_t)blockIdx.x * CNT_WARPS + w;
     if (k >= L) return;
     const longlong4 lp = loops[k];
+    long long scanned = 0;
     loop_tests_warp(byx, byy, n, lp.x, lp.y, lp.z, lp.w, (double)core[4 * k], (double)core[4 * k + 1],
-                    (double)core[4 * k + 2], win, mode, rpb, acc[w], vals[w], lane, ost[w], 0.0);
+                    (double)core[4 * k + 2], win, mode, rpb, acc[w], vals[w], lane, ost[w], 0.0, &scanned);
     if (lane < CL2_NSTAT) stats[CL2_NSTAT * k + lane] = ost[w][lane];
 }
 
 // Whole estLoopSig arithmetic for one candidate per warp, including the reference's filter cascade
 // (cis callCisLoops.py:282-347, trans callTransLoops.py:127-139): only survivors are written, flag[k] marks them.
-__global__ void __launch_bounds__(CNT_WARPS * 32) k_est_loops(const int2 *__restrict__ byx, const int2 *__restrict__ byy,
+__global__ void __launch_bounds__(CNT_WARPS * 32, 4) k_est_loops(const int2 *__restrict__ byx, const int2 *__restrict__ byy,
                                                                int64_t n, const longlong4 *__restrict__ loops, int64_t L,
                                                                int win, int mode, int minPts, int hic, double cdc,
                                                                double pseudo, double peakPcut, double rpb,
                                                                long long *__restrict__ core_out,
                                                                double *__restrict__ hyp_out,
                                                                double *__restrict__ stats_out,
-                                                               int32_t *__restrict__ flag) {
+                                                               int32_t *__restrict__ flag,
+                                                               unsigned long long *__restrict__ scanned_total) {
     __shared__ WarpAcc acc[CNT_WARPS];
     __shared__ WarpVals vals[CNT_WARPS];
     __shared__ double ost[CNT_WARPS][CL2_NSTAT];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t k = (int64_t)blockIdx.x * CNT_WARPS + w;
     if (k >= L) return;
+    long long scanned = 0;
     const longlong4 lp = loops[k];
     const long long xs = lp.x, xe = lp.y, ys = lp.z, ye = lp.w;
     const double la = (double)(xe - xs), lb = (double)(ye - ys);
@@ -505,7 +518,7 @@ __global__ void __launch_bounds__(CNT_WARPS * 32) k_est_loops(const int2 *__rest
     bool keep = !(la / lb > cdc || lb / la > cdc);                                      // :282-286 / trans :135-139
     if (keep) {
         int64_t c[4];
-        loop_core(byx, byy, n, xs, xe, ys, ye, mode, lane, c);
+        loop_core(byx, byy, n, xs, xe, ys, ye, mode, lane, c, &scanned);
         const double ra = (double)c[0], rb = (double)c[1], rab = (double)c[2];
         if (c[2] < minPts) keep = false;                                               // :290 / trans :127
         if (cis && (c[0] == c[2] || c[1] == c[2])) keep = false;                       // :293
@@ -522,7 +535,7 @@ __global__ void __launch_bounds__(CNT_WARPS * 32) k_est_loops(const int2 *__rest
         if (keep) {
             double *o = ost[w];
             keep = loop_tests_warp(byx, byy, n, xs, xe, ys, ye, ra, rb, rab, win, mode, rpb, acc[w], vals[w], lane, o,
-                                   cis ? pseudo : 0.0);
+                                   cis ? pseudo : 0.0, &scanned);
             if (keep && cis) {
                 double mrabs = o[0], fdr = o[2];
                 if (mrabs >= rab || fdr >= 0.1) keep = false;                          // :322
@@ -537,7 +550,10 @@ __global__ void __launch_bounds__(CNT_WARPS * 32) k_est_loops(const int2 *__rest
             }
         }
     }
-    if (lane == 0) flag[k] = keep ? 1 : 0;
+    if (lane == 0) {
+        flag[k] = keep ? 1 : 0;
+        if (scanned) atomicAdd(scanned_total, (unsigned long long)scanned);
+    }
 }
 
 // gather the surviving rows (flag set; pos = exclusive scan of the flags) into dense arrays, order preserved
@@ -673,17 +689,25 @@ extern "C" int cl2_est_loops(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops,
     CL2_TRY(sc.get(&d_stats, (size_t)L * CL2_NSTAT));
     CL2_TRY(sc.get(&d_flag, (size_t)L));
     CL2_TRY(sc.get(&d_total, 2));
+    CL2_CUDA(ctx, cudaMemsetAsync(d_total, 0, 16, ctx->stream));
     CL2_CUDA(ctx, cudaMemcpyAsync(d_loops, loops, (size_t)L * 32, cudaMemcpyHostToDevice, ctx->stream));
     ctx->h2d_bytes += L * 32;
     {
         FamTimer t(ctx, FAM_COUNT, 0.0);
         k_est_loops<<<cl2_grid(L, CNT_WARPS), CNT_WARPS * 32, 0, ctx->stream>>>(idx->byx, idx->byy, idx->n, d_loops, L, win, mode,
                                                                                 minPts, hic, countDiffCut, pseudo, peakPcut, rpb,
-                                                                                d_core, d_hyp, d_stats, d_flag);
+                                                                                d_core, d_hyp, d_stats, d_flag,
+                                                                                (unsigned long long *)(d_total + 1));
     }
     CL2_TRY(cl2_exclusive_scan_i32(ctx, d_flag, L, d_total));
     int64_t nk = 0;
     CL2_TRY(cl2_read_i64(ctx, d_total, &nk));
+    if (ctx->timing) {
+        // algorithmic traffic of the counting launch: 16 B per scanned member on the reference layout
+        int64_t scanned = 0;
+        CL2_TRY(cl2_read_i64(ctx, d_total + 1, &scanned));
+        ctx->fam_bytes[FAM_COUNT] += 16.0 * (double)scanned + 32.0 * (double)L;
+    }
     *n_out = nk;
     if (nk > 0) {
         // d_selbuf[0] carries the total so the compaction kernel can tell whether the last row survived
