@@ -495,7 +495,7 @@ __global__ void __launch_bounds__(CNT_WARPS * 32) k_loop_tests(const int2 *__res
 
 // Whole estLoopSig arithmetic for one candidate per warp, including the reference's filter cascade
 // (cis callCisLoops.py:282-347, trans callTransLoops.py:127-139): only survivors are written, flag[k] marks them.
-__global__ void __launch_bounds__(CNT_WARPS * 32, 4) k_est_loops(const int2 *__restrict__ byx, const int2 *__restrict__ byy,
+__global__ void __launch_bounds__(CNT_WARPS * 32) k_est_loops(const int2 *__restrict__ byx, const int2 *__restrict__ byy,
                                                                int64_t n, const longlong4 *__restrict__ loops, int64_t L,
                                                                int win, int mode, int minPts, int hic, double cdc,
                                                                double pseudo, double peakPcut, double rpb,

@@ -258,6 +258,16 @@ __device__ __forceinline__ uint64_t os_key(const cl2_keygen &g, const uint64_t *
     return (uint64_t)(uint32_t)(g.kind == CL2_KEY_X ? p.x : p.y);
 }
 
+// descriptor load / store at gpu scope (coherent in L2, never served from L1)
+__device__ __forceinline__ unsigned os_ld(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void os_st(unsigned *p, unsigned v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 #define OS_AGG 0x40000000u
 #define OS_INC 0x80000000u
 #define OS_VAL 0x3FFFFFFFu
@@ -352,8 +362,7 @@ __global__ void __launch_bounds__(OS_THREADS, 2) k_os_pass(const uint64_t *__res
         if (i < n) atomicAdd(&S.hist[(key[r] >> shift) & 255], 1);
     }
     __syncthreads();
-    volatile unsigned *vd = desc;
-    if (threadIdx.x < 256) vd[(size_t)tile * 256 + threadIdx.x] = (unsigned)S.hist[threadIdx.x] | OS_AGG;
+    if (threadIdx.x < 256) os_st(&desc[(size_t)tile * 256 + threadIdx.x], (unsigned)S.hist[threadIdx.x] | OS_AGG);
 #pragma unroll
     for (int r = 0; r < OS_IPT; r++) {
         int64_t i = wbase + r * 32 + lane;
@@ -377,15 +386,23 @@ __global__ void __launch_bounds__(OS_THREADS, 2) k_os_pass(const uint64_t *__res
             S.warp_cnt[k][d] = off;
             off += c;
         }
-        // look back for the exclusive prefix over earlier tiles
+        // look back for the exclusive prefix over earlier tiles, four descriptors per round trip
         unsigned excl = 0;
-        for (long long t = (long long)tile - 1; t >= 0;) {
-            unsigned v = vd[(size_t)t * 256 + d];
-            if (v & OS_INC) { excl += v & OS_VAL; break; }
-            if (v & OS_AGG) { excl += v & OS_VAL; t--; }
-            // else: predecessor has not published yet -- spin on the same descriptor
+        long long t = (long long)tile - 1;
+        while (t >= 0) {
+            unsigned v[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) v[j] = (t - j >= 0) ? os_ld(&desc[(size_t)(t - j) * 256 + d]) : OS_INC;
+            bool done = false;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (done) break;
+                if (v[j] & OS_INC) { excl += v[j] & OS_VAL; done = true; t = -1; }
+                else if (v[j] & OS_AGG) { excl += v[j] & OS_VAL; t--; }
+                else done = true;      // not published yet: re-read from this tile
+            }
         }
-        vd[(size_t)tile * 256 + d] = (excl + (unsigned)off) | OS_INC;
+        os_st(&desc[(size_t)tile * 256 + d], (excl + (unsigned)off) | OS_INC);
         S.gbase[d] = (int)(gprefix[d] + excl);
     }
     {

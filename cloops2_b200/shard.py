@@ -113,10 +113,10 @@ def barrier():
 def worker_contexts(device=None, nthreads=None):
     """One cl2 context (= CUDA stream + scratch) per host worker thread of this rank.  Chromosome files are
     independent units, so a rank processes several at once: while one thread's kernels run, another thread does its
-    host-side bookkeeping (ctypes calls and numpy release the GIL).  CL2_THREADS overrides the default of 4."""
+    host-side bookkeeping (ctypes calls and numpy release the GIL).  CL2_THREADS overrides the default of 6."""
     from . import _lib
     if nthreads is None:
-        nthreads = int(os.environ.get("CL2_THREADS", "4"))
+        nthreads = int(os.environ.get("CL2_THREADS", "6"))
     nthreads = max(1, nthreads)
     first = _lib.default_context(device)
     return [first] + [_lib.Context(first.device) for _ in range(nthreads - 1)]
