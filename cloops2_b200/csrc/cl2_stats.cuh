@@ -12,8 +12,10 @@
 
 #ifdef __CUDACC__
 #define CL2_HD __host__ __device__ __forceinline__
+#define CL2_HD_OUTLINE __attribute__((unused)) static __host__ __device__ __noinline__      // the three tail functions: called rarely, keep code small
 #else
 #define CL2_HD static inline
+#define CL2_HD_OUTLINE static
 #endif
 
 #define CL2_LN_SQRT_2PI 0.918938533204672741780329736406
@@ -128,7 +130,7 @@ CL2_HD double cl2_tail_down(int kind, double k, double kmin, double logpk, doubl
 }
 
 // scipy.stats.poisson.sf(k - 1, mu) = P(X >= k), k integer >= 0 as double
-CL2_HD double cl2_poisson_sf_ge(double k, double mu) {
+CL2_HD_OUTLINE double cl2_poisson_sf_ge(double k, double mu) {
     if (!(mu >= 0)) return NAN;
     if (k <= 0) return 1.0;
     if (mu == 0) return 0.0;
@@ -138,7 +140,7 @@ CL2_HD double cl2_poisson_sf_ge(double k, double mu) {
 }
 
 // scipy.stats.binom.sf(k - 1, n, p) = P(X >= k)
-CL2_HD double cl2_binom_sf_ge(double k, double n, double p) {
+CL2_HD_OUTLINE double cl2_binom_sf_ge(double k, double n, double p) {
     if (!(p >= 0 && p <= 1) || !(n >= 0)) return NAN;
     if (k <= 0) return 1.0;
     if (k > n) return 0.0;
@@ -156,7 +158,7 @@ CL2_HD double cl2_log_dhyper(double x, double M, double n, double N) {
     double p = N / M, q = (M - N) / M;
     return cl2_log_dbinom(x, n, p, q) + cl2_log_dbinom(N - x, M - n, p, q) - cl2_log_dbinom(N, M, p, q);
 }
-CL2_HD double cl2_hypergeom_sf_ge(double k, double M, double n, double N) {
+CL2_HD_OUTLINE double cl2_hypergeom_sf_ge(double k, double M, double n, double N) {
     double lo = fmax(0.0, N + n - M), hi = fmin(n, N);
     if (k <= lo) return 1.0;
     if (k > hi) return 0.0;
