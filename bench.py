@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pets", type=float, default=100e6, help="PETs per GPU (default: the 100 M of configs[1])")
-    ap.add_argument("--cpu-sample-pets", type=float, default=3.0e6)
+    ap.add_argument("--cpu-sample-pets", type=float, default=5.5e6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true", help="do not record per-kernel CUDA events in the timed steps")
     return ap.parse_args()
