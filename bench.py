@@ -386,13 +386,15 @@ def main():
         top = max(fam.items(), key=lambda kv: kv[1]["ms"])
         nm, v = top
         ach = (v["bytes"] / 1e9) / (v["ms"] / 1e3) if v["ms"] > 0 else 0.0
-        traffic = None
+        traffic, traffic_note = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(nm)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(nm)
+            traffic, traffic_note = tj["dram_bytes_per_launch"], tj["note"]
         except Exception:
             pass
         roof = {"bound": "hbm", "kernel": nm, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": traffic, "peak_source": peak_src,
+                "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
+                "measured_in": "single-stream instrumented pass of the resident step (kernels_note)",
                 "avg_launch_ms": v["ms"] / max(1, v["launches"]),
                 "algorithmic_bytes_per_launch": v["bytes"] / max(1, v["launches"])}
     h2d, d2h = int(xfer[0]) // args.steps, int(xfer[1]) // args.steps      # counted by the library per copy

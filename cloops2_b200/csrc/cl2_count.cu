@@ -719,7 +719,7 @@ extern "C" int cl2_est_loops(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops,
         CL2_TRY(sc.get(&d_stats_c, (size_t)nk * CL2_NSTAT));
         CL2_CUDA(ctx, cudaMemcpyAsync(d_selbuf, d_total, 8, cudaMemcpyDeviceToDevice, ctx->stream));
         {
-            FamTimer t(ctx, FAM_COUNT, 0.0);
+            FamTimer t(ctx, FAM_MISC, 120.0 * (double)nk + 4.0 * (double)L);
             k_est_compact<<<cl2_grid(L, 256), 256, 0, ctx->stream>>>(d_flag, d_loops, L, d_core, d_hyp, d_stats, d_sel, d_core_c,
                                                                      d_hyp_c, d_stats_c);
         }
