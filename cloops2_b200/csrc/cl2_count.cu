@@ -413,15 +413,15 @@ __device__ double warp_median(WarpVals &S, int m, int lane) {
 #define CL2_NSTAT 13
 // Permuted-window background, enrichment tests and anchor tests of one loop (one warp); results into o[13] (shared):
 // mrabs, mbps, fdr, poisson sf, binomial sf, px, esx, py, esy, count_x, wide_x, count_y, wide_y
-// early_cut > 0 (fused cis kernel): return false right after the background statistics when the candidate fails
-// `mrabs >= rab or fdr >= 0.1` / `es < 1` (callCisLoops.py:322-327), before the anchor windows and the tails.
-__device__ bool loop_tests_warp(const int2 *__restrict__ byx, const int2 *__restrict__ byy, int64_t n, long long xs,
-                                long long xe, long long ys, long long ye, double ra, double rb, double rab, int win,
-                                int mode, double rpb, WarpAcc &S, WarpVals &V, int lane, double *o, double early_cut,
-                                long long *g_scan) {
+// Background of one loop (one warp): permuted windows -> mrabs, mbps, fdr (callCisLoops.py:207-223, 315-321).
+// early_cut > 0 (cis): return false as soon as `mrabs >= rab or fdr >= 0.1` or `es < 1` (:322-327) is known.
+__device__ bool loop_background(const int2 *__restrict__ byx, const int2 *__restrict__ byy, int64_t n, long long xs,
+                                long long xe, long long ys, long long ye, double rab, int win, int mode, WarpAcc &S,
+                                WarpVals &V, int lane, double early_cut, double *o_mrabs, double *o_mbps,
+                                double *o_fdr, long long *g_scan) {
     const int W = 2 * win, m = W * W;
     loop_windows(byx, byy, n, xs, xe, ys, ye, win, lane, S, g_scan);
-    // rabs: counts of the 4*win^2 window pairs; fdr = #{rabs > rab} / m   (callCisLoops.py:315-321)
+    // rabs: counts of the 4*win^2 window pairs; fdr = #{rabs > rab} / m
     int gt = 0;
     for (int t = lane; t < m; t += 32) {
         V.v[t] = (double)S.nab[t];
@@ -430,11 +430,8 @@ __device__ bool loop_tests_warp(const int2 *__restrict__ byx, const int2 *__rest
     gt = warp_sum(gt);
     __syncwarp();
     double mrabs, mbps;
-    if (mode == CL2_MODE_CIS) {
-        mrabs = warp_median(V, m, lane);
-    } else {
-        mrabs = np_pairwise_sum(V.v, m) / (double)m;     // every lane computes the same value
-    }
+    if (mode == CL2_MODE_CIS) mrabs = warp_median(V, m, lane);
+    else mrabs = np_pairwise_sum(V.v, m) / (double)m;     // every lane computes the same value
     __syncwarp();
     const double fdr = (double)gt / (double)m;
     if (early_cut > 0) {
@@ -452,11 +449,20 @@ __device__ bool loop_tests_warp(const int2 *__restrict__ byx, const int2 *__rest
     __syncwarp();
     if (mode == CL2_MODE_CIS) mbps = warp_median(V, m, lane);
     else mbps = np_pairwise_sum(V.v, m) / (double)m;
+    __syncwarp();
+    *o_mrabs = mrabs; *o_mbps = mbps; *o_fdr = fdr;
+    return true;
+}
+
+// Anchor windows and the tail probabilities of one loop (one warp): o[3..12] = poisson sf, binomial sf, px, esx, py,
+// esy, count_x, wide_x, count_y, wide_y  (callCisLoops.py:226-247, 329-333)
+__device__ void loop_tail(const int2 *__restrict__ byx, const int2 *__restrict__ byy, int64_t n, long long xs,
+                          long long xe, long long ys, long long ye, double ra, double rb, double rab, double mrabs,
+                          double mbps, int mode, double rpb, int lane, double *o, long long *g_scan) {
     int64_t cx, wx, cy, wy;
     loop_anchor(byx, byy, n, xs, xe, lane, &cx, &wx, g_scan);
     loop_anchor(byx, byy, n, ys, ye, lane, &cy, &wy, g_scan);
     if (lane == 0) {
-        o[0] = mrabs; o[1] = mbps; o[2] = fdr;
         o[3] = cl2_poisson_sf_ge(rab, mrabs);                                            // :329
         o[9] = (double)cx; o[10] = (double)wx; o[11] = (double)cy; o[12] = (double)wy;
     } else if (lane == 1) {
@@ -472,7 +478,16 @@ __device__ bool loop_tests_warp(const int2 *__restrict__ byx, const int2 *__rest
         o[lane == 2 ? 6 : 8] = count / c;
     }
     __syncwarp();
-    return true;
+}
+
+// both parts (the two-phase API, cl2_loop_tests)
+__device__ void loop_tests_warp(const int2 *__restrict__ byx, const int2 *__restrict__ byy, int64_t n, long long xs,
+                                long long xe, long long ys, long long ye, double ra, double rb, double rab, int win,
+                                int mode, double rpb, WarpAcc &S, WarpVals &V, int lane, double *o, long long *g_scan) {
+    double mrabs, mbps, fdr;
+    loop_background(byx, byy, n, xs, xe, ys, ye, rab, win, mode, S, V, lane, 0.0, &mrabs, &mbps, &fdr, g_scan);
+    if (lane == 0) { o[0] = mrabs; o[1] = mbps; o[2] = fdr; }
+    loop_tail(byx, byy, n, xs, xe, ys, ye, ra, rb, rab, mrabs, mbps, mode, rpb, lane, o, g_scan);
 }
 
 // phase 2 as a separate launch (cl2_loop_tests)
@@ -489,24 +504,23 @@ __global__ void __launch_bounds__(CNT_WARPS * 32) k_loop_tests(const int2 *__res
     const longlong4 lp = loops[k];
     long long scanned = 0;
     loop_tests_warp(byx, byy, n, lp.x, lp.y, lp.z, lp.w, (double)core[4 * k], (double)core[4 * k + 1],
-                    (double)core[4 * k + 2], win, mode, rpb, acc[w], vals[w], lane, ost[w], 0.0, &scanned);
+                    (double)core[4 * k + 2], win, mode, rpb, acc[w], vals[w], lane, ost[w], &scanned);
     if (lane < CL2_NSTAT) stats[CL2_NSTAT * k + lane] = ost[w][lane];
 }
 
-// Whole estLoopSig arithmetic for one candidate per warp, including the reference's filter cascade
-// (cis callCisLoops.py:282-347, trans callTransLoops.py:127-139): only survivors are written, flag[k] marks them.
-__global__ void __launch_bounds__(CNT_WARPS * 32) k_est_loops(const int2 *__restrict__ byx, const int2 *__restrict__ byy,
-                                                               int64_t n, const longlong4 *__restrict__ loops, int64_t L,
-                                                               int win, int mode, int minPts, int hic, double cdc,
-                                                               double pseudo, double peakPcut, double rpb,
-                                                               long long *__restrict__ core_out,
-                                                               double *__restrict__ hyp_out,
-                                                               double *__restrict__ stats_out,
-                                                               int32_t *__restrict__ flag,
-                                                               unsigned long long *__restrict__ scanned_total) {
+// estLoopSig on the device, kernel A (every candidate, one warp each; integer counting + medians only, so the code
+// stays small): the count filters of the reference's cascade (cis callCisLoops.py:282-307, trans callTransLoops.py:
+// 127-139), the permuted-window background and, for cis, the background cut (:322-327).  Survivors get flag = 1 and
+// core[4], stats[0..2] = mrabs, mbps, fdr.  The hypergeometric cut (:311) is applied by kernel B: the cascade is a
+// conjunction, so the order of the tests does not change which candidates survive.
+__global__ void __launch_bounds__(CNT_WARPS * 32) k_est_bg(const int2 *__restrict__ byx, const int2 *__restrict__ byy,
+                                                            int64_t n, const longlong4 *__restrict__ loops, int64_t L,
+                                                            int win, int mode, int minPts, int hic, double cdc,
+                                                            double pseudo, long long *__restrict__ core_out,
+                                                            double *__restrict__ stats_out, int32_t *__restrict__ flag,
+                                                            unsigned long long *__restrict__ scanned_total) {
     __shared__ WarpAcc acc[CNT_WARPS];
     __shared__ WarpVals vals[CNT_WARPS];
-    __shared__ double ost[CNT_WARPS][CL2_NSTAT];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t k = (int64_t)blockIdx.x * CNT_WARPS + w;
     if (k >= L) return;
@@ -526,27 +540,13 @@ __global__ void __launch_bounds__(CNT_WARPS * 32) k_est_loops(const int2 *__rest
         double lower = (double)c[3];
         double p2ll = rab / (lower > pseudo ? lower : pseudo);                         // :306
         if (cis && hic && p2ll < 1.0) keep = false;                                    // :307
-        double hyp = 0.0;
         if (keep) {
-            if (lane == 0) hyp = cl2_hypergeom_sf_ge(rab, (double)n, ra, rb);          // :310
-            hyp = __shfl_sync(0xffffffffu, hyp, 0);
-            if (cis && fmax(1e-300, hyp) > 1e-2) keep = false;                         // :311
-        }
-        if (keep) {
-            double *o = ost[w];
-            keep = loop_tests_warp(byx, byy, n, xs, xe, ys, ye, ra, rb, rab, win, mode, rpb, acc[w], vals[w], lane, o,
-                                   cis ? pseudo : 0.0, &scanned);
-            if (keep && cis) {
-                double mrabs = o[0], fdr = o[2];
-                if (mrabs >= rab || fdr >= 0.1) keep = false;                          // :322
-                double es = rab / (mrabs > pseudo ? mrabs : pseudo);                   // :325
-                if (es < 1.0) keep = false;
-                if (!hic && !(fmax(1e-300, o[5]) < peakPcut && fmax(1e-300, o[7]) < peakPcut)) keep = false;   // :347
-            }
-            if (keep) {
-                if (lane < 4) core_out[4 * k + lane] = c[lane];
-                if (lane == 0) hyp_out[k] = hyp;
-                if (lane < CL2_NSTAT) stats_out[CL2_NSTAT * k + lane] = o[lane];
+            double mrabs, mbps, fdr;
+            keep = loop_background(byx, byy, n, xs, xe, ys, ye, rab, win, mode, acc[w], vals[w], lane,
+                                   cis ? pseudo : 0.0, &mrabs, &mbps, &fdr, &scanned);
+            if (keep && lane == 0) {
+                core_out[4 * k] = c[0]; core_out[4 * k + 1] = c[1]; core_out[4 * k + 2] = c[2]; core_out[4 * k + 3] = c[3];
+                stats_out[CL2_NSTAT * k] = mrabs; stats_out[CL2_NSTAT * k + 1] = mbps; stats_out[CL2_NSTAT * k + 2] = fdr;
             }
         }
     }
@@ -556,22 +556,53 @@ __global__ void __launch_bounds__(CNT_WARPS * 32) k_est_loops(const int2 *__rest
     }
 }
 
-// gather the surviving rows (flag set; pos = exclusive scan of the flags) into dense arrays, order preserved
-__global__ void __launch_bounds__(256) k_est_compact(const int32_t *__restrict__ pos, const longlong4 *__restrict__ loops,
-                                                      int64_t L, const long long *__restrict__ core,
-                                                      const double *__restrict__ hyp, const double *__restrict__ stats,
+// kernel B (survivors of kernel A, compacted; one warp each): hypergeometric / Poisson / binomial tails, anchor
+// windows and tests, and the remaining cuts (:311 hypergeometric > 1e-2, :347 anchor peaks unless -hic).
+__global__ void __launch_bounds__(CNT_WARPS * 32) k_est_tail(const int2 *__restrict__ byx, const int2 *__restrict__ byy,
+                                                              int64_t n, const longlong4 *__restrict__ loops,
+                                                              const long long *__restrict__ sel, int64_t K, int mode,
+                                                              int hic, double peakPcut, double rpb,
+                                                              const long long *__restrict__ core, double *__restrict__ hyp,
+                                                              double *__restrict__ stats, int32_t *__restrict__ flag2,
+                                                              unsigned long long *__restrict__ scanned_total) {
+    __shared__ double ost[CNT_WARPS][CL2_NSTAT];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * CNT_WARPS + w;
+    if (i >= K) return;
+    long long scanned = 0;
+    const longlong4 lp = loops[sel[i]];
+    const double ra = (double)core[4 * i], rb = (double)core[4 * i + 1], rab = (double)core[4 * i + 2];
+    const double mrabs = stats[CL2_NSTAT * i], mbps = stats[CL2_NSTAT * i + 1];
+    const bool cis = mode == CL2_MODE_CIS;
+    double *o = ost[w];
+    double h = 0.0;
+    if (lane == 4) h = cl2_hypergeom_sf_ge(rab, (double)n, ra, rb);                    // :310
+    loop_tail(byx, byy, n, lp.x, lp.y, lp.z, lp.w, ra, rb, rab, mrabs, mbps, mode, rpb, lane, o, &scanned);
+    h = __shfl_sync(0xffffffffu, h, 4);
+    bool keep = true;
+    if (cis && fmax(1e-300, h) > 1e-2) keep = false;                                   // :311
+    if (cis && !hic && !(fmax(1e-300, o[5]) < peakPcut && fmax(1e-300, o[7]) < peakPcut)) keep = false;   // :347
+    if (lane >= 3 && lane < CL2_NSTAT) stats[CL2_NSTAT * i + lane] = o[lane];
+    if (lane == 0) {
+        hyp[i] = h;
+        flag2[i] = keep ? 1 : 0;
+        if (scanned) atomicAdd(scanned_total, (unsigned long long)scanned);
+    }
+}
+
+// gather the survivors of kernel A (flag set; pos = exclusive scan of the flags) into dense arrays, order preserved
+__global__ void __launch_bounds__(256) k_est_compact(const int32_t *__restrict__ pos, int64_t L,
+                                                      const long long *__restrict__ core, const double *__restrict__ stats,
                                                       long long *__restrict__ sel, long long *__restrict__ core_c,
-                                                      double *__restrict__ hyp_c, double *__restrict__ stats_c) {
+                                                      double *__restrict__ stats_c) {
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= L) return;
     int p = pos[k];
     bool kept = (k + 1 < L) ? (pos[k + 1] != p) : (sel[-1] != (long long)p);   // sel[-1] holds the total
-    (void)loops;
     if (!kept) return;
     sel[p] = k;
     for (int j = 0; j < 4; j++) core_c[4 * (int64_t)p + j] = core[4 * k + j];
-    hyp_c[p] = hyp[k];
-    for (int j = 0; j < CL2_NSTAT; j++) stats_c[CL2_NSTAT * (int64_t)p + j] = stats[CL2_NSTAT * k + j];
+    for (int j = 0; j < 3; j++) stats_c[CL2_NSTAT * (int64_t)p + j] = stats[CL2_NSTAT * k + j];
 }
 
 extern "C" int cl2_loop_counts(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops, int64_t L, int32_t win, int32_t mode,
@@ -679,13 +710,12 @@ extern "C" int cl2_est_loops(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops,
     CL2_CUDA(ctx, cudaSetDevice(ctx->device));
     Scratch sc(ctx);
     longlong4 *d_loops;
-    long long *d_core, *d_sel, *d_core_c;
-    double *d_hyp, *d_stats, *d_hyp_c, *d_stats_c;
+    long long *d_core;
+    double *d_stats;
     int32_t *d_flag;
     int64_t *d_total;
     CL2_TRY(sc.get(&d_loops, (size_t)L));
     CL2_TRY(sc.get(&d_core, (size_t)L * 4));
-    CL2_TRY(sc.get(&d_hyp, (size_t)L));
     CL2_TRY(sc.get(&d_stats, (size_t)L * CL2_NSTAT));
     CL2_TRY(sc.get(&d_flag, (size_t)L));
     CL2_TRY(sc.get(&d_total, 2));
@@ -694,42 +724,65 @@ extern "C" int cl2_est_loops(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops,
     ctx->h2d_bytes += L * 32;
     {
         FamTimer t(ctx, FAM_COUNT, 0.0);
-        k_est_loops<<<cl2_grid(L, CNT_WARPS), CNT_WARPS * 32, 0, ctx->stream>>>(idx->byx, idx->byy, idx->n, d_loops, L, win, mode,
-                                                                                minPts, hic, countDiffCut, pseudo, peakPcut, rpb,
-                                                                                d_core, d_hyp, d_stats, d_flag,
-                                                                                (unsigned long long *)(d_total + 1));
+        k_est_bg<<<cl2_grid(L, CNT_WARPS), CNT_WARPS * 32, 0, ctx->stream>>>(idx->byx, idx->byy, idx->n, d_loops, L, win, mode,
+                                                                             minPts, hic, countDiffCut, pseudo, d_core, d_stats,
+                                                                             d_flag, (unsigned long long *)(d_total + 1));
     }
     CL2_TRY(cl2_exclusive_scan_i32(ctx, d_flag, L, d_total));
     int64_t nk = 0;
     CL2_TRY(cl2_read_i64(ctx, d_total, &nk));
-    if (ctx->timing) {
-        // algorithmic traffic of the counting launch: 16 B per scanned member on the reference layout
-        int64_t scanned = 0;
-        CL2_TRY(cl2_read_i64(ctx, d_total + 1, &scanned));
-        ctx->fam_bytes[FAM_COUNT] += 16.0 * (double)scanned + 32.0 * (double)L;
-    }
-    *n_out = nk;
+    std::vector<int32_t> f2;
     if (nk > 0) {
         // d_selbuf[0] carries the total so the compaction kernel can tell whether the last row survived
-        long long *d_selbuf;
+        long long *d_selbuf, *d_sel, *d_core_c;
+        double *d_hyp_c, *d_stats_c;
+        int32_t *d_flag2;
         CL2_TRY(sc.get(&d_selbuf, (size_t)nk + 1));
         d_sel = d_selbuf + 1;
         CL2_TRY(sc.get(&d_core_c, (size_t)nk * 4));
         CL2_TRY(sc.get(&d_hyp_c, (size_t)nk));
         CL2_TRY(sc.get(&d_stats_c, (size_t)nk * CL2_NSTAT));
+        CL2_TRY(sc.get(&d_flag2, (size_t)nk));
         CL2_CUDA(ctx, cudaMemcpyAsync(d_selbuf, d_total, 8, cudaMemcpyDeviceToDevice, ctx->stream));
         {
-            FamTimer t(ctx, FAM_MISC, 120.0 * (double)nk + 4.0 * (double)L);
-            k_est_compact<<<cl2_grid(L, 256), 256, 0, ctx->stream>>>(d_flag, d_loops, L, d_core, d_hyp, d_stats, d_sel, d_core_c,
-                                                                     d_hyp_c, d_stats_c);
+            FamTimer t(ctx, FAM_MISC, 60.0 * (double)nk + 4.0 * (double)L);
+            k_est_compact<<<cl2_grid(L, 256), 256, 0, ctx->stream>>>(d_flag, L, d_core, d_stats, d_sel, d_core_c, d_stats_c);
         }
+        {
+            FamTimer t(ctx, FAM_COUNT, 0.0);
+            k_est_tail<<<cl2_grid(nk, CNT_WARPS), CNT_WARPS * 32, 0, ctx->stream>>>(idx->byx, idx->byy, idx->n, d_loops, d_sel, nk,
+                                                                                    mode, hic, peakPcut, rpb, d_core_c, d_hyp_c,
+                                                                                    d_stats_c, d_flag2,
+                                                                                    (unsigned long long *)(d_total + 1));
+        }
+        f2.resize((size_t)nk);
         CL2_CUDA(ctx, cudaMemcpyAsync(sel, d_sel, (size_t)nk * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CL2_CUDA(ctx, cudaMemcpyAsync(core, d_core_c, (size_t)nk * 32, cudaMemcpyDeviceToHost, ctx->stream));
         CL2_CUDA(ctx, cudaMemcpyAsync(hyp, d_hyp_c, (size_t)nk * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CL2_CUDA(ctx, cudaMemcpyAsync(stats, d_stats_c, (size_t)nk * CL2_NSTAT * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        ctx->d2h_bytes += nk * (8 + 32 + 8 + CL2_NSTAT * 8);
+        CL2_CUDA(ctx, cudaMemcpyAsync(f2.data(), d_flag2, (size_t)nk * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->d2h_bytes += nk * (8 + 32 + 8 + CL2_NSTAT * 8 + 4);
         CL2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    if (ctx->timing) {
+        // algorithmic traffic of the counting launches: 16 B per scanned member on the reference layout
+        int64_t scanned = 0;
+        CL2_TRY(cl2_read_i64(ctx, d_total + 1, &scanned));
+        ctx->fam_bytes[FAM_COUNT] += 16.0 * (double)scanned + 32.0 * (double)L;
+    }
     CL2_CUDA(ctx, cudaGetLastError());
+    // rows that failed kernel B's cuts are dropped here (few rows: kernel A already removed ~95 % of the candidates)
+    int64_t m = 0;
+    for (int64_t i = 0; i < nk; i++) {
+        if (!f2[i]) continue;
+        if (m != i) {
+            sel[m] = sel[i];
+            memcpy(core + 4 * m, core + 4 * i, 32);
+            hyp[m] = hyp[i];
+            memcpy(stats + CL2_NSTAT * m, stats + CL2_NSTAT * i, CL2_NSTAT * 8);
+        }
+        m++;
+    }
+    *n_out = m;
     return CL2_OK;
 }
