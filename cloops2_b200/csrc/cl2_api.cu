@@ -273,6 +273,7 @@ void cl2_grid_free(cl2_ctx *ctx, cl2_grid_cache &g) {
     cl2_dev_free(ctx, g.ckey);
     cl2_dev_free(ctx, g.nbr);
     cl2_dev_free(ctx, g.s3);
+    cl2_dev_free(ctx, g.first);
     g = cl2_grid_cache();
 }
 
@@ -286,6 +287,8 @@ extern "C" void cl2_points_free(cl2_ctx *ctx, cl2_points *pts) {
     if (!ctx || !pts) return;
     cudaSetDevice(ctx->device);
     cl2_grid_free(ctx, pts->grid);
+    cl2_dev_free(ctx, pts->byy);
+    cl2_dev_free(ctx, pts->rowy);
     cl2_dev_free(ctx, pts->xy);
     delete pts;
 }

@@ -41,27 +41,31 @@ __global__ void __launch_bounds__(256) k_gather_xy(const int2 *__restrict__ xy, 
 }
 
 // ------------------------------------------------------------------------------------------------ K4 cells
-__global__ void __launch_bounds__(256) k_head_flags(const uint64_t *__restrict__ key, int32_t *__restrict__ flag,
-                                                     int64_t n) {
+// Cells are the runs of equal packed key in the sorted order; the key is recomputed from the sorted coordinates.
+__global__ void __launch_bounds__(256) k_head_flags(const int2 *__restrict__ sxy, const cl2_keygen gen,
+                                                     int32_t *__restrict__ flag, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    flag[i] = (i == 0 || key[i] != key[i - 1]) ? 1 : 0;
+    flag[i] = (i == 0 || cl2_cell_key(gen, sxy[i]) != cl2_cell_key(gen, sxy[i - 1])) ? 1 : 0;
 }
 
 // cid holds the exclusive scan of the head flags on entry; on exit the cell id of every sorted position.
-__global__ void __launch_bounds__(256) k_cell_table(const uint64_t *__restrict__ key, int32_t *__restrict__ cid,
+// first[c] = smallest file row of the cell (the reference's dict position of the cell, blockDBSCAN.py:83).
+__global__ void __launch_bounds__(256) k_cell_table(const int2 *__restrict__ sxy, const cl2_keygen gen,
+                                                     const uint32_t *__restrict__ row, int32_t *__restrict__ cid,
                                                      int32_t *__restrict__ cstart, uint64_t *__restrict__ ckey,
-                                                     int64_t n, int32_t ncells) {
+                                                     uint32_t *__restrict__ first, int64_t n, int32_t ncells) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint64_t k = key[i];
-    bool head = (i == 0 || k != key[i - 1]);
+    uint64_t k = cl2_cell_key(gen, sxy[i]);
+    bool head = (i == 0 || k != cl2_cell_key(gen, sxy[i - 1]));
     int32_t c = cid[i] + (head ? 1 : 0) - 1;
     cid[i] = c;
     if (head) {
         cstart[c] = (int32_t)i;
         ckey[c] = k;
     }
+    atomicMin(&first[c], row[i]);
     if (i == n - 1) cstart[ncells] = (int32_t)n;
 }
 
@@ -359,7 +363,7 @@ __global__ void __launch_bounds__(HEAVY_THREADS) k_block_adj_heavy(const int2 *_
 // near = cnt + sum of adjacent kept cells' cnt; core iff near >= minPts (blockDBSCAN.py:179-189).
 // okey orders cells like the stable sort by -cnt of blockDBSCAN.py:147 (ties: dict position = first row id).
 __global__ void __launch_bounds__(256) k_block_core(const int32_t *__restrict__ cstart, const int32_t *__restrict__ nbr,
-                                                     const unsigned *__restrict__ adj, const uint32_t *__restrict__ row,
+                                                     const unsigned *__restrict__ adj, const uint32_t *__restrict__ first,
                                                      const int32_t *__restrict__ list, int32_t nkept, int minPts,
                                                      int32_t maxcnt, uint8_t *__restrict__ core,
                                                      uint64_t *__restrict__ okey, int32_t *__restrict__ parent,
@@ -377,7 +381,7 @@ __global__ void __launch_bounds__(256) k_block_core(const int32_t *__restrict__ 
         near += cstart[b + 1] - cstart[b];
     }
     core[c] = near >= minPts ? 1 : 0;
-    okey[c] = ((uint64_t)(uint32_t)(maxcnt - cnt) << 32) | (uint64_t)row[cstart[c]];
+    okey[c] = ((uint64_t)(uint32_t)(maxcnt - cnt) << 32) | (uint64_t)first[c];
     parent[c] = c;
     minkey[c] = ~0ull;
 }
@@ -607,7 +611,17 @@ int cl2_grid_build(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int kind) {
     gen.by = by;
     gen.gx0 = rgx0;
     gen.gy0 = rgy0;
-    CL2_TRY(cl2_radix_sort_gen(ctx, gen, k0, k1, v0, v1, n, bx + by, &ks, &vs));
+    if (kind == 0) {
+        // (column, row) order = stable sort by column of the rows already sorted by y: the row index (y-miny)/eps is
+        // monotone in y, so only the bx column bits are sorted (3 passes for hg38 at eps >= 100 instead of 5-6)
+        CL2_TRY(cl2_points_yorder(ctx, pts));
+        cl2_keygen gcol = gen;
+        gcol.kind = CL2_KEY_GX_YX;
+        gcol.xy = pts->byy;
+        CL2_TRY(cl2_radix_sort_gen(ctx, gcol, k0, k1, v0, v1, n, bx, &ks, &vs, pts->rowy));
+    } else {
+        CL2_TRY(cl2_radix_sort_gen(ctx, gen, k0, k1, v0, v1, n, bx + by, &ks, &vs));
+    }
     // keep the sorted row ids (take ownership of whichever buffer holds them)
     sc.release(vs);
     g.row = vs;
@@ -621,7 +635,7 @@ int cl2_grid_build(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int kind) {
     CL2_TRY(sc.get(&d_total, 1));
     {
         FamTimer t(ctx, FAM_CELLS, 12.0 * (double)n);
-        k_head_flags<<<cl2_grid(n, 256), 256, 0, ctx->stream>>>(ks, g.cid, n);
+        k_head_flags<<<cl2_grid(n, 256), 256, 0, ctx->stream>>>(g.sxy, gen, g.cid, n);
     }
     CL2_TRY(cl2_exclusive_scan_i32(ctx, g.cid, n, d_total));
     int64_t ncells64 = 0;
@@ -631,9 +645,11 @@ int cl2_grid_build(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int kind) {
     CL2_TRY(cl2_dev_alloc(ctx, &g.ckey, (size_t)ncells));
     CL2_TRY(cl2_dev_alloc(ctx, &g.nbr, (size_t)ncells * 8));
     CL2_TRY(cl2_dev_alloc(ctx, &g.s3, (size_t)ncells));
+    CL2_TRY(cl2_dev_alloc(ctx, &g.first, (size_t)ncells));
+    CL2_CUDA(ctx, cudaMemsetAsync(g.first, 0xff, (size_t)ncells * 4, ctx->stream));
     {
-        FamTimer t(ctx, FAM_CELLS, 16.0 * (double)n);
-        k_cell_table<<<cl2_grid(n, 256), 256, 0, ctx->stream>>>(ks, g.cid, g.cstart, g.ckey, n, ncells);
+        FamTimer t(ctx, FAM_CELLS, 20.0 * (double)n);
+        k_cell_table<<<cl2_grid(n, 256), 256, 0, ctx->stream>>>(g.sxy, gen, g.row, g.cid, g.cstart, g.ckey, g.first, n, ncells);
     }
     int32_t *d_max;
     CL2_TRY(sc.get(&d_max, 1));
@@ -767,7 +783,7 @@ extern "C" int cl2_block_dbscan(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int3
         }
         {
             FamTimer t(ctx, FAM_CORE, 64.0 * (double)nkept);
-            k_block_core<<<cl2_grid(nkept, 256), 256, 0, s>>>(g.cstart, g.nbr, adj, g.row, list, nkept, minPts, g.maxcnt,
+            k_block_core<<<cl2_grid(nkept, 256), 256, 0, s>>>(g.cstart, g.nbr, adj, g.first, list, nkept, minPts, g.maxcnt,
                                                                core, okey, parent, minkey);
         }
         {

@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(256) k_c2_union(const int32_t *__restrict__ nb
 }
 // root, component order key (smallest first-row over its cells, cDBSCAN2.py:117-140) and core-point total
 __global__ void __launch_bounds__(256) k_c2_roots(const int32_t *__restrict__ ncore, const int32_t *__restrict__ cstart,
-                                                   const uint32_t *__restrict__ row, int32_t ncells,
+                                                   const uint32_t *__restrict__ first, int32_t ncells,
                                                    int32_t *__restrict__ parent, int32_t *__restrict__ root,
                                                    unsigned *__restrict__ minkey, int32_t *__restrict__ compcore) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(256) k_c2_roots(const int32_t *__restrict__ nc
     if (ncore[c] == 0) { root[c] = -1; return; }
     int r = c2_find(parent, c);
     root[c] = r;
-    atomicMin(&minkey[r], row[cstart[c]]);
+    atomicMin(&minkey[r], first[c]);
     atomicAdd(&compcore[r], ncore[c]);
 }
 __global__ void __launch_bounds__(256) k_c2_status_init(const int32_t *__restrict__ root,
@@ -533,7 +533,7 @@ extern "C" int cl2_cdbscan2(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int32_t 
     {
         FamTimer t(ctx, FAM_UNION, 56.0 * (double)ncells, 3);
         if (nactive > 0) k_c2_union<<<cl2_grid(nactive, 256), 256, 0, s>>>(g.nbr, adj, ncore, alist, nactive, parent);
-        k_c2_roots<<<cl2_grid(ncells, 256), 256, 0, s>>>(ncore, g.cstart, g.row, ncells, parent, root, minkey, compcore);
+        k_c2_roots<<<cl2_grid(ncells, 256), 256, 0, s>>>(ncore, g.cstart, g.first, ncells, parent, root, minkey, compcore);
         k_c2_status_init<<<cl2_grid(ncells, 256), 256, 0, s>>>(root, compcore, ncells, minPts, status, nunknown);
     }
     {

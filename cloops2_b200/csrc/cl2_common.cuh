@@ -198,6 +198,7 @@ static inline int cl2_grid(int64_t n, int block) { return (int)((n + block - 1) 
 #define CL2_KEY_ROT 2     // cDBSCAN2 grid: truncating division of x-y and x+y, shifted by gx0 / gy0
 #define CL2_KEY_X 3       // x coordinate (XY index)
 #define CL2_KEY_Y 4       // y coordinate
+#define CL2_KEY_GX_YX 5   // blockDBSCAN column index (x-minx)/eps from the y-sorted (y,x) array
 struct cl2_keygen {
     int kind = CL2_KEY_ARRAY;
     const int2 *xy = nullptr;
@@ -207,8 +208,26 @@ struct cl2_keygen {
     int gx0 = 0;
     unsigned gy0 = 0;
 };
+// vals_first (optional): values of the unsorted input (read by the first pass only, never written); when null the
+// first pass generates 0..n-1.
 int cl2_radix_sort_gen(cl2_ctx *ctx, const cl2_keygen &gen, uint64_t *keys0, uint64_t *keys1, uint32_t *vals0,
-                       uint32_t *vals1, int64_t n, int nbits, uint64_t **kout, uint32_t **vout);
+                       uint32_t *vals1, int64_t n, int nbits, uint64_t **kout, uint32_t **vout,
+                       const uint32_t *vals_first = nullptr);
+
+#ifdef __CUDACC__
+// packed cell key of a point for the two grids (blockDBSCAN.py:81-82 on non-negative ints; cDBSCAN2.py:67-70 with
+// truncation toward zero, shifted so both fields are non-negative)
+__device__ __forceinline__ uint64_t cl2_cell_key(const cl2_keygen &g, int2 p) {
+    if (g.kind == CL2_KEY_ROT) {
+        int u = p.x - p.y;
+        unsigned v = (unsigned)p.x + (unsigned)p.y;
+        unsigned gx = (unsigned)(u / (int)g.eps - g.gx0), gy = v / g.eps - g.gy0;
+        return ((uint64_t)gx << g.by) | (uint64_t)gy;
+    }
+    unsigned gx = (unsigned)(p.x - g.minx) / g.eps, gy = (unsigned)(p.y - g.miny) / g.eps;
+    return ((uint64_t)gx << g.by) | (uint64_t)gy;
+}
+#endif
 // Stable LSD radix sort of (uint64 key, uint32 val) pairs on bits [0, nbits).  keys/vals are double buffers;
 // on return *kout / *vout point at the buffer holding the sorted data.
 int cl2_radix_sort_pairs(cl2_ctx *ctx, uint64_t *keys0, uint64_t *keys1, uint32_t *vals0, uint32_t *vals1, int64_t n,

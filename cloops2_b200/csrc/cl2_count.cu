@@ -12,19 +12,38 @@
 #include "cl2_stats.cuh"
 
 // ------------------------------------------------------------------------------------------------ index build
-__global__ void __launch_bounds__(256) k_index_keys(const int2 *__restrict__ xy, uint64_t *__restrict__ key, int64_t n,
-                                                     int which) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int2 p = xy[i];
-    key[i] = (uint64_t)(uint32_t)(which == 0 ? p.x : p.y);
-}
 __global__ void __launch_bounds__(256) k_index_gather(const int2 *__restrict__ xy, const uint32_t *__restrict__ row,
                                                        int2 *__restrict__ out, int64_t n, int which) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int2 p = __ldg(&xy[row[i]]);
     out[i] = which == 0 ? p : make_int2(p.y, p.x);
+}
+
+// (y, x) sorted by y plus the file row of every sorted position; kept on the points object
+int cl2_points_yorder(cl2_ctx *ctx, cl2_points *pts) {
+    if (pts->byy || pts->n == 0) return CL2_OK;
+    const int64_t n = pts->n;
+    Scratch sc(ctx);
+    uint64_t *k0, *k1, *ks;
+    uint32_t *v0, *v1, *vs;
+    CL2_TRY(sc.get(&k0, (size_t)n));
+    CL2_TRY(sc.get(&k1, (size_t)n));
+    CL2_TRY(sc.get(&v0, (size_t)n));
+    CL2_TRY(sc.get(&v1, (size_t)n));
+    cl2_keygen gen;
+    gen.kind = CL2_KEY_Y;
+    gen.xy = pts->xy;
+    CL2_TRY(cl2_radix_sort_gen(ctx, gen, k0, k1, v0, v1, n, bits_for((uint64_t)pts->ext[3]), &ks, &vs));
+    CL2_TRY(cl2_dev_alloc(ctx, &pts->byy, (size_t)n));
+    {
+        FamTimer t(ctx, FAM_INDEX, 20.0 * (double)n);
+        k_index_gather<<<cl2_grid(n, 256), 256, 0, ctx->stream>>>(pts->xy, vs, pts->byy, n, 1);
+    }
+    sc.release(vs);
+    pts->rowy = vs;
+    CL2_CUDA(ctx, cudaGetLastError());
+    return CL2_OK;
 }
 
 extern "C" int cl2_index_build(cl2_ctx *ctx, cl2_points *pts, cl2_index **out) {
@@ -41,22 +60,25 @@ extern "C" int cl2_index_build(cl2_ctx *ctx, cl2_points *pts, cl2_index **out) {
         uint64_t *k0 = nullptr, *k1 = nullptr, *ks;
         uint32_t *v0 = nullptr, *v1 = nullptr, *vs;
         do {
+            if ((rc = cl2_points_yorder(ctx, pts))) break;
             if ((rc = sc.get(&k0, (size_t)n)) || (rc = sc.get(&k1, (size_t)n)) || (rc = sc.get(&v0, (size_t)n)) ||
                 (rc = sc.get(&v1, (size_t)n)))
                 break;
             if ((rc = cl2_dev_alloc(ctx, &ix->byx, (size_t)n)) || (rc = cl2_dev_alloc(ctx, &ix->byy, (size_t)n))) break;
-            for (int which = 0; which < 2 && rc == CL2_OK; which++) {
-                int64_t hi = which == 0 ? pts->ext[1] : pts->ext[3];
-                cl2_keygen gen;
-                gen.kind = which == 0 ? CL2_KEY_X : CL2_KEY_Y;
-                gen.xy = pts->xy;
-                rc = cl2_radix_sort_gen(ctx, gen, k0, k1, v0, v1, n, bits_for((uint64_t)hi), &ks, &vs);
-                if (rc) break;
-                FamTimer t(ctx, FAM_INDEX, 20.0 * (double)n);
-                k_index_gather<<<cl2_grid(n, 256), 256, 0, ctx->stream>>>(pts->xy, vs, which == 0 ? ix->byx : ix->byy, n,
-                                                                           which);
+            // the index owns a copy of the y-order so it may outlive the points object
+            if (cudaMemcpyAsync(ix->byy, pts->byy, (size_t)n * sizeof(int2), cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) {
+                rc = cl2_fail(ctx, CL2_ERR_CUDA, "cl2_index_build: copy failed");
+                break;
             }
+            cl2_keygen gen;
+            gen.kind = CL2_KEY_X;
+            gen.xy = pts->xy;
+            rc = cl2_radix_sort_gen(ctx, gen, k0, k1, v0, v1, n, bits_for((uint64_t)pts->ext[1]), &ks, &vs);
             if (rc) break;
+            {
+                FamTimer t(ctx, FAM_INDEX, 20.0 * (double)n);
+                k_index_gather<<<cl2_grid(n, 256), 256, 0, ctx->stream>>>(pts->xy, vs, ix->byx, n, 0);
+            }
             if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
                 rc = cl2_fail(ctx, CL2_ERR_CUDA, "cl2_index_build: kernel failure");
             }

@@ -19,12 +19,17 @@ struct cl2_grid_cache {
     uint64_t *ckey = nullptr;   // [ncells]
     int32_t *nbr = nullptr;     // [ncells*8] neighbour cell id or -1, order of blockDBSCAN.py:54-55
     int32_t *s3 = nullptr;      // [ncells]  population of the 3x3 block
+    uint32_t *first = nullptr;  // [ncells]  smallest file row of the cell = its dict position in the reference
 };
 
 struct cl2_points {
     int64_t n = 0;
     int2 *xy = nullptr;      // [n] int32 coordinates, file order after the cut/mcut filter
     int64_t ext[4] = {0, 0, 0, 0};  // minX, maxX, minY, maxY
+    // y-order of the points, built once (XY index, and the starting order of every blockDBSCAN grid sort: a stable
+    // sort of the y-sorted rows by column index alone yields (column, row-of-grid) order in 3 passes instead of 5-6)
+    int2 *byy = nullptr;        // [n] (y, x) sorted by y
+    uint32_t *rowy = nullptr;   // [n] file row of y-sorted position
     cl2_grid_cache grid;
     // result of the last clustering run
     int32_t ncl = 0;
@@ -41,6 +46,7 @@ struct cl2_index {
 void cl2_grid_free(cl2_ctx *ctx, cl2_grid_cache &g);
 // keygen -> radix sort -> gather -> cell table -> neighbours + 3x3 sums (cl2_block.cu); cached per (eps, kind)
 int cl2_grid_build(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int kind);
+int cl2_points_yorder(cl2_ctx *ctx, cl2_points *pts);   // cl2_count.cu
 int cl2_read_i64(cl2_ctx *ctx, const int64_t *d, int64_t *out);
 int cl2_read_i32(cl2_ctx *ctx, const int32_t *d, int32_t *out);
 

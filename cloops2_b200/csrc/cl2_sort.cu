@@ -245,16 +245,8 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_downsweep(const uint64_t *__r
 __device__ __forceinline__ uint64_t os_key(const cl2_keygen &g, const uint64_t *__restrict__ keys, int64_t i) {
     if (g.kind == CL2_KEY_ARRAY) return keys[i];
     int2 p = g.xy[i];
-    if (g.kind == CL2_KEY_BLOCK) {        // blockDBSCAN.py:81-82 on non-negative ints
-        unsigned gx = (unsigned)(p.x - g.minx) / g.eps, gy = (unsigned)(p.y - g.miny) / g.eps;
-        return ((uint64_t)gx << g.by) | (uint64_t)gy;
-    }
-    if (g.kind == CL2_KEY_ROT) {          // cDBSCAN2.py:67-70, truncation toward zero
-        int u = p.x - p.y;
-        unsigned v = (unsigned)p.x + (unsigned)p.y;
-        unsigned gx = (unsigned)(u / (int)g.eps - g.gx0), gy = v / g.eps - g.gy0;
-        return ((uint64_t)gx << g.by) | (uint64_t)gy;
-    }
+    if (g.kind == CL2_KEY_BLOCK || g.kind == CL2_KEY_ROT) return cl2_cell_key(g, p);
+    if (g.kind == CL2_KEY_GX_YX) return (uint64_t)((unsigned)(p.y - g.minx) / g.eps);   // g.xy holds (y, x) pairs
     return (uint64_t)(uint32_t)(g.kind == CL2_KEY_X ? p.x : p.y);
 }
 
@@ -434,7 +426,8 @@ __global__ void __launch_bounds__(OS_THREADS, 2) k_os_pass(const uint64_t *__res
 }
 
 static int radix_sort_onesweep(cl2_ctx *ctx, const cl2_keygen &gen, uint64_t *keys0, uint64_t *keys1, uint32_t *vals0,
-                               uint32_t *vals1, int64_t n, int passes, uint64_t **kout, uint32_t **vout) {
+                               uint32_t *vals1, int64_t n, int passes, uint64_t **kout, uint32_t **vout,
+                               const uint32_t *vals_first) {
     int ntiles = (int)((n + OS_TILE - 1) / OS_TILE);
     Scratch sc(ctx);
     unsigned *ghist, *desc, *ticket;
@@ -462,9 +455,10 @@ static int radix_sort_onesweep(cl2_ctx *ctx, const cl2_keygen &gen, uint64_t *ke
     for (int p = 0; p < passes; p++) {
         {
             FamTimer t(ctx, FAM_SORT_SCATTER, 24.0 * (double)n);
-            k_os_pass<<<ntiles, OS_THREADS, sizeof(OsSmem), ctx->stream>>>(kin, p == 0 ? gen : none, vi, ko, vo, n, p * 8, ghist + p * 256,
+            const uint32_t *vin = (p == 0 && vals_first) ? vals_first : vi;
+            k_os_pass<<<ntiles, OS_THREADS, sizeof(OsSmem), ctx->stream>>>(kin, p == 0 ? gen : none, vin, ko, vo, n, p * 8, ghist + p * 256,
                                                                             desc + (size_t)p * ntiles * 256, ticket + p,
-                                                                            p == 0 ? 1 : 0);
+                                                                            (p == 0 && !vals_first) ? 1 : 0);
         }
         uint64_t *tk = kin; kin = ko; ko = tk;
         uint32_t *tv = vi; vi = vo; vo = tv;
@@ -481,14 +475,16 @@ __global__ void __launch_bounds__(256) k_os_materialise(const cl2_keygen gen, ui
 }
 
 int cl2_radix_sort_gen(cl2_ctx *ctx, const cl2_keygen &gen, uint64_t *keys0, uint64_t *keys1, uint32_t *vals0,
-                       uint32_t *vals1, int64_t n, int nbits, uint64_t **kout, uint32_t **vout) {
+                       uint32_t *vals1, int64_t n, int nbits, uint64_t **kout, uint32_t **vout,
+                       const uint32_t *vals_first) {
     *kout = keys0;
     *vout = vals0;
     if (n <= 0) return CL2_OK;
     if (nbits < 1) nbits = 1;
     int passes = (nbits + 7) / 8;
     if (n < (int64_t)OS_VAL && passes <= OS_MAXPASS && !getenv("CL2_SORT_3KERNEL"))
-        return radix_sort_onesweep(ctx, gen, keys0, keys1, vals0, vals1, n, passes, kout, vout);
+        return radix_sort_onesweep(ctx, gen, keys0, keys1, vals0, vals1, n, passes, kout, vout, vals_first);
+    if (vals_first) return cl2_fail(ctx, CL2_ERR_RANGE, "radix sort: more than 2^30 rows with a value input");
     if (gen.kind != CL2_KEY_ARRAY) {
         FamTimer t(ctx, FAM_KEYGEN, 16.0 * (double)n);
         k_os_materialise<<<cl2_grid(n, 256), 256, 0, ctx->stream>>>(gen, keys0, n);
@@ -506,7 +502,7 @@ int cl2_radix_sort_pairs(cl2_ctx *ctx, uint64_t *keys0, uint64_t *keys1, uint32_
     if (n < (int64_t)OS_VAL && passes <= OS_MAXPASS && !getenv("CL2_SORT_3KERNEL")) {
         cl2_keygen none;
         none.kind = CL2_KEY_ARRAY;
-        return radix_sort_onesweep(ctx, none, keys0, keys1, vals0, vals1, n, passes, kout, vout);
+        return radix_sort_onesweep(ctx, none, keys0, keys1, vals0, vals1, n, passes, kout, vout, nullptr);
     }
     int ntiles = (int)((n + RS_TILE - 1) / RS_TILE);
     Scratch sc(ctx);
