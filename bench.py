@@ -332,7 +332,7 @@ def main():
         return shard.max_over_ranks(wall), dev_ms, clocks, fam, sum(c.launch_count() for c in ctxs), (int(xf[0]), int(xf[1]))
 
     wall, dev_ms, clocks, _, launches, _ = timed(step_resident, args.warmup, args.steps, False)
-    wall_e, _, clocks_e, _, _, xfer = timed(step_e2e, max(1, args.warmup - 2), args.steps, False)
+    wall_e, _, clocks_e, _, _, xfer = timed(step_e2e, args.warmup, args.steps, False)
     # Per-kernel roofline: the timed steps run several chromosome files concurrently on separate streams, where a
     # CUDA-event pair around one launch also spans other streams' kernels.  The per-kernel numbers therefore come from
     # the same resident step run once more on ONE stream at a time (same launches, same inputs), events enabled.

@@ -70,7 +70,6 @@ def cis_chromosome(ctx, key, xy, tot, eps, minPts, cut=0, mcut=-1, hic=False, em
             c, s = cluster_pass(pts, ep, mp, hic=hic, cis=True)
             _log("Clustering %s and %s finished. Estimated %s candidate loops with %s PETs." % (key[0], key[1], len(c), int(s.sum())))
             per_pass.append(c)
-        pts.drop_cache()                      # the eps grid is only reusable inside the sweep
         t1 = time.perf_counter()
         # The reference merges the passes (combineLoops), drops distance <= cut and duplicates, then tests.  A
         # candidate's test result depends on its coordinates only, so the duplicates are removed AFTER the tests, on
@@ -82,6 +81,7 @@ def cis_chromosome(ctx, key, xy, tot, eps, minPts, cut=0, mcut=-1, hic=False, em
         if logger is not None and cands.shape[0]:
             stats["candidates"] = int(hostops.combine_unique([cands]).shape[0])      # the number the reference logs
         if cands.shape[0] == 0:
+            pts.drop_cache()
             return hostops._empty_cols(), stats
         mm = min(minPts) if emPair else max(minPts)                                 # :557-560
         ext = pts.extent()
@@ -94,6 +94,7 @@ def cis_chromosome(ctx, key, xy, tot, eps, minPts, cut=0, mcut=-1, hic=False, em
             cols = hostops.est_cis(index, cands, pts.n, span, tot, mm, hic=hic)
         finally:
             index.close()
+            pts.drop_cache()                  # eps grid + y-order: derived data, rebuilt by the next call
         cols = hostops.take(cols, hostops.first_occurrence(cols["coords"]))         # filterDupLoops :159-169
         t3 = time.perf_counter()
         stats["tested"] = int(cols["coords"].shape[0])

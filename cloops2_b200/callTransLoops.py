@@ -30,13 +30,13 @@ def trans_pair(ctx, key, xy, eps, minPts, pts=None, exact=False):
             for mp in minPts:
                 c, _ = cluster_pass(pts, ep, mp, hic=False, cis=False)
                 per_pass.append(c)
-        pts.drop_cache()
         # combineLoops only (callTransLoops.py:230-234): coordinates already seen in an EARLIER pass are dropped,
         # duplicates inside one pass survive.  As on the cis path the de-duplication is applied after the tests.
         cands = np.concatenate(per_pass, axis=0) if len(per_pass) > 1 else per_pass[0]
         pass_id = np.concatenate([np.full(len(c), i, dtype=np.int64) for i, c in enumerate(per_pass)])
         stats["candidates"] = int(cands.shape[0])
         if cands.shape[0] == 0:
+            pts.drop_cache()
             return hostops._empty_cols(), stats
         ext = pts.extent()
         span = float(int(ext[3]) - int(ext[0]))
@@ -45,6 +45,7 @@ def trans_pair(ctx, key, xy, eps, minPts, pts=None, exact=False):
             cols = hostops.est_trans(index, cands, pts.n, span, max(minPts), pass_id=pass_id)
         finally:
             index.close()
+            pts.drop_cache()
         cols = hostops.take(cols, hostops.first_occurrence(cols["coords"], cols.pop("pass_id")))
         stats["tested"] = int(cols["coords"].shape[0])
         final = hostops.select_twice(cols, hostops.mark_sig_trans(cols))

@@ -281,6 +281,10 @@ extern "C" void cl2_points_drop_cache(cl2_ctx *ctx, cl2_points *pts) {
     if (!ctx || !pts) return;
     cudaSetDevice(ctx->device);
     cl2_grid_free(ctx, pts->grid);
+    cl2_dev_free(ctx, pts->byy);     // the y-order is derived data too: the next sweep rebuilds it
+    cl2_dev_free(ctx, pts->rowy);
+    pts->byy = nullptr;
+    pts->rowy = nullptr;
 }
 
 extern "C" void cl2_points_free(cl2_ctx *ctx, cl2_points *pts) {

@@ -61,7 +61,8 @@ int cl2_points_extent(cl2_ctx *ctx, const cl2_points *pts, int64_t ext[4]);
 /* kept rows back to the host as int64[n,2] (for -filter, callCisLoops.py:450-468) */
 int cl2_points_download(cl2_ctx *ctx, const cl2_points *pts, int64_t *xy_out);
 void cl2_points_free(cl2_ctx *ctx, cl2_points *pts);
-/* Release the cached eps grid of `pts` (kept between the minPts values of one eps); the points stay resident. */
+/* Release the derived data cached on `pts` (the eps grid kept between the minPts values of one eps, and the
+ * y-sorted order shared by the grid sorts and the XY index); the points themselves stay resident. */
 void cl2_points_drop_cache(cl2_ctx *ctx, cl2_points *pts);
 
 /* ---- clustering --------------------------------------------------------------------------------------- */
