@@ -307,21 +307,55 @@ __device__ void loop_windows(const int2 *__restrict__ byx, const int2 *__restric
     Range rxa = range_of(byx, n, SA), rya = range_of(byy, n, SA);
     Range rxb = range_of(byx, n, SB), ryb = range_of(byy, n, SB);
     *g_scan += (rxa.e - rxa.b) + (rya.e - rya.b) + (rxb.e - rxb.b) + (ryb.e - ryb.b);
-    // four lists; a PET is handled by the first list that contains it
+    // four lists; a PET is handled by the first list that contains it.  Each list is sorted by the coordinate that put
+    // the PET into it ("primary": x for the X-sorted lists, y for the Y-sorted ones), so the 32 PETs of a batch can
+    // only fall into the few windows [t_lo, t_hi] that meet [first, last] of the batch -- found with two ballots over
+    // the (ascending) window bounds.  The other three coordinate / window-set combinations are rare and go through
+    // the span pre-tests of coord_mask_in().
     for (int pass = 0; pass < 4; pass++) {
         const int2 *arr = (pass & 1) ? byy : byx;
-        Range r = pass == 0 ? rxa : pass == 1 ? rya : pass == 2 ? rxb : ryb;
+        const Range r = pass == 0 ? rxa : pass == 1 ? rya : pass == 2 ? rxb : ryb;
+        const bool prim_a = pass < 2;                       // primary coordinate is tested against the a-windows
+        const int *plo = prim_a ? S.alo : S.blo, *phi = prim_a ? S.ahi : S.bhi;
         for (int64_t i0 = r.b; i0 < r.e; i0 += 32) {
-            int64_t i = i0 + lane;
+            const int64_t i = i0 + lane;
+            const bool valid = i < r.e;
+            int2 p = valid ? arr[i] : make_int2(0, 0);
+            const int prim = p.x;                            // first component = the sort coordinate of this list
+            const int64_t left = r.e - i0;
+            const int first = __shfl_sync(0xffffffffu, prim, 0);
+            const int last = __shfl_sync(0xffffffffu, prim, left >= 32 ? 31 : (int)left - 1);
+            const unsigned bl = __ballot_sync(0xffffffffu, lane < W && phi[lane < W ? lane : 0] >= first);
+            const unsigned bh = __ballot_sync(0xffffffffu, lane < W && plo[lane < W ? lane : 0] <= last);
             unsigned ma = 0, mb = 0;
-            if (i < r.e) {
-                int2 p = arr[i];
-                int x = (pass & 1) ? p.y : p.x, y = (pass & 1) ? p.x : p.y;
+            if (valid) {
+                const int x = (pass & 1) ? p.y : p.x, y = (pass & 1) ? p.x : p.y;
                 bool dup = false;
                 if (pass >= 1 && in_iv(SA, x)) dup = true;                       // seen in list 0
                 if (pass >= 2 && in_iv(SA, y)) dup = true;                       // seen in list 1
                 if (pass == 3 && in_iv(SB, x)) dup = true;                       // seen in list 2
-                if (!dup) window_masks(S, W, x, y, &ma, &mb);
+                if (!dup) {
+                    unsigned mp = 0;
+                    if (bl && bh) {
+                        const int t_lo = __ffs(bl) - 1, t_hi = 31 - __clz(bh);
+                        for (int t = t_lo; t <= t_hi; t++) mp |= ((prim >= plo[t] && prim <= phi[t]) ? 1u : 0u) << t;
+                    }
+                    const int sec = (pass & 1) ? x : y;     // the other coordinate
+                    unsigned ms = 0, mo = 0;
+                    if (prim_a) {
+                        if (sec >= S.sa_lo && sec <= S.sa_hi) ms = coord_mask(S.alo, S.ahi, W, sec);
+                        if (prim >= S.sb_lo && prim <= S.sb_hi) mo |= coord_mask(S.blo, S.bhi, W, prim);
+                        if (sec >= S.sb_lo && sec <= S.sb_hi) mo |= coord_mask(S.blo, S.bhi, W, sec);
+                        ma = mp | ms;
+                        mb = mo;
+                    } else {
+                        if (sec >= S.sb_lo && sec <= S.sb_hi) ms = coord_mask(S.blo, S.bhi, W, sec);
+                        if (prim >= S.sa_lo && prim <= S.sa_hi) mo |= coord_mask(S.alo, S.ahi, W, prim);
+                        if (sec >= S.sa_lo && sec <= S.sa_hi) mo |= coord_mask(S.alo, S.ahi, W, sec);
+                        mb = mp | ms;
+                        ma = mo;
+                    }
+                }
             }
             if (__any_sync(0xffffffffu, (ma | mb) != 0)) window_accumulate(S, W, ma, mb, lane);
         }
