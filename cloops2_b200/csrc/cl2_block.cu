@@ -22,17 +22,6 @@ __constant__ int c_dy[8] = {-1, 1, 0, 0, -1, 1, -1, 1};
 // opposite direction index
 __constant__ int c_opp[8] = {1, 0, 3, 2, 7, 6, 5, 4};
 
-// ------------------------------------------------------------------------------------------------ K1 keygen
-__global__ void __launch_bounds__(256) k_block_keygen(const int2 *__restrict__ xy, uint64_t *__restrict__ key,
-                                                       int64_t n, int minx, int miny, unsigned eps, int by) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int2 p = xy[i];
-    unsigned gx = (unsigned)(p.x - minx) / eps;   // == int((X-minX)/eps) of blockDBSCAN.py:81 for non-negative ints
-    unsigned gy = (unsigned)(p.y - miny) / eps;
-    key[i] = ((uint64_t)gx << by) | (uint64_t)gy;
-}
-
 // ------------------------------------------------------------------------------------------------ K3 gather
 __global__ void __launch_bounds__(256) k_gather_xy(const int2 *__restrict__ xy, const uint32_t *__restrict__ row,
                                                     int2 *__restrict__ sxy, int64_t n) {
@@ -556,20 +545,6 @@ int cl2_read_i32(cl2_ctx *ctx, const int32_t *d, int32_t *out) {
     CL2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *out = *(int32_t *)ctx->h_scratch;
     return CL2_OK;
-}
-
-// cDBSCAN2 grid (cDBSCAN2.py:67-70): rotate by 45 degrees, cell = truncating division (toward zero) of u = X-Y and
-// v = X+Y by eps; the indices are shifted by the truncated lower bounds so the packed fields are non-negative.
-__global__ void __launch_bounds__(256) k_rot_keygen(const int2 *__restrict__ xy, uint64_t *__restrict__ key, int64_t n,
-                                                     int eps, int gx0, unsigned gy0, int by) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int2 p = xy[i];
-    int u = p.x - p.y;
-    unsigned v = (unsigned)p.x + (unsigned)p.y;
-    unsigned gx = (unsigned)(u / eps - gx0);          // C division truncates toward zero == int(x / cw)
-    unsigned gy = v / (unsigned)eps - gy0;
-    key[i] = ((uint64_t)gx << by) | (uint64_t)gy;
 }
 
 // Build (or reuse) the eps grid: keygen -> radix sort -> gather -> cell table -> neighbours + 3x3 sums.

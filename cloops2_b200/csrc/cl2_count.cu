@@ -211,18 +211,6 @@ __device__ __forceinline__ unsigned coord_mask(const int *__restrict__ lo, const
     return m;
 }
 
-// membership masks of one PET against the 2*win a-windows and b-windows (getPerRegions, callCisLoops.py:191-198).
-// A coordinate outside a span cannot be in any window of that set, which skips most of the comparisons.
-__device__ __forceinline__ void window_masks(const WarpAcc &A, int W, int x, int y, unsigned *ma, unsigned *mb) {
-    unsigned a = 0, b = 0;
-    if (x >= A.sa_lo && x <= A.sa_hi) a |= coord_mask(A.alo, A.ahi, W, x);
-    if (y >= A.sa_lo && y <= A.sa_hi) a |= coord_mask(A.alo, A.ahi, W, y);
-    if (x >= A.sb_lo && x <= A.sb_hi) b |= coord_mask(A.blo, A.bhi, W, x);
-    if (y >= A.sb_lo && y <= A.sb_hi) b |= coord_mask(A.blo, A.bhi, W, y);
-    *ma = a;
-    *mb = b;
-}
-
 __device__ __forceinline__ void window_accumulate(WarpAcc &A, int W, unsigned ma, unsigned mb, int lane) {
     for (int t = 0; t < W; t++) {
         unsigned va = __ballot_sync(0xffffffffu, (ma >> t) & 1u);
