@@ -174,3 +174,54 @@ def test_fused_est_loops_equals_step_by_step(gpu_ctx):
         finally:
             idx.close()
             pts.close()
+
+
+def test_trans_larger_vs_oracle(gpu_ctx):
+    """configs[3]-style shard (one chromosome pair at the 200 M-PET density: ~0.7 M PETs) vs the oracle pipeline."""
+    files = {"chr5-chr9": synth.trans_pair(181_538_259, 138_394_717, 700_000, 59, sigma=1000, per=20000)}
+    want = oracle.call_trans_loops(files, eps=[5000], minPts=[20, 10])
+    final, st = trans_pair(gpu_ctx, ("chr5", "chr9"), files["chr5-chr9"], [5000], [20, 10], exact=True)
+    assert len(want) > 5
+    assert _rows(cols_to_loops(("chr5", "chr9"), final, cis=False)) == _rows(want)
+
+
+def test_hic_larger_vs_oracle(gpu_ctx):
+    """-hic (cDBSCAN2) whole path on a Hi-C-like chromosome, two eps x two minPts (configs[2] parameters)."""
+    files = {"chr20-chr20": synth.cis_chrom(20_000_000, 300_000, 77, "hic")}
+    tot = len(files["chr20-chr20"])
+    want, _ = oracle.call_cis_loops(files, tot, [5000, 10000], [50, 20], hic=True)
+    final, st = cis_chromosome(gpu_ctx, ("chr20", "chr20"), files["chr20-chr20"], tot, [5000, 10000], [50, 20], hic=True,
+                               exact=True)
+    assert len(want) > 5
+    assert _rows(cols_to_loops(("chr20", "chr20"), final)) == _rows(want)
+
+
+def test_command_line_subprocess(gpu_ctx, tmp_path):
+    """`python -m cloops2_b200.cli callLoops ...` end to end (flag parsing, eps/minPts ordering, -trans, outputs)."""
+    import subprocess
+    import sys
+    g, files = golden_cis_files()
+    gt, tfiles = golden_trans_files()
+    allf = dict(files)
+    allf.update(tfiles)
+    d = str(tmp_path / "d")
+    synth.write_ixy_dir(allf, d)
+    meta = json.load(open(d + "/petMeta.json"))
+    meta["Unique PETs"] = int(g["tot"])
+    meta["data"]["cis"] = {k: meta["data"]["cis"][k] for k in g["order"].tolist()}
+    meta["data"]["trans"] = {k: meta["data"]["trans"][k] for k in gt["order"].tolist()}
+    json.dump(meta, open(d + "/petMeta.json", "w"))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "o")
+    # eps given unsorted: the command sorts ascending (cLoops2.py:69-70), so the result equals the golden run
+    r = subprocess.run([sys.executable, "-m", "cloops2_b200.cli", "callLoops", "-d", d, "-o", out, "-eps", "1000,200,500",
+                        "-minPts", "5", "-w", "-j"], cwd=str(tmp_path), env=dict(os.environ, PYTHONPATH=root),
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert open(out + "_loops.txt").read() == str(g["default_txt"])
+    assert os.path.getsize(out + "_loops_juicebox.txt") > 0 and os.path.getsize(out + "_loops_newWashU.txt") > 0
+    assert os.path.exists(str(tmp_path / "cLoops2.log"))
+    r = subprocess.run([sys.executable, "-m", "cloops2_b200.cli", "callLoops", "-d", d, "-o", out + "2", "-eps", "0",
+                        "-minPts", "5"], cwd=str(tmp_path), env=dict(os.environ, PYTHONPATH=root), capture_output=True,
+                       text=True, timeout=120)
+    assert r.returncode == 1 and not os.path.exists(out + "2_loops.txt")        # "Input eps is 0. Return."
