@@ -208,18 +208,11 @@ def selSigLoops(key, loops):
     return key, [loops[i] for i in pick]
 
 
-def filterPETs(key, predir, fixy, loops, margin=1):
-    """-filter (callCisLoops.py:425-468): keep PETs with an end inside any merged anchor."""
-    _log("Filtering PETs of %s with %s loops." % (key, len(loops)))
-    if not loops:
-        return
-    iv = []
-    for lp in loops:
-        iv.append((lp.x_start, lp.x_end))
-        iv.append((lp.y_start, lp.y_end))
-    iv.sort()
-    # getAllAnchors (:425-447): covered base pairs merged while the gap between consecutive covered positions is
-    # <= margin; the reference's loop drops the final covered position of the last anchor.
+def getAllAnchors(loops, margin=1):
+    """Merged anchor intervals (callCisLoops.py:425-447).  The reference enumerates every covered base pair; here the
+    intervals are merged directly.  Its scan closes the LAST interval one covered position early (`end = cov[j-1]`
+    after the inner loop runs out, :441-444) -- reproduced."""
+    iv = sorted([(lp.x_start, lp.x_end) for lp in loops] + [(lp.y_start, lp.y_end) for lp in loops])
     merged = []
     for s, e in iv:
         if merged and s - merged[-1][1] <= margin:
@@ -227,16 +220,27 @@ def filterPETs(key, predir, fixy, loops, margin=1):
         else:
             merged.append([s, e])
     if merged:
-        if merged[-1][1] > merged[-1][0]:
-            merged[-1][1] -= 1
-        elif len(merged) > 1:
-            merged.pop()
+        merged[-1][1] -= 1           # anchors hold >= 2 positions (x_start != x_end), so this never empties one
+    return merged
+
+
+def filterPETs(key, predir, fixy, loops, margin=1):
+    """-filter (callCisLoops.py:450-468): keep PETs with an end inside any merged anchor.  The reference collects the
+    row ids in Python sets and writes `mat[list(set)]`; the same insertions are replayed in the same order (rows by
+    ascending coordinate, ties by row, X hits then Y hits, anchor by anchor) so the row order of the new .ixy is the
+    reference's."""
+    _log("Filtering PETs of %s with %s loops." % (key, len(loops)))
+    anchors = getAllAnchors(loops, margin=margin)
     key2, mat = parseIxy(fixy)
+    ordx = np.argsort(mat[:, 0], kind="stable")
+    ordy = np.argsort(mat[:, 1], kind="stable")
+    xs, ys = mat[ordx, 0], mat[ordy, 1]
     rs = set()
-    xs, ys = mat[:, 0], mat[:, 1]
-    for s, e in merged:
-        hit = np.nonzero(((xs >= s) & (xs <= e)) | ((ys >= s) & (ys <= e)))[0]
-        rs.update(hit.tolist())
+    for l, r in anchors:
+        xps, yps = set(), set()
+        xps.update(ordx[np.searchsorted(xs, l, side="left"):np.searchsorted(xs, r, side="right")].tolist())
+        yps.update(ordy[np.searchsorted(ys, l, side="left"):np.searchsorted(ys, r, side="right")].tolist())
+        rs.update(xps.union(yps))
     rs = list(rs)
     if len(rs) == 0:
         return

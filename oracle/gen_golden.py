@@ -10,7 +10,8 @@ Contents
   dbscan_small.npz     120 random point sets (sparse, clustered, duplicate-heavy, X>Y rows) with the reference's
                        blockDBSCAN and cDBSCAN `.labels` (as int32 arrays, -1 = absent from the dict)
   cis_pipeline.npz     two synthetic chromosomes + the reference's callCisLoops `_loops.txt` (default and -hic,
-                       eps 200,500,1000 / minPts 5; plus a two-minPts, cut/mcut run)
+                       eps 200,500,1000 / minPts 5; plus a two-minPts, cut/mcut run, an -emPair run and the
+                       OUT_filtered/*.ixy matrices of a -filter run)
   trans_pipeline.npz   two synthetic chromosome pairs + the reference's callTransLoops `_trans_loops.txt`
   estsig_cis.npz       per-candidate fields of the reference's estLoopSig on one chromosome (every attribute)
 """
@@ -85,11 +86,17 @@ def gen_dbscan(ref):
                         params=np.array(params), labels_block=np.concatenate(lb), labels_c2=np.concatenate(lc))
 
 
-def run_ref_cis(ref, files, **kw):
+def run_ref_cis(ref, files, want_filtered=False, **kw):
     tmp = tempfile.mkdtemp()
     synth.write_ixy_dir(files, tmp + "/d")
-    ref.cis.callCisLoops(tmp + "/d", tmp + "/out", ref.logger, cpu=1, **kw)
+    ref.cis.callCisLoops(tmp + "/d", tmp + "/out", ref.logger, cpu=1, filter=want_filtered, **kw)
     meta = json.load(open(tmp + "/d/petMeta.json"))
+    if want_filtered:
+        import joblib
+        filt = {k: joblib.load(tmp + "/out_filtered/%s.ixy" % k) for k in files
+                if os.path.exists(tmp + "/out_filtered/%s.ixy" % k)}
+        ftot = json.load(open(tmp + "/out_filtered/petMeta.json"))["Unique PETs"]
+        return open(tmp + "/out_loops.txt").read(), filt, ftot
     return open(tmp + "/out_loops.txt").read(), list(meta["data"]["cis"].keys()), meta["Unique PETs"]
 
 
@@ -102,6 +109,11 @@ def gen_cis(ref):
     out["hic_txt"] = run_ref_cis(ref, files, eps=[200, 500, 1000], minPts=[5], hic=True)[0]
     out["cut_txt"] = run_ref_cis(ref, files, eps=[300, 800], minPts=[8, 4], cut=2000, mcut=1500000)[0]
     out["empair_txt"] = run_ref_cis(ref, files, eps=[800, 300], minPts=[4, 8], emPair=True)[0]
+    ftxt, filt, ftot = run_ref_cis(ref, files, want_filtered=True, eps=[200, 500, 1000], minPts=[5])
+    assert ftxt == txt
+    out["filter_tot"] = ftot
+    for k, v in filt.items():                     # -filter output: rows AND row order of OUT_filtered/<key>.ixy
+        out["filter_" + k.replace("-", "_")] = v
     np.savez_compressed(os.path.join(GOLD, "cis_pipeline.npz"), order=np.array(order), tot=tot,
                         **{k.replace("-", "_"): v for k, v in files.items()}, **out)
     # per-candidate estLoopSig fields on one chromosome

@@ -225,3 +225,21 @@ def test_command_line_subprocess(gpu_ctx, tmp_path):
                         "-minPts", "5"], cwd=str(tmp_path), env=dict(os.environ, PYTHONPATH=root), capture_output=True,
                        text=True, timeout=120)
     assert r.returncode == 1 and not os.path.exists(out + "2_loops.txt")        # "Input eps is 0. Return."
+
+
+def test_filter_option_files_match_golden(gpu_ctx, tmp_path):
+    """callCisLoops(..., filter=True): OUT_filtered/<key>.ixy (rows and row order) and its petMeta.json."""
+    import joblib
+    g, files = golden_cis_files()
+    d = str(tmp_path / "d")
+    synth.write_ixy_dir(files, d)
+    meta = json.load(open(d + "/petMeta.json"))
+    meta["data"]["cis"] = {k: meta["data"]["cis"][k] for k in g["order"].tolist()}
+    json.dump(meta, open(d + "/petMeta.json", "w"))
+    out = str(tmp_path / "o")
+    callCisLoops(d, out, logging.getLogger("t"), eps=[200, 500, 1000], minPts=[5], filter=True)
+    assert open(out + "_loops.txt").read() == str(g["default_txt"])
+    for k in files:
+        assert np.array_equal(joblib.load(out + "_filtered/%s.ixy" % k), g["filter_" + k.replace("-", "_")]), k
+    fmeta = json.load(open(out + "_filtered/petMeta.json"))
+    assert fmeta["Unique PETs"] == int(g["filter_tot"]) and sorted(fmeta["data"]["cis"]) == sorted(files)

@@ -3,6 +3,8 @@ Host-side logic of the product (vectorised numpy + native selection) against the
 The device index is replaced by a stand-in that answers loop_counts from the oracle's C counting, so these run
 without a GPU; the GPU tests exercise the same code with the real kernels.
 """
+import os
+
 import numpy as np
 
 import oracle
@@ -197,3 +199,23 @@ def test_first_occurrence_rules():
     assert hostops.first_occurrence(c).tolist() == [0, 1, 4]
     # trans: duplicates inside the first pass that holds them survive, later passes are dropped
     assert hostops.first_occurrence(c, np.array([0, 0, 0, 1, 1])).tolist() == [0, 1, 2, 4]
+
+
+def test_filter_pets_matches_reference_rows_and_order(tmp_path):
+    """-filter (callCisLoops.py:425-468): the rewritten .ixy matrices equal the reference's, row order included."""
+    import joblib
+    from cloops2_b200 import synth
+    from cloops2_b200.callCisLoops import filterPETs
+    g, files = golden_cis_files()
+    d = str(tmp_path / "d")
+    synth.write_ixy_dir(files, d)
+    _, per_key = oracle.call_cis_loops(files, int(g["tot"]), [200, 500, 1000], [5])
+    out = str(tmp_path / "f")
+    os.makedirs(out)
+    tot = 0
+    for k, loops in per_key.items():
+        filterPETs(k, out, d + "/%s.ixy" % k, loops, margin=1000)
+        got = joblib.load(out + "/%s.ixy" % k)
+        assert np.array_equal(got, g["filter_" + k.replace("-", "_")]), k
+        tot += len(got)
+    assert tot == int(g["filter_tot"])
