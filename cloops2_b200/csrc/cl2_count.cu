@@ -212,13 +212,19 @@ __device__ __forceinline__ unsigned coord_mask(const int *__restrict__ lo, const
 }
 
 __device__ __forceinline__ void window_accumulate(WarpAcc &A, int W, unsigned ma, unsigned mb, int lane) {
-    for (int t = 0; t < W; t++) {
-        unsigned va = __ballot_sync(0xffffffffu, (ma >> t) & 1u);
-        unsigned vb = __ballot_sync(0xffffffffu, (mb >> t) & 1u);
-        if (lane == 0) {
-            A.na[t] += __popc(va);
-            A.nb[t] += __popc(vb);
-        }
+    // only the windows some lane of this batch falls into are visited (a sorted batch touches 1-3 of them)
+    unsigned ua = __reduce_or_sync(0xffffffffu, ma), ub = __reduce_or_sync(0xffffffffu, mb);
+    while (ua) {
+        int t = __ffs(ua) - 1;
+        ua &= ua - 1;
+        unsigned v = __ballot_sync(0xffffffffu, (ma >> t) & 1u);
+        if (lane == 0) A.na[t] += __popc(v);
+    }
+    while (ub) {
+        int t = __ffs(ub) - 1;
+        ub &= ub - 1;
+        unsigned v = __ballot_sync(0xffffffffu, (mb >> t) & 1u);
+        if (lane == 0) A.nb[t] += __popc(v);
     }
     if (ma && mb) {
         unsigned a = ma;
@@ -466,15 +472,21 @@ __device__ bool loop_background(const int2 *__restrict__ byx, const int2 *__rest
     const int W = 2 * win, m = W * W;
     loop_windows(byx, byy, n, xs, xe, ys, ye, win, lane, S, g_scan);
     // rabs: counts of the 4*win^2 window pairs; fdr = #{rabs > rab} / m
-    int gt = 0;
+    int gt = 0, nzero = 0;
     for (int t = lane; t < m; t += 32) {
         V.v[t] = (double)S.nab[t];
         gt += ((double)S.nab[t] > rab) ? 1 : 0;
+        nzero += S.nab[t] == 0 ? 1 : 0;
     }
     gt = warp_sum(gt);
+    nzero = warp_sum(nzero);
     __syncwarp();
+    // cis medians: when more than half of the window pairs are empty both middle order statistics are 0, for the
+    // counts and for the densities alike (a density is 0 exactly where the count is 0) -- the common case
+    const bool zero_median = mode == CL2_MODE_CIS && nzero >= m / 2 + 1;
     double mrabs, mbps;
-    if (mode == CL2_MODE_CIS) mrabs = warp_median(V, m, lane);
+    if (zero_median) mrabs = 0.0;
+    else if (mode == CL2_MODE_CIS) mrabs = warp_median(V, m, lane);
     else mrabs = np_pairwise_sum(V.v, m) / (double)m;     // every lane computes the same value
     __syncwarp();
     const double fdr = (double)gt / (double)m;
@@ -482,18 +494,22 @@ __device__ bool loop_background(const int2 *__restrict__ byx, const int2 *__rest
         if (mrabs >= rab || fdr >= 0.1) return false;
         if (rab / (mrabs > early_cut ? mrabs : early_cut) < 1.0) return false;
     }
-    // nbps: nrab / (nac * nbc), zero rule differs between cis (:213-221) and trans (callTransLoops.py:165-169)
-    for (int t = lane; t < m; t += 32) {
-        double nrab = (double)S.nab[t], nac = (double)S.na[t / W], nbc = (double)S.nb[t % W];
-        double d;
-        if (mode == CL2_MODE_CIS) d = nrab > 0 ? nrab / (nac * nbc) : 0.0;
-        else d = (nac > 0 && nbc > 0) ? nrab / (nac * nbc) : 0.0;
-        V.v[t] = d;
+    if (zero_median) {
+        mbps = 0.0;
+    } else {
+        // nbps: nrab / (nac * nbc), zero rule differs between cis (:213-221) and trans (callTransLoops.py:165-169)
+        for (int t = lane; t < m; t += 32) {
+            double nrab = (double)S.nab[t], nac = (double)S.na[t / W], nbc = (double)S.nb[t % W];
+            double d;
+            if (mode == CL2_MODE_CIS) d = nrab > 0 ? nrab / (nac * nbc) : 0.0;
+            else d = (nac > 0 && nbc > 0) ? nrab / (nac * nbc) : 0.0;
+            V.v[t] = d;
+        }
+        __syncwarp();
+        if (mode == CL2_MODE_CIS) mbps = warp_median(V, m, lane);
+        else mbps = np_pairwise_sum(V.v, m) / (double)m;
+        __syncwarp();
     }
-    __syncwarp();
-    if (mode == CL2_MODE_CIS) mbps = warp_median(V, m, lane);
-    else mbps = np_pairwise_sum(V.v, m) / (double)m;
-    __syncwarp();
     *o_mrabs = mrabs; *o_mbps = mbps; *o_fdr = fdr;
     return true;
 }
