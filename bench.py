@@ -431,7 +431,22 @@ def _shutdown():
 
 
 if __name__ == "__main__":
+    # exactly ONE line on stdout (the JSON): libraries that print to fd 1 (NCCL's version banner) go to stderr
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    import io
+    _buf = io.StringIO()
+    _py_stdout = sys.stdout
+    sys.stdout = _buf
     try:
         main()
     finally:
         _shutdown()
+        sys.stdout = _py_stdout
+        sys.stdout.flush()
+        os.dup2(_real_stdout, 1)
+        os.close(_real_stdout)
+        out = _buf.getvalue().strip().splitlines()
+        if out:
+            print(out[-1], flush=True)
