@@ -25,6 +25,28 @@ extern "C" int cl2_ctx_create(int device, cl2_ctx **out) {
     if (ctx->pool) {
         uint64_t thr = UINT64_MAX;  // keep freed scratch in the pool: steady-state calls never reach the driver allocator
         cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        // Reserve pool memory up front (once per device and process): growing the pool maps physical memory, which
+        // costs milliseconds per call and made step times depend on the order the worker threads picked their files.
+        // CL2_POOL_RESERVE_MB overrides the default of 1/8 of the free memory (capped at 16 GB); 0 disables.
+        static bool reserved[64] = {false};
+        if (!ctx->no_pool && device < 64 && !reserved[device]) {
+            reserved[device] = true;
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            size_t want = free_b / 8;
+            if (want > ((size_t)16 << 30)) want = (size_t)16 << 30;
+            const char *rs = getenv("CL2_POOL_RESERVE_MB");
+            if (rs) want = (size_t)strtoull(rs, nullptr, 10) << 20;
+            if (want > 0 && want < free_b) {
+                void *p = nullptr;
+                if (cudaMallocAsync(&p, want, ctx->stream) == cudaSuccess) {
+                    cudaFreeAsync(p, ctx->stream);
+                    cudaStreamSynchronize(ctx->stream);
+                } else {
+                    cudaGetLastError();
+                }
+            }
+        }
     }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
