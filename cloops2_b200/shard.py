@@ -113,10 +113,13 @@ def barrier():
 def worker_contexts(device=None, nthreads=None):
     """One cl2 context (= CUDA stream + scratch) per host worker thread of this rank.  Chromosome files are
     independent units, so a rank processes several at once: while one thread's kernels run, another thread does its
-    host-side bookkeeping (ctypes calls and numpy release the GIL).  CL2_THREADS overrides the default of 6."""
+    host-side bookkeeping (ctypes calls and numpy release the GIL).  CL2_THREADS overrides the default (6, or cores/ranks - 1 if smaller)."""
     from . import _lib
     if nthreads is None:
-        nthreads = int(os.environ.get("CL2_THREADS", "6"))
+        # default: 6, fewer when the ranks of this node have to share few host cores
+        world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1)
+        fair = (os.cpu_count() or 8) // max(1, world) - 1
+        nthreads = int(os.environ.get("CL2_THREADS", str(max(2, min(6, fair)))))
     nthreads = max(1, nthreads)
     first = _lib.default_context(device)
     return [first] + [_lib.Context(first.device) for _ in range(nthreads - 1)]
