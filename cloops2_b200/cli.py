@@ -63,6 +63,15 @@ def buildParser():
     c.add_argument("-filter", dest="filterPETs", action="store_true", default=False)
     c.add_argument("-trans", dest="trans", action="store_true", default=False)
     c.add_argument("-emPair", dest="emPair", action="store_true", default=False)
+    # quant -loops (cLoops2.py quant sub-command; only the loop part is implemented here)
+    q = sub.add_parser("quant", help="Quantify given loops against a sample (quant -loops).")
+    q.add_argument("-d", dest="predir", type=str, default="")
+    q.add_argument("-o", dest="fnOut", type=str, default="cLoops2_output")
+    q.add_argument("-p", dest="cpu", type=int, default=1)
+    q.add_argument("-cut", dest="cut", type=int, default=0)
+    q.add_argument("-mcut", dest="mcut", type=int, default=-1)
+    q.add_argument("-loops", dest="loops", type=str, default="")
+    q.add_argument("-offp", dest="offp", action="store_true", default=False)
     return p
 
 
@@ -70,6 +79,14 @@ def main(argv=None):
     from .callCisLoops import callCisLoops
     from .callTransLoops import callTransLoops
     op = buildParser().parse_args(argv)
+    if op.cmd == "quant":
+        from .quant import quantLoops
+        logger = getLogger()
+        if op.loops == "" or not os.path.isfile(op.loops) or not os.path.exists(op.predir):
+            logger.error("quant needs -d DIR and -loops FILE. Return.")
+            return 1
+        quantLoops(op.predir, op.loops, op.fnOut, logger, cut=op.cut, mcut=op.mcut, cpu=op.cpu, offp=op.offp)
+        return 0
     if op.cmd != "callLoops":
         buildParser().print_help()
         return 1

@@ -14,6 +14,7 @@ Contents
                        OUT_filtered/*.ixy matrices of a -filter run)
   trans_pipeline.npz   two synthetic chromosome pairs + the reference's callTransLoops `_trans_loops.txt`
   estsig_cis.npz       per-candidate fields of the reference's estLoopSig on one chromosome (every attribute)
+  quant_loops.npz      the reference's `quant -loops` output (quant.py quantLoops, with and without -offp)
 """
 import json
 import os
@@ -144,12 +145,40 @@ def gen_trans(ref):
                         **{k.replace("-", "_"): v for k, v in files.items()})
 
 
+def gen_quant(ref):
+    """cLoops2/quant.py quantLoops on the cis golden files: the default run's loops plus shifted copies (some of them
+    without any PET), with and without -offp."""
+    from cLoops2 import quant as rq
+    g = np.load(os.path.join(GOLD, "cis_pipeline.npz"))
+    files = {k: g[k.replace("-", "_")] for k in g["order"].tolist()}
+    tmp = tempfile.mkdtemp()
+    synth.write_ixy_dir(files, tmp + "/d")
+    meta = json.load(open(tmp + "/d/petMeta.json"))
+    meta["Unique PETs"] = int(g["tot"])
+    json.dump(meta, open(tmp + "/d/petMeta.json", "w"))
+    lines = str(g["default_txt"]).rstrip("\n").split("\n")
+    extra = []
+    for i, line in enumerate(lines[1:]):
+        f = line.split("\t")
+        f[0] = "shift_%d" % i
+        for j in (2, 3):
+            f[j] = str(int(f[j]) + 40000)
+        extra.append("\t".join(f))
+    open(tmp + "/in_loops.txt", "w").write("\n".join(lines + extra) + "\n")
+    out = {}
+    for offp in (False, True):
+        rq.quantLoops(tmp + "/d", tmp + "/in_loops.txt", tmp + "/q%d" % offp, ref.logger, offp=offp)
+        out["quant_offp%d" % offp] = open(tmp + "/q%d_loops.txt" % offp).read()
+    np.savez_compressed(os.path.join(GOLD, "quant_loops.npz"), in_loops=open(tmp + "/in_loops.txt").read(), **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref = ref_shim.load()
     gen_dbscan(ref)
     gen_cis(ref)
     gen_trans(ref)
+    gen_quant(ref)
     print("golden vectors written to", GOLD)
 
 

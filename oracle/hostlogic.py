@@ -13,7 +13,7 @@ class OLoop(object):
     __slots__ = ["chromX", "chromY", "x_start", "x_end", "x_center", "ra", "y_start", "y_end", "y_center", "rb",
                  "rab", "cis", "distance", "density", "ES", "P2LL", "FDR", "hypergeometric_p_value",
                  "poisson_p_value", "binomial_p_value", "x_peak_poisson_p_value", "x_peak_es",
-                 "y_peak_poisson_p_value", "y_peak_es", "significant"]
+                 "y_peak_poisson_p_value", "y_peak_es", "significant", "id"]
 
     def coords(self):
         return (self.chromX, self.x_start, self.x_end, self.chromY, self.y_start, self.y_end)
@@ -108,11 +108,6 @@ def filter_dup(loops):
             d[lp.coords()] = lp
         out[k] = list(d.values())
     return out
-
-
-def _anchor_sig(N, span, count, wide):
-    """callCisLoops.py:226-247 (estAnchorSig) given the two counts; span = max(ys) - min(xs)."""
-    pass
 
 
 def est_loop_sig_cis(key, loops, xy, tot, minPts=5, pseudo=1, peakPcut=1e-5, win=5, countDiffCut=20, hic=False):
@@ -363,5 +358,71 @@ def loops_to_rows(loops):
                 lp.y_end, lp.distance, lp.x_center, lp.y_center, lp.ra, lp.rb, lp.cis, lp.rab, lp.density, lp.ES,
                 lp.P2LL, lp.FDR, lp.binomial_p_value, lp.hypergeometric_p_value, lp.poisson_p_value,
                 lp.x_peak_poisson_p_value, lp.y_peak_poisson_p_value, lp.significant]
+        rows.append(list(map(str, line)))
+    return rows
+
+
+def quant_loops(key, loops, xy, tot, pseudo=1, offp=False):
+    """cLoops2/quant.py:129-237 (_quantLoops) on an in-memory, already cut/mcut-filtered array.  loops: OLoop list
+    with coordinates set; returns the same objects annotated."""
+    from . import XYIndex
+    tot = float(tot)
+    idx = XYIndex(xy)
+    N = idx.n
+    rpb = float(N) / (np.max(xy[:, 1]) - np.min(xy[:, 0]))
+    arr = np.array([[lp.x_start, lp.x_end, lp.y_start, lp.y_end] for lp in loops], dtype=np.int64)
+    core, na, nb, nab, anc = idx.loop_counts(arr, win=5, mode=1)      # P2LL window lower-left in both axes (:146-149)
+    for i, lp in enumerate(loops):
+        ra, rb, rab, lower = (int(v) for v in core[i])
+        lp.P2LL = float(rab) / max(lower, pseudo)
+        lp.ra, lp.rb, lp.rab = ra, rb, rab
+        size = lp.x_end - lp.x_start + lp.y_end - lp.y_start
+        if offp:
+            lp.FDR, lp.ES = 1, 0
+            lp.density = float(rab) / size / tot * 10.0**9
+            lp.hypergeometric_p_value = lp.poisson_p_value = lp.binomial_p_value = 1
+            lp.x_peak_poisson_p_value, lp.x_peak_es, lp.y_peak_poisson_p_value, lp.y_peak_es = 1, 0, 1, 0
+            continue
+        res = []
+        for a, (left, right) in enumerate(((lp.x_start, lp.x_end), (lp.y_start, lp.y_end))):
+            length = right - left
+            count = int(anc[i, 2 * a])
+            r = (int(anc[i, 2 * a + 1]) - count) / 5 / 2
+            c = float(max([r, rpb * length, 1]))
+            res.append((max([1e-300, poisson.sf(count - 1.0, c)]), count / c))
+        (lp.x_peak_poisson_p_value, lp.x_peak_es), (lp.y_peak_poisson_p_value, lp.y_peak_es) = res
+        if rab > 0:
+            rabs, nbps = [], []
+            for a in range(10):
+                for b in range(10):
+                    nrab = float(nab[i, a * 10 + b])
+                    if nrab > 0:
+                        rabs.append(nrab)
+                        nbps.append(nrab / (float(na[i, a]) * float(nb[i, b])))
+                    else:
+                        rabs.append(0)
+                        nbps.append(0.0)
+            rabs, nbps = np.array(rabs), np.array(nbps)
+            mrabs = float(np.median(rabs)) if np.median(rabs) > 0 else pseudo
+            mbps = np.median(nbps) if np.median(nbps) > 0 else 1e-10
+            lp.FDR = len(rabs[rabs > rab]) / float(len(rabs))
+            lp.ES = rab / mrabs
+            lp.density = float(rab) / size / tot * 10.0**9
+            lp.hypergeometric_p_value = max([1e-300, hypergeom.sf(rab - 1.0, N, ra, rb)])
+            lp.poisson_p_value = max([1e-300, poisson.sf(rab - 1.0, mrabs)])
+            lp.binomial_p_value = max([1e-300, binom.sf(rab - 1.0, ra * rb - rab, mbps)])
+        else:
+            lp.FDR, lp.ES, lp.density = 1, 0, 0
+            lp.hypergeometric_p_value = lp.poisson_p_value = lp.binomial_p_value = 1
+    return key, loops
+
+
+def quant_rows(loops):
+    """Rows of quant.py:240-280 (_loops2txt), header excluded."""
+    rows = []
+    for lp in loops:
+        line = [lp.id, lp.chromX, lp.x_start, lp.x_end, lp.chromY, lp.y_start, lp.y_end, lp.distance, lp.x_center,
+                lp.y_center, lp.ra, lp.rb, lp.cis, lp.rab, lp.density, lp.ES, lp.P2LL, lp.FDR, lp.binomial_p_value,
+                lp.hypergeometric_p_value, lp.poisson_p_value, lp.x_peak_poisson_p_value, lp.y_peak_poisson_p_value]
         rows.append(list(map(str, line)))
     return rows
