@@ -86,7 +86,7 @@ SIGNATURES = {
     "cl2_block_dbscan": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _i32p, _i32p]),
     "cl2_cdbscan2": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _i32p, _i32p]),
     "cl2_cluster_bbox": (ctypes.c_int, [_vp, _vp, _i64p, _i64p]),
-    "cl2_block_noise": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _u8p]),
+    "cl2_block_noise": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _u8p, _i32p]),
     "cl2_index_build": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(_vp)]),
     "cl2_index_free": (None, [_vp, _vp]),
     "cl2_loop_counts": (ctypes.c_int, [_vp, _vp, _i64p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
@@ -292,11 +292,14 @@ class Points:
                            "cl2_cluster_bbox")
         return bbox, size
 
-    def block_noise_keep(self, eps, minPts):
+    def block_noise_keep(self, eps, minPts, with_cell_order=False):
+        """keep[n] of blockDBSCAN's removeNoiseGrids; with_cell_order also returns, per row, the first row id of its
+        cell (the reference's dict order of the cells)."""
         keep = np.zeros(self.n, dtype=np.uint8)
-        self.ctx.check(self.ctx.lib.cl2_block_noise(self.ctx.h, self.h, int(eps), int(minPts), _ptr(keep, _u8p)),
-                       "cl2_block_noise")
-        return keep.astype(bool)
+        first = np.zeros(self.n, dtype=np.int32) if with_cell_order else None
+        self.ctx.check(self.ctx.lib.cl2_block_noise(self.ctx.h, self.h, int(eps), int(minPts), _ptr(keep, _u8p),
+                                                    _ptr(first, _i32p)), "cl2_block_noise")
+        return (keep.astype(bool), first) if with_cell_order else keep.astype(bool)
 
 
 class Index:

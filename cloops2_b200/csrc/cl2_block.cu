@@ -172,10 +172,14 @@ __global__ void __launch_bounds__(256) k_block_noise(const int32_t *__restrict__
 }
 
 __global__ void __launch_bounds__(256) k_keep_points(const int32_t *__restrict__ cid, const uint32_t *__restrict__ row,
-                                                      const uint8_t *__restrict__ keep, uint8_t *__restrict__ out,
-                                                      int64_t n) {
+                                                      const uint8_t *__restrict__ keep,
+                                                      const uint32_t *__restrict__ first, uint8_t *__restrict__ out,
+                                                      int32_t *__restrict__ first_out, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[row[i]] = keep[cid[i]];
+    if (i >= n) return;
+    int c = cid[i];
+    out[row[i]] = keep[c];
+    if (first_out) first_out[row[i]] = (int32_t)first[c];
 }
 
 // ------------------------------------------------------------------------------------------------ K8 cell stats
@@ -651,7 +655,8 @@ static int block_check_args(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int32_t 
     return CL2_OK;
 }
 
-extern "C" int cl2_block_noise(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int32_t minPts, uint8_t *keep_out) {
+extern "C" int cl2_block_noise(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int32_t minPts, uint8_t *keep_out,
+                               int32_t *cell_first_out) {
     CL2_TRY(block_check_args(ctx, pts, eps, minPts));
     if (pts->n == 0) return CL2_OK;
     if (!keep_out) return CL2_ERR_ARG;
@@ -660,16 +665,22 @@ extern "C" int cl2_block_noise(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int32
     cl2_grid_cache &g = pts->grid;
     Scratch sc(ctx);
     uint8_t *keep, *pk;
+    int32_t *pf = nullptr;
     CL2_TRY(sc.get(&keep, (size_t)g.ncells));
     CL2_TRY(sc.get(&pk, (size_t)pts->n));
+    if (cell_first_out) CL2_TRY(sc.get(&pf, (size_t)pts->n));
     {
         FamTimer t(ctx, FAM_NOISE, 37.0 * (double)g.ncells);
         k_block_noise<<<cl2_grid(g.ncells, 256), 256, 0, ctx->stream>>>(g.nbr, g.s3, keep, g.ncells, minPts);
     }
-    k_keep_points<<<cl2_grid(pts->n, 256), 256, 0, ctx->stream>>>(g.cid, g.row, keep, pk, pts->n);
+    k_keep_points<<<cl2_grid(pts->n, 256), 256, 0, ctx->stream>>>(g.cid, g.row, keep, g.first, pk, pf, pts->n);
     ctx->launches++;
     CL2_CUDA(ctx, cudaMemcpyAsync(keep_out, pk, (size_t)pts->n, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->d2h_bytes += pts->n;
+    if (cell_first_out) {
+        CL2_CUDA(ctx, cudaMemcpyAsync(cell_first_out, pf, (size_t)pts->n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->d2h_bytes += pts->n * 4;
+    }
     CL2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return CL2_OK;
 }

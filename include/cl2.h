@@ -81,9 +81,12 @@ int cl2_cdbscan2(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int32_t minPts, int
  * size_out: int64[n_clusters].
  */
 int cl2_cluster_bbox(cl2_ctx *ctx, cl2_points *pts, int64_t *bbox_out, int64_t *size_out);
-/* blockDBSCAN's noise-cell removal alone (blockDBSCAN.py:69-122; also cLoops2/filter.py:223-278):
- * keep_out[i] = 1 iff row i survives removeNoiseGrids. */
-int cl2_block_noise(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int32_t minPts, uint8_t *keep_out);
+/* blockDBSCAN's noise-cell removal alone (blockDBSCAN.py:69-122; also cLoops2/filter.py:223-278, `filterPETs -knn`):
+ * keep_out[i] = 1 iff row i survives removeNoiseGrids.  cell_first_out (int32[n], may be NULL) receives for every row
+ * the smallest row id of its grid cell = the cell's position in the reference's dict, which is the order
+ * filter.py:273-275 writes the surviving rows in. */
+int cl2_block_noise(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int32_t minPts, uint8_t *keep_out,
+                    int32_t *cell_first_out);
 
 /* ---- counting ----------------------------------------------------------------------------------------- */
 /* XY(xs, ys) -- cLoops2/ds.py:146-163, built by ixy2pet (io.py:294-300). */

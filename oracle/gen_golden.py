@@ -15,6 +15,7 @@ Contents
   trans_pipeline.npz   two synthetic chromosome pairs + the reference's callTransLoops `_trans_loops.txt`
   estsig_cis.npz       per-candidate fields of the reference's estLoopSig on one chromosome (every attribute)
   quant_loops.npz      the reference's `quant -loops` output (quant.py quantLoops, with and without -offp)
+  filter_knn.npz       the reference's `filterPETs -knn` output matrices (filter.py _filterPETsByKNNs)
 """
 import json
 import os
@@ -172,6 +173,22 @@ def gen_quant(ref):
     np.savez_compressed(os.path.join(GOLD, "quant_loops.npz"), in_loops=open(tmp + "/in_loops.txt").read(), **out)
 
 
+def gen_filter_knn(ref):
+    """cLoops2/filter.py _filterPETsByKNNs (filterPETs -knn) on the cis golden files, eps 500, minPts 5."""
+    import joblib
+    from cLoops2 import filter as rf
+    g = np.load(os.path.join(GOLD, "cis_pipeline.npz"))
+    files = {k: g[k.replace("-", "_")] for k in g["order"].tolist()}
+    tmp = tempfile.mkdtemp()
+    synth.write_ixy_dir(files, tmp + "/d")
+    os.makedirs(tmp + "/o")
+    out = {}
+    for k in files:
+        rf._filterPETsByKNNs(tmp + "/d/%s.ixy" % k, tmp + "/o", 500, 5)
+        out["knn_" + k.replace("-", "_")] = joblib.load(tmp + "/o/%s.ixy" % k)
+    np.savez_compressed(os.path.join(GOLD, "filter_knn.npz"), eps=500, minPts=5, **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref = ref_shim.load()
@@ -179,6 +196,7 @@ def main():
     gen_cis(ref)
     gen_trans(ref)
     gen_quant(ref)
+    gen_filter_knn(ref)
     print("golden vectors written to", GOLD)
 
 
