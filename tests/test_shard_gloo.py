@@ -60,3 +60,20 @@ def test_two_rank_gloo_roundtrip():
     assert s0 == s1 == [5, 3]
     assert k0 == ["a", "b", "c", "d", "e"] and k1 == []
     assert t0 == t1 == 1.0
+
+
+def test_map_units_order_and_error_propagation():
+    """Worker-thread fan-out used inside a rank: results come back in unit order; the first failure is re-raised."""
+    import pytest
+    ctxs = ["c0", "c1", "c2"]
+    out = shard.map_units(ctxs, list(range(20)), lambda c, u: (u * u, c))
+    assert [o[0] for o in out] == [u * u for u in range(20)]
+    assert {o[1] for o in out} <= set(ctxs)
+    assert shard.map_units(ctxs[:1], [1, 2], lambda c, u: u + 1) == [2, 3]
+
+    def boom(c, u):
+        if u == 7:
+            raise ValueError("unit 7")
+        return u
+    with pytest.raises(ValueError):
+        shard.map_units(ctxs, list(range(20)), boom)
