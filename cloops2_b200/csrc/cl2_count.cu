@@ -10,6 +10,7 @@
 // scaled by 4, so l <= X <= r is decided in exact integer arithmetic.  One warp per candidate loop.
 #include "cl2_points.cuh"
 #include "cl2_stats.cuh"
+#include <math_constants.h>
 
 // ------------------------------------------------------------------------------------------------ index build
 __global__ void __launch_bounds__(256) k_index_gather(const int2 *__restrict__ xy, const uint32_t *__restrict__ row,
@@ -18,6 +19,34 @@ __global__ void __launch_bounds__(256) k_index_gather(const int2 *__restrict__ x
     if (i >= n) return;
     int2 p = __ldg(&xy[row[i]]);
     out[i] = which == 0 ? p : make_int2(p.y, p.x);
+}
+
+// bucket table over a coordinate-sorted array: tab[b] = first position whose coordinate is >= b << shift; tab[nb] = n
+__global__ void __launch_bounds__(256) k_bucket_table(const int2 *__restrict__ a, int64_t n, int shift, int nb,
+                                                       uint32_t *__restrict__ tab) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int bi = a[i].x >> shift;
+    const int bp = i > 0 ? a[i - 1].x >> shift : -1;
+    for (int b = bp + 1; b <= bi; b++) tab[b] = (uint32_t)i;
+    if (i == n - 1)
+        for (int b = bi + 1; b <= nb; b++) tab[b] = (uint32_t)n;
+}
+static int bucket_shift(int64_t maxcoord, int64_t n) {        // about 16 rows per bucket
+    int64_t want = n / 16 > 1024 ? n / 16 : 1024;
+    int s = 0;
+    while ((maxcoord >> s) + 1 > want) s++;
+    return s;
+}
+static int build_table(cl2_ctx *ctx, const int2 *a, int64_t n, int64_t maxcoord, uint32_t **tab, int *shift, int *nb) {
+    *tab = nullptr;
+    if (n <= 0 || n > (int64_t)UINT32_MAX) return CL2_OK;
+    *shift = bucket_shift(maxcoord, n);
+    *nb = (int)(maxcoord >> *shift) + 1;
+    CL2_TRY(cl2_dev_alloc(ctx, tab, (size_t)*nb + 1));
+    FamTimer t(ctx, FAM_INDEX, 8.0 * (double)n + 4.0 * (double)*nb);
+    k_bucket_table<<<cl2_grid(n, 256), 256, 0, ctx->stream>>>(a, n, *shift, *nb, *tab);
+    return CL2_OK;
 }
 
 // (y, x) sorted by y plus the file row of every sorted position; kept on the points object
@@ -79,6 +108,8 @@ extern "C" int cl2_index_build(cl2_ctx *ctx, cl2_points *pts, cl2_index **out) {
                 FamTimer t(ctx, FAM_INDEX, 20.0 * (double)n);
                 k_index_gather<<<cl2_grid(n, 256), 256, 0, ctx->stream>>>(pts->xy, vs, ix->byx, n, 0);
             }
+            if ((rc = build_table(ctx, ix->byx, n, pts->ext[1], &ix->tx, &ix->sx, &ix->nbx))) break;
+            if ((rc = build_table(ctx, ix->byy, n, pts->ext[3], &ix->ty, &ix->sy, &ix->nby))) break;
             if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
                 rc = cl2_fail(ctx, CL2_ERR_CUDA, "cl2_index_build: kernel failure");
             }
@@ -87,6 +118,8 @@ extern "C" int cl2_index_build(cl2_ctx *ctx, cl2_points *pts, cl2_index **out) {
     if (rc != CL2_OK) {
         cl2_dev_free(ctx, ix->byx);
         cl2_dev_free(ctx, ix->byy);
+        cl2_dev_free(ctx, ix->tx);
+        cl2_dev_free(ctx, ix->ty);
         delete ix;
         return rc;
     }
@@ -99,12 +132,35 @@ extern "C" void cl2_index_free(cl2_ctx *ctx, cl2_index *idx) {
     cudaSetDevice(ctx->device);
     cl2_dev_free(ctx, idx->byx);
     cl2_dev_free(ctx, idx->byy);
+    cl2_dev_free(ctx, idx->tx);
+    cl2_dev_free(ctx, idx->ty);
     delete idx;
 }
 
 // ------------------------------------------------------------------------------------------------ counting
 #define CNT_WARPS 8
 #define CNT_MAXW 16   // 2*win <= 16
+
+// What the kernels see of a cl2_index.  tx / ty are bucket tables over the sorted coordinate: t[b] = first position
+// whose coordinate is >= b << shift (nb + 1 entries, t[nb] = n), so a search starts from a ~16-row bracket instead
+// of the whole array.
+struct IdxView {
+    const int2 *byx, *byy;
+    const uint32_t *tx, *ty;
+    int64_t n;
+    int sx, sy, nbx, nby;
+};
+struct Arr {
+    const int2 *a;
+    const uint32_t *tab;
+    int shift, nb;
+};
+static IdxView cl2_view(const cl2_index *idx) {
+    IdxView v = {idx->byx, idx->byy, idx->tx, idx->ty, idx->n, idx->sx, idx->sy, idx->nbx, idx->nby};
+    return v;
+}
+__device__ __forceinline__ Arr arr_x(const IdxView &ix) { Arr r = {ix.byx, ix.tx, ix.sx, ix.nbx}; return r; }
+__device__ __forceinline__ Arr arr_y(const IdxView &ix) { Arr r = {ix.byy, ix.ty, ix.sy, ix.nby}; return r; }
 
 struct Iv {           // closed integer interval; empty when lo > hi
     long long lo, hi;
@@ -118,74 +174,105 @@ __device__ __forceinline__ Iv iv4(long long lo4, long long hi4) {
     r.hi = floordiv4(hi4);
     return r;
 }
-__device__ __forceinline__ bool in_iv(const Iv &I, int v) { return (long long)v >= I.lo && (long long)v <= I.hi; }
+// The same interval cut to the coordinate domain [0, INT_MAX) (cl2_points_upload refuses anything else), held as
+// {lo, width} so that membership is one subtract and one unsigned compare.  Empty: lo = INT_MAX, which no coordinate
+// reaches.
+struct Iv32 {
+    int lo;
+    unsigned wd;
+};
+__device__ __forceinline__ Iv32 iv32(long long lo, long long hi) {
+    Iv32 r;
+    if (lo < 0) lo = 0;
+    if (hi > (long long)INT_MAX) hi = INT_MAX;
+    if (lo > hi) { r.lo = INT_MAX; r.wd = 0; }
+    else { r.lo = (int)lo; r.wd = (unsigned)(hi - lo); }
+    return r;
+}
+__device__ __forceinline__ Iv32 iv32(const Iv &I) { return iv32(I.lo, I.hi); }
+__device__ __forceinline__ bool in32(const Iv32 &I, int v) { return (unsigned)(v - I.lo) <= I.wd; }
 
-// first index with first-coordinate >= v (np.searchsorted side="left", ds.py:170), searched by the whole warp:
-// every step 32 lanes probe 32 evenly spaced positions and a ballot picks the sub-range, so a search over 10^8 rows
-// is 6 dependent loads instead of 27.  All lanes must call it with the same arguments; all get the same result.
-__device__ __forceinline__ int64_t lower_first(const int2 *__restrict__ a, int64_t n, long long v) {
-    const int lane = threadIdx.x & 31;
-    int64_t lo = 0, hi = n;                    // answer in [lo, hi]
+// Bracket [lo, hi] that holds "first index with first-coordinate >= v" (np.searchsorted side="left", ds.py:170)
+__device__ __forceinline__ void bracket(const Arr &A, int64_t n, long long v, int64_t &lo, int64_t &hi) {
+    if (v <= 0) { lo = hi = 0; return; }                    // coordinates are >= 0
+    if (v > (long long)INT_MAX) { lo = hi = n; return; }    // and < INT_MAX
+    lo = 0;
+    hi = n;
+    if (A.tab) {
+        int b = (int)v >> A.shift;
+        if (b >= A.nb) { lo = hi = n; }
+        else { lo = A.tab[b]; hi = A.tab[b + 1]; }
+    }
+}
+// The search inside a bracket, by the whole warp: every step 32 lanes probe 32 evenly spaced positions and a ballot
+// picks the sub-range, so even a search over 10^8 rows is 6 dependent loads instead of 27; with the bucket table the
+// loop body rarely runs at all.  All lanes call with the same arguments and get the same result.
+__device__ __forceinline__ void narrow(const int2 *__restrict__ a, int v, int64_t &lo, int64_t &hi, int lane) {
     while (hi - lo > 32) {
         int64_t step = (hi - lo) >> 5;
         int64_t pos = lo + step * (lane + 1) - 1;
-        bool less = (long long)a[pos].x < v;
+        bool less = a[pos].x < v;
         int k = __popc(__ballot_sync(0xffffffffu, less));   // monotone: lanes 0..k-1 are "less"
         int64_t nlo = k > 0 ? lo + step * k : lo;
         int64_t nhi = k < 32 ? lo + step * (k + 1) - 1 : hi;
         lo = nlo;
         hi = nhi;
     }
-    int64_t pos = lo + lane;
-    bool less = pos < hi && (long long)a[pos].x < v;
-    return lo + __popc(__ballot_sync(0xffffffffu, less));
 }
 struct Range {
     int64_t b, e;
 };
-__device__ __forceinline__ Range range_of(const int2 *__restrict__ a, int64_t n, const Iv &I) {
+// positions of the rows whose sort coordinate lies in I; both ends are searched side by side so their loads overlap
+__device__ __forceinline__ Range range_of(const Arr &A, int64_t n, const Iv &I, int lane) {
     Range r;
     if (I.lo > I.hi) { r.b = r.e = 0; return r; }
-    r.b = lower_first(a, n, I.lo);
-    r.e = lower_first(a, n, I.hi + 1);   // side="right" on integers
+    int64_t lo1, hi1, lo2, hi2;
+    bracket(A, n, I.lo, lo1, hi1);
+    bracket(A, n, I.hi + 1, lo2, hi2);                       // side="right" on integers
+    const int v1 = (int)(I.lo < 0 ? 0 : (I.lo > (long long)INT_MAX ? INT_MAX : I.lo));
+    const int v2 = (int)(I.hi + 1 < 0 ? 0 : (I.hi + 1 > (long long)INT_MAX ? INT_MAX : I.hi + 1));
+    narrow(A.a, v1, lo1, hi1, lane);
+    narrow(A.a, v2, lo2, hi2, lane);
+    const int64_t p1 = lo1 + lane, p2 = lo2 + lane;
+    const bool l1 = p1 < hi1 && A.a[p1].x < v1;
+    const bool l2 = p2 < hi2 && A.a[p2].x < v2;
+    r.b = lo1 + __popc(__ballot_sync(0xffffffffu, l1));
+    r.e = lo2 + __popc(__ballot_sync(0xffffffffu, l2));
     return r;
 }
-__device__ __forceinline__ int warp_sum(int v) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
+__device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }
 
 // |P(I)|  (queryPeak, ds.py:176-182)
 // g_scan: members visited by this warp so far (the counting kernel's algorithmic traffic is 16 B per member on the
 // reference layout); every lane carries the same value
-__device__ __noinline__ int64_t count_peak(const int2 *__restrict__ byx, const int2 *__restrict__ byy, int64_t n, const Iv &I,
-                              int lane, long long *g_scan) {
-    Range rx = range_of(byx, n, I), ry = range_of(byy, n, I);
+__device__ __noinline__ int64_t count_peak(const IdxView &ix, const Iv &I, int lane, long long *g_scan) {
+    Range rx = range_of(arr_x(ix), ix.n, I, lane), ry = range_of(arr_y(ix), ix.n, I, lane);
     *g_scan += ry.e - ry.b;
+    const Iv32 J = iv32(I);
     int c = 0;
     for (int64_t j = ry.b + lane; j < ry.e; j += 32) {
-        int2 p = byy[j];                      // (y, x)
-        if (!in_iv(I, p.y)) c++;
+        int2 p = ix.byy[j];                   // (y, x)
+        if (!in32(J, p.y)) c++;
     }
     return (rx.e - rx.b) + (int64_t)warp_sum(c);
 }
 
 // |P(I1)| and |P(I1) & P(I2)|  (queryLoop, ds.py:184-190)
-__device__ __noinline__ void count_pair(const int2 *__restrict__ byx, const int2 *__restrict__ byy, int64_t n, const Iv &I1,
-                           const Iv &I2, int lane, int64_t *n1, int64_t *n12, long long *g_scan) {
-    Range rx = range_of(byx, n, I1), ry = range_of(byy, n, I1);
+__device__ __noinline__ void count_pair(const IdxView &ix, const Iv &I1, const Iv &I2, int lane, int64_t *n1, int64_t *n12,
+                                        long long *g_scan) {
+    Range rx = range_of(arr_x(ix), ix.n, I1, lane), ry = range_of(arr_y(ix), ix.n, I1, lane);
     *g_scan += (rx.e - rx.b) + (ry.e - ry.b);
+    const Iv32 J1 = iv32(I1), J2 = iv32(I2);
     int c1 = 0, c12 = 0;
     for (int64_t i = rx.b + lane; i < rx.e; i += 32) {
-        int2 p = byx[i];                      // (x, y)
-        if (in_iv(I2, p.x) || in_iv(I2, p.y)) c12++;
+        int2 p = ix.byx[i];                   // (x, y)
+        if (in32(J2, p.x) || in32(J2, p.y)) c12++;
     }
     for (int64_t j = ry.b + lane; j < ry.e; j += 32) {
-        int2 p = byy[j];                      // (y, x)
-        if (!in_iv(I1, p.y)) {
+        int2 p = ix.byy[j];                   // (y, x)
+        if (!in32(J1, p.y)) {
             c1++;
-            if (in_iv(I2, p.y) || in_iv(I2, p.x)) c12++;
+            if (in32(J2, p.y) || in32(J2, p.x)) c12++;
         }
     }
     *n1 = (rx.e - rx.b) + (int64_t)warp_sum(c1);
@@ -196,18 +283,26 @@ struct WarpAcc {
     int na[CNT_MAXW];
     int nb[CNT_MAXW];
     int nab[CNT_MAXW * CNT_MAXW];
-    // window bounds as int32 (coordinates are < 2^31-1, so clamping the bounds into [0, INT_MAX] changes nothing)
-    int alo[CNT_MAXW], ahi[CNT_MAXW], blo[CNT_MAXW], bhi[CNT_MAXW];
-    int sa_lo, sa_hi, sb_lo, sb_hi;     // spans covering all a- / b-windows
+    // permuted windows as {lo, width} (Iv32 layout, one 8-byte load per test) and their upper bounds
+    int2 aw[CNT_MAXW], bw[CNT_MAXW];
+    int ahi[CNT_MAXW], bhi[CNT_MAXW];
 };
 
-__device__ __forceinline__ int clamp_i32(long long v) { return v < 0 ? 0 : (v > (long long)INT_MAX ? INT_MAX : (int)v); }
-
-// bit t set iff lo[t] <= c <= hi[t]
-__device__ __forceinline__ unsigned coord_mask(const int *__restrict__ lo, const int *__restrict__ hi, int W, int c) {
+// bit t set iff window t holds c
+__device__ __noinline__ unsigned coord_mask(const int2 *__restrict__ w, int W, int c) {
     unsigned m = 0;
-#pragma unroll 2
-    for (int t = 0; t < W; t++) m |= ((c >= lo[t] && c <= hi[t]) ? 1u : 0u) << t;
+    if (W == 10) {
+#pragma unroll
+        for (int t = 0; t < 10; t++) {
+            const int2 q = w[t];
+            m |= ((unsigned)(c - q.x) <= (unsigned)q.y) ? (1u << t) : 0u;
+        }
+    } else {
+        for (int t = 0; t < W; t++) {
+            const int2 q = w[t];
+            m |= ((unsigned)(c - q.x) <= (unsigned)q.y) ? (1u << t) : 0u;
+        }
+    }
     return m;
 }
 
@@ -243,40 +338,39 @@ __device__ __forceinline__ void window_accumulate(WarpAcc &A, int W, unsigned ma
 
 // ---- per-loop building blocks (one warp) -------------------------------------------------------------------
 // queryLoop counts + the P2LL window (cis callCisLoops.py:287-289, 302-305; trans callTransLoops.py:124-126, 142-144)
-__device__ void loop_core(const int2 *__restrict__ byx, const int2 *__restrict__ byy, int64_t n, long long xs,
-                          long long xe, long long ys, long long ye, int mode, int lane, int64_t out[4],
-                          long long *g_scan) {
+__device__ void loop_core(const IdxView &ix, long long xs, long long xe, long long ys, long long ye, int mode, int lane,
+                          int64_t out[4], long long *g_scan) {
     const Iv A = {xs, xe}, B = {ys, ye};
     int64_t ra, rab, rb;
-    count_pair(byx, byy, n, A, B, lane, &ra, &rab, g_scan);
-    rb = count_peak(byx, byy, n, B, lane, g_scan);
+    count_pair(ix, A, B, lane, &ra, &rab, g_scan);
+    rb = count_peak(ix, B, lane, g_scan);
     Iv A2, B2;
     if (mode == CL2_MODE_CIS) { A2.lo = xe; A2.hi = xe + (xe - xs); }
     else { A2.lo = xs - (xe - xs); A2.hi = xs; }
     B2.lo = ys - (ye - ys); B2.hi = ys;
     int64_t t1, lower;
-    count_pair(byx, byy, n, A2, B2, lane, &t1, &lower, g_scan);
+    count_pair(ix, A2, B2, lane, &t1, &lower, g_scan);
     out[0] = ra; out[1] = rb; out[2] = rab; out[3] = lower;
 }
 
 // estAnchorSig counts (callCisLoops.py:226-247): count = |P(l,r)|, wide = |P(max(0, m-5len), m+5len)|
-__device__ void loop_anchor(const int2 *__restrict__ byx, const int2 *__restrict__ byy, int64_t n, long long l,
-                            long long r, int lane, int64_t *count, int64_t *wide, long long *g_scan) {
+__device__ void loop_anchor(const IdxView &ix, long long l, long long r, int lane, int64_t *count, int64_t *wide,
+                            long long *g_scan) {
     long long m4 = 2 * (l + r), len = r - l;
     long long s4 = m4 - 20 * len;
     if (s4 < 0) s4 = 0;
     Iv I = {l, r};
     Iv Wd = iv4(s4, m4 + 20 * len);
-    *count = count_peak(byx, byy, n, I, lane, g_scan);
-    *wide = count_peak(byx, byy, n, Wd, lane, g_scan);
+    *count = count_peak(ix, I, lane, g_scan);
+    *wide = count_peak(ix, Wd, lane, g_scan);
 }
 
 // getPerRegions + getLoopNearbyPETs counts into the warp's accumulator (callCisLoops.py:173-223)
-__device__ void loop_windows(const int2 *__restrict__ byx, const int2 *__restrict__ byy, int64_t n, long long xs,
-                             long long xe, long long ys, long long ye, int win, int lane, WarpAcc &S,
-                             long long *g_scan) {
+__device__ void loop_windows(const IdxView &ix, long long xs, long long xe, long long ys, long long ye, int win, int lane,
+                             WarpAcc &S, long long *g_scan) {
     const int W = 2 * win;
     for (int t = lane; t < W * W; t += 32) S.nab[t] = 0;
+    long long a_lo = 0, a_hi = -1, b_lo = 0, b_hi = -1;
     if (lane < W) {
         S.na[lane] = 0; S.nb[lane] = 0;
         // windows i = -win..-1, 1..win (callCisLoops.py:191-198), all bounds scaled by 4
@@ -290,27 +384,34 @@ __device__ void loop_windows(const int2 *__restrict__ byx, const int2 *__restric
         if (bl < 0) bl = 0;
         if (bh < 0) bh = 0;
         Iv a = iv4(al, ah), b = iv4(bl, bh);
-        S.alo[lane] = clamp_i32(a.lo); S.ahi[lane] = clamp_i32(a.hi);
-        S.blo[lane] = clamp_i32(b.lo); S.bhi[lane] = clamp_i32(b.hi);
+        a_lo = a.lo; a_hi = a.hi; b_lo = b.lo; b_hi = b.hi;
+        const Iv32 a32 = iv32(a), b32 = iv32(b);
+        S.aw[lane] = make_int2(a32.lo, (int)a32.wd);
+        S.bw[lane] = make_int2(b32.lo, (int)b32.wd);
+        S.ahi[lane] = a32.lo == INT_MAX ? -1 : (int)(a32.lo + a32.wd);
+        S.bhi[lane] = b32.lo == INT_MAX ? -1 : (int)(b32.lo + b32.wd);
     }
-    __syncwarp();
     // spans covering all a-windows / all b-windows (window centres are monotone in i)
-    if (lane == 0) { S.sa_lo = S.alo[0]; S.sa_hi = S.ahi[W - 1]; S.sb_lo = S.blo[0]; S.sb_hi = S.bhi[W - 1]; }
+    Iv SA, SB;
+    SA.lo = __shfl_sync(0xffffffffu, a_lo, 0); SA.hi = __shfl_sync(0xffffffffu, a_hi, W - 1);
+    SB.lo = __shfl_sync(0xffffffffu, b_lo, 0); SB.hi = __shfl_sync(0xffffffffu, b_hi, W - 1);
+    const Iv32 SA32 = iv32(SA), SB32 = iv32(SB);
     __syncwarp();
-    Iv SA = {S.alo[0], S.ahi[W - 1]}, SB = {S.blo[0], S.bhi[W - 1]};
-    Range rxa = range_of(byx, n, SA), rya = range_of(byy, n, SA);
-    Range rxb = range_of(byx, n, SB), ryb = range_of(byy, n, SB);
+    Range rxa = range_of(arr_x(ix), ix.n, SA, lane), rya = range_of(arr_y(ix), ix.n, SA, lane);
+    Range rxb = range_of(arr_x(ix), ix.n, SB, lane), ryb = range_of(arr_y(ix), ix.n, SB, lane);
     *g_scan += (rxa.e - rxa.b) + (rya.e - rya.b) + (rxb.e - rxb.b) + (ryb.e - ryb.b);
     // four lists; a PET is handled by the first list that contains it.  Each list is sorted by the coordinate that put
     // the PET into it ("primary": x for the X-sorted lists, y for the Y-sorted ones), so the 32 PETs of a batch can
     // only fall into the few windows [t_lo, t_hi] that meet [first, last] of the batch -- found with two ballots over
-    // the (ascending) window bounds.  The other three coordinate / window-set combinations are rare and go through
-    // the span pre-tests of coord_mask_in().
+    // the window bounds.  The other three coordinate / window-set combinations are rare and go through a span
+    // pre-test and coord_mask().
     for (int pass = 0; pass < 4; pass++) {
-        const int2 *arr = (pass & 1) ? byy : byx;
+        const int2 *arr = (pass & 1) ? ix.byy : ix.byx;
         const Range r = pass == 0 ? rxa : pass == 1 ? rya : pass == 2 ? rxb : ryb;
         const bool prim_a = pass < 2;                       // primary coordinate is tested against the a-windows
-        const int *plo = prim_a ? S.alo : S.blo, *phi = prim_a ? S.ahi : S.bhi;
+        const int2 *pw = prim_a ? S.aw : S.bw, *ow = prim_a ? S.bw : S.aw;
+        const int *phi = prim_a ? S.ahi : S.bhi;
+        const Iv32 PS = prim_a ? SA32 : SB32, OS = prim_a ? SB32 : SA32;   // spans of the primary / the other set
         for (int64_t i0 = r.b; i0 < r.e; i0 += 32) {
             const int64_t i = i0 + lane;
             const bool valid = i < r.e;
@@ -320,35 +421,30 @@ __device__ void loop_windows(const int2 *__restrict__ byx, const int2 *__restric
             const int first = __shfl_sync(0xffffffffu, prim, 0);
             const int last = __shfl_sync(0xffffffffu, prim, left >= 32 ? 31 : (int)left - 1);
             const unsigned bl = __ballot_sync(0xffffffffu, lane < W && phi[lane < W ? lane : 0] >= first);
-            const unsigned bh = __ballot_sync(0xffffffffu, lane < W && plo[lane < W ? lane : 0] <= last);
+            const unsigned bh = __ballot_sync(0xffffffffu, lane < W && pw[lane < W ? lane : 0].x <= last);
             unsigned ma = 0, mb = 0;
             if (valid) {
                 const int x = (pass & 1) ? p.y : p.x, y = (pass & 1) ? p.x : p.y;
                 bool dup = false;
-                if (pass >= 1 && in_iv(SA, x)) dup = true;                       // seen in list 0
-                if (pass >= 2 && in_iv(SA, y)) dup = true;                       // seen in list 1
-                if (pass == 3 && in_iv(SB, x)) dup = true;                       // seen in list 2
+                if (pass >= 1 && in32(SA32, x)) dup = true;                      // seen in list 0
+                if (pass >= 2 && in32(SA32, y)) dup = true;                      // seen in list 1
+                if (pass == 3 && in32(SB32, x)) dup = true;                      // seen in list 2
                 if (!dup) {
                     unsigned mp = 0;
                     if (bl && bh) {
                         const int t_lo = __ffs(bl) - 1, t_hi = 31 - __clz(bh);
-                        for (int t = t_lo; t <= t_hi; t++) mp |= ((prim >= plo[t] && prim <= phi[t]) ? 1u : 0u) << t;
+                        for (int t = t_lo; t <= t_hi; t++) {
+                            const int2 q = pw[t];
+                            mp |= ((unsigned)(prim - q.x) <= (unsigned)q.y) ? (1u << t) : 0u;
+                        }
                     }
-                    const int sec = (pass & 1) ? x : y;     // the other coordinate
-                    unsigned ms = 0, mo = 0;
-                    if (prim_a) {
-                        if (sec >= S.sa_lo && sec <= S.sa_hi) ms = coord_mask(S.alo, S.ahi, W, sec);
-                        if (prim >= S.sb_lo && prim <= S.sb_hi) mo |= coord_mask(S.blo, S.bhi, W, prim);
-                        if (sec >= S.sb_lo && sec <= S.sb_hi) mo |= coord_mask(S.blo, S.bhi, W, sec);
-                        ma = mp | ms;
-                        mb = mo;
-                    } else {
-                        if (sec >= S.sb_lo && sec <= S.sb_hi) ms = coord_mask(S.blo, S.bhi, W, sec);
-                        if (prim >= S.sa_lo && prim <= S.sa_hi) mo |= coord_mask(S.alo, S.ahi, W, prim);
-                        if (sec >= S.sa_lo && sec <= S.sa_hi) mo |= coord_mask(S.alo, S.ahi, W, sec);
-                        mb = mp | ms;
-                        ma = mo;
-                    }
+                    const int sec = p.y;                    // the other coordinate
+                    unsigned mo = 0;
+                    if (in32(PS, sec)) mp |= coord_mask(pw, W, sec);
+                    if (in32(OS, prim)) mo |= coord_mask(ow, W, prim);
+                    if (in32(OS, sec)) mo |= coord_mask(ow, W, sec);
+                    ma = prim_a ? mp : mo;
+                    mb = prim_a ? mo : mp;
                 }
             }
             if (__any_sync(0xffffffffu, (ma | mb) != 0)) window_accumulate(S, W, ma, mb, lane);
@@ -358,8 +454,7 @@ __device__ void loop_windows(const int2 *__restrict__ byx, const int2 *__restric
 }
 
 // ---- raw counts (cl2_loop_counts) ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(CNT_WARPS * 32) k_loop_counts(const int2 *__restrict__ byx, const int2 *__restrict__ byy,
-                                                                 int64_t n, const longlong4 *__restrict__ loops, int64_t L,
+__global__ void __launch_bounds__(CNT_WARPS * 32) k_loop_counts(const IdxView ix, const longlong4 *__restrict__ loops, int64_t L,
                                                                  int win, int mode, long long *__restrict__ core,
                                                                  long long *__restrict__ na_out, long long *__restrict__ nb_out,
                                                                  long long *__restrict__ nab_out,
@@ -373,20 +468,20 @@ __global__ void __launch_bounds__(CNT_WARPS * 32) k_loop_counts(const int2 *__re
     long long scanned = 0;
     if (core) {
         int64_t c[4];
-        loop_core(byx, byy, n, xs, xe, ys, ye, mode, lane, c, &scanned);
+        loop_core(ix, xs, xe, ys, ye, mode, lane, c, &scanned);
         if (lane == 0) { core[4 * k] = c[0]; core[4 * k + 1] = c[1]; core[4 * k + 2] = c[2]; core[4 * k + 3] = c[3]; }
     }
     if (anchors) {
         for (int a = 0; a < 2; a++) {
             int64_t c, wd;
-            loop_anchor(byx, byy, n, a == 0 ? xs : ys, a == 0 ? xe : ye, lane, &c, &wd, &scanned);
+            loop_anchor(ix, a == 0 ? xs : ys, a == 0 ? xe : ye, lane, &c, &wd, &scanned);
             if (lane == 0) { anchors[4 * k + 2 * a] = c; anchors[4 * k + 2 * a + 1] = wd; }
         }
     }
     if (na_out || nb_out || nab_out) {
         const int W = 2 * win;
         WarpAcc &S = acc[w];
-        loop_windows(byx, byy, n, xs, xe, ys, ye, win, lane, S, &scanned);
+        loop_windows(ix, xs, xe, ys, ye, win, lane, S, &scanned);
         if (na_out && lane < W) na_out[(int64_t)W * k + lane] = S.na[lane];
         if (nb_out && lane < W) nb_out[(int64_t)W * k + lane] = S.nb[lane];
         if (nab_out)
@@ -396,8 +491,7 @@ __global__ void __launch_bounds__(CNT_WARPS * 32) k_loop_counts(const int2 *__re
 
 // ---- fused counting + statistics ----------------------------------------------------------------------------
 // phase 1: ra, rb, rab, lower and the hypergeometric tail hypergeom.sf(rab-1, N, ra, rb) (callCisLoops.py:310)
-__global__ void __launch_bounds__(CNT_WARPS * 32) k_loop_core(const int2 *__restrict__ byx, const int2 *__restrict__ byy,
-                                                               int64_t n, const longlong4 *__restrict__ loops, int64_t L,
+__global__ void __launch_bounds__(CNT_WARPS * 32) k_loop_core(const IdxView ix, const longlong4 *__restrict__ loops, int64_t L,
                                                                int mode, long long *__restrict__ core,
                                                                double *__restrict__ hyp) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -406,10 +500,10 @@ __global__ void __launch_bounds__(CNT_WARPS * 32) k_loop_core(const int2 *__rest
     const longlong4 lp = loops[k];
     int64_t c[4];
     long long scanned = 0;
-    loop_core(byx, byy, n, lp.x, lp.y, lp.z, lp.w, mode, lane, c, &scanned);
+    loop_core(ix, lp.x, lp.y, lp.z, lp.w, mode, lane, c, &scanned);
     if (lane == 0) {
         core[4 * k] = c[0]; core[4 * k + 1] = c[1]; core[4 * k + 2] = c[2]; core[4 * k + 3] = c[3];
-        hyp[k] = cl2_hypergeom_sf_ge((double)c[2], (double)n, (double)c[0], (double)c[1]);
+        hyp[k] = cl2_hypergeom_sf_ge((double)c[2], (double)ix.n, (double)c[0], (double)c[1]);
     }
 }
 
@@ -438,26 +532,51 @@ __device__ double np_pairwise_sum(const double *a, int n) {
 
 struct WarpVals {
     double v[CNT_MAXW * CNT_MAXW];
-    double pick[2];
 };
 
-// median of m values held in S.v (np.median: mean of the two middle order statistics for even m), by rank counting
+// median of the m non-negative values in S.v (np.median: mean of the two middle order statistics), by selection:
+// keep an open value bracket (lo, hi) around the wanted order statistic, take some element inside it as pivot, count
+// the values below / not above the pivot, shrink.  The pivot choice only affects the number of rounds (about log m).
 __device__ double warp_median(WarpVals &S, int m, int lane) {
-    int lo = (m - 1) / 2, hi = m / 2;
-    for (int i = lane; i < m; i += 32) {
-        double x = S.v[i];
-        int rank = 0;
-        for (int j = 0; j < m; j++) {
-            double y = S.v[j];
-            rank += (y < x || (y == x && j < i)) ? 1 : 0;
+    const int k1 = (m - 1) / 2, k2 = m / 2;
+    double lo = -1.0, hi = CUDART_INF;
+    double p = 0.0;
+    int le = 0;
+    for (int round = 0;; round++) {
+        double cand = 0.0;
+        bool has = false;
+        for (int i = lane; i < m; i += 32) {
+            const double y = S.v[i];
+            if (!has && y > lo && y < hi) { cand = y; has = true; }
         }
-        if (rank == lo) S.pick[0] = x;
-        if (rank == hi) S.pick[1] = x;
+        const unsigned bal = __ballot_sync(0xffffffffu, has);     // never empty: the answer itself is inside
+        const int rot = (round * 11 + 5) & 31;                    // vary the lane the pivot comes from
+        const int src = (__ffs(__funnelshift_r(bal, bal, rot)) - 1 + rot) & 31;
+        p = __shfl_sync(0xffffffffu, cand, src);
+        int lt = 0;
+        le = 0;
+        for (int i = lane; i < m; i += 32) {
+            const double y = S.v[i];
+            lt += y < p ? 1 : 0;
+            le += y <= p ? 1 : 0;
+        }
+        lt = warp_sum(lt);
+        le = warp_sum(le);
+        if (k1 < lt) hi = p;
+        else if (k1 >= le) lo = p;
+        else break;
     }
-    __syncwarp();
-    double r = (S.pick[0] + S.pick[1]) / 2.0;
-    __syncwarp();
-    return r;
+    double q = p;                                                  // order statistic k2 = k1 or k1 + 1
+    if (k2 >= le) {
+        q = CUDART_INF;                                            // smallest value above p
+        for (int i = lane; i < m; i += 32) {
+            const double y = S.v[i];
+            if (y > p && y < q) q = y;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) q = fmin(q, __shfl_xor_sync(0xffffffffu, q, o));
+    }
+    return (p + q) / 2.0;
 }
 
 #define CL2_NSTAT 13
@@ -465,12 +584,12 @@ __device__ double warp_median(WarpVals &S, int m, int lane) {
 // mrabs, mbps, fdr, poisson sf, binomial sf, px, esx, py, esy, count_x, wide_x, count_y, wide_y
 // Background of one loop (one warp): permuted windows -> mrabs, mbps, fdr (callCisLoops.py:207-223, 315-321).
 // early_cut > 0 (cis): return false as soon as `mrabs >= rab or fdr >= 0.1` or `es < 1` (:322-327) is known.
-__device__ bool loop_background(const int2 *__restrict__ byx, const int2 *__restrict__ byy, int64_t n, long long xs,
+__device__ bool loop_background(const IdxView &ix, long long xs,
                                 long long xe, long long ys, long long ye, double rab, int win, int mode, WarpAcc &S,
                                 WarpVals &V, int lane, double early_cut, double *o_mrabs, double *o_mbps,
                                 double *o_fdr, long long *g_scan) {
     const int W = 2 * win, m = W * W;
-    loop_windows(byx, byy, n, xs, xe, ys, ye, win, lane, S, g_scan);
+    loop_windows(ix, xs, xe, ys, ye, win, lane, S, g_scan);
     // rabs: counts of the 4*win^2 window pairs; fdr = #{rabs > rab} / m
     int gt = 0, nzero = 0;
     for (int t = lane; t < m; t += 32) {
@@ -484,12 +603,13 @@ __device__ bool loop_background(const int2 *__restrict__ byx, const int2 *__rest
     // cis medians: when more than half of the window pairs are empty both middle order statistics are 0, for the
     // counts and for the densities alike (a density is 0 exactly where the count is 0) -- the common case
     const bool zero_median = mode == CL2_MODE_CIS && nzero >= m / 2 + 1;
+    const double fdr = (double)gt / (double)m;
+    if (early_cut > 0 && fdr >= 0.1) return false;         // the cheap half of the background cut first
     double mrabs, mbps;
     if (zero_median) mrabs = 0.0;
     else if (mode == CL2_MODE_CIS) mrabs = warp_median(V, m, lane);
     else mrabs = np_pairwise_sum(V.v, m) / (double)m;     // every lane computes the same value
     __syncwarp();
-    const double fdr = (double)gt / (double)m;
     if (early_cut > 0) {
         if (mrabs >= rab || fdr >= 0.1) return false;
         if (rab / (mrabs > early_cut ? mrabs : early_cut) < 1.0) return false;
@@ -516,12 +636,12 @@ __device__ bool loop_background(const int2 *__restrict__ byx, const int2 *__rest
 
 // Anchor windows and the tail probabilities of one loop (one warp): o[3..12] = poisson sf, binomial sf, px, esx, py,
 // esy, count_x, wide_x, count_y, wide_y  (callCisLoops.py:226-247, 329-333)
-__device__ void loop_tail(const int2 *__restrict__ byx, const int2 *__restrict__ byy, int64_t n, long long xs,
+__device__ void loop_tail(const IdxView &ix, long long xs,
                           long long xe, long long ys, long long ye, double ra, double rb, double rab, double mrabs,
                           double mbps, int mode, double rpb, int lane, double *o, long long *g_scan) {
     int64_t cx, wx, cy, wy;
-    loop_anchor(byx, byy, n, xs, xe, lane, &cx, &wx, g_scan);
-    loop_anchor(byx, byy, n, ys, ye, lane, &cy, &wy, g_scan);
+    loop_anchor(ix, xs, xe, lane, &cx, &wx, g_scan);
+    loop_anchor(ix, ys, ye, lane, &cy, &wy, g_scan);
     if (lane == 0) {
         o[3] = cl2_poisson_sf_ge(rab, mrabs);                                            // :329
         o[9] = (double)cx; o[10] = (double)wx; o[11] = (double)cy; o[12] = (double)wy;
@@ -541,18 +661,17 @@ __device__ void loop_tail(const int2 *__restrict__ byx, const int2 *__restrict__
 }
 
 // both parts (the two-phase API, cl2_loop_tests)
-__device__ void loop_tests_warp(const int2 *__restrict__ byx, const int2 *__restrict__ byy, int64_t n, long long xs,
+__device__ void loop_tests_warp(const IdxView &ix, long long xs,
                                 long long xe, long long ys, long long ye, double ra, double rb, double rab, int win,
                                 int mode, double rpb, WarpAcc &S, WarpVals &V, int lane, double *o, long long *g_scan) {
     double mrabs, mbps, fdr;
-    loop_background(byx, byy, n, xs, xe, ys, ye, rab, win, mode, S, V, lane, 0.0, &mrabs, &mbps, &fdr, g_scan);
+    loop_background(ix, xs, xe, ys, ye, rab, win, mode, S, V, lane, 0.0, &mrabs, &mbps, &fdr, g_scan);
     if (lane == 0) { o[0] = mrabs; o[1] = mbps; o[2] = fdr; }
-    loop_tail(byx, byy, n, xs, xe, ys, ye, ra, rb, rab, mrabs, mbps, mode, rpb, lane, o, g_scan);
+    loop_tail(ix, xs, xe, ys, ye, ra, rb, rab, mrabs, mbps, mode, rpb, lane, o, g_scan);
 }
 
 // phase 2 as a separate launch (cl2_loop_tests)
-__global__ void __launch_bounds__(CNT_WARPS * 32) k_loop_tests(const int2 *__restrict__ byx, const int2 *__restrict__ byy,
-                                                                int64_t n, const longlong4 *__restrict__ loops,
+__global__ void __launch_bounds__(CNT_WARPS * 32) k_loop_tests(const IdxView ix, const longlong4 *__restrict__ loops,
                                                                 const long long *__restrict__ core, int64_t L, int win,
                                                                 int mode, double rpb, double *__restrict__ stats) {
     __shared__ WarpAcc acc[CNT_WARPS];
@@ -563,7 +682,7 @@ __global__ void __launch_bounds__(CNT_WARPS * 32) k_loop_tests(const int2 *__res
     if (k >= L) return;
     const longlong4 lp = loops[k];
     long long scanned = 0;
-    loop_tests_warp(byx, byy, n, lp.x, lp.y, lp.z, lp.w, (double)core[4 * k], (double)core[4 * k + 1],
+    loop_tests_warp(ix, lp.x, lp.y, lp.z, lp.w, (double)core[4 * k], (double)core[4 * k + 1],
                     (double)core[4 * k + 2], win, mode, rpb, acc[w], vals[w], lane, ost[w], &scanned);
     if (lane < CL2_NSTAT) stats[CL2_NSTAT * k + lane] = ost[w][lane];
 }
@@ -573,8 +692,7 @@ __global__ void __launch_bounds__(CNT_WARPS * 32) k_loop_tests(const int2 *__res
 // 127-139), the permuted-window background and, for cis, the background cut (:322-327).  Survivors get flag = 1 and
 // core[4], stats[0..2] = mrabs, mbps, fdr.  The hypergeometric cut (:311) is applied by kernel B: the cascade is a
 // conjunction, so the order of the tests does not change which candidates survive.
-__global__ void __launch_bounds__(CNT_WARPS * 32) k_est_bg(const int2 *__restrict__ byx, const int2 *__restrict__ byy,
-                                                            int64_t n, const longlong4 *__restrict__ loops, int64_t L,
+__global__ void __launch_bounds__(CNT_WARPS * 32, 4) k_est_bg(const IdxView ix, const longlong4 *__restrict__ loops, int64_t L,
                                                             int win, int mode, int minPts, int hic, double cdc,
                                                             double pseudo, long long *__restrict__ core_out,
                                                             double *__restrict__ stats_out, int32_t *__restrict__ flag,
@@ -592,7 +710,7 @@ __global__ void __launch_bounds__(CNT_WARPS * 32) k_est_bg(const int2 *__restric
     bool keep = !(la / lb > cdc || lb / la > cdc);                                      // :282-286 / trans :135-139
     if (keep) {
         int64_t c[4];
-        loop_core(byx, byy, n, xs, xe, ys, ye, mode, lane, c, &scanned);
+        loop_core(ix, xs, xe, ys, ye, mode, lane, c, &scanned);
         const double ra = (double)c[0], rb = (double)c[1], rab = (double)c[2];
         if (c[2] < minPts) keep = false;                                               // :290 / trans :127
         if (cis && (c[0] == c[2] || c[1] == c[2])) keep = false;                       // :293
@@ -602,7 +720,7 @@ __global__ void __launch_bounds__(CNT_WARPS * 32) k_est_bg(const int2 *__restric
         if (cis && hic && p2ll < 1.0) keep = false;                                    // :307
         if (keep) {
             double mrabs, mbps, fdr;
-            keep = loop_background(byx, byy, n, xs, xe, ys, ye, rab, win, mode, acc[w], vals[w], lane,
+            keep = loop_background(ix, xs, xe, ys, ye, rab, win, mode, acc[w], vals[w], lane,
                                    cis ? pseudo : 0.0, &mrabs, &mbps, &fdr, &scanned);
             if (keep && lane == 0) {
                 core_out[4 * k] = c[0]; core_out[4 * k + 1] = c[1]; core_out[4 * k + 2] = c[2]; core_out[4 * k + 3] = c[3];
@@ -618,8 +736,7 @@ __global__ void __launch_bounds__(CNT_WARPS * 32) k_est_bg(const int2 *__restric
 
 // kernel B (survivors of kernel A, compacted; one warp each): hypergeometric / Poisson / binomial tails, anchor
 // windows and tests, and the remaining cuts (:311 hypergeometric > 1e-2, :347 anchor peaks unless -hic).
-__global__ void __launch_bounds__(CNT_WARPS * 32) k_est_tail(const int2 *__restrict__ byx, const int2 *__restrict__ byy,
-                                                              int64_t n, const longlong4 *__restrict__ loops,
+__global__ void __launch_bounds__(CNT_WARPS * 32) k_est_tail(const IdxView ix, const longlong4 *__restrict__ loops,
                                                               const long long *__restrict__ sel, int64_t K, int mode,
                                                               int hic, double peakPcut, double rpb,
                                                               const long long *__restrict__ core, double *__restrict__ hyp,
@@ -636,8 +753,8 @@ __global__ void __launch_bounds__(CNT_WARPS * 32) k_est_tail(const int2 *__restr
     const bool cis = mode == CL2_MODE_CIS;
     double *o = ost[w];
     double h = 0.0;
-    if (lane == 4) h = cl2_hypergeom_sf_ge(rab, (double)n, ra, rb);                    // :310
-    loop_tail(byx, byy, n, lp.x, lp.y, lp.z, lp.w, ra, rb, rab, mrabs, mbps, mode, rpb, lane, o, &scanned);
+    if (lane == 4) h = cl2_hypergeom_sf_ge(rab, (double)ix.n, ra, rb);                    // :310
+    loop_tail(ix, lp.x, lp.y, lp.z, lp.w, ra, rb, rab, mrabs, mbps, mode, rpb, lane, o, &scanned);
     h = __shfl_sync(0xffffffffu, h, 4);
     bool keep = true;
     if (cis && fmax(1e-300, h) > 1e-2) keep = false;                                   // :311
@@ -685,7 +802,7 @@ extern "C" int cl2_loop_counts(cl2_ctx *ctx, cl2_index *idx, const int64_t *loop
     CL2_CUDA(ctx, cudaMemcpyAsync(d_loops, loops, (size_t)L * 32, cudaMemcpyHostToDevice, ctx->stream));
     {
         FamTimer t(ctx, FAM_COUNT, 0.0);
-        k_loop_counts<<<cl2_grid(L, CNT_WARPS), CNT_WARPS * 32, 0, ctx->stream>>>(idx->byx, idx->byy, idx->n, d_loops, L, win,
+        k_loop_counts<<<cl2_grid(L, CNT_WARPS), CNT_WARPS * 32, 0, ctx->stream>>>(cl2_view(idx), d_loops, L, win,
                                                                                   mode, d_core, d_na, d_nb, d_nab, d_anc);
     }
     if (core) CL2_CUDA(ctx, cudaMemcpyAsync(core, d_core, (size_t)L * 32, cudaMemcpyDeviceToHost, ctx->stream));
@@ -716,7 +833,7 @@ extern "C" int cl2_loop_core(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops,
     CL2_CUDA(ctx, cudaMemcpyAsync(d_loops, loops, (size_t)L * 32, cudaMemcpyHostToDevice, ctx->stream));
     {
         FamTimer t(ctx, FAM_COUNT, 0.0);
-        k_loop_core<<<cl2_grid(L, CNT_WARPS), CNT_WARPS * 32, 0, ctx->stream>>>(idx->byx, idx->byy, idx->n, d_loops, L, mode,
+        k_loop_core<<<cl2_grid(L, CNT_WARPS), CNT_WARPS * 32, 0, ctx->stream>>>(cl2_view(idx), d_loops, L, mode,
                                                                                 d_core, d_hyp);
     }
     CL2_CUDA(ctx, cudaMemcpyAsync(core, d_core, (size_t)L * 32, cudaMemcpyDeviceToHost, ctx->stream));
@@ -746,7 +863,7 @@ extern "C" int cl2_loop_tests(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops
     CL2_CUDA(ctx, cudaMemcpyAsync(d_core, core, (size_t)L * 32, cudaMemcpyHostToDevice, ctx->stream));
     {
         FamTimer t(ctx, FAM_COUNT, 0.0);
-        k_loop_tests<<<cl2_grid(L, CNT_WARPS), CNT_WARPS * 32, 0, ctx->stream>>>(idx->byx, idx->byy, idx->n, d_loops, d_core, L,
+        k_loop_tests<<<cl2_grid(L, CNT_WARPS), CNT_WARPS * 32, 0, ctx->stream>>>(cl2_view(idx), d_loops, d_core, L,
                                                                                  win, mode, rpb, d_stats);
     }
     CL2_CUDA(ctx, cudaMemcpyAsync(stats, d_stats, (size_t)L * CL2_NSTAT * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -784,7 +901,7 @@ extern "C" int cl2_est_loops(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops,
     ctx->h2d_bytes += L * 32;
     {
         FamTimer t(ctx, FAM_COUNT, 0.0);
-        k_est_bg<<<cl2_grid(L, CNT_WARPS), CNT_WARPS * 32, 0, ctx->stream>>>(idx->byx, idx->byy, idx->n, d_loops, L, win, mode,
+        k_est_bg<<<cl2_grid(L, CNT_WARPS), CNT_WARPS * 32, 0, ctx->stream>>>(cl2_view(idx), d_loops, L, win, mode,
                                                                              minPts, hic, countDiffCut, pseudo, d_core, d_stats,
                                                                              d_flag, (unsigned long long *)(d_total + 1));
     }
@@ -810,7 +927,7 @@ extern "C" int cl2_est_loops(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops,
         }
         {
             FamTimer t(ctx, FAM_COUNT, 0.0);
-            k_est_tail<<<cl2_grid(nk, CNT_WARPS), CNT_WARPS * 32, 0, ctx->stream>>>(idx->byx, idx->byy, idx->n, d_loops, d_sel, nk,
+            k_est_tail<<<cl2_grid(nk, CNT_WARPS), CNT_WARPS * 32, 0, ctx->stream>>>(cl2_view(idx), d_loops, d_sel, nk,
                                                                                     mode, hic, peakPcut, rpb, d_core_c, d_hyp_c,
                                                                                     d_stats_c, d_flag2,
                                                                                     (unsigned long long *)(d_total + 1));

@@ -41,6 +41,9 @@ struct cl2_index {
     int64_t n = 0;
     int2 *byx = nullptr;  // [n] (x, y) sorted by x
     int2 *byy = nullptr;  // [n] (y, x) sorted by y
+    // bucket tables over the sorted coordinate (cl2_count.cu): t[b] = first position with coordinate >= b << shift
+    uint32_t *tx = nullptr, *ty = nullptr;
+    int sx = 0, sy = 0, nbx = 0, nby = 0;
 };
 
 void cl2_grid_free(cl2_ctx *ctx, cl2_grid_cache &g);

@@ -265,7 +265,8 @@ __device__ __forceinline__ void os_st(unsigned *p, unsigned v) {
 #define OS_VAL 0x3FFFFFFFu
 #define OS_MAXPASS 8
 
-__global__ void __launch_bounds__(256) k_os_hist(const uint64_t *__restrict__ keys, const cl2_keygen gen, int64_t n,
+template <typename K>
+__global__ void __launch_bounds__(256) k_os_hist(const K *__restrict__ keys, const cl2_keygen gen, int64_t n,
                                                   int passes, unsigned *__restrict__ ghist) {
     __shared__ unsigned h[OS_MAXPASS][256];
     for (int i = threadIdx.x; i < OS_MAXPASS * 256; i += 256) (&h[0][0])[i] = 0;
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(256) k_os_hist(const uint64_t *__restrict__ ke
     int64_t nround = ((n + 31) / 32) * 32;      // whole warps stay in the loop together
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
         bool valid = i < n;
-        uint64_t k = valid ? os_key(gen, keys, i) : 0;
+        uint64_t k = valid ? (gen.kind == CL2_KEY_ARRAY ? (uint64_t)keys[i] : os_key(gen, nullptr, i)) : 0;
         unsigned act = __ballot_sync(0xffffffffu, valid);
         for (int p = 0; p < passes; p++) {
             unsigned d = (unsigned)((k >> (8 * p)) & 255);
@@ -306,8 +307,9 @@ __global__ void __launch_bounds__(256) k_os_prefix(unsigned *__restrict__ ghist)
 #define OS_IPT 8
 #define OS_TILE (OS_THREADS * OS_IPT)
 
+template <typename K>
 struct OsSmem {
-    uint64_t keys[OS_TILE];
+    K keys[OS_TILE];
     uint32_t vals[OS_TILE];
     int warp_cnt[OS_WARPS][256];
     int hist[256];
@@ -315,14 +317,17 @@ struct OsSmem {
     int gbase[256];
 };
 
-__global__ void __launch_bounds__(OS_THREADS, 2) k_os_pass(const uint64_t *__restrict__ kin, const cl2_keygen gen,
+template <typename K, int MINB>
+__global__ void __launch_bounds__(OS_THREADS, MINB) k_os_pass(const K *__restrict__ kin, const cl2_keygen gen,
                                                            const uint32_t *__restrict__ vin,
-                                                           uint64_t *__restrict__ kout, uint32_t *__restrict__ vout,
+                                                           K *__restrict__ kout, uint32_t *__restrict__ vout,
                                                            int64_t n, int shift, const unsigned *__restrict__ gprefix,
                                                            unsigned *__restrict__ desc, unsigned *__restrict__ ticket,
-                                                           int iota) {
+                                                           int flags) {
+    const int iota = flags & 1;
+    const bool put_keys = !(flags & 2);   // the last pass of a sort whose caller only wants the row order
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    OsSmem &S = *reinterpret_cast<OsSmem *>(smem_raw);
+    OsSmem<K> &S = *reinterpret_cast<OsSmem<K> *>(smem_raw);
     __shared__ unsigned s_tile;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
@@ -331,7 +336,7 @@ __global__ void __launch_bounds__(OS_THREADS, 2) k_os_pass(const uint64_t *__res
     const unsigned tile = s_tile;
     const int64_t tbase = (int64_t)tile * OS_TILE;
     const int64_t wbase = tbase + (int64_t)w * (32 * OS_IPT);
-    uint64_t key[OS_IPT];
+    K key[OS_IPT];
     uint32_t val[OS_IPT];
     unsigned short rank[OS_IPT];
     const unsigned lt = (1u << lane) - 1u;
@@ -339,7 +344,7 @@ __global__ void __launch_bounds__(OS_THREADS, 2) k_os_pass(const uint64_t *__res
 #pragma unroll
     for (int r = 0; r < OS_IPT; r++) {
         int64_t i = wbase + r * 32 + lane;
-        key[r] = (i < n) ? os_key(gen, kin, i) : ~0ull;
+        key[r] = (i < n) ? (gen.kind == CL2_KEY_ARRAY ? kin[i] : (K)os_key(gen, nullptr, i)) : (K)~(K)0;
     }
 #pragma unroll
     for (int r = 0; r < OS_IPT; r++) {
@@ -417,16 +422,17 @@ __global__ void __launch_bounds__(OS_THREADS, 2) k_os_pass(const uint64_t *__res
     int cnt = (int)((n - tbase) < OS_TILE ? (n - tbase) : OS_TILE);
 #pragma unroll 4
     for (int j = threadIdx.x; j < cnt; j += OS_THREADS) {
-        uint64_t k = S.keys[j];
+        K k = S.keys[j];
         int d = (int)((k >> shift) & 255);
         int64_t dst = (int64_t)S.gbase[d] + (j - S.dprefix[d]);
-        kout[dst] = k;
+        if (put_keys) kout[dst] = k;
         vout[dst] = S.vals[j];
     }
 }
 
-static int radix_sort_onesweep(cl2_ctx *ctx, const cl2_keygen &gen, uint64_t *keys0, uint64_t *keys1, uint32_t *vals0,
-                               uint32_t *vals1, int64_t n, int passes, uint64_t **kout, uint32_t **vout,
+template <typename K>
+static int radix_sort_onesweep(cl2_ctx *ctx, const cl2_keygen &gen, K *keys0, K *keys1, uint32_t *vals0,
+                               uint32_t *vals1, int64_t n, int passes, K **kout, uint32_t **vout,
                                const uint32_t *vals_first) {
     int ntiles = (int)((n + OS_TILE - 1) / OS_TILE);
     Scratch sc(ctx);
@@ -436,35 +442,43 @@ static int radix_sort_onesweep(cl2_ctx *ctx, const cl2_keygen &gen, uint64_t *ke
     ticket = ghist + OS_MAXPASS * 256;
     CL2_CUDA(ctx, cudaMemsetAsync(ghist, 0, ((size_t)OS_MAXPASS * 256 + OS_MAXPASS) * 4, ctx->stream));
     CL2_CUDA(ctx, cudaMemsetAsync(desc, 0, (size_t)passes * ntiles * 256 * 4, ctx->stream));
-    static bool attr_set = false;
+    static bool attr_set = false;      // one flag per instantiation
     if (!attr_set) {
-        CL2_CUDA(ctx, cudaFuncSetAttribute(k_os_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OsSmem)));
+        CL2_CUDA(ctx, cudaFuncSetAttribute(k_os_pass<K, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sizeof(OsSmem<K>)));
+        CL2_CUDA(ctx, cudaFuncSetAttribute(k_os_pass<K, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sizeof(OsSmem<K>)));
         attr_set = true;
     }
     {
         FamTimer t(ctx, FAM_SORT_HIST, 8.0 * (double)n, 2);
         int grid = ctx->sm_count * 8;
         int need = cl2_grid(n, 256);
-        k_os_hist<<<need < grid ? need : grid, 256, 0, ctx->stream>>>(keys0, gen, n, passes, ghist);
+        k_os_hist<K><<<need < grid ? need : grid, 256, 0, ctx->stream>>>(keys0, gen, n, passes, ghist);
         k_os_prefix<<<passes, 256, 0, ctx->stream>>>(ghist);
     }
-    uint64_t *kin = keys0, *ko = keys1;
+    const bool want_keys = kout != nullptr;
+    static const bool occ3 = sizeof(K) == 4 && getenv("CL2_SORT_OCC3") != nullptr;
+    K *kin = keys0, *ko = keys1;
     uint32_t *vi = vals0, *vo = vals1;
     cl2_keygen none;
     none.kind = CL2_KEY_ARRAY;
     for (int p = 0; p < passes; p++) {
         {
-            FamTimer t(ctx, FAM_SORT_SCATTER, 24.0 * (double)n);
+            FamTimer t(ctx, FAM_SORT_SCATTER,
+                       ((p == passes - 1 && !want_keys ? 1.0 : 2.0) * sizeof(K) + 8.0) * (double)n);
             const uint32_t *vin = (p == 0 && vals_first) ? vals_first : vi;
-            k_os_pass<<<ntiles, OS_THREADS, sizeof(OsSmem), ctx->stream>>>(kin, p == 0 ? gen : none, vin, ko, vo, n, p * 8, ghist + p * 256,
-                                                                            desc + (size_t)p * ntiles * 256, ticket + p,
-                                                                            (p == 0 && !vals_first) ? 1 : 0);
+            const int flags = ((p == 0 && !vals_first) ? 1 : 0) | ((p == passes - 1 && !want_keys) ? 2 : 0);
+            auto kern = occ3 ? k_os_pass<K, 3> : k_os_pass<K, 2>;
+            kern<<<ntiles, OS_THREADS, sizeof(OsSmem<K>), ctx->stream>>>(kin, p == 0 ? gen : none, vin, ko, vo, n, p * 8,
+                                                                         ghist + p * 256, desc + (size_t)p * ntiles * 256,
+                                                                         ticket + p, flags);
         }
-        uint64_t *tk = kin; kin = ko; ko = tk;
+        K *tk = kin; kin = ko; ko = tk;
         uint32_t *tv = vi; vi = vo; vo = tv;
     }
     CL2_CUDA(ctx, cudaGetLastError());
-    *kout = kin;
+    if (kout) *kout = kin;
     *vout = vi;
     return CL2_OK;
 }
@@ -482,8 +496,16 @@ int cl2_radix_sort_gen(cl2_ctx *ctx, const cl2_keygen &gen, uint64_t *keys0, uin
     if (n <= 0) return CL2_OK;
     if (nbits < 1) nbits = 1;
     int passes = (nbits + 7) / 8;
-    if (n < (int64_t)OS_VAL && passes <= OS_MAXPASS && !getenv("CL2_SORT_3KERNEL"))
-        return radix_sort_onesweep(ctx, gen, keys0, keys1, vals0, vals1, n, passes, kout, vout, vals_first);
+    if (n < (int64_t)OS_VAL && passes <= OS_MAXPASS && !getenv("CL2_SORT_3KERNEL")) {
+        if (nbits <= 32 && gen.kind != CL2_KEY_ARRAY && !getenv("CL2_SORT_U64")) {
+            // every generated key of this path fits 32 bits: sort (u32 key, u32 row) pairs, 16 B per PET per pass.
+            // The caller's 8-byte key buffers are simply used as 4-byte ones; sorted keys are not handed back.
+            *kout = nullptr;
+            return radix_sort_onesweep<uint32_t>(ctx, gen, (uint32_t *)keys0, (uint32_t *)keys1, vals0, vals1, n, passes,
+                                                 nullptr, vout, vals_first);
+        }
+        return radix_sort_onesweep<uint64_t>(ctx, gen, keys0, keys1, vals0, vals1, n, passes, kout, vout, vals_first);
+    }
     if (vals_first) return cl2_fail(ctx, CL2_ERR_RANGE, "radix sort: more than 2^30 rows with a value input");
     if (gen.kind != CL2_KEY_ARRAY) {
         FamTimer t(ctx, FAM_KEYGEN, 16.0 * (double)n);
@@ -502,7 +524,7 @@ int cl2_radix_sort_pairs(cl2_ctx *ctx, uint64_t *keys0, uint64_t *keys1, uint32_
     if (n < (int64_t)OS_VAL && passes <= OS_MAXPASS && !getenv("CL2_SORT_3KERNEL")) {
         cl2_keygen none;
         none.kind = CL2_KEY_ARRAY;
-        return radix_sort_onesweep(ctx, none, keys0, keys1, vals0, vals1, n, passes, kout, vout, nullptr);
+        return radix_sort_onesweep<uint64_t>(ctx, none, keys0, keys1, vals0, vals1, n, passes, kout, vout, nullptr);
     }
     int ntiles = (int)((n + RS_TILE - 1) / RS_TILE);
     Scratch sc(ctx);
