@@ -200,16 +200,21 @@ __global__ void __launch_bounds__(256) k_keep_list(const uint8_t *__restrict__ k
     if (c < ncells && keep[c]) list[pos[c]] = c;
 }
 #define CELLSTAT_SERIAL_MAX 48
-// kept cells with few points (the common case): one thread per cell, consecutive threads read consecutive segments
+// kept cells with few points (the common case): one thread per cell, consecutive threads read consecutive segments;
+// crowded cells are only listed here and summed by k_block_cellstat_list
 __global__ void __launch_bounds__(256) k_block_cellstat_small(const int2 *__restrict__ sxy,
                                                                const int32_t *__restrict__ cstart,
                                                                const int32_t *__restrict__ list,
-                                                               CellStat *__restrict__ st, int32_t nkept) {
+                                                               CellStat *__restrict__ st, int32_t nkept,
+                                                               int32_t *__restrict__ crowd, int32_t *__restrict__ ncrowd) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nkept) return;
     int c = list[k];
     int b = cstart[c], e = cstart[c + 1];
-    if (e - b > CELLSTAT_SERIAL_MAX) return;
+    if (e - b > CELLSTAT_SERIAL_MAX) {
+        crowd[atomicAdd(ncrowd, 1)] = c;
+        return;
+    }
     long long sx = 0, sy = 0;
     int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
     for (int i = b; i < e; i++) {
@@ -222,38 +227,41 @@ __global__ void __launch_bounds__(256) k_block_cellstat_small(const int2 *__rest
     s.sx = sx; s.sy = sy; s.xmin = xmin; s.xmax = xmax; s.ymin = ymin; s.ymax = ymax;
     st[c] = s;
 }
-// crowded cells: one warp per cell
+// crowded cells: one warp per listed cell, the warps of a fixed-size grid stride over the list (its length stays on
+// the device)
 __global__ void __launch_bounds__(256) k_block_cellstat_list(const int2 *__restrict__ sxy,
                                                               const int32_t *__restrict__ cstart,
-                                                              const int32_t *__restrict__ list,
-                                                              CellStat *__restrict__ st, int32_t nkept) {
-    int k = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    int lane = threadIdx.x & 31;
-    if (k >= nkept) return;
-    int c = list[k];
-    int b = cstart[c], e = cstart[c + 1];
-    if (e - b <= CELLSTAT_SERIAL_MAX) return;
-    long long sx = 0, sy = 0;
-    int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
-    for (int i = b + lane; i < e; i += 32) {
-        int2 p = sxy[i];
-        sx += p.x; sy += p.y;
-        xmin = min(xmin, p.x); xmax = max(xmax, p.x);
-        ymin = min(ymin, p.y); ymax = max(ymax, p.y);
-    }
+                                                              const int32_t *__restrict__ crowd,
+                                                              const int32_t *__restrict__ ncrowd,
+                                                              CellStat *__restrict__ st) {
+    const int lane = threadIdx.x & 31;
+    const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+    const int m = *ncrowd;
+    for (int k = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); k < m; k += nwarps) {
+        int c = crowd[k];
+        int b = cstart[c], e = cstart[c + 1];
+        long long sx = 0, sy = 0;
+        int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
+        for (int i = b + lane; i < e; i += 32) {
+            int2 p = sxy[i];
+            sx += p.x; sy += p.y;
+            xmin = min(xmin, p.x); xmax = max(xmax, p.x);
+            ymin = min(ymin, p.y); ymax = max(ymax, p.y);
+        }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        sx += __shfl_xor_sync(0xffffffffu, sx, o);
-        sy += __shfl_xor_sync(0xffffffffu, sy, o);
-        xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
-        xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
-        ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
-        ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
-    }
-    if (lane == 0) {
-        CellStat s;
-        s.sx = sx; s.sy = sy; s.xmin = xmin; s.xmax = xmax; s.ymin = ymin; s.ymax = ymax;
-        st[c] = s;
+        for (int o = 16; o; o >>= 1) {
+            sx += __shfl_xor_sync(0xffffffffu, sx, o);
+            sy += __shfl_xor_sync(0xffffffffu, sy, o);
+            xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+            xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+            ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+            ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+        }
+        if (lane == 0) {
+            CellStat s;
+            s.sx = sx; s.sy = sy; s.xmin = xmin; s.xmax = xmax; s.ymin = ymin; s.ymax = ymax;
+            st[c] = s;
+        }
     }
 }
 
@@ -734,7 +742,7 @@ extern "C" int cl2_block_dbscan(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int3
         unsigned *adj;
         uint8_t *core;
         uint64_t *okey, *minkey;
-        int32_t *parent, *root, *compid, *nheavy;
+        int32_t *parent, *root, *compid, *nheavy, *crowd = nullptr;
         int2 *heavy;
         // cell-indexed arrays are sized by ncells but only touched at kept cells
         CL2_TRY(sc.get(&st, (size_t)ncells));
@@ -746,15 +754,18 @@ extern "C" int cl2_block_dbscan(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int3
         CL2_TRY(sc.get(&root, (size_t)ncells));
         CL2_TRY(sc.get(&compid, (size_t)ncells));
         CL2_TRY(sc.get(&heavy, (size_t)nkept * 4));
-        CL2_TRY(sc.get(&nheavy, 1));
+        CL2_TRY(sc.get(&nheavy, 2));                 // [0] heavy pairs, [1] crowded cells
+        if (g.maxcnt > CELLSTAT_SERIAL_MAX) CL2_TRY(sc.get(&crowd, (size_t)nkept));
         CL2_CUDA(ctx, cudaMemsetAsync(adj, 0, (size_t)ncells * 4, s));
         CL2_CUDA(ctx, cudaMemsetAsync(core, 0, (size_t)ncells, s));
-        CL2_CUDA(ctx, cudaMemsetAsync(nheavy, 0, 4, s));
+        CL2_CUDA(ctx, cudaMemsetAsync(nheavy, 0, 8, s));
         {
             FamTimer t(ctx, FAM_CELLSTAT, 8.0 * (double)n, 2);
-            k_block_cellstat_small<<<cl2_grid(nkept, 256), 256, 0, s>>>(g.sxy, g.cstart, list, st, nkept);
-            if (g.maxcnt > CELLSTAT_SERIAL_MAX)
-                k_block_cellstat_list<<<cl2_grid((int64_t)nkept * 32, 256), 256, 0, s>>>(g.sxy, g.cstart, list, st, nkept);
+            k_block_cellstat_small<<<cl2_grid(nkept, 256), 256, 0, s>>>(g.sxy, g.cstart, list, st, nkept, crowd, nheavy + 1);
+            if (g.maxcnt > CELLSTAT_SERIAL_MAX) {
+                int64_t want = cl2_grid((int64_t)nkept * 32, 256), cap = (int64_t)ctx->sm_count * 8;
+                k_block_cellstat_list<<<(unsigned)(want < cap ? want : cap), 256, 0, s>>>(g.sxy, g.cstart, crowd, nheavy + 1, st);
+            }
         }
         {
             FamTimer t(ctx, FAM_ADJ, 8.0 * (double)n);

@@ -306,20 +306,22 @@ __device__ __noinline__ unsigned coord_mask(const int2 *__restrict__ w, int W, i
     return m;
 }
 
-__device__ __forceinline__ void window_accumulate(WarpAcc &A, int W, unsigned ma, unsigned mb, int lane) {
+// na / nb live in registers: lane t carries the count of window t
+__device__ __forceinline__ void window_accumulate(WarpAcc &A, int W, unsigned ma, unsigned mb, int lane, int &na_r,
+                                                  int &nb_r) {
     // only the windows some lane of this batch falls into are visited (a sorted batch touches 1-3 of them)
     unsigned ua = __reduce_or_sync(0xffffffffu, ma), ub = __reduce_or_sync(0xffffffffu, mb);
     while (ua) {
         int t = __ffs(ua) - 1;
         ua &= ua - 1;
-        unsigned v = __ballot_sync(0xffffffffu, (ma >> t) & 1u);
-        if (lane == 0) A.na[t] += __popc(v);
+        int c = __popc(__ballot_sync(0xffffffffu, (ma >> t) & 1u));
+        na_r += lane == t ? c : 0;
     }
     while (ub) {
         int t = __ffs(ub) - 1;
         ub &= ub - 1;
-        unsigned v = __ballot_sync(0xffffffffu, (mb >> t) & 1u);
-        if (lane == 0) A.nb[t] += __popc(v);
+        int c = __popc(__ballot_sync(0xffffffffu, (mb >> t) & 1u));
+        nb_r += lane == t ? c : 0;
     }
     if (ma && mb) {
         unsigned a = ma;
@@ -371,8 +373,8 @@ __device__ void loop_windows(const IdxView &ix, long long xs, long long xe, long
     const int W = 2 * win;
     for (int t = lane; t < W * W; t += 32) S.nab[t] = 0;
     long long a_lo = 0, a_hi = -1, b_lo = 0, b_hi = -1;
+    int na_r = 0, nb_r = 0;
     if (lane < W) {
-        S.na[lane] = 0; S.nb[lane] = 0;
         // windows i = -win..-1, 1..win (callCisLoops.py:191-198), all bounds scaled by 4
         int i = lane < win ? lane - win : lane - win + 1;
         long long ca4 = 2 * (xs + xe), cb4 = 2 * (ys + ye), sa4 = 2 * (xe - xs), sb4 = 2 * (ye - ys);
@@ -412,10 +414,12 @@ __device__ void loop_windows(const IdxView &ix, long long xs, long long xe, long
         const int2 *pw = prim_a ? S.aw : S.bw, *ow = prim_a ? S.bw : S.aw;
         const int *phi = prim_a ? S.ahi : S.bhi;
         const Iv32 PS = prim_a ? SA32 : SB32, OS = prim_a ? SB32 : SA32;   // spans of the primary / the other set
+        int2 pnext = (r.b + lane < r.e) ? arr[r.b + lane] : make_int2(0, 0);
         for (int64_t i0 = r.b; i0 < r.e; i0 += 32) {
             const int64_t i = i0 + lane;
             const bool valid = i < r.e;
-            int2 p = valid ? arr[i] : make_int2(0, 0);
+            const int2 p = pnext;
+            pnext = (i + 32 < r.e) ? arr[i + 32] : make_int2(0, 0);     // next batch in flight while this one is tested
             const int prim = p.x;                            // first component = the sort coordinate of this list
             const int64_t left = r.e - i0;
             const int first = __shfl_sync(0xffffffffu, prim, 0);
@@ -447,9 +451,10 @@ __device__ void loop_windows(const IdxView &ix, long long xs, long long xe, long
                     mb = prim_a ? mo : mp;
                 }
             }
-            if (__any_sync(0xffffffffu, (ma | mb) != 0)) window_accumulate(S, W, ma, mb, lane);
+            if (__any_sync(0xffffffffu, (ma | mb) != 0)) window_accumulate(S, W, ma, mb, lane, na_r, nb_r);
         }
     }
+    if (lane < W) { S.na[lane] = na_r; S.nb[lane] = nb_r; }
     __syncwarp();
 }
 
