@@ -79,6 +79,10 @@ def main(argv=None):
     from .callCisLoops import callCisLoops
     from .callTransLoops import callTransLoops
     op = buildParser().parse_args(argv)
+    # keep the collector away from the objects numpy / scipy / torch created at import (a full pass over them costs
+    # tens of milliseconds in the middle of the run)
+    import gc
+    gc.freeze()
     if op.cmd == "quant":
         from .quant import quantLoops
         logger = getLogger()
