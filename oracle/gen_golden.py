@@ -16,6 +16,8 @@ Contents
   estsig_cis.npz       per-candidate fields of the reference's estLoopSig on one chromosome (every attribute)
   quant_loops.npz      the reference's `quant -loops` output (quant.py quantLoops, with and without -offp)
   filter_knn.npz       the reference's `filterPETs -knn` output matrices (filter.py _filterPETsByKNNs)
+  dloops.npz           the reference's callDiffLoops.quantDloops fields + background lists for two samples
+  peaks.npz            the reference's callPeaks.runDBSCANPeaks peaks (paired and -split)
 """
 import json
 import os
@@ -189,6 +191,63 @@ def gen_filter_knn(ref):
     np.savez_compressed(os.path.join(GOLD, "filter_knn.npz"), eps=500, minPts=5, **out)
 
 
+def gen_dloops(ref):
+    """cLoops2/callDiffLoops.py quantDloops: the default run's loops quantified against two samples (chr21 of the cis
+    golden files as target, a differently seeded chromosome of the same shape as control), win=1 and win=2."""
+    from cLoops2 import callDiffLoops as rd
+    from cLoops2 import io as rio
+    g = np.load(os.path.join(GOLD, "cis_pipeline.npz"))
+    a = g["chr21_chr21"]
+    # control: every second PET of the target plus an independent background, so both samples see the loops
+    b = np.concatenate([a[::2], synth.cis_chrom(4_000_000, 12000, 77, "hitrac")])
+    tmp = tempfile.mkdtemp()
+    synth.write_ixy_dir({"chr21-chr21": a}, tmp + "/a")
+    synth.write_ixy_dir({"chr21-chr21": b}, tmp + "/b")
+    open(tmp + "/loops.txt", "w").write(str(g["default_txt"]))
+    lines = str(g["default_txt"]).rstrip("\n").split("\n")
+    extra = []
+    for sh in (-1500, 900, 6000, 50000):                      # shifted copies: partial overlap, flanks, empty regions
+        for i, line in enumerate(lines[1:]):
+            f = line.split("\t")
+            if f[1] != "chr21":
+                continue
+            f[0] = "shift%d_%d" % (sh, i)
+            for j in (2, 3, 5, 6):
+                f[j] = str(max(0, int(f[j]) + sh))
+            extra.append("\t".join(f))
+    open(tmp + "/loops.txt", "w").write("\n".join(lines + extra) + "\n")
+    loops = rio.parseTxt2Loops(tmp + "/loops.txt")["chr21-chr21"]
+    coords = np.array([[lp.x_start, lp.x_end, lp.y_start, lp.y_end] for lp in loops], dtype=np.int64)
+    out = {}
+    fields = ["raw_trt_ra", "raw_trt_rb", "raw_con_ra", "raw_con_rb", "raw_trt_rab", "raw_con_rab", "raw_trt_mrab",
+              "raw_con_mrab", "trt_es", "con_es", "distance", "size"]
+    for win, cut in ((1, 0), (2, 3000)):
+        _, ts, cs, dl = rd.quantDloops("chr21-chr21", loops, tmp + "/a/chr21-chr21.ixy", tmp + "/b/chr21-chr21.ixy",
+                                       cut=cut, win=win)
+        out["ts_w%d" % win] = np.array(ts, dtype=np.float64)
+        out["cs_w%d" % win] = np.array(cs, dtype=np.float64)
+        out["rows_w%d" % win] = np.array([[float(getattr(d, f)) for f in fields] for d in dl], dtype=np.float64)
+    np.savez_compressed(os.path.join(GOLD, "dloops.npz"), loops=coords, control=b, fields=np.array(fields),
+                        loops_txt=open(tmp + "/loops.txt").read(), **out)
+
+
+def gen_peaks(ref):
+    """cLoops2/callPeaks.py runDBSCANPeaks (clustering + stichPeaks) on chr21 of the cis golden files, PETs closer than
+    1 kb as `callPeaks` uses them, paired and -split."""
+    from cLoops2 import callPeaks as rp
+    rp.logger = ref.logger
+    g = np.load(os.path.join(GOLD, "cis_pipeline.npz"))
+    tmp = tempfile.mkdtemp()
+    synth.write_ixy_dir({"chr21-chr21": g["chr21_chr21"]}, tmp + "/d")
+    fixy = tmp + "/d/chr21-chr21.ixy"
+    out = {}
+    for name, kw in (("e200", dict(eps=200, minPts=3, mcut=1000)), ("e300", dict(eps=300, minPts=4, mcut=2000)),
+                     ("split", dict(eps=150, minPts=5, mcut=1000, split=True, splitExt=50))):
+        peaks = rp.runDBSCANPeaks(fixy, kw.pop("eps"), kw.pop("minPts"), **kw)
+        out[name] = np.array([[p.start, p.end, p.length] for p in peaks], dtype=np.int64).reshape(-1, 3)
+    np.savez_compressed(os.path.join(GOLD, "peaks.npz"), **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref = ref_shim.load()
@@ -197,6 +256,8 @@ def main():
     gen_trans(ref)
     gen_quant(ref)
     gen_filter_knn(ref)
+    gen_dloops(ref)
+    gen_peaks(ref)
     print("golden vectors written to", GOLD)
 
 

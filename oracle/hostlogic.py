@@ -426,3 +426,80 @@ def quant_rows(loops):
                 lp.hypergeometric_p_value, lp.poisson_p_value, lp.x_peak_poisson_p_value, lp.y_peak_poisson_p_value]
         rows.append(list(map(str, line)))
     return rows
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# "next" rows of SURVEY.md 8f that reuse the path's kernels: callDiffLoops.quantDloops and callPeaks' clustering
+def quant_dloops(loops, xy_a, xy_b, win=1, pseudo=1.0):
+    """cLoops2/callDiffLoops.py:110-161 (quantDloops) on in-memory, already cut/mcut-filtered arrays of the target
+    (a) and control (b) samples.  loops: int64[L,4].  Returns (ts, cs, rows): the concatenated nearby counts of both
+    samples (:154-155) and per loop (raw_trt_ra, raw_trt_rb, raw_con_ra, raw_con_rb, raw_trt_rab, raw_con_rab,
+    raw_trt_mrab, raw_con_mrab, trt_es, con_es)."""
+    from . import XYIndex
+    loops = np.asarray(loops, dtype=np.int64).reshape(-1, 4)
+    ia, ib = XYIndex(xy_a), XYIndex(xy_b)
+    ca, _, _, naba, _ = ia.loop_counts(loops, win=win, mode=0)
+    cb, _, _, nabb, _ = ib.loop_counts(loops, win=win, mode=0)
+    ts, cs, rows = [], [], []
+    for i in range(len(loops)):
+        arabs = [float(v) for v in naba[i]]                    # getLoopNearbyPETs order: a-windows outer, b-windows inner
+        brabs = [float(v) for v in nabb[i]]
+        tm, cm = float(np.mean(np.array(arabs))), float(np.mean(np.array(brabs)))       # :152-153
+        ts.extend(arabs)
+        cs.extend(brabs)
+        rows.append((int(ca[i, 0]), int(ca[i, 1]), int(cb[i, 0]), int(cb[i, 1]), int(ca[i, 2]), int(cb[i, 2]), tm, cm,
+                     int(ca[i, 2]) / max(tm, pseudo), int(cb[i, 2]) / max(cm, pseudo)))         # :156-157
+    return ts, cs, rows
+
+
+def split_mat(xy, splitExt):
+    """callPeaks.py:51-60 (getSplitMat): every PET becomes two single-end intervals."""
+    xy = np.asarray(xy, dtype=np.int64)
+    out = np.empty((2 * len(xy), 2), dtype=np.int64)
+    out[0::2, 0] = xy[:, 0] - splitExt
+    out[0::2, 1] = xy[:, 0] + splitExt
+    out[1::2, 0] = xy[:, 1] - splitExt
+    out[1::2, 1] = xy[:, 1] + splitExt
+    return out
+
+
+def stich_peaks(peaks, margin=1):
+    """cLoops2/geo.py:35-61 (stichPeaks) on [(start, end)] closed intervals, replayed on the covered positions."""
+    cov = set()
+    for s, e in peaks:
+        cov.update(range(s, e + 1))
+    cov = sorted(cov)
+    out = []
+    i = 0
+    while i < len(cov) - 1:
+        j = i + 1
+        for j in range(i + 1, len(cov)):
+            if cov[j] - cov[j - 1] > margin:
+                break
+        out.append((cov[i], cov[j - 1]))
+        i = j
+    return out
+
+
+def dbscan_peaks(xy, eps, minPts, split=False, splitExt=50):
+    """callPeaks.py:63-138 (runDBSCANPeaks) on an in-memory, already cut/mcut-filtered cis array: blockDBSCAN,
+    clusters whose anchors are within eps of each other become candidate peaks (:113), then stichPeaks.
+    Returns (candidates [(start, end)], stitched [(start, end)], reads in candidates)."""
+    from . import block_dbscan, cluster_bbox
+    xy = np.asarray(xy, dtype=np.int64)
+    if split:
+        xy = split_mat(xy, splitExt)
+    shift = min(0, int(xy.min())) if len(xy) else 0            # blockDBSCAN is translation invariant (cells from minX/minY)
+    labels, ncl = block_dbscan(xy - shift, eps, minPts)
+    bbox, size = cluster_bbox(xy - shift, labels, ncl)
+    cands, reads = [], 0
+    for c in range(ncl):                                       # set(labels) of 0..k-1 iterates ascending
+        if size[c] == 0:
+            continue
+        xs, xe, ys, ye = (int(v) + shift for v in bbox[c])
+        if xs == xe or ys == ye:                               # :104-106
+            continue
+        if xe + eps >= ys and size[c] >= minPts:               # :113
+            cands.append((xs, ye))
+            reads += int(size[c])
+    return cands, (stich_peaks(cands, margin=eps) if cands else []), reads

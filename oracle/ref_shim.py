@@ -31,7 +31,8 @@ def load():
         raise RuntimeError("reference checkout not present at %s" % REF_ROOT)
     for name in ("matplotlib", "matplotlib.colors", "matplotlib.pyplot", "matplotlib.ticker",
                  "matplotlib.patches", "matplotlib.gridspec", "matplotlib.backends",
-                 "matplotlib.backends.backend_pdf", "seaborn", "pylab", "pyBigWig"):
+                 "matplotlib.backends.backend_pdf", "seaborn", "pylab", "pyBigWig", "mpl_toolkits",
+                 "mpl_toolkits.axes_grid1", "mpl_toolkits.axes_grid1.inset_locator"):
         if name not in sys.modules:
             try:
                 __import__(name)
