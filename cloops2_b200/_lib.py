@@ -83,6 +83,7 @@ SIGNATURES = {
     "cl2_points_download": (ctypes.c_int, [_vp, _vp, _i64p]),
     "cl2_points_free": (None, [_vp, _vp]),
     "cl2_points_drop_cache": (None, [_vp, _vp]),
+    "cl2_points_sweep_hint": (ctypes.c_int, [_vp, _vp, ctypes.c_int32]),
     "cl2_block_dbscan": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _i32p, _i32p]),
     "cl2_cdbscan2": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _i32p, _i32p]),
     "cl2_cluster_bbox": (ctypes.c_int, [_vp, _vp, _i64p, _i64p]),
@@ -260,6 +261,12 @@ class Points:
         """Free the cached eps grid (the points stay resident)."""
         if getattr(self, "h", None) and self.ctx.h:
             self.ctx.lib.cl2_points_drop_cache(self.ctx.h, self.h)
+
+    def sweep_hint(self, enable=True):
+        """Announce blockDBSCAN runs with decreasing eps: later runs then skip the rows an earlier run proved to be
+        noise for them (cl2_points_sweep_hint); results do not change.  enable: False/0 off, True/1 remember and
+        use, 2 use only."""
+        self.ctx.check(self.ctx.lib.cl2_points_sweep_hint(self.ctx.h, self.h, int(enable)), "cl2_points_sweep_hint")
 
     def extent(self):
         ext = np.zeros(4, dtype=np.int64)

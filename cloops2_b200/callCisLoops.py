@@ -45,6 +45,35 @@ def cluster_pass(pts, eps, minPts, hic=False, cis=True):
     return bbox[ok], size[ok]
 
 
+def _rows_carry_over(E, m, e, m2):
+    """May a run (e, m2) skip the rows in noise cells removed by run (E, m)?  (include/cl2.h, cl2_points_sweep_hint)"""
+    import math
+    return e < E and m2 >= m and E >= 3 * e - math.gcd(int(e), int(E))
+
+
+def sweep_passes(pts, passes, hic=False, cis=True, log=None):
+    """All clustering runs of a sweep, results in sweep order.  The blockDBSCAN runs are executed from the largest
+    eps down (smallest minPts first): every run then tells the later ones which rows sit in noise cells it removed,
+    and those runs bin and sort only the remaining rows (cl2_points_sweep_hint).  The result of a run does not depend
+    on the order."""
+    order = list(range(len(passes)))
+    hint = not hic and len(set(e for e, _ in passes)) > 1
+    if hint:
+        order.sort(key=lambda i: (-passes[i][0], passes[i][1], i))
+    out = [None] * len(passes)
+    for pos, i in enumerate(order):
+        ep, mp = passes[i]
+        if hint:
+            # remembering rows costs a pass over the points: only when a later run can use them (the library checks
+            # the same condition again before it does)
+            useful = any(_rows_carry_over(ep, mp, *passes[j]) for j in order[pos + 1:])
+            pts.sweep_hint(1 if useful else 2)
+        out[i] = cluster_pass(pts, ep, mp, hic=hic, cis=cis)
+        if log is not None:
+            log(ep, mp, out[i])
+    return out
+
+
 def exact_default():
     """Whether final loops get their tail probabilities re-evaluated by scipy (the reference's printed digits) or keep
     the device fp64 values.  CL2_PVALUES=device|scipy overrides; the drop-in entry points default to scipy."""
@@ -64,12 +93,10 @@ def cis_chromosome(ctx, key, xy, tot, eps, minPts, cut=0, mcut=-1, hic=False, em
             return hostops._empty_cols(), stats
         import time
         t0 = time.perf_counter()
-        per_pass = []
-        for ep, mp in _sweep(eps, minPts, emPair):
-            _log("Clustering %s and %s using eps %s, minPts %s,pre-set distance cutoff > %s" % (key[0], key[1], ep, mp, cut))
-            c, s = cluster_pass(pts, ep, mp, hic=hic, cis=True)
-            _log("Clustering %s and %s finished. Estimated %s candidate loops with %s PETs." % (key[0], key[1], len(c), int(s.sum())))
-            per_pass.append(c)
+        def note(ep, mp, res):
+            _log("Clustering %s and %s using eps %s, minPts %s,pre-set distance cutoff > %s finished. Estimated %s "
+                 "candidate loops with %s PETs." % (key[0], key[1], ep, mp, cut, len(res[0]), int(res[1].sum())))
+        per_pass = [c for c, _ in sweep_passes(pts, _sweep(eps, minPts, emPair), hic=hic, cis=True, log=note)]
         t1 = time.perf_counter()
         # The reference merges the passes (combineLoops), drops distance <= cut and duplicates, then tests.  A
         # candidate's test result depends on its coordinates only, so the duplicates are removed AFTER the tests, on

@@ -13,7 +13,7 @@ import numpy as np
 from . import _lib, hostops, shard
 from .ds import Loop
 from .io import ixyKey, loadIxy, loops2txt, loops2juiceTxt, loops2washuTxt
-from .callCisLoops import cluster_pass, cols_to_loops, selSigLoops, _loops_to_cands, exact_default  # noqa: F401
+from .callCisLoops import cluster_pass, sweep_passes, cols_to_loops, selSigLoops, _loops_to_cands, exact_default  # noqa: F401
 
 
 def trans_pair(ctx, key, xy, eps, minPts, pts=None, exact=False):
@@ -25,11 +25,7 @@ def trans_pair(ctx, key, xy, eps, minPts, pts=None, exact=False):
         stats = {"pets": pts.n, "candidates": 0, "tested": 0, "loops": 0}
         if pts.n == 0:
             return hostops._empty_cols(), stats
-        per_pass = []
-        for ep in eps:
-            for mp in minPts:
-                c, _ = cluster_pass(pts, ep, mp, hic=False, cis=False)
-                per_pass.append(c)
+        per_pass = [c for c, _ in sweep_passes(pts, [(ep, mp) for ep in eps for mp in minPts], hic=False, cis=False)]
         # combineLoops only (callTransLoops.py:230-234): coordinates already seen in an EARLIER pass are dropped,
         # duplicates inside one pass survive.  As on the cis path the de-duplication is applied after the tests.
         cands = np.concatenate(per_pass, axis=0) if len(per_pass) > 1 else per_pass[0]

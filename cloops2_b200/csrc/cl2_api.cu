@@ -299,10 +299,30 @@ void cl2_grid_free(cl2_ctx *ctx, cl2_grid_cache &g) {
     g = cl2_grid_cache();
 }
 
+void cl2_subsets_free(cl2_ctx *ctx, cl2_points *pts, size_t keep_levels) {
+    while (pts->subs.size() > keep_levels) {
+        cl2_dev_free(ctx, pts->subs.back().byy);
+        cl2_dev_free(ctx, pts->subs.back().rowy);
+        pts->subs.pop_back();
+    }
+}
+
+extern "C" int cl2_points_sweep_hint(cl2_ctx *ctx, cl2_points *pts, int32_t enable) {
+    if (!ctx || !pts) return CL2_ERR_ARG;
+    pts->sweep_hint = enable == 0 ? 0 : (enable == 2 ? 2 : 1);
+    if (!pts->sweep_hint) {
+        cudaSetDevice(ctx->device);
+        if (pts->grid.min_minpts >= 0) cl2_grid_free(ctx, pts->grid);
+        cl2_subsets_free(ctx, pts);
+    }
+    return CL2_OK;
+}
+
 extern "C" void cl2_points_drop_cache(cl2_ctx *ctx, cl2_points *pts) {
     if (!ctx || !pts) return;
     cudaSetDevice(ctx->device);
     cl2_grid_free(ctx, pts->grid);
+    cl2_subsets_free(ctx, pts);
     cl2_dev_free(ctx, pts->byy);     // the y-order is derived data too: the next sweep rebuilds it
     cl2_dev_free(ctx, pts->rowy);
     pts->byy = nullptr;
@@ -313,6 +333,7 @@ extern "C" void cl2_points_free(cl2_ctx *ctx, cl2_points *pts) {
     if (!ctx || !pts) return;
     cudaSetDevice(ctx->device);
     cl2_grid_free(ctx, pts->grid);
+    cl2_subsets_free(ctx, pts);
     cl2_dev_free(ctx, pts->byy);
     cl2_dev_free(ctx, pts->rowy);
     cl2_dev_free(ctx, pts->xy);

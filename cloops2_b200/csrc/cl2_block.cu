@@ -561,11 +561,34 @@ int cl2_read_i32(cl2_ctx *ctx, const int32_t *d, int32_t *out) {
 
 // Build (or reuse) the eps grid: keygen -> radix sort -> gather -> cell table -> neighbours + 3x3 sums.
 // kind 0: blockDBSCAN grid anchored at (minX, minY) (blockDBSCAN.py:69-86); kind 1: cDBSCAN2 rotated grid.
-int cl2_grid_build(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int kind) {
+static int64_t gcd64(int64_t a, int64_t b) {
+    while (b) { int64_t t = a % b; a = b; b = t; }
+    return a;
+}
+// may a run (eps, minPts) work on the rows of `sub` alone?  (cl2_points.cuh: cl2_subset)
+static bool subset_usable(const cl2_subset &sub, int64_t eps, int32_t minPts) {
+    if (sub.n <= 0 || sub.nlinks == 0 || minPts < 0) return false;
+    for (int i = 0; i < sub.nlinks; i++) {
+        const int64_t E = sub.link_eps[i];
+        if (eps >= E || minPts < sub.link_minpts[i]) return false;
+        if (E < 3 * eps - gcd64(eps, E)) return false;
+    }
+    return true;
+}
+
+int cl2_grid_build(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int kind, int32_t minPts) {
     cl2_grid_cache &g = pts->grid;
-    if (g.valid && g.kind == kind && g.eps == eps && g.n == pts->n) return CL2_OK;
+    if (g.valid && g.kind == kind && g.eps == eps && (g.min_minpts < 0 || (minPts >= 0 && minPts >= g.min_minpts)))
+        return CL2_OK;
     cl2_grid_free(ctx, g);
-    const int64_t n = pts->n;
+    static const bool no_subset = getenv("CL2_NO_SUBSET") != nullptr;
+    int level = -1;                                           // deepest (smallest) usable subset
+    if (kind == 0 && pts->sweep_hint && !no_subset)
+        for (int k = (int)pts->subs.size() - 1; k >= 0 && level < 0; k--)
+            if (subset_usable(pts->subs[k], eps, minPts)) level = k;
+    const bool use_sub = level >= 0;
+    const cl2_subset *sub = use_sub ? &pts->subs[level] : nullptr;
+    const int64_t n = use_sub ? sub->n : pts->n;
     unsigned e32 = eps >= (int64_t)INT32_MAX ? (unsigned)INT32_MAX : (unsigned)eps;
     uint64_t gxmax, gymax;
     int rgx0 = 0;
@@ -601,11 +624,11 @@ int cl2_grid_build(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int kind) {
     if (kind == 0) {
         // (column, row) order = stable sort by column of the rows already sorted by y: the row index (y-miny)/eps is
         // monotone in y, so only the bx column bits are sorted (3 passes for hg38 at eps >= 100 instead of 5-6)
-        CL2_TRY(cl2_points_yorder(ctx, pts));
+        if (!use_sub) CL2_TRY(cl2_points_yorder(ctx, pts));
         cl2_keygen gcol = gen;
         gcol.kind = CL2_KEY_GX_YX;
-        gcol.xy = pts->byy;
-        CL2_TRY(cl2_radix_sort_gen(ctx, gcol, k0, k1, v0, v1, n, bx, &ks, &vs, pts->rowy));
+        gcol.xy = use_sub ? sub->byy : pts->byy;
+        CL2_TRY(cl2_radix_sort_gen(ctx, gcol, k0, k1, v0, v1, n, bx, &ks, &vs, use_sub ? sub->rowy : pts->rowy));
     } else {
         CL2_TRY(cl2_radix_sort_gen(ctx, gen, k0, k1, v0, v1, n, bx + by, &ks, &vs));
     }
@@ -651,8 +674,95 @@ int cl2_grid_build(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int kind) {
     g.kind = kind;
     g.eps = eps;
     g.n = n;
+    g.min_minpts = -1;
+    g.sub_level = level;
+    if (use_sub)
+        for (int i = 0; i < sub->nlinks; i++) g.min_minpts = std::max(g.min_minpts, sub->link_minpts[i]);
     g.ncells = ncells;
     g.by = by;
+    return CL2_OK;
+}
+
+// ---- rows outside the removed noise cells, in y order (cl2_subset) ---------------------------------------------
+__global__ void __launch_bounds__(256) k_mark_rows(const int32_t *__restrict__ cid, const uint32_t *__restrict__ row,
+                                                    const uint8_t *__restrict__ keep, uint8_t *__restrict__ rowflag,
+                                                    int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) rowflag[row[i]] = keep[cid[i]];
+}
+__global__ void __launch_bounds__(256) k_sub_flags(const uint32_t *__restrict__ rowy, const uint8_t *__restrict__ rowflag,
+                                                    int32_t *__restrict__ f, int64_t n) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) f[j] = rowflag[rowy[j]];
+}
+__global__ void __launch_bounds__(256) k_sub_compact(const int2 *__restrict__ byy, const uint32_t *__restrict__ rowy,
+                                                      const int32_t *__restrict__ pos, int64_t n, int64_t total,
+                                                      int2 *__restrict__ oby, uint32_t *__restrict__ orow) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int32_t p = pos[j];
+    const bool kept = (j + 1 < n) ? (pos[j + 1] != p) : ((int64_t)p != total);
+    if (kept) {
+        oby[p] = byy[j];
+        orow[p] = rowy[j];
+    }
+}
+// After the noise step of a run (eps, minPts) on grid g: remember the rows of the kept cells when that shrinks the
+// working set enough to pay for itself.  keep: per cell of g.
+static int subset_update(cl2_ctx *ctx, cl2_points *pts, const uint8_t *keep, int64_t eps, int32_t minPts) {
+    cl2_grid_cache &g = pts->grid;
+    const int level = g.sub_level;                           // the subset this run worked on (-1: every point)
+    if (level < 0 && !pts->subs.empty()) return CL2_OK;      // a chain exists and this run is not part of it
+    if (level >= (int)pts->subs.size()) return CL2_OK;
+    cl2_subset link;                                         // links of the new subset = its parent's + this run
+    if (level >= 0) {
+        const cl2_subset &par = pts->subs[level];
+        if (par.nlinks >= CL2_SUB_MAXLINKS) return CL2_OK;
+        link.nlinks = par.nlinks;
+        for (int i = 0; i < par.nlinks; i++) { link.link_eps[i] = par.link_eps[i]; link.link_minpts[i] = par.link_minpts[i]; }
+        if ((int)pts->subs.size() > level + 1) {
+            // a child of the same parent exists: keep the one made at the larger eps (valid for more later runs)
+            const cl2_subset &ch = pts->subs[level + 1];
+            if (ch.link_eps[ch.nlinks - 1] >= eps) return CL2_OK;
+        }
+    }
+    link.link_eps[link.nlinks] = eps;
+    link.link_minpts[link.nlinks] = minPts;
+    link.nlinks++;
+    const int64_t nsrc = g.n;
+    const int2 *sby = level >= 0 ? pts->subs[level].byy : pts->byy;
+    const uint32_t *srow = level >= 0 ? pts->subs[level].rowy : pts->rowy;
+    if (!sby || !srow || nsrc >= (int64_t)INT32_MAX) return CL2_OK;
+    Scratch sc(ctx);
+    uint8_t *rowflag;
+    int32_t *f;
+    int64_t *d_total;
+    CL2_TRY(sc.get(&rowflag, (size_t)pts->n));
+    CL2_TRY(sc.get(&f, (size_t)nsrc));
+    CL2_TRY(sc.get(&d_total, 1));
+    {
+        FamTimer t(ctx, FAM_NOISE, 18.0 * (double)nsrc, 2);
+        k_mark_rows<<<cl2_grid(nsrc, 256), 256, 0, ctx->stream>>>(g.cid, g.row, keep, rowflag, nsrc);
+        k_sub_flags<<<cl2_grid(nsrc, 256), 256, 0, ctx->stream>>>(srow, rowflag, f, nsrc);
+    }
+    CL2_TRY(cl2_exclusive_scan_i32(ctx, f, nsrc, d_total));
+    int64_t total = 0;
+    CL2_TRY(cl2_read_i64(ctx, d_total, &total));
+    if (total <= 0 || total > nsrc - nsrc / 8) return CL2_OK;   // nothing left, or less than 1/8 dropped: not worth it
+    int2 *oby = nullptr;
+    uint32_t *orow = nullptr;
+    CL2_TRY(cl2_dev_alloc(ctx, &oby, (size_t)total));
+    int rc = cl2_dev_alloc(ctx, &orow, (size_t)total);
+    if (rc) { cl2_dev_free(ctx, oby); return rc; }
+    {
+        FamTimer t(ctx, FAM_NOISE, 16.0 * (double)nsrc + 12.0 * (double)total);
+        k_sub_compact<<<cl2_grid(nsrc, 256), 256, 0, ctx->stream>>>(sby, srow, f, nsrc, total, oby, orow);
+    }
+    cl2_subsets_free(ctx, pts, (size_t)(level + 1));          // deeper levels hang off a sibling: gone with it
+    link.byy = oby;
+    link.rowy = orow;
+    link.n = total;
+    pts->subs.push_back(link);
     return CL2_OK;
 }
 
@@ -700,11 +810,11 @@ extern "C" int cl2_block_dbscan(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int3
     pts->ncl = 0;
     pts->bbox.clear();
     pts->size.clear();
-    const int64_t n = pts->n;
-    if (n == 0) return CL2_OK;
+    if (pts->n == 0) return CL2_OK;
     CL2_CUDA(ctx, cudaSetDevice(ctx->device));
-    CL2_TRY(cl2_grid_build(ctx, pts, eps, 0));
+    CL2_TRY(cl2_grid_build(ctx, pts, eps, 0, minPts));
     cl2_grid_cache &g = pts->grid;
+    const int64_t n = g.n;                 // rows in the grid: every point, or the rows earlier runs did not rule out
     const int32_t ncells = g.ncells;
     cudaStream_t s = ctx->stream;
     Scratch sc(ctx);
@@ -725,6 +835,7 @@ extern "C" int cl2_block_dbscan(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int3
     int64_t nkept64 = 0;
     CL2_TRY(cl2_read_i64(ctx, d_total, &nkept64));
     const int32_t nkept = (int32_t)nkept64;
+    if (pts->sweep_hint == 1 && nkept > 0) CL2_TRY(subset_update(ctx, pts, keep, eps, minPts));
 
     int32_t *clabel;
     CL2_TRY(sc.get(&clabel, (size_t)ncells));
@@ -867,8 +978,10 @@ extern "C" int cl2_block_dbscan(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int3
     }
     if (labels_out) {
         int32_t *dl, *dmap;
-        CL2_TRY(sc.get(&dl, (size_t)n));
+        const int64_t nall = pts->n;
+        CL2_TRY(sc.get(&dl, (size_t)nall));
         CL2_TRY(sc.get(&dmap, (size_t)ncomp));
+        if (n < nall) CL2_CUDA(ctx, cudaMemsetAsync(dl, 0xff, (size_t)nall * 4, s));   // rows not in the grid are noise
         std::vector<int32_t> final_of_prov((size_t)ncomp);
         for (int32_t i = 0; i < ncomp; i++) final_of_prov[order[i]] = i;
         if (ncomp > 0) CL2_CUDA(ctx, cudaMemcpyAsync(dmap, final_of_prov.data(), (size_t)ncomp * 4, cudaMemcpyHostToDevice, s));
@@ -876,8 +989,8 @@ extern "C" int cl2_block_dbscan(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int3
             FamTimer t(ctx, FAM_LABEL, 12.0 * (double)n);
             k_point_labels<<<cl2_grid(n, 256), 256, 0, s>>>(g.cid, g.row, clabel, dmap, dl, n);
         }
-        CL2_CUDA(ctx, cudaMemcpyAsync(labels_out, dl, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
-        ctx->d2h_bytes += n * 4;
+        CL2_CUDA(ctx, cudaMemcpyAsync(labels_out, dl, (size_t)nall * 4, cudaMemcpyDeviceToHost, s));
+        ctx->d2h_bytes += nall * 4;
         ctx->h2d_bytes += (int64_t)ncomp * 4;
         CL2_CUDA(ctx, cudaStreamSynchronize(s));
         CL2_CUDA(ctx, cudaGetLastError());

@@ -8,7 +8,9 @@ struct cl2_grid_cache {
     bool valid = false;
     int kind = 0;             // 0 = blockDBSCAN grid (min-anchored, axis aligned), 1 = cDBSCAN2 grid (rotated)
     int64_t eps = 0;
-    int64_t n = 0;
+    int64_t n = 0;            // points in the grid: all of them, or the rows of the subset it was built from
+    int32_t min_minpts = -1;  // -1: built from every point; else valid for minPts >= this (built from a cl2_subset)
+    int sub_level = -1;       // which pts->subs[] entry it was built from (-1: every point)
     int32_t ncells = 0;
     int by = 0;               // bits of the low (gy) field of the packed key
     int32_t maxcnt = 0;       // largest cell population
@@ -22,6 +24,19 @@ struct cl2_grid_cache {
     uint32_t *first = nullptr;  // [ncells]  smallest file row of the cell = its dict position in the reference
 };
 
+// Rows that survive the noise-cell removal of earlier blockDBSCAN runs with larger eps (cl2_block.cu).  A point in a
+// cell that run (E, m) removed is also removed by any run (e, m') with m' >= m and E >= 3e - gcd(e, E), and removing it
+// beforehand changes nothing for the points that stay, so such runs bin and sort only these rows.
+#define CL2_SUB_MAXLINKS 8
+struct cl2_subset {
+    int64_t n = 0;
+    int2 *byy = nullptr;        // [n] (y, x) of the kept rows, sorted by y
+    uint32_t *rowy = nullptr;   // [n] their file rows
+    int nlinks = 0;             // the runs that produced it
+    int64_t link_eps[CL2_SUB_MAXLINKS];
+    int32_t link_minpts[CL2_SUB_MAXLINKS];
+};
+
 struct cl2_points {
     int64_t n = 0;
     int2 *xy = nullptr;      // [n] int32 coordinates, file order after the cut/mcut filter
@@ -31,6 +46,8 @@ struct cl2_points {
     int2 *byy = nullptr;        // [n] (y, x) sorted by y
     uint32_t *rowy = nullptr;   // [n] file row of y-sorted position
     cl2_grid_cache grid;
+    std::vector<cl2_subset> subs;   // nested subsets, subs[k+1] derived from subs[k]; only kept when sweep_hint is set
+    int sweep_hint = 0;         // cl2_points_sweep_hint: 0 off, 1 remember rows and use them, 2 use only
     // result of the last clustering run
     int32_t ncl = 0;
     std::vector<int64_t> bbox;  // [ncl*4]
@@ -47,8 +64,10 @@ struct cl2_index {
 };
 
 void cl2_grid_free(cl2_ctx *ctx, cl2_grid_cache &g);
-// keygen -> radix sort -> gather -> cell table -> neighbours + 3x3 sums (cl2_block.cu); cached per (eps, kind)
-int cl2_grid_build(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int kind);
+void cl2_subsets_free(cl2_ctx *ctx, cl2_points *pts, size_t keep_levels = 0);
+// keygen -> radix sort -> gather -> cell table -> neighbours + 3x3 sums (cl2_block.cu); cached per (eps, kind).
+// minPts >= 0 allows a grid over the smallest pts->subs[] entry valid for (eps, minPts); -1 asks for every point.
+int cl2_grid_build(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int kind, int32_t minPts = -1);
 int cl2_points_yorder(cl2_ctx *ctx, cl2_points *pts);   // cl2_count.cu
 int cl2_read_i64(cl2_ctx *ctx, const int64_t *d, int64_t *out);
 int cl2_read_i32(cl2_ctx *ctx, const int32_t *d, int32_t *out);

@@ -64,6 +64,13 @@ void cl2_points_free(cl2_ctx *ctx, cl2_points *pts);
 /* Release the derived data cached on `pts` (the eps grid kept between the minPts values of one eps, and the
  * y-sorted order shared by the grid sorts and the XY index); the points themselves stay resident. */
 void cl2_points_drop_cache(cl2_ctx *ctx, cl2_points *pts);
+/* Announce (enable != 0) that several cl2_block_dbscan runs with decreasing eps follow on `pts`, as the eps loop of
+ * callCisLoops.py:541-551 / callTransLoops.py:241-251 does.  Each run then remembers the rows outside the noise
+ * cells it removed (blockDBSCAN.py:101-122); a later run (e, m') after a run (E, m) with m' >= m and
+ * E >= 3e - gcd(e, E) would remove those rows too and is unaffected by their absence, so it bins and sorts only the
+ * remembered rows.  enable = 2 keeps using what is remembered without remembering more (the runs at the smallest eps
+ * of a sweep).  Results are identical with and without the hint; 0 disables it and frees the remembered rows. */
+int cl2_points_sweep_hint(cl2_ctx *ctx, cl2_points *pts, int32_t enable);
 
 /* ---- clustering --------------------------------------------------------------------------------------- */
 /*

@@ -151,3 +151,53 @@ def test_full_size_chr1_of_config2(gpu_ctx):
             assert ncl2 == ncl and np.array_equal(lab2, lab)
     finally:
         pts.close()
+
+
+@pytest.mark.parametrize("runs", [
+    [(1000, 5), (500, 5), (200, 5)],             # chain of nested subsets (1000 -> 500 -> 200)
+    [(1000, 4), (1000, 7), (500, 7), (500, 4), (200, 6)],
+    [(1000, 5), (500, 5), (400, 5), (200, 5)],   # 500 -> 400 is not a safe pair: 400 falls back to the 1000 subset
+    [(450, 5), (333, 5), (100, 5)],              # 450 -> 333 unsafe (every point), 450 -> 100 safe
+    [(900, 6), (300, 3), (300, 8), (290, 6)],    # smaller minPts than the link: every point again
+    [(200, 5), (1000, 5), (500, 5)],             # ascending eps after the first run: the chain is left alone
+])
+def test_sweep_hint_changes_nothing(gpu_ctx, runs):
+    """cl2_points_sweep_hint: later runs work on the rows earlier runs left, labels / boxes stay those of the oracle
+    (which knows nothing of the shortcut)."""
+    xy = synth.cis_chrom(6_000_000, 90_000, 31, "hitrac")
+    pts = _lib.Points(gpu_ctx, xy)
+    try:
+        pts.sweep_hint(True)
+        for eps, minPts in runs:
+            lab, ncl = pts.block_dbscan(eps, minPts)
+            bbox, size = pts.cluster_bbox()
+            want, wn = oracle.block_dbscan(xy, eps, minPts)
+            wb, ws = oracle.cluster_bbox(xy, want, wn)
+            assert ncl == wn and np.array_equal(lab, want), (eps, minPts)
+            assert np.array_equal(bbox, wb) and np.array_equal(size, ws), (eps, minPts)
+        keep = pts.block_noise_keep(runs[-1][0], runs[-1][1])          # always on every point
+        assert np.array_equal(keep, oracle.block_noise_keep(xy, runs[-1][0], runs[-1][1]))
+        pts.sweep_hint(False)
+        lab, ncl = pts.block_dbscan(runs[-1][0], runs[-1][1])
+        want, wn = oracle.block_dbscan(xy, runs[-1][0], runs[-1][1])
+        assert ncl == wn and np.array_equal(lab, want)
+    finally:
+        pts.close()
+
+
+def test_sweep_hint_random_small_cases(gpu_ctx):
+    rng = np.random.default_rng(77)
+    for it in range(60):
+        xy, eps, minPts = random_case(rng, it)
+        big = eps * int(rng.choice([2, 3, 5]))
+        pts = _lib.Points(gpu_ctx, xy)
+        try:
+            if pts.n == 0:
+                continue
+            pts.sweep_hint(True)
+            for e, m in ((big, minPts), (eps, minPts + int(rng.integers(0, 3)))):
+                lab, ncl = pts.block_dbscan(e, m)
+                want, wn = oracle.block_dbscan(xy, e, m)
+                assert ncl == wn and np.array_equal(lab, want), (it, e, m)
+        finally:
+            pts.close()
