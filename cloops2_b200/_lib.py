@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.path.join(_HERE, "libcl2.so")
-SOURCES = ["cl2_api.cu", "cl2_sort.cu", "cl2_block.cu", "cl2_cdbscan.cu", "cl2_count.cu", "cl2_host.cu"]
+SOURCES = ["cl2_api.cu", "cl2_sort.cu", "cl2_block.cu", "cl2_cdbscan.cu", "cl2_count.cu", "cl2_host.cu", "cl2_pre.cu"]
 HEADERS = ["cl2_common.cuh", "cl2_points.cuh", "cl2_stats.cuh", os.path.join("..", "..", "include", "cl2.h")]
 # -fmad=false: no FMA contraction, so the fp64 statistics give the same bits in every kernel they are inlined into
 # (and the same bits as the host build of cl2_stats.cuh); the path is integer / bandwidth work, nothing is lost.
@@ -84,6 +84,12 @@ SIGNATURES = {
     "cl2_points_free": (None, [_vp, _vp]),
     "cl2_points_drop_cache": (None, [_vp, _vp]),
     "cl2_points_sweep_hint": (ctypes.c_int, [_vp, _vp, ctypes.c_int32]),
+    "cl2_points_unique": (ctypes.c_int, [_vp, _vp, _i64p, ctypes.POINTER(ctypes.c_int64)]),
+    "cl2_bedpe_create": (ctypes.c_int, [ctypes.POINTER(_vp)]),
+    "cl2_bedpe_destroy": (None, [_vp]),
+    "cl2_bedpe_parse": (ctypes.c_int64, [_vp, ctypes.c_char_p, ctypes.c_int64, ctypes.c_int64, _i32p, _i64p, _i32p,
+                                         ctypes.POINTER(ctypes.c_int64)]),
+    "cl2_bedpe_names": (ctypes.c_char_p, [_vp, ctypes.POINTER(ctypes.c_int32)]),
     "cl2_block_dbscan": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _i32p, _i32p]),
     "cl2_cdbscan2": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _i32p, _i32p]),
     "cl2_cluster_bbox": (ctypes.c_int, [_vp, _vp, _i64p, _i64p]),
@@ -261,6 +267,14 @@ class Points:
         """Free the cached eps grid (the points stay resident)."""
         if getattr(self, "h", None) and self.ctx.h:
             self.ctx.lib.cl2_points_drop_cache(self.ctx.h, self.h)
+
+    def unique(self):
+        """Rows without exact duplicates, ascending by (X, Y): int64[m,2] (cl2_points_unique, the dedup of `pre`)."""
+        out = np.empty((self.n, 2), dtype=np.int64)
+        m = ctypes.c_int64(0)
+        self.ctx.check(self.ctx.lib.cl2_points_unique(self.ctx.h, self.h, _ptr(out, _i64p), ctypes.byref(m)),
+                       "cl2_points_unique")
+        return out[:m.value]
 
     def sweep_hint(self, enable=True):
         """Announce blockDBSCAN runs with decreasing eps: later runs then skip the rows an earlier run proved to be

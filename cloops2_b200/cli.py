@@ -64,6 +64,17 @@ def buildParser():
     c.add_argument("-trans", dest="trans", action="store_true", default=False)
     c.add_argument("-emPair", dest="emPair", action="store_true", default=False)
     # quant -loops (cLoops2.py quant sub-command; only the loop part is implemented here)
+    r = sub.add_parser("pre", help="BEDPE(.gz) files -> per chromosome pair .ixy files + petMeta.json.")
+    r.add_argument("-f", dest="fnIn", type=str, default="")
+    r.add_argument("-o", dest="fnOut", type=str, default="cLoops2_output")
+    r.add_argument("-p", dest="cpu", type=int, default=1)
+    r.add_argument("-c", dest="chroms", type=str, default="")
+    r.add_argument("-cut", dest="cut", type=int, default=0)
+    r.add_argument("-mcut", dest="mcut", type=int, default=-1)
+    r.add_argument("-mapq", dest="mapq", type=int, default=10)
+    r.add_argument("-trans", dest="trans", action="store_true", default=False)
+    r.add_argument("-format", dest="format", type=str, default="bedpe", choices=["bedpe"])
+
     q = sub.add_parser("quant", help="Quantify given loops against a sample (quant -loops).")
     q.add_argument("-d", dest="predir", type=str, default="")
     q.add_argument("-o", dest="fnOut", type=str, default="cLoops2_output")
@@ -83,6 +94,22 @@ def main(argv=None):
     # tens of milliseconds in the middle of the run)
     import gc
     gc.freeze()
+    if op.cmd == "pre":                                        # cLoops2.py:2914-2975
+        from .pre import parseBedpe
+        logger = getLogger()
+        if not os.path.isdir(op.fnOut):
+            os.mkdir(op.fnOut)
+        elif len(os.listdir(op.fnOut)) > 0:
+            logger.error("working directory %s exists and not empty." % op.fnOut)
+            return 1
+        fs = op.fnIn.split(",")
+        for f in fs:
+            if not os.path.isfile(f):
+                logger.error("Input file %s not exitst!" % f)
+                return 1
+        parseBedpe(fs, op.fnOut, logger, mapq=op.mapq, cs=set(op.chroms.split(",")) if op.chroms else [], cut=op.cut,
+                   mcut=op.mcut, cis=not op.trans, cpu=op.cpu)
+        return 0
     if op.cmd == "quant":
         from .quant import quantLoops
         logger = getLogger()

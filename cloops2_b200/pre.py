@@ -1,0 +1,179 @@
+"""
+`cLoops2 pre` on B200 -- drop-in for cLoops2/io.py:71-164 (parseBedpe): BEDPE(.gz) text -> one `.ixy` file of unique
+(cA, cB) PET centres per chromosome pair + petMeta.json (third "next" row).
+
+Where the reference loops over the lines in Python, keeps one text file per chromosome pair and de-duplicates each
+through a Python set (getUniqueTxt, io.py:40-52), this module
+  * tokenises the text with the library's native parser (cl2_bedpe_parse: the field handling of PET.__init__,
+    ds.py:42-57, same accept / skip decisions),
+  * applies the PET arithmetic (end swap, centres, distance, ds.py:58-88) and parseBedpe's filters and counters
+    (io.py:101-125) to whole chunks with numpy,
+  * de-duplicates every chromosome pair on the GPU (cl2_points_unique: radix sort by the packed (cA, cB) key, first
+    row of every run).
+The `.ixy` rows come out ascending by (cA, cB); the reference's order is that of a Python set of strings (different in
+every process), so files agree as sets of rows.  Counters and petMeta.json keys are the reference's.
+"""
+import ctypes
+import gzip
+import json
+import os
+
+import numpy as np
+
+from . import _lib
+from .io import updateJson
+
+CHUNK = 64 << 20
+
+
+class BedpeParser:
+    """cl2_bedpe: text chunks -> (chrom ids int32[n,2], positions int64[n,4], mapq int32[n])."""
+
+    def __init__(self):
+        self.lib = _lib.load()
+        self.h = ctypes.c_void_p()
+        if self.lib.cl2_bedpe_create(ctypes.byref(self.h)) != 0:
+            raise _lib.Cl2Error("cl2_bedpe_create failed")
+
+    def close(self):
+        if self.h:
+            self.lib.cl2_bedpe_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def parse(self, buf):
+        cap = buf.count(b"\n") + 1
+        chrom = np.empty((cap, 2), dtype=np.int32)
+        pos = np.empty((cap, 4), dtype=np.int64)
+        mapq = np.empty(cap, dtype=np.int32)
+        n = self.lib.cl2_bedpe_parse(self.h, buf, len(buf), cap, chrom.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                     pos.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                     mapq.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), None)
+        if n < 0:
+            raise _lib.Cl2Error("cl2_bedpe_parse failed rc=%d" % n)
+        return chrom[:n], pos[:n], mapq[:n]
+
+    def names(self):
+        k = ctypes.c_int32(0)
+        s = self.lib.cl2_bedpe_names(self.h, ctypes.byref(k))
+        return s.decode().split("\n") if k.value else []
+
+
+def _chunks(f):
+    """Whole-line byte chunks of a plain or gzipped text file."""
+    of = gzip.open(f, "rb") if f.endswith(".gz") else open(f, "rb")
+    with of:
+        rest = b""
+        while True:
+            b = of.read(CHUNK)
+            if not b:
+                break
+            b = rest + b
+            cutp = b.rfind(b"\n")
+            if cutp < 0:
+                rest = b
+                continue
+            rest = b[cutp + 1:]
+            yield b[:cutp + 1]
+        if rest:
+            yield rest
+
+
+def collect_pets(fs, logger=None, mapq=1, cs=[], cut=0, mcut=-1, cis=False):
+    """The parsing loop of parseBedpe (io.py:84-133) without the de-duplication: returns ({"chrA-chrB": int64[k,2]
+    (cA, cB) rows in file order}, counters dict with total / hiq / trans / cis / closeCis / farCis)."""
+    parser = BedpeParser()
+    total = hiq = t = c = closeCis = farCis = 0
+    parts = {}                                   # (idA, idB) -> [int64[k,2]]
+    try:
+        for f in fs:
+            if logger is not None:
+                logger.info("Parsing PETs from %s, requiring initial distance cutoff >%s and <%s" % (f, cut, mcut))
+            for buf in _chunks(f):
+                chrom, pos, mq = parser.parse(buf)
+                if len(mq) == 0:
+                    continue
+                names = parser.names()
+                rank = np.empty(len(names), dtype=np.int64)              # string order of the names (ds.py:82)
+                rank[np.array(sorted(range(len(names)), key=lambda i: names[i]), dtype=np.int64)] = np.arange(len(names))
+                ida, idb = chrom[:, 0].astype(np.int64), chrom[:, 1].astype(np.int64)
+                sA, eA, sB, eB = pos[:, 0], pos[:, 1], pos[:, 2], pos[:, 3]
+                is_cis = ida == idb
+                swap = np.where(is_cis, sA + eA > sB + eB, rank[ida] > rank[idb])      # ds.py:61-64, 82-86
+                ida, idb = np.where(swap, idb, ida), np.where(swap, ida, idb)
+                sumA, sumB = np.where(swap, sB + eB, sA + eA), np.where(swap, sA + eA, sB + eB)
+                cA = np.trunc(sumA / 2).astype(np.int64)                                 # int((s + e) / 2)
+                cB = np.trunc(sumB / 2).astype(np.int64)
+                keep = np.ones(len(mq), dtype=bool)
+                if len(cs) > 0:                                                          # io.py:102-103
+                    incs = np.array([nm in cs for nm in names], dtype=bool)
+                    keep &= incs[ida] & incs[idb]
+                total += int(keep.sum())
+                keep &= mq >= mapq                                                       # io.py:105-106
+                hiq += int(keep.sum())
+                c += int((keep & is_cis).sum())
+                t += int((keep & ~is_cis).sum())
+                if cis:
+                    keep &= is_cis                                                       # io.py:113-114
+                dist = np.abs(cB - cA)
+                if cut > 0:                                                              # io.py:116-118
+                    close = keep & is_cis & (dist < cut)
+                    closeCis += int(close.sum())
+                    keep &= ~close
+                if mcut > 0:                                                             # io.py:119-121
+                    far = keep & is_cis & (dist > mcut)
+                    farCis += int(far.sum())
+                    keep &= ~far
+                ida, idb, cA, cB = ida[keep], idb[keep], cA[keep], cB[keep]
+                kid = ida * len(names) + idb
+                for k in np.unique(kid).tolist():
+                    m = kid == k
+                    parts.setdefault((k // len(names), k % len(names)), []).append(np.stack([cA[m], cB[m]], axis=1))
+        names = parser.names()
+    finally:
+        parser.close()
+    rows = {"%s-%s" % (names[a], names[b]): np.ascontiguousarray(np.concatenate(ch, axis=0), dtype=np.int64)
+            for (a, b), ch in parts.items()}
+    return rows, {"total": total, "hiq": hiq, "trans": t, "cis": c, "closeCis": closeCis, "farCis": farCis}
+
+
+def parseBedpe(fs, fout, logger, mapq=1, cs=[], cut=0, mcut=-1, cis=False, cpu=1, ctx=None):
+    """Drop-in for io.py:71-164.  fs: BEDPE / BEDPE.gz files of the replicates; fout: output directory (must exist,
+    as in the reference); cs: wanted chromosomes.  `cpu` is accepted and ignored."""
+    ctx = ctx or _lib.default_context()
+    pets, cnt = collect_pets(fs, logger, mapq=mapq, cs=cs, cut=cut, mcut=mcut, cis=cis)
+    total, hiq, t, c, closeCis, farCis = (cnt[k] for k in ("total", "hiq", "trans", "cis", "closeCis", "farCis"))
+    # unique PETs of every chromosome pair (getUniqueTxt, io.py:40-52) and the .ixy files (txt2ixy, io.py:55-67)
+    import joblib
+    uniques = 0
+    ixyfs = []
+    for key, xy in pets.items():
+        pts = _lib.Points(ctx, xy)
+        try:
+            rows = pts.unique()
+        finally:
+            pts.close()
+        uniques += len(rows)
+        fn = os.path.join(fout, key + ".ixy")
+        joblib.dump(np.ascontiguousarray(rows), fn)
+        ixyfs.append(fn)
+    if logger is not None:
+        logger.info("Totaly %s PETs in target chromosomes from %s, in which %s high quality unqiue PETs" % (
+            total, ",".join(fs), uniques))
+    nr = 1 - uniques / 1.0 / (c - closeCis) if c > 0 else 0
+    ds = {
+        "Total PETs": total,
+        "High Mapq(>=%s) PETs" % mapq: hiq,
+        "Total Trans PETs": t,
+        "Total Cis PETs": c,
+        "Filtered too close (<%s) PETs" % cut: closeCis,
+        "Filtered too distant (>%s) PETs" % mcut: farCis,
+        "Unique PETs": uniques,
+        "Cis PETs Redundancy": nr,
+    }
+    metaf = fout + "/petMeta.json"
+    with open(metaf, "w") as fo:
+        json.dump(ds, fo)
+    updateJson(ixyfs, metaf)
+    return metaf

@@ -113,13 +113,14 @@ def barrier():
 def worker_contexts(device=None, nthreads=None):
     """One cl2 context (= CUDA stream + scratch) per host worker thread of this rank.  Chromosome files are
     independent units, so a rank processes several at once: while one thread's kernels run, another thread does its
-    host-side bookkeeping (ctypes calls and numpy release the GIL).  CL2_THREADS overrides the default (6, or cores/ranks - 1 if smaller)."""
+    host-side bookkeeping (ctypes calls and numpy release the GIL).  CL2_THREADS overrides the default (8, or cores/ranks - 1 if smaller)."""
     from . import _lib
     if nthreads is None:
-        # default: 6, fewer when the ranks of this node have to share few host cores
+        # default: 8 (measured 4: 104 ms, 6: 96, 8: 93, 12: 97 per 100M-PET step), fewer when the ranks of this node
+        # have to share few host cores
         world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1)
         fair = (os.cpu_count() or 8) // max(1, world) - 1
-        nthreads = int(os.environ.get("CL2_THREADS", str(max(2, min(6, fair)))))
+        nthreads = int(os.environ.get("CL2_THREADS", str(max(2, min(8, fair)))))
     nthreads = max(1, nthreads)
     first = _lib.default_context(device)
     return [first] + [_lib.Context(first.device) for _ in range(nthreads - 1)]

@@ -31,6 +31,7 @@ extern "C" {
 typedef struct cl2_ctx cl2_ctx;        /* one GPU: stream, memory pool, timers */
 typedef struct cl2_points cl2_points;  /* one .ixy file resident in HBM (kept across the eps x minPts sweep) */
 typedef struct cl2_index cl2_index;    /* device form of cLoops2/ds.py:141-198 (XY): X-sorted and Y-sorted arrays */
+typedef struct cl2_bedpe cl2_bedpe;    /* BEDPE tokeniser state of `pre`: chromosome name <-> id table */
 
 /* version string of the library, e.g. "cl2-b200 0.1 sm_100a" */
 const char *cl2_version(void);
@@ -71,6 +72,10 @@ void cl2_points_drop_cache(cl2_ctx *ctx, cl2_points *pts);
  * remembered rows.  enable = 2 keeps using what is remembered without remembering more (the runs at the smallest eps
  * of a sweep).  Results are identical with and without the hint; 0 disables it and frees the remembered rows. */
 int cl2_points_sweep_hint(cl2_ctx *ctx, cl2_points *pts, int32_t enable);
+/* Rows of `pts` without exact duplicates, ascending by (X, Y) -- the de-duplication of `cLoops2 pre` (getUniqueTxt,
+ * cLoops2/io.py:40-52, which keeps a Python set of the text rows of one chromosome pair).  xy_out: int64[n,2] host
+ * buffer with n = cl2_points_count(pts); *n_out rows are written. */
+int cl2_points_unique(cl2_ctx *ctx, cl2_points *pts, int64_t *xy_out, int64_t *n_out);
 
 /* ---- clustering --------------------------------------------------------------------------------------- */
 /*
@@ -156,6 +161,22 @@ int cl2_sel_sig_loops(const int64_t *coords, const double *es, int64_t L, int64_
 double cl2_stat_poisson_sf(double k, double mu);
 double cl2_stat_binom_sf(double k, double n, double p);
 double cl2_stat_hypergeom_sf(double k, double M, double n, double N);
+
+/* ---- `cLoops2 pre`: BEDPE text -> records (host code, no GPU) -------------------------------------------- */
+/*
+ * The field handling of PET.__init__ (cLoops2/ds.py:42-57) for every whole line of buf[0, len): a line needs at least
+ * 10 tab-separated fields and integer fields 1, 2, 4, 5, otherwise it is skipped as io.py:97-100 skips it.  For the
+ * i-th accepted line: chrom[2i], chrom[2i+1] = ids of fields 0 and 3 (ids number the names in first-seen order over
+ * the life of `p`), pos[4i..4i+3] = fields 1, 2, 4, 5, mapq[i] = field 7 or 255 when that is not an integer
+ * (ds.py:54-57).  cap = rows the output arrays can hold.  Returns the number of accepted lines (>= 0) or an error
+ * code; *n_lines (optional) = lines seen.
+ */
+int cl2_bedpe_create(cl2_bedpe **out);
+void cl2_bedpe_destroy(cl2_bedpe *p);
+int64_t cl2_bedpe_parse(cl2_bedpe *p, const char *buf, int64_t len, int64_t cap, int32_t *chrom, int64_t *pos,
+                        int32_t *mapq, int64_t *n_lines);
+/* Names seen so far, '\n'-joined in id order; valid until the next call on `p`. */
+const char *cl2_bedpe_names(cl2_bedpe *p, int32_t *count);
 
 /* ---- measurement -------------------------------------------------------------------------------------- */
 /* Kernel launches issued by this context since creation (or since the last reset). */

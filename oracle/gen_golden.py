@@ -18,6 +18,7 @@ Contents
   filter_knn.npz       the reference's `filterPETs -knn` output matrices (filter.py _filterPETsByKNNs)
   dloops.npz           the reference's callDiffLoops.quantDloops fields + background lists for two samples
   peaks.npz            the reference's callPeaks.runDBSCANPeaks peaks (paired and -split)
+  pre_bedpe.npz        two synthetic BEDPE files + the reference's `pre` output (io.py parseBedpe): rows per key, counters
 """
 import json
 import os
@@ -248,6 +249,70 @@ def gen_peaks(ref):
     np.savez_compressed(os.path.join(GOLD, "peaks.npz"), **out)
 
 
+def synth_bedpe(seed, n):
+    """BEDPE text with everything parseBedpe has a branch for: cis / trans pairs on three chromosomes, ends in either
+    order, exact and centre-only duplicates, low and missing MAPQ, short and non-numeric lines."""
+    rng = np.random.default_rng(seed)
+    chroms = ["chr21", "chr22", "chrX"]
+    out = []
+    for i in range(n):
+        u = rng.random()
+        ca = chroms[int(rng.integers(0, 3))]
+        cb = ca if u < 0.8 else chroms[int(rng.integers(0, 3))]
+        x = int(rng.integers(100, 200_000))
+        y = x + int(np.exp(rng.uniform(np.log(50), np.log(100_000)))) if ca == cb else int(rng.integers(100, 200_000))
+        la, lb = int(rng.integers(30, 150)), int(rng.integers(30, 150))
+        a = (ca, x - la // 2, x - la // 2 + la, "+-"[int(rng.integers(0, 2))])
+        b = (cb, y - lb // 2, y - lb // 2 + lb, "+-"[int(rng.integers(0, 2))])
+        if rng.random() < 0.5:
+            a, b = b, a
+        q = rng.random()
+        mq = "0" if q < 0.1 else ("." if q < 0.15 else str(int(rng.integers(1, 61))))
+        line = [a[0], str(a[1]), str(a[2]), b[0], str(b[1]), str(b[2]), "r%d" % i, mq, a[3], b[3]]
+        out.append("\t".join(line))
+        if rng.random() < 0.08:                                  # exact duplicate
+            out.append("\t".join(line))
+        if rng.random() < 0.05:                                  # same centres, different fragment
+            line2 = list(line)
+            line2[1], line2[2] = str(int(line[1]) - 2), str(int(line[2]) + 2)
+            out.append("\t".join(line2))
+        if rng.random() < 0.02:
+            out.append("\t".join(line[:7]))                      # too few columns
+        if rng.random() < 0.02:
+            bad = list(line)
+            bad[4] = "*"
+            out.append("\t".join(bad))                           # non-numeric coordinate
+    return "\n".join(out) + "\n"
+
+
+def gen_pre(ref):
+    """cLoops2/io.py parseBedpe (`cLoops2 pre`) on two synthetic BEDPE files (one gzipped): per-key rows (sorted; the
+    reference writes them in set order) and the petMeta.json counters, for the default options and for
+    -c chr21,chr22 -cut 1000 -mcut 50000 -trans off."""
+    import gzip
+    import joblib
+    tmp = tempfile.mkdtemp()
+    t1, t2 = synth_bedpe(101, 6000), synth_bedpe(202, 4000)
+    open(tmp + "/a.bedpe", "w").write(t1)
+    with gzip.open(tmp + "/b.bedpe.gz", "wt") as fo:
+        fo.write(t2)
+    out = {"bedpe_a": t1, "bedpe_b": t2}
+    for name, kw in (("default", dict(mapq=1, cs=[], cut=0, mcut=-1, cis=False)),
+                     ("filtered", dict(mapq=10, cs=["chr21", "chr22"], cut=1000, mcut=50000, cis=True))):
+        d = tmp + "/" + name
+        os.makedirs(d)
+        ref.io.parseBedpe([tmp + "/a.bedpe", tmp + "/b.bedpe.gz"], d, ref.logger, cpu=1, **kw)
+        meta = json.load(open(d + "/petMeta.json"))
+        keys = sorted(list(meta["data"]["cis"].keys()) + list(meta["data"]["trans"].keys()))
+        out[name + "_keys"] = np.array(keys)
+        for k in keys:
+            m = np.asarray(joblib.load(d + "/%s.ixy" % k), dtype=np.int64).reshape(-1, 2)
+            out[name + "_" + k.replace("-", "_")] = m[np.lexsort((m[:, 1], m[:, 0]))]
+        meta.pop("data")
+        out[name + "_meta"] = json.dumps(meta)
+    np.savez_compressed(os.path.join(GOLD, "pre_bedpe.npz"), **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref = ref_shim.load()
@@ -258,6 +323,7 @@ def main():
     gen_filter_knn(ref)
     gen_dloops(ref)
     gen_peaks(ref)
+    gen_pre(ref)
     print("golden vectors written to", GOLD)
 
 

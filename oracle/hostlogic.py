@@ -503,3 +503,57 @@ def dbscan_peaks(xy, eps, minPts, split=False, splitExt=50):
             cands.append((xs, ye))
             reads += int(size[c])
     return cands, (stich_peaks(cands, margin=eps) if cands else []), reads
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# `cLoops2 pre` (third "next" row): BEDPE -> per-chromosome-pair unique (cA, cB) rows + counters
+def pre_bedpe(lines, mapq=1, cs=(), cut=0, mcut=-1, cis=False):
+    """cLoops2/io.py:71-157 (parseBedpe) + ds.py:42-88 (PET) on an iterable of text lines, in plain Python.  Returns
+    ({"chrA-chrB": sorted unique [(cA, cB)]}, meta) where meta holds the reference's petMeta.json counters.  The
+    reference writes the unique rows in Python-set order (random per process), so rows are compared as sorted sets."""
+    rows = {}
+    total = hiq = t = c = closeCis = farCis = 0
+    for line in lines:
+        d = line.split("\n")[0].split("\t")
+        try:                                                   # PET.__init__, ds.py:42-88; any failure skips the line
+            chromA, startA, endA, strandA = d[0], int(d[1]), int(d[2]), d[8]
+            chromB, startB, endB, strandB = d[3], int(d[4]), int(d[5]), d[9]
+            try:
+                q = int(d[7])
+            except Exception:
+                q = 255
+            is_cis = chromA == chromB
+            if is_cis:
+                if startA + endA > startB + endB:
+                    startA, startB, endA, endB = startB, startA, endB, endA
+            elif chromA > chromB:
+                chromA, chromB = chromB, chromA
+                startA, startB, endA, endB = startB, startA, endB, endA
+            cA, cB = int((startA + endA) / 2), int((startB + endB) / 2)
+            distance = int(abs(cB - cA)) if is_cis else None
+        except Exception:
+            continue
+        if len(cs) > 0 and not (chromA in cs and chromB in cs):      # io.py:102-103
+            continue
+        total += 1
+        if q < mapq:
+            continue
+        hiq += 1
+        if is_cis:
+            c += 1
+        else:
+            t += 1
+        if cis and not is_cis:
+            continue
+        if cut > 0 and is_cis and distance < cut:
+            closeCis += 1
+            continue
+        if mcut > 0 and is_cis and distance > mcut:
+            farCis += 1
+            continue
+        rows.setdefault("%s-%s" % (chromA, chromB), set()).add((cA, cB))
+    uniques = sum(len(v) for v in rows.values())
+    meta = {"Total PETs": total, "High Mapq(>=%s) PETs" % mapq: hiq, "Total Trans PETs": t, "Total Cis PETs": c,
+            "Filtered too close (<%s) PETs" % cut: closeCis, "Filtered too distant (>%s) PETs" % mcut: farCis,
+            "Unique PETs": uniques, "Cis PETs Redundancy": (1 - uniques / 1.0 / (c - closeCis)) if c > 0 else 0}
+    return {k: sorted(v) for k, v in rows.items()}, meta
