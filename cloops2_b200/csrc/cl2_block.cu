@@ -155,7 +155,8 @@ __global__ void __launch_bounds__(256) k_block_nbr(const uint64_t *__restrict__ 
 // ------------------------------------------------------------------------------------------------ K7 noise
 // keep[c] = 0 iff s3[c] < minPts and every existing neighbour has s3 < minPts (blockDBSCAN.py:101-122)
 __global__ void __launch_bounds__(256) k_block_noise(const int32_t *__restrict__ nbr, const int32_t *__restrict__ s3,
-                                                      uint8_t *__restrict__ keep, int32_t ncells, int minPts) {
+                                                      uint8_t *__restrict__ keep, int32_t ncells, int minPts,
+                                                      int32_t *__restrict__ keep_i32 = nullptr) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncells) return;
     bool k = true;
@@ -169,6 +170,7 @@ __global__ void __launch_bounds__(256) k_block_noise(const int32_t *__restrict__
             if (nb[d] >= 0 && s3[nb[d]] >= minPts) k = true;
     }
     keep[c] = k ? 1 : 0;
+    if (keep_i32) keep_i32[c] = k ? 1 : 0;       // the same flag as scan input (compact list of kept cells)
 }
 
 __global__ void __launch_bounds__(256) k_keep_points(const int32_t *__restrict__ cid, const uint32_t *__restrict__ row,
@@ -189,11 +191,6 @@ struct CellStat {
 };
 
 // compact list of kept cells (so later kernels launch one unit per kept cell)
-__global__ void __launch_bounds__(256) k_keep_flags_i32(const uint8_t *__restrict__ keep, int32_t *__restrict__ f,
-                                                         int32_t ncells) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < ncells) f[c] = keep[c];
-}
 __global__ void __launch_bounds__(256) k_keep_list(const uint8_t *__restrict__ keep, const int32_t *__restrict__ pos,
                                                     int32_t *__restrict__ list, int32_t ncells) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -827,9 +824,8 @@ extern "C" int cl2_block_dbscan(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int3
     CL2_TRY(sc.get(&kpos, (size_t)ncells));
     CL2_TRY(sc.get(&d_total, 1));
     {
-        FamTimer t(ctx, FAM_NOISE, 41.0 * (double)ncells, 2);
-        k_block_noise<<<cl2_grid(ncells, 256), 256, 0, s>>>(g.nbr, g.s3, keep, ncells, minPts);
-        k_keep_flags_i32<<<cl2_grid(ncells, 256), 256, 0, s>>>(keep, kpos, ncells);
+        FamTimer t(ctx, FAM_NOISE, 41.0 * (double)ncells);
+        k_block_noise<<<cl2_grid(ncells, 256), 256, 0, s>>>(g.nbr, g.s3, keep, ncells, minPts, kpos);
     }
     CL2_TRY(cl2_exclusive_scan_i32(ctx, kpos, ncells, d_total));
     int64_t nkept64 = 0;

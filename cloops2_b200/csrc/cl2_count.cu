@@ -739,36 +739,78 @@ __global__ void __launch_bounds__(CNT_WARPS * 32, 4) k_est_bg(const IdxView ix, 
     }
 }
 
-// kernel B (survivors of kernel A, compacted; one warp each): hypergeometric / Poisson / binomial tails, anchor
+// kernel B (survivors of kernel A, compacted): hypergeometric / Poisson / binomial tails, anchor
 // windows and tests, and the remaining cuts (:311 hypergeometric > 1e-2, :347 anchor peaks unless -hic).
-__global__ void __launch_bounds__(CNT_WARPS * 32) k_est_tail(const IdxView ix, const longlong4 *__restrict__ loops,
-                                                              const long long *__restrict__ sel, int64_t K, int mode,
-                                                              int hic, double peakPcut, double rpb,
-                                                              const long long *__restrict__ core, double *__restrict__ hyp,
-                                                              double *__restrict__ stats, int32_t *__restrict__ flag2,
-                                                              unsigned long long *__restrict__ scanned_total) {
-    __shared__ double ost[CNT_WARPS][CL2_NSTAT];
+// Kernel B runs in two launches so that the fp64 series of the five tests do not run one after the other on a single
+// lane: B1 (one warp per survivor) counts the anchor windows, B2 gives every survivor eight threads, five of which
+// evaluate one tail probability each (same routines, same arguments as loop_tail()).
+__global__ void __launch_bounds__(CNT_WARPS * 32) k_est_anchor(const IdxView ix, const longlong4 *__restrict__ loops,
+                                                                const long long *__restrict__ sel, int64_t K,
+                                                                double *__restrict__ stats,
+                                                                unsigned long long *__restrict__ scanned_total) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t i = (int64_t)blockIdx.x * CNT_WARPS + w;
     if (i >= K) return;
     long long scanned = 0;
     const longlong4 lp = loops[sel[i]];
-    const double ra = (double)core[4 * i], rb = (double)core[4 * i + 1], rab = (double)core[4 * i + 2];
-    const double mrabs = stats[CL2_NSTAT * i], mbps = stats[CL2_NSTAT * i + 1];
-    const bool cis = mode == CL2_MODE_CIS;
-    double *o = ost[w];
-    double h = 0.0;
-    if (lane == 4) h = cl2_hypergeom_sf_ge(rab, (double)ix.n, ra, rb);                    // :310
-    loop_tail(ix, lp.x, lp.y, lp.z, lp.w, ra, rb, rab, mrabs, mbps, mode, rpb, lane, o, &scanned);
-    h = __shfl_sync(0xffffffffu, h, 4);
-    bool keep = true;
-    if (cis && fmax(1e-300, h) > 1e-2) keep = false;                                   // :311
-    if (cis && !hic && !(fmax(1e-300, o[5]) < peakPcut && fmax(1e-300, o[7]) < peakPcut)) keep = false;   // :347
-    if (lane >= 3 && lane < CL2_NSTAT) stats[CL2_NSTAT * i + lane] = o[lane];
+    int64_t cx, wx, cy, wy;
+    loop_anchor(ix, lp.x, lp.y, lane, &cx, &wx, &scanned);
+    loop_anchor(ix, lp.z, lp.w, lane, &cy, &wy, &scanned);
     if (lane == 0) {
+        double *o = stats + CL2_NSTAT * i;
+        o[9] = (double)cx; o[10] = (double)wx; o[11] = (double)cy; o[12] = (double)wy;
+        if (scanned) atomicAdd(scanned_total, (unsigned long long)scanned);
+    }
+}
+
+#define EST_GROUP 8      // threads per survivor in k_est_stats
+__global__ void __launch_bounds__(256) k_est_stats(const longlong4 *__restrict__ loops, const long long *__restrict__ sel,
+                                                    int64_t K, int64_t n, int mode, int hic, double peakPcut, double rpb,
+                                                    const long long *__restrict__ core, double *__restrict__ hyp,
+                                                    double *__restrict__ stats, int32_t *__restrict__ flag2) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = t / EST_GROUP;
+    const int s = (int)(t % EST_GROUP);
+    const bool live = i < K;
+    const bool cis = mode == CL2_MODE_CIS;
+    double v = 0.0, es = 0.0;
+    if (live && s < 5) {
+        const double ra = (double)core[4 * i], rb = (double)core[4 * i + 1], rab = (double)core[4 * i + 2];
+        double *o = stats + CL2_NSTAT * i;
+        if (s == 0) {
+            v = cl2_poisson_sf_ge(rab, o[0]);                                             // :329
+        } else if (s == 1) {
+            double nn = cis ? ra * rb - rab : ra * rb;                                    // :332 / callTransLoops.py:181
+            v = cl2_binom_sf_ge(rab, nn, o[1]);
+        } else if (s == 4) {
+            v = cl2_hypergeom_sf_ge(rab, (double)n, ra, rb);                              // :310
+        } else {
+            // estAnchorSig (:226-247): c = max(local mean of the +-5x window, global rate * length, 1)
+            const longlong4 lp = loops[sel[i]];
+            double count = o[s == 2 ? 9 : 11], wide = o[s == 2 ? 10 : 12];
+            double len = (double)(s == 2 ? lp.y - lp.x : lp.w - lp.z);
+            double r = (wide - count) / 5.0 / 2.0;
+            double c = fmax(fmax(r, rpb * len), 1.0);
+            v = cl2_poisson_sf_ge(count, c);
+            es = count / c;
+        }
+    }
+    // the group's five results meet in its first lane for the cuts (:311, :347)
+    const int base = (threadIdx.x & 31) & ~(EST_GROUP - 1);
+    const double px = __shfl_sync(0xffffffffu, v, base + 2), py = __shfl_sync(0xffffffffu, v, base + 3);
+    const double h = __shfl_sync(0xffffffffu, v, base + 4);
+    if (!live) return;
+    double *o = stats + CL2_NSTAT * i;
+    if (s == 0) o[3] = v;
+    else if (s == 1) o[4] = v;
+    else if (s == 2) { o[5] = v; o[6] = es; }
+    else if (s == 3) { o[7] = v; o[8] = es; }
+    if (s == 0) {
+        bool keep = true;
+        if (cis && fmax(1e-300, h) > 1e-2) keep = false;                                  // :311
+        if (cis && !hic && !(fmax(1e-300, px) < peakPcut && fmax(1e-300, py) < peakPcut)) keep = false;   // :347
         hyp[i] = h;
         flag2[i] = keep ? 1 : 0;
-        if (scanned) atomicAdd(scanned_total, (unsigned long long)scanned);
     }
 }
 
@@ -931,11 +973,11 @@ extern "C" int cl2_est_loops(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops,
             k_est_compact<<<cl2_grid(L, 256), 256, 0, ctx->stream>>>(d_flag, L, d_core, d_stats, d_sel, d_core_c, d_stats_c);
         }
         {
-            FamTimer t(ctx, FAM_COUNT, 0.0);
-            k_est_tail<<<cl2_grid(nk, CNT_WARPS), CNT_WARPS * 32, 0, ctx->stream>>>(cl2_view(idx), d_loops, d_sel, nk,
-                                                                                    mode, hic, peakPcut, rpb, d_core_c, d_hyp_c,
-                                                                                    d_stats_c, d_flag2,
-                                                                                    (unsigned long long *)(d_total + 1));
+            FamTimer t(ctx, FAM_COUNT, 0.0, 2);
+            k_est_anchor<<<cl2_grid(nk, CNT_WARPS), CNT_WARPS * 32, 0, ctx->stream>>>(cl2_view(idx), d_loops, d_sel, nk, d_stats_c,
+                                                                                      (unsigned long long *)(d_total + 1));
+            k_est_stats<<<cl2_grid(nk * EST_GROUP, 256), 256, 0, ctx->stream>>>(d_loops, d_sel, nk, idx->n, mode, hic, peakPcut,
+                                                                                rpb, d_core_c, d_hyp_c, d_stats_c, d_flag2);
         }
         f2.resize((size_t)nk);
         CL2_CUDA(ctx, cudaMemcpyAsync(sel, d_sel, (size_t)nk * 8, cudaMemcpyDeviceToHost, ctx->stream));
