@@ -262,25 +262,9 @@ def main():
         counters[name + "_host_ms"] = host
 
     def step_resident():
-        # resident points belong to one context each; group the units by owner so every thread uses its own
-        def run(c, k):
-            return cis_chromosome(owner[k], tuple(k.split("-")), None, job_tot, EPS, MINPTS, pts=resident[k])
-        _sum(shard.map_units(ctxs, keys, run) if len(ctxs) == 1 else _owner_map(run), "stats")
-
-    def _owner_map(run):
-        import threading
-        out = {}
-
-        def work(c):
-            for k in keys:
-                if owner[k] is c:
-                    out[k] = run(c, k)
-        ths = [threading.Thread(target=work, args=(c,)) for c in ctxs]
-        for t in ths:
-            t.start()
-        for t in ths:
-            t.join()
-        return [out[k] for k in keys]
+        # the same dynamic hand-out as the e2e arm; a resident file is driven by whichever worker takes it
+        _sum(shard.map_units(ctxs, keys, lambda c, k: cis_chromosome(c, tuple(k.split("-")), None, job_tot, EPS, MINPTS,
+                                                                      pts=resident[k].on(c))), "stats")
 
     def step_e2e():
         _sum(shard.map_units(ctxs, keys, lambda c, k: cis_chromosome(c, tuple(k.split("-")), pinned[k], job_tot, EPS, MINPTS)),

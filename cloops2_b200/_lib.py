@@ -253,7 +253,7 @@ class Points:
         self.ncl = 0
 
     def close(self):
-        if getattr(self, "h", None) and self.ctx.h:
+        if getattr(self, "h", None) and self.ctx.h and not getattr(self, "_view", False):
             self.ctx.lib.cl2_points_free(self.ctx.h, self.h)
         self.h = None
 
@@ -262,6 +262,14 @@ class Points:
             self.close()
         except Exception:
             pass
+
+    def on(self, ctx):
+        """The same resident points driven through another context (stream) of the same GPU; the view does not own
+        them.  The C ABI takes the context with every call, so a file uploaded once can be processed by whichever
+        worker is free."""
+        v = object.__new__(Points)
+        v.ctx, v.h, v.n, v.ncl, v._view = ctx, self.h, self.n, 0, True
+        return v
 
     def drop_cache(self):
         """Free the cached eps grid (the points stay resident)."""

@@ -201,3 +201,31 @@ def test_sweep_hint_random_small_cases(gpu_ctx):
                 assert ncl == wn and np.array_equal(lab, want), (it, e, m)
         finally:
             pts.close()
+
+
+def test_resident_points_through_another_context(gpu_ctx):
+    """Points uploaded through one context, clustered and indexed through another (Points.on): same answers, and the
+    owner can still use and free them afterwards."""
+    xy = synth.cis_chrom(3_000_000, 40_000, 5, "hitrac")
+    other = _lib.Context(gpu_ctx.device)
+    pts = _lib.Points(gpu_ctx, xy)
+    try:
+        want, wn = oracle.block_dbscan(xy, 500, 5)
+        view = pts.on(other)
+        lab, ncl = view.block_dbscan(500, 5)
+        assert ncl == wn and np.array_equal(lab, want)
+        bbox, size = view.cluster_bbox()
+        idx = _lib.Index(view)
+        core, _, _, _, _ = idx.loop_counts(bbox[:50], win=5, mode=0, windows=False, anchors=False)
+        idx.close()
+        view.drop_cache()
+        view.close()                                   # a view owns nothing
+        lab2, ncl2 = pts.block_dbscan(500, 5)
+        assert ncl2 == wn and np.array_equal(lab2, want)
+        idx = _lib.Index(pts)
+        core2, _, _, _, _ = idx.loop_counts(bbox[:50], win=5, mode=0, windows=False, anchors=False)
+        idx.close()
+        assert np.array_equal(core, core2)
+    finally:
+        pts.close()
+        other.close()
