@@ -273,7 +273,7 @@ __device__ __forceinline__ bool centroid_close(const CellStat &a, int na, const 
 }
 
 // forward directions (neighbour index > own index in key order): (0,+1)=1, (+1,-1)=6, (+1,0)=3, (+1,+1)=7
-__global__ void __launch_bounds__(128) k_block_adj(const int2 *__restrict__ sxy, const int32_t *__restrict__ cstart,
+__global__ void __launch_bounds__(128, 10) k_block_adj(const int2 *__restrict__ sxy, const int32_t *__restrict__ cstart,
                                                     const int32_t *__restrict__ nbr, const uint8_t *__restrict__ keep,
                                                     const CellStat *__restrict__ st, const int32_t *__restrict__ list,
                                                     int32_t nkept, unsigned *__restrict__ adj, int64_t eps,
@@ -285,13 +285,19 @@ __global__ void __launch_bounds__(128) k_block_adj(const int2 *__restrict__ sxy,
     int d = fdir[t & 3];
     int a = list[k];
     int b = nbr[8 * (int64_t)a + d];
-    if (b < 0 || !keep[b]) return;
-    int a0 = cstart[a], a1 = cstart[a + 1], b0 = cstart[b], b1 = cstart[b + 1];
+    // the kernel waits on memory: everything that only needs `a`, then everything that only needs `b`, is requested
+    // before the first use (b clamped so the loads are unconditional)
+    const int a0 = cstart[a], a1 = cstart[a + 1];
+    const CellStat A = st[a];
+    const int bb = b < 0 ? a : b;
+    const uint8_t kb = keep[bb];
+    const int b0 = cstart[bb], b1 = cstart[bb + 1];
+    const CellStat B = st[bb];
+    if (b < 0 || !kb) return;
     int na = a1 - a0, nb = b1 - b0;
-    bool close = centroid_close(st[a], na, st[b], nb, (double)eps);
+    bool close = centroid_close(A, na, B, nb, (double)eps);
     if (!close) {
         // bounding boxes further apart than eps in L1 can hold no close pair
-        const CellStat &A = st[a], &B = st[b];
         long long gx = max(0, max(A.xmin - B.xmax, B.xmin - A.xmax));
         long long gy = max(0, max(A.ymin - B.ymax, B.ymin - A.ymax));
         if (gx + gy > eps) return;
