@@ -956,7 +956,10 @@ extern "C" int cl2_block_dbscan(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int3
         CL2_TRY(sc.get(&ck1, (size_t)ncomp));
         CL2_TRY(sc.get(&o0, (size_t)ncomp));
         CL2_TRY(sc.get(&o1, (size_t)ncomp));
-        CL2_TRY(cl2_radix_sort_pairs(ctx, ckeys, ck1, o0, o1, ncomp, 32 + bits_for((uint64_t)g.maxcnt), &cks, &os));
+        ctx->sort_family = FAM_COMP;   // a few thousand keys: part of the component ordering, not of the PET sorts
+        const int src = cl2_radix_sort_pairs(ctx, ckeys, ck1, o0, o1, ncomp, 32 + bits_for((uint64_t)g.maxcnt), &cks, &os);
+        ctx->sort_family = -1;
+        CL2_TRY(src);
         (void)cks;
         CL2_CUDA(ctx, cudaMemcpyAsync(order.data(), os, (size_t)ncomp * 4, cudaMemcpyDeviceToHost, s));
         ctx->d2h_bytes += (int64_t)ncomp * 4;

@@ -589,7 +589,10 @@ extern "C" int cl2_cdbscan2(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int32_t 
             CL2_TRY(sc.get(&o1, (size_t)ncomp));
             k_c2_widen<<<cl2_grid(ncomp, 256), 256, 0, s>>>(dkeys, k0, ncomp);
             ctx->launches++;
-            CL2_TRY(cl2_radix_sort_pairs(ctx, k0, k1, o0, o1, ncomp, bits_for((uint64_t)n), &cks, &os));
+            ctx->sort_family = FAM_COMP;   // a few thousand keys: part of the component ordering, not of the PET sorts
+            const int src = cl2_radix_sort_pairs(ctx, k0, k1, o0, o1, ncomp, bits_for((uint64_t)n), &cks, &os);
+            ctx->sort_family = -1;
+            CL2_TRY(src);
             (void)cks;
             CL2_CUDA(ctx, cudaMemcpyAsync(order.data(), os, (size_t)ncomp * 4, cudaMemcpyDeviceToHost, s));
             CL2_CUDA(ctx, cudaStreamSynchronize(s));

@@ -49,6 +49,7 @@ struct cl2_ctx {
     cudaMemPool_t pool = nullptr;
     char err[512] = {0};
     int64_t launches = 0;
+    int sort_family = -1;      // >= 0: the radix sort books its launches under this family (small auxiliary sorts)
     int64_t h2d_bytes = 0, d2h_bytes = 0;
     int timing = 0;
     double fam_ms[CL2_NFAM] = {0};

@@ -451,7 +451,7 @@ static int radix_sort_onesweep(cl2_ctx *ctx, const cl2_keygen &gen, K *keys0, K 
         attr_set = true;
     }
     {
-        FamTimer t(ctx, FAM_SORT_HIST, 8.0 * (double)n, 2);
+        FamTimer t(ctx, ctx->sort_family >= 0 ? ctx->sort_family : FAM_SORT_HIST, 8.0 * (double)n, 2);
         int grid = ctx->sm_count * 8;
         int need = cl2_grid(n, 256);
         k_os_hist<K><<<need < grid ? need : grid, 256, 0, ctx->stream>>>(keys0, gen, n, passes, ghist);
@@ -465,7 +465,7 @@ static int radix_sort_onesweep(cl2_ctx *ctx, const cl2_keygen &gen, K *keys0, K 
     none.kind = CL2_KEY_ARRAY;
     for (int p = 0; p < passes; p++) {
         {
-            FamTimer t(ctx, FAM_SORT_SCATTER,
+            FamTimer t(ctx, ctx->sort_family >= 0 ? ctx->sort_family : FAM_SORT_SCATTER,
                        ((p == passes - 1 && !want_keys ? 1.0 : 2.0) * sizeof(K) + 8.0) * (double)n);
             const uint32_t *vin = (p == 0 && vals_first) ? vals_first : vi;
             const int flags = ((p == 0 && !vals_first) ? 1 : 0) | ((p == passes - 1 && !want_keys) ? 2 : 0);
