@@ -353,10 +353,17 @@ __global__ void __launch_bounds__(OS_THREADS, MINB) k_os_pass(const K *__restric
     }
     // tile histogram first, so the tile's digit counts are published (AGGREGATE) before the longer ranking phase:
     // by the time this tile looks back, its predecessors have usually published their inclusive prefixes
+    // (one shared atomic per group of equal digits in the warp: sorted-ish input, e.g. the column digit of y-ordered
+    // PETs, would otherwise serialise on a few hot bins)
+    unsigned peers_of[OS_IPT];
 #pragma unroll
     for (int r = 0; r < OS_IPT; r++) {
         int64_t i = wbase + r * 32 + lane;
-        if (i < n) atomicAdd(&S.hist[(key[r] >> shift) & 255], 1);
+        bool valid = i < n;
+        unsigned d = valid ? (unsigned)((key[r] >> shift) & 255) : (0x10000u | lane);
+        unsigned peers = __match_any_sync(0xffffffffu, d);
+        peers_of[r] = peers;
+        if (valid && (peers & lt) == 0) atomicAdd(&S.hist[d], __popc(peers));
     }
     __syncthreads();
     if (threadIdx.x < 256) os_st(&desc[(size_t)tile * 256 + threadIdx.x], (unsigned)S.hist[threadIdx.x] | OS_AGG);
@@ -365,7 +372,7 @@ __global__ void __launch_bounds__(OS_THREADS, MINB) k_os_pass(const K *__restric
         int64_t i = wbase + r * 32 + lane;
         bool valid = i < n;
         unsigned d = valid ? (unsigned)((key[r] >> shift) & 255) : (0x10000u | lane);
-        unsigned peers = __match_any_sync(0xffffffffu, d);
+        unsigned peers = peers_of[r];
         int before = 0;
         if (valid) before = S.warp_cnt[w][d];
         __syncwarp();
