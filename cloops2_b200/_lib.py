@@ -85,6 +85,7 @@ SIGNATURES = {
     "cl2_points_drop_cache": (None, [_vp, _vp]),
     "cl2_points_sweep_hint": (ctypes.c_int, [_vp, _vp, ctypes.c_int32]),
     "cl2_points_unique": (ctypes.c_int, [_vp, _vp, _i64p, ctypes.POINTER(ctypes.c_int64)]),
+    "cl2_set_sync_mode": (None, [ctypes.c_int32]),
     "cl2_bedpe_create": (ctypes.c_int, [ctypes.POINTER(_vp)]),
     "cl2_bedpe_destroy": (None, [_vp]),
     "cl2_bedpe_parse": (ctypes.c_int64, [_vp, ctypes.c_char_p, ctypes.c_int64, ctypes.c_int64, _i32p, _i64p, _i32p,
@@ -130,6 +131,8 @@ def load():
             f = getattr(L, name)
             f.restype = res
             f.argtypes = args
+        if os.environ.get("CL2_BLOCKING_SYNC", "0") not in ("0", ""):
+            L.cl2_set_sync_mode(1)
         _lib = L
     return _lib
 

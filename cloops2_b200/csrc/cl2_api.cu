@@ -318,6 +318,9 @@ extern "C" int cl2_points_sweep_hint(cl2_ctx *ctx, cl2_points *pts, int32_t enab
     return CL2_OK;
 }
 
+int g_cl2_sync_mode = 0;
+extern "C" void cl2_set_sync_mode(int32_t blocking) { g_cl2_sync_mode = blocking ? 1 : 0; }
+
 extern "C" void cl2_points_drop_cache(cl2_ctx *ctx, cl2_points *pts) {
     if (!ctx || !pts) return;
     cudaSetDevice(ctx->device);

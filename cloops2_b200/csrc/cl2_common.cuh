@@ -1,6 +1,28 @@
 // cl2_common.cuh -- context, stream-ordered scratch memory, error handling, per-kernel timing.
 #pragma once
 #include <cuda_runtime.h>
+
+// Every wait on a stream goes through here.  Mode 0: cudaStreamSynchronize (the runtime spins: lowest latency, one
+// busy host core per waiting thread).  Mode 1: record a blocking-sync event and sleep on it, for hosts with fewer
+// cores than worker threads (cl2_set_sync_mode; 8 ranks x several workers on a 32-core box).
+extern int g_cl2_sync_mode;
+inline cudaError_t cl2_sync_stream(cudaStream_t s) {
+    if (g_cl2_sync_mode == 0) return cudaStreamSynchronize(s);
+    thread_local cudaEvent_t ev = nullptr;
+    thread_local int ev_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!ev || ev_dev != dev) {
+        if (ev) cudaEventDestroy(ev);
+        cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming);
+        if (e != cudaSuccess) { ev = nullptr; return e; }
+        ev_dev = dev;
+    }
+    cudaError_t e = cudaEventRecord(ev, s);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(ev);
+}
+#define cudaStreamSynchronize(s) cl2_sync_stream(s)
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>

@@ -113,14 +113,23 @@ def barrier():
 def worker_contexts(device=None, nthreads=None):
     """One cl2 context (= CUDA stream + scratch) per host worker thread of this rank.  Chromosome files are
     independent units, so a rank processes several at once: while one thread's kernels run, another thread does its
-    host-side bookkeeping (ctypes calls and numpy release the GIL).  CL2_THREADS overrides the default (8, or cores/ranks - 1 if smaller)."""
+    host-side bookkeeping (ctypes calls and numpy release the GIL).  CL2_THREADS overrides the default of 8;
+    CL2_BLOCKING_SYNC=0/1 overrides how the workers wait (spin when every worker has a core, else sleep)."""
     from . import _lib
+    world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1)
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 8
+    share = max(1, cores // max(1, world))                   # host cores this rank can count on
     if nthreads is None:
-        # default: 8 (measured 4: 104 ms, 6: 96, 8: 93, 12: 97 per 100M-PET step), fewer when the ranks of this node
-        # have to share few host cores
-        world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1)
-        fair = (os.cpu_count() or 8) // max(1, world) - 1
-        nthreads = int(os.environ.get("CL2_THREADS", str(max(2, min(8, fair)))))
+        # default: 8 workers (measured 4: 104 ms, 6: 96, 8: 93, 12: 97 per 100M-PET step with a core per worker)
+        nthreads = int(os.environ.get("CL2_THREADS", "8"))
+    # A worker waiting for its stream spins by default; when the rank has fewer cores than workers the waits sleep
+    # instead (cl2_set_sync_mode), so the workers that do have something to launch get the cores.
+    blocking = os.environ.get("CL2_BLOCKING_SYNC")
+    blocking = (nthreads + 1 > share) if blocking is None else blocking not in ("0", "")
+    _lib.load().cl2_set_sync_mode(1 if blocking else 0)
     nthreads = max(1, nthreads)
     first = _lib.default_context(device)
     return [first] + [_lib.Context(first.device) for _ in range(nthreads - 1)]

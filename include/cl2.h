@@ -178,6 +178,10 @@ int64_t cl2_bedpe_parse(cl2_bedpe *p, const char *buf, int64_t len, int64_t cap,
 /* Names seen so far, '\n'-joined in id order; valid until the next call on `p`. */
 const char *cl2_bedpe_names(cl2_bedpe *p, int32_t *count);
 
+/* How the library waits for its streams, process wide: 0 (default) spin in cudaStreamSynchronize, 1 sleep on a
+ * blocking-sync event -- for hosts with fewer cores than worker threads (several ranks x several contexts). */
+void cl2_set_sync_mode(int32_t blocking);
+
 /* ---- measurement -------------------------------------------------------------------------------------- */
 /* Kernel launches issued by this context since creation (or since the last reset). */
 int64_t cl2_launch_count(cl2_ctx *ctx);
