@@ -291,10 +291,12 @@ def main():
         t = time.perf_counter()
         ev0.record()
         step_marks = [t]
+        cpu0 = time.process_time()
         for _ in range(steps):
             fn()
             step_marks.append(time.perf_counter())       # every unit's results are on the host when fn returns
         timed.last_step_ms = [round(1e3 * (b - a), 2) for a, b in zip(step_marks, step_marks[1:])]
+        timed.last_cpu_ms = round(1e3 * (time.process_time() - cpu0) / max(1, steps), 1)   # host CPU (all threads) per step
         for c in ctxs:
             c.sync()
         ev1.record()
@@ -324,9 +326,9 @@ def main():
     gc.collect()
     gc.freeze()
     wall, dev_ms, clocks, _, launches, _ = timed(step_resident, args.warmup, args.steps, False)
-    steps_ms = timed.last_step_ms
+    steps_ms, cpu_ms = timed.last_step_ms, timed.last_cpu_ms
     wall_e, _, clocks_e, _, _, xfer = timed(step_e2e, args.warmup, args.steps, False)
-    steps_ms_e = timed.last_step_ms
+    steps_ms_e, cpu_ms_e = timed.last_step_ms, timed.last_cpu_ms
     # Per-kernel roofline: the timed steps run several chromosome files concurrently on separate streams, where a
     # CUDA-event pair around one launch also spans other streams' kernels.  The per-kernel numbers therefore come from
     # the same resident step run once more on ONE stream at a time (same launches, same inputs), events enabled.
@@ -398,8 +400,9 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": workload_config(args, world),
         "e2e": {"value": e2e_val, "unit": "PETs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": 1000.0 * wall_e / args.steps, "step_ms": steps_ms_e},
-        "step_ms": steps_ms,
+                "ms_per_step": 1000.0 * wall_e / args.steps, "step_ms": steps_ms_e,
+                "host_cpu_ms_per_step": cpu_ms_e},
+        "step_ms": steps_ms, "host_cpu_ms_per_step": cpu_ms,
         "e2e_exact_scipy": {"value": job_tot / (wall_x / ex_steps), "unit": "PETs/s", "steps": ex_steps,
                             "note": "same call with the final loops' five tail probabilities re-evaluated by scipy on "
                                     "the host (byte-identical _loops.txt; scipy.hypergeom.sf ~150 us per loop)"},

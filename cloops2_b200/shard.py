@@ -113,8 +113,8 @@ def barrier():
 def worker_contexts(device=None, nthreads=None):
     """One cl2 context (= CUDA stream + scratch) per host worker thread of this rank.  Chromosome files are
     independent units, so a rank processes several at once: while one thread's kernels run, another thread does its
-    host-side bookkeeping (ctypes calls and numpy release the GIL).  CL2_THREADS overrides the default of 8;
-    CL2_BLOCKING_SYNC=0/1 overrides how the workers wait (spin when every worker has a core, else sleep)."""
+    host-side bookkeeping (ctypes calls and numpy release the GIL).  CL2_THREADS overrides the number of workers,
+    CL2_BLOCKING_SYNC=0/1 how they wait."""
     from . import _lib
     world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1)
     try:
@@ -122,13 +122,16 @@ def worker_contexts(device=None, nthreads=None):
     except AttributeError:
         cores = os.cpu_count() or 8
     share = max(1, cores // max(1, world))                   # host cores this rank can count on
+    # Default: 8 workers that spin while they wait (measured per 100M-PET step with a core per worker: 4 workers 104 ms,
+    # 6: 96, 8: 93, 12: 97; sleeping waits cost ~12 % when cores are plentiful).  With 6-8 cores per rank: one worker
+    # per core but one, still spinning (4 GPUs on 32 cores: 7 workers, 99 ms).  Below that spinning workers starve each
+    # other, so the waits sleep (cl2_set_sync_mode) and the worker count stays at 8 (4 cores: 3 spinning workers 118 ms,
+    # 8 sleeping workers 114 ms).  CL2_THREADS / CL2_BLOCKING_SYNC override either choice.
+    blocking = share < 6
     if nthreads is None:
-        # default: 8 workers (measured 4: 104 ms, 6: 96, 8: 93, 12: 97 per 100M-PET step with a core per worker)
-        nthreads = int(os.environ.get("CL2_THREADS", "8"))
-    # A worker waiting for its stream spins by default; when the rank has fewer cores than workers the waits sleep
-    # instead (cl2_set_sync_mode), so the workers that do have something to launch get the cores.
-    blocking = os.environ.get("CL2_BLOCKING_SYNC")
-    blocking = (nthreads + 1 > share) if blocking is None else blocking not in ("0", "")
+        nthreads = int(os.environ.get("CL2_THREADS", "8" if blocking else str(max(2, min(8, share - 1)))))
+    if os.environ.get("CL2_BLOCKING_SYNC") is not None:
+        blocking = os.environ["CL2_BLOCKING_SYNC"] not in ("0", "")
     _lib.load().cl2_set_sync_mode(1 if blocking else 0)
     nthreads = max(1, nthreads)
     first = _lib.default_context(device)
