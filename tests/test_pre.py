@@ -102,3 +102,42 @@ def test_gpu_unique_rows_random(gpu_ctx):
             assert np.array_equal(pts.unique(), np.unique(xy, axis=0))
         finally:
             pts.close()
+
+
+def test_tokeniser_fuzz_against_python_parser(tmp_path):
+    """Random well-formed and malformed lines: the native tokeniser + numpy PET logic keeps exactly the rows and
+    counters the line-by-line restatement keeps."""
+    from cloops2_b200.pre import collect_pets
+    rng = np.random.default_rng(123)
+    chroms = ["chr1", "chr10", "chr2", "chrX", "chrM", "1", "scaffold_12"]
+    # (int() would also take non-ASCII decimal digits and "1_000"; the tokeniser does not -- DESIGN.md section 1)
+    junk = ["", "*", ".", "NA", "1.5", "-", "+7", " 12", "12 ", "0x10", "1e3", "12a", "-5", "--5", "+", "1 2"]
+
+    def field_int():
+        if rng.random() < 0.06:
+            return junk[int(rng.integers(0, len(junk)))]
+        return str(int(rng.integers(0, 5_000_000)))
+
+    lines = []
+    for _ in range(4000):
+        a, b = chroms[int(rng.integers(0, len(chroms)))], chroms[int(rng.integers(0, len(chroms)))]
+        if rng.random() < 0.6:
+            b = a
+        f = [a, field_int(), field_int(), b, field_int(), field_int(), "id", junk[int(rng.integers(0, len(junk)))]
+             if rng.random() < 0.2 else str(int(rng.integers(0, 61))), "+", "-"]
+        k = rng.random()
+        if k < 0.04:
+            f = f[:int(rng.integers(1, 10))]                   # short line
+        elif k < 0.08:
+            f = f + ["x", "y"]                                 # extra columns
+        lines.append("\t".join(f))
+    for kw in (dict(mapq=1), dict(mapq=20, cs=["chr1", "chr2", "chrX"], cut=1000, mcut=2_000_000, cis=True)):
+        path = tmp_path / ("fuzz%d.bedpe" % kw["mapq"])
+        path.write_text("\n".join(lines) + "\n", encoding="utf-8")
+        pets, cnt = collect_pets([str(path)], None, **kw)
+        want, meta = oracle.pre_bedpe(lines, **kw)
+        assert cnt["total"] == meta["Total PETs"] and cnt["cis"] == meta["Total Cis PETs"]
+        assert cnt["trans"] == meta["Total Trans PETs"] and cnt["hiq"] == meta["High Mapq(>=%s) PETs" % kw["mapq"]]
+        assert sorted(pets) == sorted(want)
+        for k, xy in pets.items():
+            assert np.unique(xy, axis=0).tolist() == [list(r) for r in want[k]], k
