@@ -90,6 +90,8 @@ SIGNATURES = {
     "cl2_bedpe_destroy": (None, [_vp]),
     "cl2_bedpe_parse": (ctypes.c_int64, [_vp, ctypes.c_char_p, ctypes.c_int64, ctypes.c_int64, _i32p, _i64p, _i32p,
                                          ctypes.POINTER(ctypes.c_int64)]),
+    "cl2_pairs_parse": (ctypes.c_int64, [_vp, ctypes.c_char_p, ctypes.c_int64, ctypes.c_int64, _i32p, _i64p,
+                                         ctypes.POINTER(ctypes.c_int64)]),
     "cl2_bedpe_names": (ctypes.c_char_p, [_vp, ctypes.POINTER(ctypes.c_int32)]),
     "cl2_block_dbscan": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _i32p, _i32p]),
     "cl2_cdbscan2": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _i32p, _i32p]),

@@ -73,7 +73,7 @@ def buildParser():
     r.add_argument("-mcut", dest="mcut", type=int, default=-1)
     r.add_argument("-mapq", dest="mapq", type=int, default=10)
     r.add_argument("-trans", dest="trans", action="store_true", default=False)
-    r.add_argument("-format", dest="format", type=str, default="bedpe", choices=["bedpe"])
+    r.add_argument("-format", dest="format", type=str, default="bedpe", choices=["bedpe", "pairs"])
 
     q = sub.add_parser("quant", help="Quantify given loops against a sample (quant -loops).")
     q.add_argument("-d", dest="predir", type=str, default="")
@@ -95,7 +95,7 @@ def main(argv=None):
     import gc
     gc.freeze()
     if op.cmd == "pre":                                        # cLoops2.py:2914-2975
-        from .pre import parseBedpe
+        from .pre import parseBedpe, parsePairs
         logger = getLogger()
         if not os.path.isdir(op.fnOut):
             os.mkdir(op.fnOut)
@@ -107,8 +107,11 @@ def main(argv=None):
             if not os.path.isfile(f):
                 logger.error("Input file %s not exitst!" % f)
                 return 1
-        parseBedpe(fs, op.fnOut, logger, mapq=op.mapq, cs=set(op.chroms.split(",")) if op.chroms else [], cut=op.cut,
-                   mcut=op.mcut, cis=not op.trans, cpu=op.cpu)
+        cs = set(op.chroms.split(",")) if op.chroms else []
+        if op.format == "pairs":
+            parsePairs(fs, op.fnOut, logger, cs=cs, cut=op.cut, mcut=op.mcut, cis=not op.trans, cpu=op.cpu)
+        else:
+            parseBedpe(fs, op.fnOut, logger, mapq=op.mapq, cs=cs, cut=op.cut, mcut=op.mcut, cis=not op.trans, cpu=op.cpu)
         return 0
     if op.cmd == "quant":
         from .quant import quantLoops

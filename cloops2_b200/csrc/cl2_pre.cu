@@ -177,3 +177,63 @@ extern "C" const char *cl2_bedpe_names(cl2_bedpe *p, int32_t *count) {
     if (count) *count = (int32_t)p->names.size();
     return p->joined.c_str();
 }
+
+// .pairs text (https://pairtools.readthedocs.io formats) -> records: the line handling of parsePairs and Pair.__init__
+// (cLoops2/io.py:189-207, ds.py:111-137).  A record line has exactly 7 or 8 tab-separated fields; with 8 the pair type
+// (field 7) must be one of UU, MR, MU, RU, UR; fields 2 and 4 must be integers; lines starting with '#' are headers.
+// For the i-th accepted line: chrom[2i], chrom[2i+1] = ids of fields 1 and 3, pos[2i], pos[2i+1] = fields 2 and 4.
+extern "C" int64_t cl2_pairs_parse(cl2_bedpe *p, const char *buf, int64_t len, int64_t cap, int32_t *chrom, int64_t *pos,
+                                   int64_t *n_lines) {
+    if (!p || (len > 0 && !buf) || !chrom || !pos) return CL2_ERR_ARG;
+    int64_t n = 0, lines = 0;
+    const char *cur = buf, *end = buf + len;
+    std::string key;
+    while (cur < end) {
+        const char *nl = (const char *)memchr(cur, '\n', (size_t)(end - cur));
+        const char *le = nl ? nl : end;
+        lines++;
+        const char *fb[9], *fe[9];
+        int nf = 0;
+        const char *q = cur;
+        const bool header = cur < le && *cur == '#';
+        while (!header && nf < 9) {                           // a ninth field already disqualifies the line
+            const char *tab = (const char *)memchr(q, '\t', (size_t)(le - q));
+            fb[nf] = q;
+            fe[nf] = tab ? tab : le;
+            nf++;
+            if (!tab) break;
+            q = tab + 1;
+        }
+        cur = nl ? nl + 1 : end;
+        if (header || (nf != 7 && nf != 8)) continue;
+        if (nf == 8) {
+            const char *t = fb[7];
+            const bool ok = fe[7] - t == 2 && ((t[0] == 'U' && t[1] == 'U') || (t[0] == 'M' && t[1] == 'R') ||
+                                               (t[0] == 'M' && t[1] == 'U') || (t[0] == 'R' && t[1] == 'U') ||
+                                               (t[0] == 'U' && t[1] == 'R'));
+            if (!ok) continue;
+        }
+        int64_t v[2];
+        if (!parse_int_field(fb[2], fe[2], &v[0]) || !parse_int_field(fb[4], fe[4], &v[1])) continue;
+        if (n >= cap) return CL2_ERR_RANGE;
+        for (int s = 0; s < 2; s++) {
+            const int f = s == 0 ? 1 : 3;
+            key.assign(fb[f], (size_t)(fe[f] - fb[f]));
+            auto it = p->ids.find(key);
+            int32_t id;
+            if (it == p->ids.end()) {
+                id = (int32_t)p->names.size();
+                p->ids.emplace(key, id);
+                p->names.push_back(key);
+            } else {
+                id = it->second;
+            }
+            chrom[2 * n + s] = id;
+        }
+        pos[2 * n] = v[0];
+        pos[2 * n + 1] = v[1];
+        n++;
+    }
+    if (n_lines) *n_lines = lines;
+    return n;
+}

@@ -54,6 +54,17 @@ class BedpeParser:
             raise _lib.Cl2Error("cl2_bedpe_parse failed rc=%d" % n)
         return chrom[:n], pos[:n], mapq[:n]
 
+    def parse_pairs(self, buf):
+        """.pairs text -> (chrom ids int32[n,2], (cA, cB) int64[n,2])."""
+        cap = buf.count(b"\n") + 1
+        chrom = np.empty((cap, 2), dtype=np.int32)
+        pos = np.empty((cap, 2), dtype=np.int64)
+        n = self.lib.cl2_pairs_parse(self.h, buf, len(buf), cap, chrom.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                     pos.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), None)
+        if n < 0:
+            raise _lib.Cl2Error("cl2_pairs_parse failed rc=%d" % n)
+        return chrom[:n], pos[:n]
+
     def names(self):
         k = ctypes.c_int32(0)
         s = self.lib.cl2_bedpe_names(self.h, ctypes.byref(k))
@@ -80,9 +91,10 @@ def _chunks(f):
             yield rest
 
 
-def collect_pets(fs, logger=None, mapq=1, cs=[], cut=0, mcut=-1, cis=False):
-    """The parsing loop of parseBedpe (io.py:84-133) without the de-duplication: returns ({"chrA-chrB": int64[k,2]
-    (cA, cB) rows in file order}, counters dict with total / hiq / trans / cis / closeCis / farCis)."""
+def collect_pets(fs, logger=None, mapq=1, cs=[], cut=0, mcut=-1, cis=False, fmt="bedpe"):
+    """The parsing loop of parseBedpe (io.py:84-133) or, with fmt="pairs", of parsePairs (io.py:178-234; no MAPQ)
+    without the de-duplication: returns ({"chrA-chrB": int64[k,2] (cA, cB) rows in file order}, counters dict with
+    total / hiq / trans / cis / closeCis / farCis)."""
     parser = BedpeParser()
     total = hiq = t = c = closeCis = farCis = 0
     parts = {}                                   # (idA, idB) -> [int64[k,2]]
@@ -91,26 +103,36 @@ def collect_pets(fs, logger=None, mapq=1, cs=[], cut=0, mcut=-1, cis=False):
             if logger is not None:
                 logger.info("Parsing PETs from %s, requiring initial distance cutoff >%s and <%s" % (f, cut, mcut))
             for buf in _chunks(f):
-                chrom, pos, mq = parser.parse(buf)
+                if fmt == "pairs":
+                    chrom, pos = parser.parse_pairs(buf)
+                    mq = np.full(len(pos), 255, dtype=np.int32)
+                else:
+                    chrom, pos, mq = parser.parse(buf)
                 if len(mq) == 0:
                     continue
                 names = parser.names()
-                rank = np.empty(len(names), dtype=np.int64)              # string order of the names (ds.py:82)
+                rank = np.empty(len(names), dtype=np.int64)              # string order of the names (ds.py:82, :134)
                 rank[np.array(sorted(range(len(names)), key=lambda i: names[i]), dtype=np.int64)] = np.arange(len(names))
                 ida, idb = chrom[:, 0].astype(np.int64), chrom[:, 1].astype(np.int64)
-                sA, eA, sB, eB = pos[:, 0], pos[:, 1], pos[:, 2], pos[:, 3]
                 is_cis = ida == idb
-                swap = np.where(is_cis, sA + eA > sB + eB, rank[ida] > rank[idb])      # ds.py:61-64, 82-86
+                if fmt == "pairs":
+                    pA, pB = pos[:, 0], pos[:, 1]
+                    swap = np.where(is_cis, pA > pB, rank[ida] > rank[idb])               # ds.py:124-126, 134-137
+                    cA, cB = np.where(swap, pB, pA), np.where(swap, pA, pB)
+                else:
+                    sA, eA, sB, eB = pos[:, 0], pos[:, 1], pos[:, 2], pos[:, 3]
+                    swap = np.where(is_cis, sA + eA > sB + eB, rank[ida] > rank[idb])     # ds.py:61-64, 82-86
+                    sumA, sumB = np.where(swap, sB + eB, sA + eA), np.where(swap, sA + eA, sB + eB)
+                    cA = np.trunc(sumA / 2).astype(np.int64)                              # int((s + e) / 2)
+                    cB = np.trunc(sumB / 2).astype(np.int64)
                 ida, idb = np.where(swap, idb, ida), np.where(swap, ida, idb)
-                sumA, sumB = np.where(swap, sB + eB, sA + eA), np.where(swap, sA + eA, sB + eB)
-                cA = np.trunc(sumA / 2).astype(np.int64)                                 # int((s + e) / 2)
-                cB = np.trunc(sumB / 2).astype(np.int64)
                 keep = np.ones(len(mq), dtype=bool)
                 if len(cs) > 0:                                                          # io.py:102-103
                     incs = np.array([nm in cs for nm in names], dtype=bool)
                     keep &= incs[ida] & incs[idb]
                 total += int(keep.sum())
-                keep &= mq >= mapq                                                       # io.py:105-106
+                if fmt != "pairs":
+                    keep &= mq >= mapq                                                   # io.py:105-106
                 hiq += int(keep.sum())
                 c += int((keep & is_cis).sum())
                 t += int((keep & ~is_cis).sum())
@@ -138,14 +160,10 @@ def collect_pets(fs, logger=None, mapq=1, cs=[], cut=0, mcut=-1, cis=False):
     return rows, {"total": total, "hiq": hiq, "trans": t, "cis": c, "closeCis": closeCis, "farCis": farCis}
 
 
-def parseBedpe(fs, fout, logger, mapq=1, cs=[], cut=0, mcut=-1, cis=False, cpu=1, ctx=None):
-    """Drop-in for io.py:71-164.  fs: BEDPE / BEDPE.gz files of the replicates; fout: output directory (must exist,
-    as in the reference); cs: wanted chromosomes.  `cpu` is accepted and ignored."""
-    ctx = ctx or _lib.default_context()
-    pets, cnt = collect_pets(fs, logger, mapq=mapq, cs=cs, cut=cut, mcut=mcut, cis=cis)
-    total, hiq, t, c, closeCis, farCis = (cnt[k] for k in ("total", "hiq", "trans", "cis", "closeCis", "farCis"))
-    # unique PETs of every chromosome pair (getUniqueTxt, io.py:40-52) and the .ixy files (txt2ixy, io.py:55-67)
+def _write_dir(pets, cnt, fs, fout, logger, cut, mcut, mapq, ctx):
+    """getUniqueTxt + txt2ixy + petMeta.json (io.py:134-164 / 235-265) for the collected rows."""
     import joblib
+    total, hiq, t, c, closeCis, farCis = (cnt[k] for k in ("total", "hiq", "trans", "cis", "closeCis", "farCis"))
     uniques = 0
     ixyfs = []
     for key, xy in pets.items():
@@ -162,18 +180,34 @@ def parseBedpe(fs, fout, logger, mapq=1, cs=[], cut=0, mcut=-1, cis=False, cpu=1
         logger.info("Totaly %s PETs in target chromosomes from %s, in which %s high quality unqiue PETs" % (
             total, ",".join(fs), uniques))
     nr = 1 - uniques / 1.0 / (c - closeCis) if c > 0 else 0
-    ds = {
-        "Total PETs": total,
-        "High Mapq(>=%s) PETs" % mapq: hiq,
+    ds = {"Total PETs": total}
+    if mapq is not None:
+        ds["High Mapq(>=%s) PETs" % mapq] = hiq
+    ds.update({
         "Total Trans PETs": t,
         "Total Cis PETs": c,
         "Filtered too close (<%s) PETs" % cut: closeCis,
         "Filtered too distant (>%s) PETs" % mcut: farCis,
         "Unique PETs": uniques,
         "Cis PETs Redundancy": nr,
-    }
+    })
     metaf = fout + "/petMeta.json"
     with open(metaf, "w") as fo:
         json.dump(ds, fo)
     updateJson(ixyfs, metaf)
     return metaf
+
+
+def parseBedpe(fs, fout, logger, mapq=1, cs=[], cut=0, mcut=-1, cis=False, cpu=1, ctx=None):
+    """Drop-in for io.py:71-164.  fs: BEDPE / BEDPE.gz files of the replicates; fout: output directory (must exist,
+    as in the reference); cs: wanted chromosomes.  `cpu` is accepted and ignored."""
+    ctx = ctx or _lib.default_context()
+    pets, cnt = collect_pets(fs, logger, mapq=mapq, cs=cs, cut=cut, mcut=mcut, cis=cis)
+    return _write_dir(pets, cnt, fs, fout, logger, cut, mcut, mapq, ctx)
+
+
+def parsePairs(fs, fout, logger, cs=[], cut=0, mcut=-1, cis=False, cpu=1, ctx=None):
+    """Drop-in for io.py:166-265: the same for .pairs / .pairs.gz input (no MAPQ column, so no MAPQ counter)."""
+    ctx = ctx or _lib.default_context()
+    pets, cnt = collect_pets(fs, logger, cs=cs, cut=cut, mcut=mcut, cis=cis, fmt="pairs")
+    return _write_dir(pets, cnt, fs, fout, logger, cut, mcut, None, ctx)

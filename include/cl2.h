@@ -175,6 +175,14 @@ int cl2_bedpe_create(cl2_bedpe **out);
 void cl2_bedpe_destroy(cl2_bedpe *p);
 int64_t cl2_bedpe_parse(cl2_bedpe *p, const char *buf, int64_t len, int64_t cap, int32_t *chrom, int64_t *pos,
                         int32_t *mapq, int64_t *n_lines);
+/*
+ * The same for .pairs text: the line handling of parsePairs / Pair.__init__ (cLoops2/io.py:189-207, ds.py:111-137).
+ * A record has exactly 7 or 8 tab-separated fields, with 8 the pair type (field 7) must be UU, MR, MU, RU or UR,
+ * fields 2 and 4 must be integers, '#' lines are headers.  chrom[2i], chrom[2i+1] = ids of fields 1 and 3,
+ * pos[2i], pos[2i+1] = fields 2 and 4.
+ */
+int64_t cl2_pairs_parse(cl2_bedpe *p, const char *buf, int64_t len, int64_t cap, int32_t *chrom, int64_t *pos,
+                        int64_t *n_lines);
 /* Names seen so far, '\n'-joined in id order; valid until the next call on `p`. */
 const char *cl2_bedpe_names(cl2_bedpe *p, int32_t *count);
 

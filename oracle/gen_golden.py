@@ -19,6 +19,7 @@ Contents
   dloops.npz           the reference's callDiffLoops.quantDloops fields + background lists for two samples
   peaks.npz            the reference's callPeaks.runDBSCANPeaks peaks (paired and -split)
   pre_bedpe.npz        two synthetic BEDPE files + the reference's `pre` output (io.py parseBedpe): rows per key, counters
+  pre_pairs.npz        the same for .pairs input (io.py parsePairs)
 """
 import json
 import os
@@ -313,6 +314,67 @@ def gen_pre(ref):
     np.savez_compressed(os.path.join(GOLD, "pre_bedpe.npz"), **out)
 
 
+def synth_pairs(seed, n):
+    """.pairs text: header lines, 7- and 8-column records, all pair types, ends in either order, duplicates, bad
+    lines."""
+    rng = np.random.default_rng(seed)
+    chroms = ["chr21", "chr22", "chrX"]
+    types = ["UU", "UR", "RU", "MU", "MR", "NN", "DD", "WW", "MM"]
+    out = ["## pairs format v1.0", "#columns: readID chr1 pos1 chr2 pos2 strand1 strand2 pair_type"]
+    for i in range(n):
+        ca = chroms[int(rng.integers(0, 3))]
+        cb = ca if rng.random() < 0.8 else chroms[int(rng.integers(0, 3))]
+        x = int(rng.integers(100, 200_000))
+        y = x + int(np.exp(rng.uniform(np.log(50), np.log(100_000)))) if ca == cb else int(rng.integers(100, 200_000))
+        a, b = (ca, x), (cb, y)
+        if rng.random() < 0.5:
+            a, b = b, a
+        f = ["r%d" % i, a[0], str(a[1]), b[0], str(b[1]), "+-"[int(rng.integers(0, 2))], "+-"[int(rng.integers(0, 2))]]
+        if rng.random() < 0.7:
+            f.append(types[int(rng.integers(0, len(types)))])
+        out.append("\t".join(f))
+        if rng.random() < 0.08:
+            out.append("\t".join(f))
+        if rng.random() < 0.02:
+            out.append("\t".join(f[:5]))                          # too few columns
+        if rng.random() < 0.02:
+            out.append("\t".join(f + ["extra", "cols"]))          # too many columns
+        if rng.random() < 0.02:
+            bad = list(f)
+            bad[2] = "!"
+            out.append("\t".join(bad))                            # non-numeric position
+    return "\n".join(out) + "\n"
+
+
+def gen_pre_pairs(ref):
+    """cLoops2/io.py parsePairs on two synthetic .pairs files (one gzipped), default options and filtered."""
+    import gzip
+    import joblib
+    tmp = tempfile.mkdtemp()
+    t1, t2 = synth_pairs(303, 6000), synth_pairs(404, 4000)
+    open(tmp + "/a.pairs", "w").write(t1)
+    with gzip.open(tmp + "/b.pairs.gz", "wt") as fo:
+        fo.write(t2)
+    out = {"pairs_a": t1, "pairs_b": t2}
+    import contextlib
+    import io as _io
+    for name, kw in (("default", dict(cs=[], cut=0, mcut=-1, cis=False)),
+                     ("filtered", dict(cs=["chr21", "chr22"], cut=1000, mcut=50000, cis=True))):
+        d = tmp + "/" + name
+        os.makedirs(d)
+        with contextlib.redirect_stdout(_io.StringIO()):          # "Missing information ..." for every odd line
+            ref.io.parsePairs([tmp + "/a.pairs", tmp + "/b.pairs.gz"], d, ref.logger, cpu=1, **kw)
+        meta = json.load(open(d + "/petMeta.json"))
+        keys = sorted(list(meta["data"]["cis"].keys()) + list(meta["data"]["trans"].keys()))
+        out[name + "_keys"] = np.array(keys)
+        for k in keys:
+            m = np.asarray(joblib.load(d + "/%s.ixy" % k), dtype=np.int64).reshape(-1, 2)
+            out[name + "_" + k.replace("-", "_")] = m[np.lexsort((m[:, 1], m[:, 0]))]
+        meta.pop("data")
+        out[name + "_meta"] = json.dumps(meta)
+    np.savez_compressed(os.path.join(GOLD, "pre_pairs.npz"), **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref = ref_shim.load()
@@ -324,6 +386,7 @@ def main():
     gen_dloops(ref)
     gen_peaks(ref)
     gen_pre(ref)
+    gen_pre_pairs(ref)
     print("golden vectors written to", GOLD)
 
 

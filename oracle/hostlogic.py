@@ -557,3 +557,51 @@ def pre_bedpe(lines, mapq=1, cs=(), cut=0, mcut=-1, cis=False):
             "Filtered too close (<%s) PETs" % cut: closeCis, "Filtered too distant (>%s) PETs" % mcut: farCis,
             "Unique PETs": uniques, "Cis PETs Redundancy": (1 - uniques / 1.0 / (c - closeCis)) if c > 0 else 0}
     return {k: sorted(v) for k, v in rows.items()}, meta
+
+
+def pre_pairs(lines, cs=(), cut=0, mcut=-1, cis=False):
+    """cLoops2/io.py:166-245 (parsePairs) + ds.py:111-137 (Pair) on an iterable of text lines, in plain Python; same
+    return convention as pre_bedpe (no MAPQ counter: .pairs has no MAPQ column)."""
+    rows = {}
+    total = t = c = closeCis = farCis = 0
+    for line in lines:
+        if line.startswith("#"):
+            continue
+        d = line.split("\n")[0].split("\t")
+        if len(d) == 8:
+            if d[7] not in ["UU", "MR", "MU", "RU", "UR"]:
+                continue
+        elif len(d) != 7:
+            continue
+        try:                                                   # Pair.__init__, ds.py:111-137
+            chromA, cA, chromB, cB = d[1], int(d[2]), d[3], int(d[4])
+        except Exception:
+            continue
+        is_cis = chromA == chromB
+        if is_cis:
+            if cA > cB:
+                cA, cB = cB, cA
+            distance = int(abs(cB - cA))
+        elif chromA > chromB:
+            chromA, chromB, cA, cB = chromB, chromA, cB, cA
+        if len(cs) > 0 and not (chromA in cs and chromB in cs):
+            continue
+        total += 1
+        if is_cis:
+            c += 1
+        else:
+            t += 1
+        if cis and not is_cis:
+            continue
+        if cut > 0 and is_cis and distance < cut:
+            closeCis += 1
+            continue
+        if mcut > 0 and is_cis and distance > mcut:
+            farCis += 1
+            continue
+        rows.setdefault("%s-%s" % (chromA, chromB), set()).add((cA, cB))
+    uniques = sum(len(v) for v in rows.values())
+    meta = {"Total PETs": total, "Total Trans PETs": t, "Total Cis PETs": c,
+            "Filtered too close (<%s) PETs" % cut: closeCis, "Filtered too distant (>%s) PETs" % mcut: farCis,
+            "Unique PETs": uniques, "Cis PETs Redundancy": (1 - uniques / 1.0 / (c - closeCis)) if c > 0 else 0}
+    return {k: sorted(v) for k, v in rows.items()}, meta

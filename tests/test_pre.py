@@ -141,3 +141,60 @@ def test_tokeniser_fuzz_against_python_parser(tmp_path):
         assert sorted(pets) == sorted(want)
         for k, xy in pets.items():
             assert np.unique(xy, axis=0).tolist() == [list(r) for r in want[k]], k
+
+
+# ---- .pairs input (parsePairs) ------------------------------------------------------------------------------------
+PCASES = (("default", dict(cs=[], cut=0, mcut=-1, cis=False)),
+          ("filtered", dict(cs=["chr21", "chr22"], cut=1000, mcut=50000, cis=True)))
+
+
+def _write_pairs(g, d):
+    (d / "a.pairs").write_text(str(g["pairs_a"]))
+    with gzip.open(str(d / "b.pairs.gz"), "wt") as fo:
+        fo.write(str(g["pairs_b"]))
+    return [str(d / "a.pairs"), str(d / "b.pairs.gz")]
+
+
+@pytest.mark.parametrize("name,kw", PCASES)
+def test_oracle_pre_pairs_matches_reference(name, kw):
+    g = load_golden("pre_pairs.npz")
+    lines = (str(g["pairs_a"]) + str(g["pairs_b"])).split("\n")[:-1]
+    rows, meta = oracle.pre_pairs(lines, **kw)
+    assert meta == json.loads(str(g[name + "_meta"]))
+    assert sorted(rows) == g[name + "_keys"].tolist()
+    for k, v in rows.items():
+        assert np.array_equal(np.array(v, dtype=np.int64), g[name + "_" + k.replace("-", "_")]), k
+
+
+@pytest.mark.parametrize("name,kw", PCASES)
+def test_native_pairs_tokeniser_and_logic(tmp_path, name, kw):
+    from cloops2_b200.pre import collect_pets
+    g = load_golden("pre_pairs.npz")
+    pets, cnt = collect_pets(_write_pairs(g, tmp_path), None, fmt="pairs", **kw)
+    want = json.loads(str(g[name + "_meta"]))
+    for k, mk in META.items():
+        assert cnt[k] == want[mk], k
+    assert cnt["closeCis"] == want["Filtered too close (<%s) PETs" % kw["cut"]]
+    assert cnt["farCis"] == want["Filtered too distant (>%s) PETs" % kw["mcut"]]
+    assert sorted(pets) == g[name + "_keys"].tolist()
+    for k, xy in pets.items():
+        assert np.array_equal(np.unique(xy, axis=0), g[name + "_" + k.replace("-", "_")]), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,kw", PCASES)
+def test_gpu_pre_pairs_command(gpu_ctx, tmp_path, name, kw):
+    import joblib
+    from cloops2_b200.pre import parsePairs
+    g = load_golden("pre_pairs.npz")
+    out = tmp_path / "out"
+    out.mkdir()
+    parsePairs(_write_pairs(g, tmp_path), str(out), None, ctx=gpu_ctx, **kw)
+    meta = json.load(open(str(out / "petMeta.json")))
+    data = meta.pop("data")
+    assert meta == json.loads(str(g[name + "_meta"]))
+    keys = sorted(list(data["cis"]) + list(data["trans"]))
+    assert keys == g[name + "_keys"].tolist()
+    for k in keys:
+        m = joblib.load(data["cis" if k in data["cis"] else "trans"][k]["ixy"])
+        assert np.array_equal(m, g[name + "_" + k.replace("-", "_")]), k
