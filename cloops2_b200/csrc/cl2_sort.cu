@@ -1,10 +1,12 @@
 // cl2_sort.cu -- hand-written device primitives for the binning stage: a stable LSD radix sort of
-// (uint64 cell key, uint32 row id) pairs and an int32 exclusive scan.  sm_100a.
+// (cell key, uint32 row id) pairs and an int32 exclusive scan.  sm_100a.
 //
-// Radix pass = upsweep (per-tile digit histogram, 8 B/PET read) + scan of the [256][ntiles] table + downsweep
-// (stable ranking with __match_any_sync, shared-memory reorder so each digit run leaves the SM as a contiguous,
-// coalesced store; 12 B read + 12 B written per PET).  Only ceil(nbits/8) passes are run, nbits being the number
-// of significant bits of the packed cell key for this chromosome and eps.
+// The sort in use is the one-kernel-per-pass "onesweep" variant further down (k_os_hist / k_os_pass), on 32-bit keys
+// whenever the key fits (every grid, x-order and y-order sort of the path), on 64-bit keys otherwise.  Only
+// ceil(nbits/8) passes are run, nbits being the number of significant bits of the key for this chromosome and eps.
+// The three-kernel pass right below -- upsweep (per-tile digit histogram) + scan of the [256][ntiles] table +
+// downsweep (stable ranking with __match_any_sync, shared-memory reorder so each digit run leaves the SM as a
+// contiguous store) -- remains as the fallback for n >= 2^30 rows and as CL2_SORT_3KERNEL=1.
 #include "cl2_common.cuh"
 #include <stdlib.h>
 
@@ -238,7 +240,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_downsweep(const uint64_t *__r
 }
 
 // ------------------------------------------------------------------------------------------------ onesweep variant
-// One kernel per pass (24 B/PET): digit histograms of ALL passes are taken once up front (they do not depend on the
+// One kernel per pass (16 B/PET with 32-bit keys, 24 with 64-bit): digit histograms of ALL passes are taken once up front (they do not depend on the
 // element order), tiles are claimed through an atomic ticket and obtain their per-digit base by decoupled look-back
 // over the tile descriptors (count | AGGREGATE, later inclusive | INCLUSIVE), so no per-pass upsweep read and no
 // table scan.  Tiles are ticket-ordered, so every predecessor a tile waits on is already running or finished.
