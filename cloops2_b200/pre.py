@@ -23,7 +23,7 @@ import numpy as np
 from . import _lib
 from .io import updateJson
 
-CHUNK = 64 << 20
+CHUNK = 16 << 20
 
 
 class BedpeParser:
@@ -91,73 +91,96 @@ def _chunks(f):
             yield rest
 
 
-def collect_pets(fs, logger=None, mapq=1, cs=[], cut=0, mcut=-1, cis=False, fmt="bedpe"):
-    """The parsing loop of parseBedpe (io.py:84-133) or, with fmt="pairs", of parsePairs (io.py:178-234; no MAPQ)
-    without the de-duplication: returns ({"chrA-chrB": int64[k,2] (cA, cB) rows in file order}, counters dict with
-    total / hiq / trans / cis / closeCis / farCis)."""
+def _chunk_pets(buf, mapq, cs, cut, mcut, cis, fmt):
+    """One text chunk -> ({(chrA, chrB): int64[k,2]}, counters).  Self-contained (own name table), so chunks can be
+    handled by several threads; the tokeniser and most of numpy run without the GIL."""
     parser = BedpeParser()
-    total = hiq = t = c = closeCis = farCis = 0
-    parts = {}                                   # (idA, idB) -> [int64[k,2]]
     try:
-        for f in fs:
-            if logger is not None:
-                logger.info("Parsing PETs from %s, requiring initial distance cutoff >%s and <%s" % (f, cut, mcut))
-            for buf in _chunks(f):
-                if fmt == "pairs":
-                    chrom, pos = parser.parse_pairs(buf)
-                    mq = np.full(len(pos), 255, dtype=np.int32)
-                else:
-                    chrom, pos, mq = parser.parse(buf)
-                if len(mq) == 0:
-                    continue
-                names = parser.names()
-                rank = np.empty(len(names), dtype=np.int64)              # string order of the names (ds.py:82, :134)
-                rank[np.array(sorted(range(len(names)), key=lambda i: names[i]), dtype=np.int64)] = np.arange(len(names))
-                ida, idb = chrom[:, 0].astype(np.int64), chrom[:, 1].astype(np.int64)
-                is_cis = ida == idb
-                if fmt == "pairs":
-                    pA, pB = pos[:, 0], pos[:, 1]
-                    swap = np.where(is_cis, pA > pB, rank[ida] > rank[idb])               # ds.py:124-126, 134-137
-                    cA, cB = np.where(swap, pB, pA), np.where(swap, pA, pB)
-                else:
-                    sA, eA, sB, eB = pos[:, 0], pos[:, 1], pos[:, 2], pos[:, 3]
-                    swap = np.where(is_cis, sA + eA > sB + eB, rank[ida] > rank[idb])     # ds.py:61-64, 82-86
-                    sumA, sumB = np.where(swap, sB + eB, sA + eA), np.where(swap, sA + eA, sB + eB)
-                    cA = np.trunc(sumA / 2).astype(np.int64)                              # int((s + e) / 2)
-                    cB = np.trunc(sumB / 2).astype(np.int64)
-                ida, idb = np.where(swap, idb, ida), np.where(swap, ida, idb)
-                keep = np.ones(len(mq), dtype=bool)
-                if len(cs) > 0:                                                          # io.py:102-103
-                    incs = np.array([nm in cs for nm in names], dtype=bool)
-                    keep &= incs[ida] & incs[idb]
-                total += int(keep.sum())
-                if fmt != "pairs":
-                    keep &= mq >= mapq                                                   # io.py:105-106
-                hiq += int(keep.sum())
-                c += int((keep & is_cis).sum())
-                t += int((keep & ~is_cis).sum())
-                if cis:
-                    keep &= is_cis                                                       # io.py:113-114
-                dist = np.abs(cB - cA)
-                if cut > 0:                                                              # io.py:116-118
-                    close = keep & is_cis & (dist < cut)
-                    closeCis += int(close.sum())
-                    keep &= ~close
-                if mcut > 0:                                                             # io.py:119-121
-                    far = keep & is_cis & (dist > mcut)
-                    farCis += int(far.sum())
-                    keep &= ~far
-                ida, idb, cA, cB = ida[keep], idb[keep], cA[keep], cB[keep]
-                kid = ida * len(names) + idb
-                for k in np.unique(kid).tolist():
-                    m = kid == k
-                    parts.setdefault((k // len(names), k % len(names)), []).append(np.stack([cA[m], cB[m]], axis=1))
+        if fmt == "pairs":
+            chrom, pos = parser.parse_pairs(buf)
+            mq = np.full(len(pos), 255, dtype=np.int32)
+        else:
+            chrom, pos, mq = parser.parse(buf)
         names = parser.names()
     finally:
         parser.close()
-    rows = {"%s-%s" % (names[a], names[b]): np.ascontiguousarray(np.concatenate(ch, axis=0), dtype=np.int64)
-            for (a, b), ch in parts.items()}
-    return rows, {"total": total, "hiq": hiq, "trans": t, "cis": c, "closeCis": closeCis, "farCis": farCis}
+    cnt = {"total": 0, "hiq": 0, "trans": 0, "cis": 0, "closeCis": 0, "farCis": 0}
+    if len(mq) == 0:
+        return {}, cnt
+    rank = np.empty(len(names), dtype=np.int64)                          # string order of the names (ds.py:82, :134)
+    rank[np.array(sorted(range(len(names)), key=lambda i: names[i]), dtype=np.int64)] = np.arange(len(names))
+    ida, idb = chrom[:, 0].astype(np.int64), chrom[:, 1].astype(np.int64)
+    is_cis = ida == idb
+    if fmt == "pairs":
+        pA, pB = pos[:, 0], pos[:, 1]
+        swap = np.where(is_cis, pA > pB, rank[ida] > rank[idb])           # ds.py:124-126, 134-137
+        cA, cB = np.where(swap, pB, pA), np.where(swap, pA, pB)
+    else:
+        sA, eA, sB, eB = pos[:, 0], pos[:, 1], pos[:, 2], pos[:, 3]
+        swap = np.where(is_cis, sA + eA > sB + eB, rank[ida] > rank[idb])  # ds.py:61-64, 82-86
+        sumA, sumB = np.where(swap, sB + eB, sA + eA), np.where(swap, sA + eA, sB + eB)
+        cA = np.trunc(sumA / 2).astype(np.int64)                          # int((s + e) / 2)
+        cB = np.trunc(sumB / 2).astype(np.int64)
+    ida, idb = np.where(swap, idb, ida), np.where(swap, ida, idb)
+    keep = np.ones(len(mq), dtype=bool)
+    if len(cs) > 0:                                                      # io.py:102-103
+        incs = np.array([nm in cs for nm in names], dtype=bool)
+        keep &= incs[ida] & incs[idb]
+    cnt["total"] = int(keep.sum())
+    if fmt != "pairs":
+        keep &= mq >= mapq                                               # io.py:105-106
+    cnt["hiq"] = int(keep.sum())
+    cnt["cis"] = int((keep & is_cis).sum())
+    cnt["trans"] = int((keep & ~is_cis).sum())
+    if cis:
+        keep &= is_cis                                                   # io.py:113-114
+    dist = np.abs(cB - cA)
+    if cut > 0:                                                          # io.py:116-118
+        close = keep & is_cis & (dist < cut)
+        cnt["closeCis"] = int(close.sum())
+        keep &= ~close
+    if mcut > 0:                                                         # io.py:119-121
+        far = keep & is_cis & (dist > mcut)
+        cnt["farCis"] = int(far.sum())
+        keep &= ~far
+    ida, idb, cA, cB = ida[keep], idb[keep], cA[keep], cB[keep]
+    kid = ida * len(names) + idb
+    parts = {}
+    for k in np.unique(kid).tolist():
+        m = kid == k
+        parts[(names[k // len(names)], names[k % len(names)])] = np.stack([cA[m], cB[m]], axis=1)
+    return parts, cnt
+
+
+def collect_pets(fs, logger=None, mapq=1, cs=[], cut=0, mcut=-1, cis=False, fmt="bedpe", cpu=1):
+    """The parsing loop of parseBedpe (io.py:84-133) or, with fmt="pairs", of parsePairs (io.py:178-234; no MAPQ)
+    without the de-duplication: returns ({"chrA-chrB": int64[k,2] (cA, cB) rows in file order}, counters dict with
+    total / hiq / trans / cis / closeCis / farCis).  cpu > 1: that many threads work on the text chunks."""
+    from concurrent.futures import ThreadPoolExecutor
+    cnt = {"total": 0, "hiq": 0, "trans": 0, "cis": 0, "closeCis": 0, "farCis": 0}
+    parts = {}                                   # (chrA, chrB) -> [int64[k,2]], chunks in file order
+
+    def absorb(res):
+        p, c = res
+        for k, v in c.items():
+            cnt[k] += v
+        for k, v in p.items():
+            parts.setdefault(k, []).append(v)
+
+    nthreads = max(1, int(cpu))
+    with ThreadPoolExecutor(nthreads) as pool:
+        for f in fs:
+            if logger is not None:
+                logger.info("Parsing PETs from %s, requiring initial distance cutoff >%s and <%s" % (f, cut, mcut))
+            pending = []
+            for buf in _chunks(f):
+                pending.append(pool.submit(_chunk_pets, buf, mapq, cs, cut, mcut, cis, fmt))
+                while len(pending) > 2 * nthreads:            # bounded look-ahead: chunks are large
+                    absorb(pending.pop(0).result())
+            for fut in pending:
+                absorb(fut.result())
+    rows = {"%s-%s" % k: np.ascontiguousarray(np.concatenate(ch, axis=0), dtype=np.int64) for k, ch in parts.items()}
+    return rows, cnt
 
 
 def _write_dir(pets, cnt, fs, fout, logger, cut, mcut, mapq, ctx):
@@ -200,14 +223,14 @@ def _write_dir(pets, cnt, fs, fout, logger, cut, mcut, mapq, ctx):
 
 def parseBedpe(fs, fout, logger, mapq=1, cs=[], cut=0, mcut=-1, cis=False, cpu=1, ctx=None):
     """Drop-in for io.py:71-164.  fs: BEDPE / BEDPE.gz files of the replicates; fout: output directory (must exist,
-    as in the reference); cs: wanted chromosomes.  `cpu` is accepted and ignored."""
+    as in the reference); cs: wanted chromosomes; cpu: threads that parse the text."""
     ctx = ctx or _lib.default_context()
-    pets, cnt = collect_pets(fs, logger, mapq=mapq, cs=cs, cut=cut, mcut=mcut, cis=cis)
+    pets, cnt = collect_pets(fs, logger, mapq=mapq, cs=cs, cut=cut, mcut=mcut, cis=cis, cpu=cpu)
     return _write_dir(pets, cnt, fs, fout, logger, cut, mcut, mapq, ctx)
 
 
 def parsePairs(fs, fout, logger, cs=[], cut=0, mcut=-1, cis=False, cpu=1, ctx=None):
     """Drop-in for io.py:166-265: the same for .pairs / .pairs.gz input (no MAPQ column, so no MAPQ counter)."""
     ctx = ctx or _lib.default_context()
-    pets, cnt = collect_pets(fs, logger, cs=cs, cut=cut, mcut=mcut, cis=cis, fmt="pairs")
+    pets, cnt = collect_pets(fs, logger, cs=cs, cut=cut, mcut=mcut, cis=cis, fmt="pairs", cpu=cpu)
     return _write_dir(pets, cnt, fs, fout, logger, cut, mcut, None, ctx)
