@@ -83,9 +83,11 @@ class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, device):
+    def __init__(self, device, enabled=True):
         self.rows = []
         self.proc = None
+        if not enabled:          # only rank 0 reports clocks; the other ranks keep their host cores for the work
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "200"],
@@ -286,7 +288,7 @@ def main():
                 c.timing_reset()
                 c.timing_enable(True)
             c.launch_count_reset()
-        sampler = ClockSampler(local)
+        sampler = ClockSampler(local, enabled=(rank == 0))
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t = time.perf_counter()
         ev0.record()
