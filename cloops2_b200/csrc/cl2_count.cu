@@ -149,6 +149,7 @@ struct IdxView {
     const uint32_t *tx, *ty;
     int64_t n;
     int sx, sy, nbx, nby;
+    int lg;               // ceil(log2 n): depth of one binary search in SURVEY.md 8d's byte count
 };
 struct Arr {
     const int2 *a;
@@ -156,7 +157,8 @@ struct Arr {
     int shift, nb;
 };
 static IdxView cl2_view(const cl2_index *idx) {
-    IdxView v = {idx->byx, idx->byy, idx->tx, idx->ty, idx->n, idx->sx, idx->sy, idx->nbx, idx->nby};
+    IdxView v = {idx->byx, idx->byy, idx->tx, idx->ty, idx->n, idx->sx, idx->sy, idx->nbx, idx->nby, 1};
+    while (((int64_t)1 << v.lg) < idx->n) v.lg++;
     return v;
 }
 __device__ __forceinline__ Arr arr_x(const IdxView &ix) { Arr r = {ix.byx, ix.tx, ix.sx, ix.nbx}; return r; }
@@ -242,41 +244,95 @@ __device__ __forceinline__ Range range_of(const Arr &A, int64_t n, const Iv &I, 
 }
 __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }
 
-// |P(I)|  (queryPeak, ds.py:176-182)
-// g_scan: members visited by this warp so far (the counting kernel's algorithmic traffic is 16 B per member on the
-// reference layout); every lane carries the same value
-__device__ __noinline__ int64_t count_peak(const IdxView &ix, const Iv &I, int lane, long long *g_scan) {
-    Range rx = range_of(arr_x(ix), ix.n, I, lane), ry = range_of(arr_y(ix), ix.n, I, lane);
-    *g_scan += ry.e - ry.b;
-    const Iv32 J = iv32(I);
-    int c = 0;
-    for (int64_t j = ry.b + lane; j < ry.e; j += 32) {
-        int2 p = ix.byy[j];                   // (y, x)
-        if (!in32(J, p.y)) c++;
+// ---- counting on the X-sorted list only ---------------------------------------------------------------------
+// Every set size of the reference is a combination of 1-D range counts (pure position arithmetic on the two sorted
+// arrays) and sums over the rows of an X-range (checked against the oracle for ordered, unordered, overlapping and
+// clipped intervals):
+//     |P(I)|          = cX(I) + cY(I) - #{x in I and y in I}
+//     |P(U) & P(V)|   = cY(U & V) + sum over rows with x in U | V of  [(x in U or y in U) and (x in V or y in V)]
+//                                                                   - [y in U and y in V]
+// (a row whose x lies outside U | V can only be in both sets through y, which is what cY(U & V) counts; the rows
+// scanned are subtracted from it again).  The Y-sorted array is only ever searched, never scanned, and no row is
+// visited through two lists, so there is no de-duplication.
+
+// lower bound (first position whose sort coordinate is >= v) searched by ONE lane for its own value: the bucket
+// table brackets the answer to ~16 rows, then a plain binary search.  32 lanes run 32 independent searches.
+__device__ __forceinline__ uint32_t lane_lb(const Arr &A, int64_t n, long long v) {
+    if (v <= 0) return 0u;                                   // coordinates are >= 0
+    if (v > (long long)INT_MAX) return (uint32_t)n;          // and < INT_MAX
+    uint32_t lo = 0, hi = (uint32_t)n;
+    if (A.tab) {
+        const int b = (int)v >> A.shift;
+        if (b >= A.nb) return (uint32_t)n;
+        lo = A.tab[b];
+        hi = A.tab[b + 1];
     }
-    return (rx.e - rx.b) + (int64_t)warp_sum(c);
+    const int key = (int)v;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;                 // n < 2^31: no overflow
+        if (A.a[mid].x < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+// one bound of the closed interval [lo, hi] in one of the two lists: end 0 = first position inside, 1 = one past the
+// last (searchsorted left / right, ds.py:170-171); an empty interval gets the empty range [0, 0)
+__device__ __forceinline__ uint32_t bound_task(const IdxView &ix, long long lo, long long hi, int list, int end) {
+    if (lo > hi) return 0u;
+    return list ? lane_lb(arr_y(ix), ix.n, end ? hi + 1 : lo) : lane_lb(arr_x(ix), ix.n, end ? hi + 1 : lo);
+}
+struct IvPos {        // X-list range [xb, xe) and Y-list range [yb, ye) of an interval
+    uint32_t xb, xe, yb, ye;
+};
+// lanes 4k .. 4k+3 hold xb, xe, yb, ye of interval k
+__device__ __forceinline__ IvPos gather_pos(uint32_t pos, int k) {
+    IvPos P;
+    P.xb = __shfl_sync(0xffffffffu, pos, 4 * k);
+    P.xe = __shfl_sync(0xffffffffu, pos, 4 * k + 1);
+    P.yb = __shfl_sync(0xffffffffu, pos, 4 * k + 2);
+    P.ye = __shfl_sync(0xffffffffu, pos, 4 * k + 3);
+    return P;
+}
+__device__ __forceinline__ long long pos_max(const IvPos &P) {   // lower bound of |P(I)| (SURVEY.md 8d's R / W)
+    const long long a = (long long)P.xe - P.xb, b = (long long)P.ye - P.yb;
+    return a > b ? a : b;
+}
+// cY(U & V) from the Y ranges of U and V (lower / upper bounds are monotone in the coordinate)
+__device__ __forceinline__ long long ycount_both(const IvPos &U, const IvPos &V) {
+    const long long b = U.yb > V.yb ? U.yb : V.yb, e = U.ye < V.ye ? U.ye : V.ye;
+    return e > b ? e - b : 0;
 }
 
-// |P(I1)| and |P(I1) & P(I2)|  (queryLoop, ds.py:184-190)
-__device__ __noinline__ void count_pair(const IdxView &ix, const Iv &I1, const Iv &I2, int lane, int64_t *n1, int64_t *n12,
-                                        long long *g_scan) {
-    Range rx = range_of(arr_x(ix), ix.n, I1, lane), ry = range_of(arr_y(ix), ix.n, I1, lane);
-    *g_scan += (rx.e - rx.b) + (ry.e - ry.b);
-    const Iv32 J1 = iv32(I1), J2 = iv32(I2);
-    int c1 = 0, c12 = 0;
-    for (int64_t i = rx.b + lane; i < rx.e; i += 32) {
-        int2 p = ix.byx[i];                   // (x, y)
-        if (in32(J2, p.x) || in32(J2, p.y)) c12++;
+// sum over the rows with x in U | V:  cnt = [(x|y in U) and (x|y in V)] - [y in U and y in V],
+// eu = [x in U and y in U], ev = [x in V and y in V]
+__device__ __forceinline__ void pair_scan(const int2 *__restrict__ byx, const Iv32 U, const Iv32 V, const IvPos &PU,
+                                          const IvPos &PV, int lane, int &cnt, int &eu, int &ev) {
+    uint32_t b0 = PU.xb, e0 = PU.xe, b1 = PV.xb, e1 = PV.xe;
+    if (b0 <= e1 && b1 <= e0) {                              // overlapping or touching ranges: one scan
+        b0 = b0 < b1 ? b0 : b1;
+        e0 = e0 > e1 ? e0 : e1;
+        b1 = e1 = 0;
     }
-    for (int64_t j = ry.b + lane; j < ry.e; j += 32) {
-        int2 p = ix.byy[j];                   // (y, x)
-        if (!in32(J1, p.y)) {
-            c1++;
-            if (in32(J2, p.y) || in32(J2, p.x)) c12++;
+    int c = 0, u = 0, v = 0;
+#pragma unroll 1
+    for (int rr = 0; rr < 2; rr++) {
+        const uint32_t b = rr ? b1 : b0, e = rr ? e1 : e0;
+        for (uint32_t p = b + lane; p < e; p += 32) {
+            const int2 P = byx[p];
+            const bool px = in32(U, P.x), qy = in32(U, P.y), rx = in32(V, P.x), sy = in32(V, P.y);
+            c += (int)((px || qy) && (rx || sy)) - (int)(qy && sy);
+            u += (int)(px && qy);
+            v += (int)(rx && sy);
         }
     }
-    *n1 = (rx.e - rx.b) + (int64_t)warp_sum(c1);
-    *n12 = (int64_t)warp_sum(c12);
+    cnt = warp_sum(c);
+    eu = warp_sum(u);
+    ev = warp_sum(v);
+}
+// #{x in I and y in I} over the X range of I
+__device__ __forceinline__ int both_scan(const int2 *__restrict__ byx, const Iv32 I, const IvPos &P, int lane) {
+    int c = 0;
+    for (uint32_t p = P.xb + lane; p < P.xe; p += 32) c += (int)in32(I, byx[p].y);
+    return warp_sum(c);
 }
 
 struct WarpAcc {
@@ -286,6 +342,9 @@ struct WarpAcc {
     // permuted windows as {lo, width} (Iv32 layout, one 8-byte load per test) and their upper bounds
     int2 aw[CNT_MAXW], bw[CNT_MAXW];
     int ahi[CNT_MAXW], bhi[CNT_MAXW];
+    // 2*win <= 10: window bounds (a-windows then b-windows) and their positions xb, xe, yb, ye in the two lists
+    long long wlo[2 * CNT_MAXW], whi[2 * CNT_MAXW];
+    uint32_t pos[4][2 * CNT_MAXW];
 };
 
 // bit t set iff window t holds c
@@ -339,37 +398,190 @@ __device__ __forceinline__ void window_accumulate(WarpAcc &A, int W, unsigned ma
 }
 
 // ---- per-loop building blocks (one warp) -------------------------------------------------------------------
+// g_bytes: algorithmic bytes of the work done for this candidate: 16 B per member of every region
+// queried, members counted from below as max(cX, cY), plus 2 arrays x 2 searches x ceil(log2 N) x 8 B per interval
+// query; every lane carries the same value.
 // queryLoop counts + the P2LL window (cis callCisLoops.py:287-289, 302-305; trans callTransLoops.py:124-126, 142-144)
 __device__ void loop_core(const IdxView &ix, long long xs, long long xe, long long ys, long long ye, int mode, int lane,
-                          int64_t out[4], long long *g_scan) {
-    const Iv A = {xs, xe}, B = {ys, ye};
-    int64_t ra, rab, rb;
-    count_pair(ix, A, B, lane, &ra, &rab, g_scan);
-    rb = count_peak(ix, B, lane, g_scan);
-    Iv A2, B2;
-    if (mode == CL2_MODE_CIS) { A2.lo = xe; A2.hi = xe + (xe - xs); }
-    else { A2.lo = xs - (xe - xs); A2.hi = xs; }
-    B2.lo = ys - (ye - ys); B2.hi = ys;
-    int64_t t1, lower;
-    count_pair(ix, A2, B2, lane, &t1, &lower, g_scan);
-    out[0] = ra; out[1] = rb; out[2] = rab; out[3] = lower;
+                          int64_t out[4], long long *g_bytes) {
+    // intervals 0..3: A, B, the lower-left pair A2, B2; lane 4k + 2*list + end searches one bound of interval k
+    const int k = (lane >> 2) & 3;
+    long long lo, hi;
+    if (k == 0) { lo = xs; hi = xe; }
+    else if (k == 1) { lo = ys; hi = ye; }
+    else if (k == 2) {
+        if (mode == CL2_MODE_CIS) { lo = xe; hi = xe + (xe - xs); }
+        else { lo = xs - (xe - xs); hi = xs; }
+    } else { lo = ys - (ye - ys); hi = ys; }
+    const uint32_t pos = lane < 16 ? bound_task(ix, lo, hi, (lane >> 1) & 1, lane & 1) : 0u;
+    const IvPos PA = gather_pos(pos, 0), PB = gather_pos(pos, 1), PA2 = gather_pos(pos, 2), PB2 = gather_pos(pos, 3);
+    const Iv32 A = iv32(xs, xe), B = iv32(ys, ye);
+    Iv32 A2 = mode == CL2_MODE_CIS ? iv32(xe, xe + (xe - xs)) : iv32(xs - (xe - xs), xs);
+    const Iv32 B2 = iv32(ys - (ye - ys), ys);
+    int cab, ea, eb, clow, t1, t2;
+    pair_scan(ix.byx, A, B, PA, PB, lane, cab, ea, eb);
+    pair_scan(ix.byx, A2, B2, PA2, PB2, lane, clow, t1, t2);
+    out[0] = ((int64_t)PA.xe - PA.xb) + ((int64_t)PA.ye - PA.yb) - ea;
+    out[1] = ((int64_t)PB.xe - PB.xb) + ((int64_t)PB.ye - PB.yb) - eb;
+    out[2] = ycount_both(PA, PB) + cab;
+    out[3] = ycount_both(PA2, PB2) + clow;
+    *g_bytes += 16 * (pos_max(PA) + pos_max(PB) + pos_max(PA2) + pos_max(PB2)) + 4 * 32 * (long long)ix.lg;
 }
 
-// estAnchorSig counts (callCisLoops.py:226-247): count = |P(l,r)|, wide = |P(max(0, m-5len), m+5len)|
-__device__ void loop_anchor(const IdxView &ix, long long l, long long r, int lane, int64_t *count, int64_t *wide,
-                            long long *g_scan) {
-    long long m4 = 2 * (l + r), len = r - l;
+// estAnchorSig counts of both anchors (callCisLoops.py:226-247): count = |P(l,r)|, wide = |P(max(0, m-5len), m+5len)|
+__device__ void loop_anchors(const IdxView &ix, long long xs, long long xe, long long ys, long long ye, int lane,
+                             int64_t *cx, int64_t *wx, int64_t *cy, int64_t *wy, long long *g_bytes) {
+    // intervals 0..3: anchor x, its wide window, anchor y, its wide window
+    const int k = (lane >> 2) & 3;
+    const long long l = k < 2 ? xs : ys, r = k < 2 ? xe : ye;
+    const long long m4 = 2 * (l + r), len = r - l;
     long long s4 = m4 - 20 * len;
     if (s4 < 0) s4 = 0;
-    Iv I = {l, r};
-    Iv Wd = iv4(s4, m4 + 20 * len);
-    *count = count_peak(ix, I, lane, g_scan);
-    *wide = count_peak(ix, Wd, lane, g_scan);
+    const Iv Wd = iv4(s4, m4 + 20 * len);
+    Iv I;
+    if (k & 1) I = Wd; else { I.lo = l; I.hi = r; }
+    const uint32_t pos = lane < 16 ? bound_task(ix, I.lo, I.hi, (lane >> 1) & 1, lane & 1) : 0u;
+    int64_t res[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const IvPos P = gather_pos(pos, q);
+        const long long il = __shfl_sync(0xffffffffu, I.lo, 4 * q), ih = __shfl_sync(0xffffffffu, I.hi, 4 * q);
+        res[q] = ((int64_t)P.xe - P.xb) + ((int64_t)P.ye - P.yb) - both_scan(ix.byx, iv32(il, ih), P, lane);
+        if (q & 1) *g_bytes += 16 * pos_max(P) + 2 * 32 * (long long)ix.lg;
+    }
+    *cx = res[0]; *wx = res[1]; *cy = res[2]; *wy = res[3];
 }
 
+// transpose of the 32 x 32 bit matrix held one row per lane: afterwards lane t holds column t (bit l = bit t of lane
+// l's word), i.e. the ballot of bit t, for all 32 bits in 5 exchange steps
+__device__ __forceinline__ unsigned warp_transpose32(unsigned x, int lane) {
+#pragma unroll
+    for (int s = 16; s; s >>= 1) {
+        const unsigned m = s == 16 ? 0x0000FFFFu : s == 8 ? 0x00FF00FFu : s == 4 ? 0x0F0F0F0Fu : s == 2 ? 0x33333333u : 0x55555555u;
+        const unsigned y = __shfl_xor_sync(0xffffffffu, x, s);
+        x = (lane & s) ? ((x & ~m) | ((y >> s) & m)) : ((x & m) | ((y << s) & ~m));
+    }
+    return x;
+}
+
+// membership masks of one coordinate in the W windows of a family ({lo, width} pairs in shared memory)
+__device__ __forceinline__ unsigned win_mask(const int2 *__restrict__ w, int W, int c) {
+    unsigned m = 0;
+#pragma unroll
+    for (int t = 0; t < 10; t++) {
+        if (t < W) {
+            const int2 q = w[t];
+            m |= ((unsigned)(c - q.x) <= (unsigned)q.y) ? (1u << t) : 0u;
+        }
+    }
+    return m;
+}
+
+// getPerRegions + getLoopNearbyPETs counts into the warp's accumulator (callCisLoops.py:173-223), W = 2*win <= 10.
+// With ax / ay / bx / by the masks of the a- and b-windows holding a row's x and y (ma = ax | ay, mb = bx | by):
+//     na[i]     = cX(a_i) + cY(a_i) - sum [ax_i and ay_i]
+//     nab[i][j] = cY(a_i & b_j) + sum ([ma_i and mb_j] - [ay_i and by_j])       sums over the rows with x in any window
+// One X-range scan; per batch of 32 rows the three 10-bit fields (ma, mb, ax & ay) and (ay, by, bx & by) are
+// transposed across the warp so that lane t owns the ballot of bit t, and every lane accumulates its share of the
+// W*W pair counters in registers from four shuffled columns -- no shared-memory atomics, no data-dependent loops.
+__device__ void loop_windows10(const IdxView &ix, long long xs, long long xe, long long ys, long long ye, int win, int lane,
+                               WarpAcc &S, long long *g_bytes) {
+    const int W = 2 * win;
+    if (lane < W) {
+        // windows i = -win..-1, 1..win (callCisLoops.py:191-198), all bounds scaled by 4
+        int i = lane < win ? lane - win : lane - win + 1;
+        long long ca4 = 2 * (xs + xe), cb4 = 2 * (ys + ye), sa4 = 2 * (xe - xs), sb4 = 2 * (ye - ys);
+        long long step4 = (xe - xs) + (ye - ys);
+        long long al = ca4 + i * step4 - sa4, ah = ca4 + i * step4 + sa4;
+        long long bl = cb4 + i * step4 - sb4, bh = cb4 + i * step4 + sb4;
+        if (al < 0) al = 0;
+        if (ah < 0) ah = 0;
+        if (bl < 0) bl = 0;
+        if (bh < 0) bh = 0;
+        const Iv a = iv4(al, ah), b = iv4(bl, bh);
+        const Iv32 a32 = iv32(a), b32 = iv32(b);
+        S.aw[lane] = make_int2(a32.lo, (int)a32.wd);
+        S.bw[lane] = make_int2(b32.lo, (int)b32.wd);
+        S.wlo[lane] = a.lo; S.whi[lane] = a.hi;
+        S.wlo[W + lane] = b.lo; S.whi[W + lane] = b.hi;
+    }
+    __syncwarp();
+    // 2W windows x 2 lists x 2 bounds: one search per lane and round
+    for (int t = lane; t < 8 * W; t += 32) {
+        const int w = t >> 2;
+        S.pos[t & 3][w] = bound_task(ix, S.wlo[w], S.whi[w], (t >> 1) & 1, t & 1);
+    }
+    __syncwarp();
+    // X ranges of the two spans (window centres are monotone in i, so are the positions)
+    uint32_t b0 = S.pos[0][0], e0 = S.pos[1][W - 1], b1 = S.pos[0][W], e1 = S.pos[1][2 * W - 1];
+    *g_bytes += 16 * ((long long)max(e0 > b0 ? e0 - b0 : 0u, S.pos[3][W - 1] > S.pos[2][0] ? S.pos[3][W - 1] - S.pos[2][0] : 0u) +
+                      (long long)max(e1 > b1 ? e1 - b1 : 0u, S.pos[3][2 * W - 1] > S.pos[2][W] ? S.pos[3][2 * W - 1] - S.pos[2][W] : 0u)) +
+                (2 * W + 1) * 32 * (long long)ix.lg;
+    if (e0 < b0) e0 = b0;
+    if (e1 < b1) e1 = b1;
+    if (b0 <= e1 && b1 <= e0) {
+        b0 = b0 < b1 ? b0 : b1;
+        e0 = e0 > e1 ? e0 : e1;
+        b1 = e1 = 0;
+    }
+    // this lane's pairs: lane + 32 g, a-major
+    int pi[4], pj[4];
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        const int pr = lane + 32 * g;
+        pi[g] = pr < W * W ? pr / W : 0;
+        pj[g] = pr < W * W ? 10 + pr % W : 10;
+    }
+    int acc[4] = {0, 0, 0, 0};
+    int e_a = 0, e_b = 0;                // lanes 20 .. 20+W-1: sum [ax_i and ay_i], sum [bx_j and by_j]
+    const int2 *__restrict__ byx = ix.byx;
+#pragma unroll 1
+    for (int rr = 0; rr < 2; rr++) {
+        const uint32_t rb = rr ? b1 : b0, re = rr ? e1 : e0;
+        int2 pnext = (rb + lane < re) ? byx[rb + lane] : make_int2(-1, -1);
+        for (uint32_t p0 = rb; p0 < re; p0 += 32) {
+            const int2 P = pnext;                            // (-1, -1) beyond the range: in no window
+            pnext = (p0 + 32 + lane < re) ? byx[p0 + 32 + lane] : make_int2(-1, -1);
+            const unsigned ax = win_mask(S.aw, W, P.x), ay = win_mask(S.aw, W, P.y);
+            const unsigned bx = win_mask(S.bw, W, P.x), by = win_mask(S.bw, W, P.y);
+            const unsigned w1 = (ax | ay) | ((bx | by) << 10) | ((ax & ay) << 20);
+            if (!__any_sync(0xffffffffu, w1 != 0)) continue; // rows in the gaps between windows
+            const unsigned w2 = ay | (by << 10) | ((bx & by) << 20);
+            const unsigned c1 = warp_transpose32(w1, lane), c2 = warp_transpose32(w2, lane);
+            e_a += __popc(c1);                               // meaningful in lanes 20..29 only
+            e_b += __popc(c2);
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                const unsigned A = __shfl_sync(0xffffffffu, c1, pi[g]), B = __shfl_sync(0xffffffffu, c1, pj[g]);
+                const unsigned C = __shfl_sync(0xffffffffu, c2, pi[g]), D = __shfl_sync(0xffffffffu, c2, pj[g]);
+                acc[g] += __popc(A & B & ~(C & D));
+            }
+        }
+    }
+    const int src = 20 + (lane < W ? lane : 0);
+    const int ea_i = __shfl_sync(0xffffffffu, e_a, src), eb_i = __shfl_sync(0xffffffffu, e_b, src);
+    if (lane < W) {
+        S.na[lane] = (int)(((long long)S.pos[1][lane] - S.pos[0][lane]) + ((long long)S.pos[3][lane] - S.pos[2][lane]) - ea_i);
+        S.nb[lane] = (int)(((long long)S.pos[1][W + lane] - S.pos[0][W + lane]) +
+                           ((long long)S.pos[3][W + lane] - S.pos[2][W + lane]) - eb_i);
+    }
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        const int pr = lane + 32 * g;
+        if (pr < W * W) {
+            const int i = pi[g], j = W + (pj[g] - 10);
+            const uint32_t yb = S.pos[2][i] > S.pos[2][j] ? S.pos[2][i] : S.pos[2][j];
+            const uint32_t ye_ = S.pos[3][i] < S.pos[3][j] ? S.pos[3][i] : S.pos[3][j];
+            S.nab[pr] = acc[g] + (ye_ > yb ? (int)(ye_ - yb) : 0);
+        }
+    }
+    __syncwarp();
+}
+
+// ---- the same counts for 2*win > 10 (up to 16): four range scans with de-duplication --------------------------
 // getPerRegions + getLoopNearbyPETs counts into the warp's accumulator (callCisLoops.py:173-223)
-__device__ void loop_windows(const IdxView &ix, long long xs, long long xe, long long ys, long long ye, int win, int lane,
-                             WarpAcc &S, long long *g_scan) {
+__device__ void loop_windows_wide(const IdxView &ix, long long xs, long long xe, long long ys, long long ye, int win, int lane,
+                             WarpAcc &S, long long *g_bytes) {
     const int W = 2 * win;
     for (int t = lane; t < W * W; t += 32) S.nab[t] = 0;
     long long a_lo = 0, a_hi = -1, b_lo = 0, b_hi = -1;
@@ -401,7 +613,10 @@ __device__ void loop_windows(const IdxView &ix, long long xs, long long xe, long
     __syncwarp();
     Range rxa = range_of(arr_x(ix), ix.n, SA, lane), rya = range_of(arr_y(ix), ix.n, SA, lane);
     Range rxb = range_of(arr_x(ix), ix.n, SB, lane), ryb = range_of(arr_y(ix), ix.n, SB, lane);
-    *g_scan += (rxa.e - rxa.b) + (rya.e - rya.b) + (rxb.e - rxb.b) + (ryb.e - ryb.b);
+    {
+        const long long ma_ = max(rxa.e - rxa.b, rya.e - rya.b), mb_ = max(rxb.e - rxb.b, ryb.e - ryb.b);
+        *g_bytes += 16 * (ma_ + mb_) + (2 * W + 1) * 32 * (long long)ix.lg;
+    }
     // four lists; a PET is handled by the first list that contains it.  Each list is sorted by the coordinate that put
     // the PET into it ("primary": x for the X-sorted lists, y for the Y-sorted ones), so the 32 PETs of a batch can
     // only fall into the few windows [t_lo, t_hi] that meet [first, last] of the batch -- found with two ballots over
@@ -458,6 +673,12 @@ __device__ void loop_windows(const IdxView &ix, long long xs, long long xe, long
     __syncwarp();
 }
 
+__device__ __forceinline__ void loop_windows(const IdxView &ix, long long xs, long long xe, long long ys, long long ye,
+                                             int win, int lane, WarpAcc &S, long long *g_bytes) {
+    if (2 * win <= 10) loop_windows10(ix, xs, xe, ys, ye, win, lane, S, g_bytes);
+    else loop_windows_wide(ix, xs, xe, ys, ye, win, lane, S, g_bytes);
+}
+
 // ---- raw counts (cl2_loop_counts) ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(CNT_WARPS * 32) k_loop_counts(const IdxView ix, const longlong4 *__restrict__ loops, int64_t L,
                                                                  int win, int mode, long long *__restrict__ core,
@@ -477,11 +698,9 @@ __global__ void __launch_bounds__(CNT_WARPS * 32) k_loop_counts(const IdxView ix
         if (lane == 0) { core[4 * k] = c[0]; core[4 * k + 1] = c[1]; core[4 * k + 2] = c[2]; core[4 * k + 3] = c[3]; }
     }
     if (anchors) {
-        for (int a = 0; a < 2; a++) {
-            int64_t c, wd;
-            loop_anchor(ix, a == 0 ? xs : ys, a == 0 ? xe : ye, lane, &c, &wd, &scanned);
-            if (lane == 0) { anchors[4 * k + 2 * a] = c; anchors[4 * k + 2 * a + 1] = wd; }
-        }
+        int64_t cx, wx, cy, wy;
+        loop_anchors(ix, xs, xe, ys, ye, lane, &cx, &wx, &cy, &wy, &scanned);
+        if (lane == 0) { anchors[4 * k] = cx; anchors[4 * k + 1] = wx; anchors[4 * k + 2] = cy; anchors[4 * k + 3] = wy; }
     }
     if (na_out || nb_out || nab_out) {
         const int W = 2 * win;
@@ -645,8 +864,7 @@ __device__ void loop_tail(const IdxView &ix, long long xs,
                           long long xe, long long ys, long long ye, double ra, double rb, double rab, double mrabs,
                           double mbps, int mode, double rpb, int lane, double *o, long long *g_scan) {
     int64_t cx, wx, cy, wy;
-    loop_anchor(ix, xs, xe, lane, &cx, &wx, g_scan);
-    loop_anchor(ix, ys, ye, lane, &cy, &wy, g_scan);
+    loop_anchors(ix, xs, xe, ys, ye, lane, &cx, &wx, &cy, &wy, g_scan);
     if (lane == 0) {
         o[3] = cl2_poisson_sf_ge(rab, mrabs);                                            // :329
         o[9] = (double)cx; o[10] = (double)wx; o[11] = (double)cy; o[12] = (double)wy;
@@ -754,8 +972,7 @@ __global__ void __launch_bounds__(CNT_WARPS * 32) k_est_anchor(const IdxView ix,
     long long scanned = 0;
     const longlong4 lp = loops[sel[i]];
     int64_t cx, wx, cy, wy;
-    loop_anchor(ix, lp.x, lp.y, lane, &cx, &wx, &scanned);
-    loop_anchor(ix, lp.z, lp.w, lane, &cy, &wy, &scanned);
+    loop_anchors(ix, lp.x, lp.y, lp.z, lp.w, lane, &cx, &wx, &cy, &wy, &scanned);
     if (lane == 0) {
         double *o = stats + CL2_NSTAT * i;
         o[9] = (double)cx; o[10] = (double)wx; o[11] = (double)cy; o[12] = (double)wy;
@@ -989,10 +1206,11 @@ extern "C" int cl2_est_loops(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops,
         CL2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     if (ctx->timing) {
-        // algorithmic traffic of the counting launches: 16 B per scanned member on the reference layout
-        int64_t scanned = 0;
-        CL2_TRY(cl2_read_i64(ctx, d_total + 1, &scanned));
-        ctx->fam_bytes[FAM_COUNT] += 16.0 * (double)scanned + 32.0 * (double)L;
+        // algorithmic bytes of the counting launches, summed by the kernels per candidate (16 B per
+        // member of every queried region + the binary searches) + the candidate rows themselves
+        int64_t abytes = 0;
+        CL2_TRY(cl2_read_i64(ctx, d_total + 1, &abytes));
+        ctx->fam_bytes[FAM_COUNT] += (double)abytes + 32.0 * (double)L;
     }
     CL2_CUDA(ctx, cudaGetLastError());
     // rows that failed kernel B's cuts are dropped here (few rows: kernel A already removed ~95 % of the candidates)

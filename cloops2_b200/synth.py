@@ -23,6 +23,7 @@ HG38_TOTAL = sum(l for _, l in HG38)
 PROFILES = {
     # name: d_min, sigma range, PETs per loop range, loops per PET
     "hitrac": dict(d_min=100, sigma=(150, 300), npl=(10, 80), per=5000),
+    "c1": dict(d_min=100, sigma=(150, 150), npl=(10, 80), per=5000),      # SURVEY.md 8d C1' (chr21 stand-in)
     "hic": dict(d_min=1000, sigma=(2000, 5000), npl=(40, 400), per=5000),
     "chiapet": dict(d_min=1000, sigma=(500, 500), npl=(10, 80), per=5000),
 }
