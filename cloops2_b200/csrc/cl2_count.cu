@@ -11,6 +11,7 @@
 #include "cl2_points.cuh"
 #include "cl2_stats.cuh"
 #include <math_constants.h>
+#include <stdlib.h>
 
 // ------------------------------------------------------------------------------------------------ index build
 __global__ void __launch_bounds__(256) k_index_gather(const int2 *__restrict__ xy, const uint32_t *__restrict__ row,
@@ -83,6 +84,7 @@ extern "C" int cl2_index_build(cl2_ctx *ctx, cl2_points *pts, cl2_index **out) {
     if (!ix) return CL2_ERR_NOMEM;
     const int64_t n = pts->n;
     ix->n = n;
+    ix->small = (pts->ext[1] < (1ll << 29) && pts->ext[3] < (1ll << 29)) ? 1 : 0;
     int rc = CL2_OK;
     if (n > 0) {
         Scratch sc(ctx);
@@ -150,6 +152,7 @@ struct IdxView {
     int64_t n;
     int sx, sy, nbx, nby;
     int lg;               // ceil(log2 n): depth of one binary search in SURVEY.md 8d's byte count
+    int small;            // every coordinate is below 2^29 (4 * c fits an int: closed-form window masks)
 };
 struct Arr {
     const int2 *a;
@@ -157,7 +160,7 @@ struct Arr {
     int shift, nb;
 };
 static IdxView cl2_view(const cl2_index *idx) {
-    IdxView v = {idx->byx, idx->byy, idx->tx, idx->ty, idx->n, idx->sx, idx->sy, idx->nbx, idx->nby, 1};
+    IdxView v = {idx->byx, idx->byy, idx->tx, idx->ty, idx->n, idx->sx, idx->sy, idx->nbx, idx->nby, 1, idx->small};
     while (((int64_t)1 << v.lg) < idx->n) v.lg++;
     return v;
 }
@@ -476,6 +479,31 @@ __device__ __forceinline__ unsigned win_mask(const int2 *__restrict__ w, int W, 
     }
     return m;
 }
+// The same mask in closed form.  The windows of a family are regular: window k (k = 0..2*win, k = win being the
+// anchor itself, which is not a window) covers base4 + k*s4 <= 4c <= base4 + k*s4 + w2, so with t = 4c - base4 the
+// windows holding c are k = ceil((t - w2) / s4) .. floor(t / s4); the two quotients come from a multiply-shift by the
+// reciprocal of s4 (exact for numerators below 2^31).  Valid when no window was clipped at 0 on its upper end
+// (callCisLoops.py:193-196 clips to max(0, .), which turns such a window into [0, 0]), coordinates stay below 2^29 and
+// the family spans less than 2^30 quarter base pairs; otherwise win_mask() is used.
+struct FamDiv {
+    int base4;
+    unsigned tmax, w2;
+};
+struct WinDiv {
+    FamDiv a, b;
+    unsigned s4m1, magic, valid11, lowmask;
+    int shift, win;
+};
+__device__ __forceinline__ unsigned div_mask(const FamDiv &F, const WinDiv &D, int c) {
+    const unsigned t = (unsigned)(4 * c - F.base4);
+    const unsigned khi = (unsigned)(((unsigned long long)t * D.magic) >> D.shift);
+    int u = (int)(t - F.w2 + D.s4m1);
+    u = u < 0 ? 0 : u;
+    const unsigned klo = (unsigned)(((unsigned long long)(unsigned)u * D.magic) >> D.shift);
+    unsigned m = ((2u << (khi & 31u)) - 1u) & (0xFFFFFFFFu << (klo & 31u)) & D.valid11;
+    m = t <= F.tmax ? m : 0u;
+    return (m & D.lowmask) | ((m >> (D.win + 1)) << D.win);
+}
 
 // getPerRegions + getLoopNearbyPETs counts into the warp's accumulator (callCisLoops.py:173-223), W = 2*win <= 10.
 // With ax / ay / bx / by the masks of the a- and b-windows holding a row's x and y (ma = ax | ay, mb = bx | by):
@@ -483,27 +511,51 @@ __device__ __forceinline__ unsigned win_mask(const int2 *__restrict__ w, int W, 
 //     nab[i][j] = cY(a_i & b_j) + sum ([ma_i and mb_j] - [ay_i and by_j])       sums over the rows with x in any window
 // One X-range scan; per batch of 32 rows the three 10-bit fields (ma, mb, ax & ay) and (ay, by, bx & by) are
 // transposed across the warp so that lane t owns the ballot of bit t, and every lane accumulates its share of the
-// W*W pair counters in registers from four shuffled columns -- no shared-memory atomics, no data-dependent loops.
-__device__ void loop_windows10(const IdxView &ix, long long xs, long long xe, long long ys, long long ye, int win, int lane,
-                               WarpAcc &S, long long *g_bytes) {
+// W*W pair counters in registers from shuffled columns -- no shared-memory atomics, no data-dependent loops.
+// fdr_stop > 0: the scan may stop as soon as fdr_stop window pairs are known to hold more than `rab` rows (the
+// counters only grow), which decides the reference's `fdr >= 0.1` cut (callCisLoops.py:322); returns false then.
+__device__ bool loop_windows10(const IdxView &ix, long long xs, long long xe, long long ys, long long ye, int win, int lane,
+                               WarpAcc &S, long long *g_bytes, int fdr_stop = 0, long long rab = 0) {
     const int W = 2 * win;
-    if (lane < W) {
-        // windows i = -win..-1, 1..win (callCisLoops.py:191-198), all bounds scaled by 4
-        int i = lane < win ? lane - win : lane - win + 1;
-        long long ca4 = 2 * (xs + xe), cb4 = 2 * (ys + ye), sa4 = 2 * (xe - xs), sb4 = 2 * (ye - ys);
-        long long step4 = (xe - xs) + (ye - ys);
-        long long al = ca4 + i * step4 - sa4, ah = ca4 + i * step4 + sa4;
-        long long bl = cb4 + i * step4 - sb4, bh = cb4 + i * step4 + sb4;
-        if (al < 0) al = 0;
-        if (ah < 0) ah = 0;
-        if (bl < 0) bl = 0;
-        if (bh < 0) bh = 0;
-        const Iv a = iv4(al, ah), b = iv4(bl, bh);
-        const Iv32 a32 = iv32(a), b32 = iv32(b);
-        S.aw[lane] = make_int2(a32.lo, (int)a32.wd);
-        S.bw[lane] = make_int2(b32.lo, (int)b32.wd);
-        S.wlo[lane] = a.lo; S.whi[lane] = a.hi;
-        S.wlo[W + lane] = b.lo; S.whi[W + lane] = b.hi;
+    bool regular = ix.small != 0;
+    WinDiv D;
+    {
+        const long long ca4 = 2 * (xs + xe), cb4 = 2 * (ys + ye), sa4 = 2 * (xe - xs), sb4 = 2 * (ye - ys);
+        const long long step4 = (xe - xs) + (ye - ys);
+        if (lane < W) {
+            // windows i = -win..-1, 1..win (callCisLoops.py:191-198), all bounds scaled by 4
+            const int i = lane < win ? lane - win : lane - win + 1;
+            long long al = ca4 + i * step4 - sa4, ah = ca4 + i * step4 + sa4;
+            long long bl = cb4 + i * step4 - sb4, bh = cb4 + i * step4 + sb4;
+            if (al < 0) al = 0;
+            if (ah < 0) ah = 0;
+            if (bl < 0) bl = 0;
+            if (bh < 0) bh = 0;
+            const Iv a = iv4(al, ah), b = iv4(bl, bh);
+            const Iv32 a32 = iv32(a), b32 = iv32(b);
+            S.aw[lane] = make_int2(a32.lo, (int)a32.wd);
+            S.bw[lane] = make_int2(b32.lo, (int)b32.wd);
+            S.wlo[lane] = a.lo; S.whi[lane] = a.hi;
+            S.wlo[W + lane] = b.lo; S.whi[W + lane] = b.hi;
+        }
+        // closed-form masks: every lane derives the same family parameters
+        const long long basea = ca4 - win * step4 - sa4, baseb = cb4 - win * step4 - sb4;
+        const long long tmaxa = 2 * win * step4 + 2 * sa4, tmaxb = 2 * win * step4 + 2 * sb4;
+        const long long lim = 1ll << 30;
+        if (step4 < 1 || step4 >= lim || basea + 2 * sa4 < 0 || baseb + 2 * sb4 < 0 || basea <= -lim || baseb <= -lim ||
+            basea >= lim || baseb >= lim || tmaxa >= lim || tmaxb >= lim)
+            regular = false;
+        D.a.base4 = (int)basea; D.a.tmax = (unsigned)tmaxa; D.a.w2 = (unsigned)(2 * sa4);
+        D.b.base4 = (int)baseb; D.b.tmax = (unsigned)tmaxb; D.b.w2 = (unsigned)(2 * sb4);
+        const unsigned d = (unsigned)(step4 < 1 ? 1 : (step4 >= lim ? 1 : step4));
+        int l = 0;
+        while ((1u << l) < d) l++;                           // d < 2^30
+        D.shift = 31 + l;
+        D.magic = (unsigned)(((1ull << (31 + l)) + d - 1) / d);
+        D.s4m1 = d - 1;
+        D.win = win;
+        D.lowmask = (1u << win) - 1u;
+        D.valid11 = ((2u << (2 * win)) - 1u) & ~(1u << win);
     }
     __syncwarp();
     // 2W windows x 2 lists x 2 bounds: one search per lane and round
@@ -514,9 +566,9 @@ __device__ void loop_windows10(const IdxView &ix, long long xs, long long xe, lo
     __syncwarp();
     // X ranges of the two spans (window centres are monotone in i, so are the positions)
     uint32_t b0 = S.pos[0][0], e0 = S.pos[1][W - 1], b1 = S.pos[0][W], e1 = S.pos[1][2 * W - 1];
-    *g_bytes += 16 * ((long long)max(e0 > b0 ? e0 - b0 : 0u, S.pos[3][W - 1] > S.pos[2][0] ? S.pos[3][W - 1] - S.pos[2][0] : 0u) +
-                      (long long)max(e1 > b1 ? e1 - b1 : 0u, S.pos[3][2 * W - 1] > S.pos[2][W] ? S.pos[3][2 * W - 1] - S.pos[2][W] : 0u)) +
-                (2 * W + 1) * 32 * (long long)ix.lg;
+    const long long span_rows = (long long)max(e0 > b0 ? e0 - b0 : 0u, S.pos[3][W - 1] > S.pos[2][0] ? S.pos[3][W - 1] - S.pos[2][0] : 0u) +
+                                (long long)max(e1 > b1 ? e1 - b1 : 0u, S.pos[3][2 * W - 1] > S.pos[2][W] ? S.pos[3][2 * W - 1] - S.pos[2][W] : 0u);
+    *g_bytes += (2 * W + 1) * 32 * (long long)ix.lg;
     if (e0 < b0) e0 = b0;
     if (e1 < b1) e1 = b1;
     if (b0 <= e1 && b1 <= e0) {
@@ -524,40 +576,76 @@ __device__ void loop_windows10(const IdxView &ix, long long xs, long long xe, lo
         e0 = e0 > e1 ? e0 : e1;
         b1 = e1 = 0;
     }
-    // this lane's pairs: lane + 32 g, a-major
-    int pi[4], pj[4];
+    const long long scan_rows = (long long)(e0 - b0) + (long long)(e1 - b1);
+    // this lane's pairs: lanes 0..29 own a-window lane / 3 and up to four b-windows from 4 * (lane % 3)
+    const int pi = lane / 3, pj0 = 4 * (lane - 3 * pi);
+    const bool own = lane < 30 && pi < W;
+    int cy[4];                           // cY(a_i & b_j) of the lane's pairs
 #pragma unroll
-    for (int g = 0; g < 4; g++) {
-        const int pr = lane + 32 * g;
-        pi[g] = pr < W * W ? pr / W : 0;
-        pj[g] = pr < W * W ? 10 + pr % W : 10;
+    for (int q = 0; q < 4; q++) {
+        cy[q] = 0;
+        if (own && pj0 + q < W) {
+            const int i = pi, j = W + pj0 + q;
+            const uint32_t yb = S.pos[2][i] > S.pos[2][j] ? S.pos[2][i] : S.pos[2][j];
+            const uint32_t ye_ = S.pos[3][i] < S.pos[3][j] ? S.pos[3][i] : S.pos[3][j];
+            cy[q] = ye_ > yb ? (int)(ye_ - yb) : 0;
+        }
     }
+    const int srca = own ? pi : 0;
     int acc[4] = {0, 0, 0, 0};
     int e_a = 0, e_b = 0;                // lanes 20 .. 20+W-1: sum [ax_i and ay_i], sum [bx_j and by_j]
     const int2 *__restrict__ byx = ix.byx;
+    bool stopped = false;
+    long long done_rows = 0;
 #pragma unroll 1
-    for (int rr = 0; rr < 2; rr++) {
+    for (int rr = 0; rr < 2 && !stopped; rr++) {
         const uint32_t rb = rr ? b1 : b0, re = rr ? e1 : e0;
-        int2 pnext = (rb + lane < re) ? byx[rb + lane] : make_int2(-1, -1);
+        int2 pnext = (rb + lane < re) ? byx[rb + lane] : make_int2(0, 0);
+        int since = 0;
         for (uint32_t p0 = rb; p0 < re; p0 += 32) {
-            const int2 P = pnext;                            // (-1, -1) beyond the range: in no window
-            pnext = (p0 + 32 + lane < re) ? byx[p0 + 32 + lane] : make_int2(-1, -1);
-            const unsigned ax = win_mask(S.aw, W, P.x), ay = win_mask(S.aw, W, P.y);
-            const unsigned bx = win_mask(S.bw, W, P.x), by = win_mask(S.bw, W, P.y);
-            const unsigned w1 = (ax | ay) | ((bx | by) << 10) | ((ax & ay) << 20);
+            const bool valid = p0 + lane < re;
+            const int2 P = pnext;
+            pnext = (p0 + 32 + lane < re) ? byx[p0 + 32 + lane] : make_int2(0, 0);
+            unsigned ax, ay, bx, by;
+            if (regular) {
+                ax = div_mask(D.a, D, P.x); ay = div_mask(D.a, D, P.y);
+                bx = div_mask(D.b, D, P.x); by = div_mask(D.b, D, P.y);
+            } else {
+                ax = win_mask(S.aw, W, P.x); ay = win_mask(S.aw, W, P.y);
+                bx = win_mask(S.bw, W, P.x); by = win_mask(S.bw, W, P.y);
+            }
+            unsigned w1 = (ax | ay) | ((bx | by) << 10) | ((ax & ay) << 20);
+            w1 = valid ? w1 : 0u;
             if (!__any_sync(0xffffffffu, w1 != 0)) continue; // rows in the gaps between windows
-            const unsigned w2 = ay | (by << 10) | ((bx & by) << 20);
+            unsigned w2 = ay | (by << 10) | ((bx & by) << 20);
+            w2 = valid ? w2 : 0u;
             const unsigned c1 = warp_transpose32(w1, lane), c2 = warp_transpose32(w2, lane);
             e_a += __popc(c1);                               // meaningful in lanes 20..29 only
             e_b += __popc(c2);
+            const unsigned A = __shfl_sync(0xffffffffu, c1, srca), C = __shfl_sync(0xffffffffu, c2, srca);
 #pragma unroll
-            for (int g = 0; g < 4; g++) {
-                const unsigned A = __shfl_sync(0xffffffffu, c1, pi[g]), B = __shfl_sync(0xffffffffu, c1, pj[g]);
-                const unsigned C = __shfl_sync(0xffffffffu, c2, pi[g]), D = __shfl_sync(0xffffffffu, c2, pj[g]);
-                acc[g] += __popc(A & B & ~(C & D));
+            for (int q = 0; q < 4; q++) {
+                const int sj = 10 + ((pj0 + q) < 10 ? pj0 + q : 9);
+                const unsigned B = __shfl_sync(0xffffffffu, c1, sj), Dd = __shfl_sync(0xffffffffu, c2, sj);
+                acc[q] += __popc(A & B & ~(C & Dd));
+            }
+            if (fdr_stop > 0 && ++since == 4) {
+                since = 0;
+                int over = 0;
+#pragma unroll
+                for (int q = 0; q < 4; q++) over += (own && pj0 + q < W && (long long)acc[q] + cy[q] > rab) ? 1 : 0;
+                if (warp_sum(over) >= fdr_stop) {
+                    stopped = true;
+                    done_rows += (long long)(p0 + 32 - rb);
+                    break;
+                }
             }
         }
+        if (!stopped) done_rows += (long long)(re - rb);
     }
+    // rows of the regions actually needed: all of them, or the part scanned before the fdr cut was decided
+    *g_bytes += 16 * (stopped && scan_rows > 0 ? (span_rows * done_rows) / scan_rows : span_rows);
+    if (stopped) return false;
     const int src = 20 + (lane < W ? lane : 0);
     const int ea_i = __shfl_sync(0xffffffffu, e_a, src), eb_i = __shfl_sync(0xffffffffu, e_b, src);
     if (lane < W) {
@@ -566,16 +654,10 @@ __device__ void loop_windows10(const IdxView &ix, long long xs, long long xe, lo
                            ((long long)S.pos[3][W + lane] - S.pos[2][W + lane]) - eb_i);
     }
 #pragma unroll
-    for (int g = 0; g < 4; g++) {
-        const int pr = lane + 32 * g;
-        if (pr < W * W) {
-            const int i = pi[g], j = W + (pj[g] - 10);
-            const uint32_t yb = S.pos[2][i] > S.pos[2][j] ? S.pos[2][i] : S.pos[2][j];
-            const uint32_t ye_ = S.pos[3][i] < S.pos[3][j] ? S.pos[3][i] : S.pos[3][j];
-            S.nab[pr] = acc[g] + (ye_ > yb ? (int)(ye_ - yb) : 0);
-        }
-    }
+    for (int q = 0; q < 4; q++)
+        if (own && pj0 + q < W) S.nab[pi * W + pj0 + q] = acc[q] + cy[q];
     __syncwarp();
+    return true;
 }
 
 // ---- the same counts for 2*win > 10 (up to 16): four range scans with de-duplication --------------------------
@@ -673,10 +755,12 @@ __device__ void loop_windows_wide(const IdxView &ix, long long xs, long long xe,
     __syncwarp();
 }
 
-__device__ __forceinline__ void loop_windows(const IdxView &ix, long long xs, long long xe, long long ys, long long ye,
-                                             int win, int lane, WarpAcc &S, long long *g_bytes) {
-    if (2 * win <= 10) loop_windows10(ix, xs, xe, ys, ye, win, lane, S, g_bytes);
-    else loop_windows_wide(ix, xs, xe, ys, ye, win, lane, S, g_bytes);
+__device__ __forceinline__ bool loop_windows(const IdxView &ix, long long xs, long long xe, long long ys, long long ye,
+                                             int win, int lane, WarpAcc &S, long long *g_bytes, int fdr_stop = 0,
+                                             long long rab = 0) {
+    if (2 * win <= 10) return loop_windows10(ix, xs, xe, ys, ye, win, lane, S, g_bytes, fdr_stop, rab);
+    loop_windows_wide(ix, xs, xe, ys, ye, win, lane, S, g_bytes);
+    return true;
 }
 
 // ---- raw counts (cl2_loop_counts) ---------------------------------------------------------------------------
@@ -813,7 +897,14 @@ __device__ bool loop_background(const IdxView &ix, long long xs,
                                 WarpVals &V, int lane, double early_cut, double *o_mrabs, double *o_mbps,
                                 double *o_fdr, long long *g_scan) {
     const int W = 2 * win, m = W * W;
-    loop_windows(ix, xs, xe, ys, ye, win, lane, S, g_scan);
+    // smallest number of window pairs above rab that makes fdr = gt / m >= 0.1 (the comparison the reference makes)
+    int fdr_stop = 0;
+    if (early_cut > 0) {
+        fdr_stop = m / 10;
+        while ((double)fdr_stop / (double)m < 0.1) fdr_stop++;
+        while (fdr_stop > 1 && (double)(fdr_stop - 1) / (double)m >= 0.1) fdr_stop--;
+    }
+    if (!loop_windows(ix, xs, xe, ys, ye, win, lane, S, g_scan, fdr_stop, (long long)rab)) return false;
     // rabs: counts of the 4*win^2 window pairs; fdr = #{rabs > rab} / m
     int gt = 0, nzero = 0;
     for (int t = lane; t < m; t += 32) {
@@ -915,7 +1006,8 @@ __global__ void __launch_bounds__(CNT_WARPS * 32) k_loop_tests(const IdxView ix,
 // 127-139), the permuted-window background and, for cis, the background cut (:322-327).  Survivors get flag = 1 and
 // core[4], stats[0..2] = mrabs, mbps, fdr.  The hypergeometric cut (:311) is applied by kernel B: the cascade is a
 // conjunction, so the order of the tests does not change which candidates survive.
-__global__ void __launch_bounds__(CNT_WARPS * 32, 4) k_est_bg(const IdxView ix, const longlong4 *__restrict__ loops, int64_t L,
+template <int MINB>
+__global__ void __launch_bounds__(CNT_WARPS * 32, MINB) k_est_bg(const IdxView ix, const longlong4 *__restrict__ loops, int64_t L,
                                                             int win, int mode, int minPts, int hic, double cdc,
                                                             double pseudo, long long *__restrict__ core_out,
                                                             double *__restrict__ stats_out, int32_t *__restrict__ flag,
@@ -1165,9 +1257,11 @@ extern "C" int cl2_est_loops(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops,
     ctx->h2d_bytes += L * 32;
     {
         FamTimer t(ctx, FAM_COUNT, 0.0);
-        k_est_bg<<<cl2_grid(L, CNT_WARPS), CNT_WARPS * 32, 0, ctx->stream>>>(cl2_view(idx), d_loops, L, win, mode,
-                                                                             minPts, hic, countDiffCut, pseudo, d_core, d_stats,
-                                                                             d_flag, (unsigned long long *)(d_total + 1));
+        static const int occ = getenv("CL2_EST_OCC") ? atoi(getenv("CL2_EST_OCC")) : 4;
+        auto kern = occ == 3 ? k_est_bg<3> : (occ == 2 ? k_est_bg<2> : k_est_bg<4>);
+        kern<<<cl2_grid(L, CNT_WARPS), CNT_WARPS * 32, 0, ctx->stream>>>(cl2_view(idx), d_loops, L, win, mode, minPts, hic,
+                                                                         countDiffCut, pseudo, d_core, d_stats, d_flag,
+                                                                         (unsigned long long *)(d_total + 1));
     }
     CL2_TRY(cl2_exclusive_scan_i32(ctx, d_flag, L, d_total));
     int64_t nk = 0;

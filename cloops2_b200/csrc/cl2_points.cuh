@@ -61,6 +61,7 @@ struct cl2_index {
     // bucket tables over the sorted coordinate (cl2_count.cu): t[b] = first position with coordinate >= b << shift
     uint32_t *tx = nullptr, *ty = nullptr;
     int sx = 0, sy = 0, nbx = 0, nby = 0;
+    int small = 0;        // every coordinate < 2^29
 };
 
 void cl2_grid_free(cl2_ctx *ctx, cl2_grid_cache &g);
