@@ -14,7 +14,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.path.join(_HERE, "libcl2.so")
-SOURCES = ["cl2_api.cu", "cl2_sort.cu", "cl2_block.cu", "cl2_cdbscan.cu", "cl2_count.cu", "cl2_host.cu", "cl2_pre.cu"]
+SOURCES = ["cl2_api.cu", "cl2_sort.cu", "cl2_block.cu", "cl2_cdbscan.cu", "cl2_count.cu", "cl2_driver.cu", "cl2_host.cu",
+           "cl2_pre.cu"]
 HEADERS = ["cl2_common.cuh", "cl2_points.cuh", "cl2_stats.cuh", os.path.join("..", "..", "include", "cl2.h")]
 # -fmad=false: no FMA contraction, so the fp64 statistics give the same bits in every kernel they are inlined into
 # (and the same bits as the host build of cl2_stats.cuh); the path is integer / bandwidth work, nothing is lost.
@@ -107,6 +108,14 @@ SIGNATURES = {
     "cl2_est_loops": (ctypes.c_int, [_vp, _vp, _i64p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                      ctypes.c_int32, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                      _i64p, _i64p, _i64p, _f64p, _f64p]),
+    "cl2_set_pvalue_margin": (ctypes.c_int, [_vp, ctypes.c_double]),
+    "cl2_call_loops": (ctypes.c_int, [_vp, _vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _i64p, _i32p, ctypes.c_int64,
+                                      ctypes.c_int32, ctypes.c_int32, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                      ctypes.c_int32, ctypes.POINTER(_vp)]),
+    "cl2_loops_count": (ctypes.c_int64, [_vp]),
+    "cl2_loops_info": (ctypes.c_int, [_vp, _i64p, _i64p, _i64p, _f64p]),
+    "cl2_loops_read": (ctypes.c_int, [_vp, _i64p, _i32p, _i64p, _f64p, _f64p]),
+    "cl2_loops_free": (None, [_vp]),
     "cl2_sel_sig_loops": (ctypes.c_int, [_i64p, _f64p, ctypes.c_int64, _i64p, _i64p]),
     "cl2_stat_poisson_sf": (ctypes.c_double, [ctypes.c_double, ctypes.c_double]),
     "cl2_stat_binom_sf": (ctypes.c_double, [ctypes.c_double, ctypes.c_double, ctypes.c_double]),
@@ -174,6 +183,10 @@ class Context:
     def sync(self):
         self.check(self.lib.cl2_ctx_sync(self.h), "cl2_ctx_sync")
 
+    def set_pvalue_margin(self, margin):
+        """Widen the device-side p-value cuts by 1 + margin (cl2_set_pvalue_margin)."""
+        self.check(self.lib.cl2_set_pvalue_margin(self.h, float(margin)), "cl2_set_pvalue_margin")
+
     # ---- pinned host staging
     def pinned_empty(self, shape, dtype=np.int64):
         """numpy array backed by page-locked memory (freed with the returned array's owner)."""
@@ -188,6 +201,17 @@ class Context:
         arr = arr.view(_PinnedArray)
         arr._owner = owner
         return arr
+
+    def staging(self, shape, dtype=np.int64):
+        """A view of this context's grow-only page-locked staging buffer (one per worker; reused between files)."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape))
+        nbytes = max(1, n * dtype.itemsize)
+        buf = getattr(self, "_staging", None)
+        if buf is None or buf.nbytes < nbytes:
+            self._staging = None
+            buf = self._staging = self.pinned_empty(nbytes + nbytes // 8, np.uint8)
+        return buf[:n * dtype.itemsize].view(dtype).reshape(shape)
 
     # ---- measurement
     def launch_count(self):
@@ -325,6 +349,35 @@ class Points:
             self.ctx.check(self.ctx.lib.cl2_cluster_bbox(self.ctx.h, self.h, _ptr(bbox, _i64p), _ptr(size, _i64p)),
                            "cl2_cluster_bbox")
         return bbox, size
+
+    def call_loops(self, passes, mode=MODE_CIS, hic=False, cut=0, min_pts_test=5, win=5, countDiffCut=20, pseudo=1,
+                   peakPcut=1e-5, want_unique=False):
+        """The whole per-file work unit in one native call (cl2_call_loops): every clustering run of `passes`
+        [(eps, minPts), ...], candidate filters, estLoopSig, de-duplication.  Returns a dict: coords int64[K,4],
+        pass_id int32[K], core int64[K,4], hyp float64[K], stats float64[K,13] of the surviving loops in candidate
+        order, plus pass_cand / pass_pets per run, totals and the host seconds per stage."""
+        npass = len(passes)
+        eps = np.array([int(e) for e, _ in passes], dtype=np.int64)
+        mps = np.array([int(m) for _, m in passes], dtype=np.int32)
+        h = _vp()
+        lib, ctx = self.ctx.lib, self.ctx
+        ctx.check(lib.cl2_call_loops(ctx.h, self.h, int(mode), 1 if hic else 0, npass, _ptr(eps, _i64p), _ptr(mps, _i32p),
+                                     int(cut), int(min_pts_test), int(win), float(countDiffCut), float(pseudo),
+                                     float(peakPcut), 1 if want_unique else 0, ctypes.byref(h)), "cl2_call_loops")
+        try:
+            k = int(lib.cl2_loops_count(h))
+            out = {"coords": np.empty((k, 4), dtype=np.int64), "pass_id": np.empty(k, dtype=np.int32),
+                   "core": np.empty((k, 4), dtype=np.int64), "hyp": np.empty(k, dtype=np.float64),
+                   "stats": np.empty((k, 13), dtype=np.float64), "pass_cand": np.zeros(npass, dtype=np.int64),
+                   "pass_pets": np.zeros(npass, dtype=np.int64), "totals": np.zeros(8, dtype=np.int64),
+                   "seconds": np.zeros(3, dtype=np.float64)}
+            ctx.check(lib.cl2_loops_info(h, _ptr(out["pass_cand"], _i64p), _ptr(out["pass_pets"], _i64p),
+                                         _ptr(out["totals"], _i64p), _ptr(out["seconds"], _f64p)), "cl2_loops_info")
+            ctx.check(lib.cl2_loops_read(h, _ptr(out["coords"], _i64p), _ptr(out["pass_id"], _i32p), _ptr(out["core"], _i64p),
+                                         _ptr(out["hyp"], _f64p), _ptr(out["stats"], _f64p)), "cl2_loops_read")
+        finally:
+            lib.cl2_loops_free(h)
+        return out
 
     def block_noise_keep(self, eps, minPts, with_cell_order=False):
         """keep[n] of blockDBSCAN's removeNoiseGrids; with_cell_order also returns, per row, the first row id of its

@@ -81,56 +81,50 @@ def exact_default():
 
 
 def cis_chromosome(ctx, key, xy, tot, eps, minPts, cut=0, mcut=-1, hic=False, emPair=False, pts=None, exact=False):
-    """Whole per-chromosome path: sweep -> combine -> count -> test -> mark -> select.
+    """Whole per-chromosome path: sweep -> combine -> count -> test -> mark -> select, the clustering runs, candidate
+    filters, estLoopSig and the de-duplication in ONE native call (cl2_call_loops).
     xy: host int64[N,2] (ignored when a resident `pts` is passed).  Returns (final cols, stats dict).
-    exact: re-evaluate the tail probabilities of the FINAL loops with scipy (hostops.scipy_pvalues)."""
+    exact: True re-evaluates the tail probabilities of the FINAL loops with scipy (hostops.scipy_pvalues) so the
+    printed digits are the reference's; "defer" leaves that to the caller (hostops.scipy_pvalues_many over all
+    files of a rank at once) and only makes the cut decisions exact."""
     own = pts is None
     if own:
         pts = _lib.Points(ctx, xy, cut=cut, mcut=mcut)
     try:
-        stats = {"pets": pts.n, "candidates": 0, "tested": 0, "loops": 0}
+        stats = {"pets": pts.n, "candidates": 0, "tested": 0, "loops": 0, "first_pass": -1}
         if pts.n == 0:
             return hostops._empty_cols(), stats
-        import time
-        t0 = time.perf_counter()
-        def note(ep, mp, res):
-            _log("Clustering %s and %s using eps %s, minPts %s,pre-set distance cutoff > %s finished. Estimated %s "
-                 "candidate loops with %s PETs." % (key[0], key[1], ep, mp, cut, len(res[0]), int(res[1].sum())))
-        per_pass = [c for c, _ in sweep_passes(pts, _sweep(eps, minPts, emPair), hic=hic, cis=True, log=note)]
-        t1 = time.perf_counter()
-        # The reference merges the passes (combineLoops), drops distance <= cut and duplicates, then tests.  A
-        # candidate's test result depends on its coordinates only, so the duplicates are removed AFTER the tests, on
-        # the few survivors (same loops, same order) instead of sorting ~10^5 boxes per chromosome on the host.
-        cands = np.concatenate(per_pass, axis=0) if len(per_pass) > 1 else per_pass[0]
-        if cands.shape[0]:
-            cands = cands[hostops.cis_distance(cands) > cut]                         # filterLoopsByDis :146-156
-        stats["candidates"] = int(cands.shape[0])
-        if logger is not None and cands.shape[0]:
-            stats["candidates"] = int(hostops.combine_unique([cands]).shape[0])      # the number the reference logs
-        if cands.shape[0] == 0:
-            pts.drop_cache()
-            return hostops._empty_cols(), stats
+        passes = _sweep(eps, minPts, emPair)
         mm = min(minPts) if emPair else max(minPts)                                 # :557-560
-        ext = pts.extent()
+        ctx.set_pvalue_margin(hostops.PV_MARGIN if exact else 0.0)
+        res = pts.call_loops(passes, mode=_lib.MODE_CIS, hic=hic, cut=cut, min_pts_test=mm, want_unique=logger is not None)
+        for (ep, mp), nc, npets in zip(passes, res["pass_cand"], res["pass_pets"]):
+            _log("Clustering %s and %s using eps %s, minPts %s,pre-set distance cutoff > %s finished. Estimated %s "
+                 "candidate loops with %s PETs." % (key[0], key[1], ep, mp, cut, int(nc), int(npets)))
+        tested, unique = int(res["totals"][1]), int(res["totals"][2])
+        stats["candidates"] = unique if unique >= 0 else tested
+        nz = np.nonzero(res["pass_cand"])[0]
+        stats["first_pass"] = int(nz[0]) if len(nz) else -1     # the reference's dicts list a chromosome from that run on
+        stats["host_s"] = dict(zip(("cluster", "index", "test"), (float(v) for v in res["seconds"])))
+        if tested == 0:
+            return hostops._empty_cols(), stats
+        ext = res["totals"][4:8]
         span = float(int(ext[3]) - int(ext[0]))
-        index = _lib.Index(pts)
-        t2 = time.perf_counter()
-        try:
-            _log("Estimate significance for %s candidate interactions in %s with %s PETs distance > =%s and <=%s,requiring minPts >=%s."
-                 % (stats["candidates"], "-".join(key), pts.n, cut, mcut, mm))
-            cols = hostops.est_cis(index, cands, pts.n, span, tot, mm, hic=hic)
-        finally:
-            index.close()
-            pts.drop_cache()                  # eps grid + y-order: derived data, rebuilt by the next call
-        cols = hostops.take(cols, hostops.first_occurrence(cols["coords"]))         # filterDupLoops :159-169
+        rpb = float(pts.n) / span
+        _log("Estimate significance for %s candidate interactions in %s with %s PETs distance > =%s and <=%s,requiring minPts >=%s."
+             % (stats["candidates"], "-".join(key), pts.n, cut, mcut, mm))
+        import time
         t3 = time.perf_counter()
+        cols = hostops._cols_from_stats(res["coords"], res["core"], res["hyp"], res["stats"], 1, tot)
+        if exact:
+            cols = hostops.exact_cuts(cols, pts.n, rpb, cis=True, hic=hic)
         stats["tested"] = int(cols["coords"].shape[0])
         sig = hostops.mark_sig_cis(cols, hic=hic)
         final = hostops.select_twice(cols, sig)
-        if exact:
-            final = hostops.scipy_pvalues(final, pts.n, float(pts.n) / span, cis=True)
-        t4 = time.perf_counter()
-        stats["host_s"] = {"cluster": t1 - t0, "index": t2 - t1, "test": t3 - t2, "select": t4 - t3}
+        if exact and exact != "defer":
+            final = hostops.scipy_pvalues(final, pts.n, rpb, cis=True)
+        final["N"], final["rpb"] = pts.n, rpb
+        stats["host_s"]["select"] = time.perf_counter() - t3
         stats["loops"] = int(final["coords"].shape[0])
         return final, stats
     finally:
@@ -278,7 +272,8 @@ def filterPETs(key, predir, fixy, loops, margin=1):
 def callCisLoops(predir, fout, log, eps=[2000, 5000], minPts=[5, 10], cpu=1, cut=0, mcut=-1, plot=False,
                  max_cut=False, hic=False, filter=False, ucsc=False, juicebox=False, washU=False, emPair=False):
     """Drop-in for callCisLoops.py:471-628.  `cpu` is accepted for compatibility; parallelism is one process per GPU
-    (launch under torchrun for more than one), chromosomes sharded by PET count."""
+    (launch under torchrun for more than one), chromosomes sharded by PET count.  Returns the job's counters
+    (PETs, candidates, tested, loops) on rank 0, None on the other ranks and on the reference's early returns."""
     global logger
     logger = log
     if hic:
@@ -290,42 +285,53 @@ def callCisLoops(predir, fout, log, eps=[2000, 5000], minPts=[5, 10], cpu=1, cut
     tot = meta["Unique PETs"]
     rank, world = shard.rank_world()
     fdir = fout + "_filtered"
-    if filter and rank == 0:
-        _log("-filter option chosed, will filter raw PETs based on called loops, for any PET that any end overlaps loop anchors will be kept. ")
-        if not os.path.exists(fdir):
-            os.mkdir(fdir)
-        elif len(os.listdir(fdir)) > 0:
-            if logger is not None:
-                logger.error("working directory %s exists and not empty." % fdir)
+    if filter:
+        # the reference's early return (:518-524) is taken by every rank or by none: rank 0 looks, all ranks hear
+        ok = 1
+        if rank == 0:
+            _log("-filter option chosed, will filter raw PETs based on called loops, for any PET that any end overlaps loop anchors will be kept. ")
+            if not os.path.exists(fdir):
+                os.mkdir(fdir)
+            elif len(os.listdir(fdir)) > 0:
+                if logger is not None:
+                    logger.error("working directory %s exists and not empty." % fdir)
+                ok = 0
+        if shard.broadcast_flag(ok) == 0:
             return
     keys = list(meta["data"]["cis"].keys())
     files = {k: meta["data"]["cis"][k]["ixy"] for k in keys}
     mine = shard.assign(keys, [shard.ixy_rows(files[k]) for k in keys], world)[rank]
     ctxs = shard.worker_contexts()
-    ex = exact_default()
+    ex = "defer" if exact_default() else False
 
     def one(ctx, k):
-        return cis_chromosome(ctx, tuple(k.split("-")), loadIxy(files[k]), tot, eps, minPts, cut=cut, mcut=mcut, hic=hic,
-                              emPair=emPair, exact=ex)
+        return cis_chromosome(ctx, tuple(k.split("-")), shard.load_pinned(ctx, files[k]), tot, eps, minPts, cut=cut, mcut=mcut,
+                              hic=hic, emPair=emPair, exact=ex)
 
     results = {}
+    first = {}
     stats = np.zeros(4, dtype=np.int64)
     for k, (final, st) in zip(mine, shard.map_units(ctxs, mine, one)):
         stats += np.array([st["pets"], st["candidates"], st["tested"], st["loops"]], dtype=np.int64)
-        if st["tested"] > 0:
+        if st["first_pass"] >= 0:
             results[k] = final
+            first[k] = st["first_pass"]
+    if ex:
+        hostops.scipy_pvalues_many([results[k] for k in results], cis=True)      # once per rank, one thread pool
     stats = shard.allreduce_stats(stats)
-    gathered = shard.gather_results(results)
+    gathered = shard.gather_results({k: (first[k], results[k]) for k in results})
     if rank != 0:
         return
     _log("Estimating loop statstical significance.")
     _log("Selecting the most significant loops of overlapped ones. ")
     per_key = {}
     loops = []
-    for k in keys:                                   # meta key order, as the reference's dicts (:137, :572, :597-599)
-        if k in gathered:
-            per_key[k] = cols_to_loops(tuple(k.split("-")), gathered[k], cis=True)
-            loops.extend(per_key[k])
+    # the reference's dict order: chromosomes enter `loops` in the run that first finds a candidate for them, in meta
+    # key order within a run (parallelRunCisDBSCANLoops :140-143 skips empty results, combineLoops appends new keys)
+    order = sorted((k for k in keys if k in gathered), key=lambda k: (gathered[k][0], keys.index(k)))
+    for k in order:
+        per_key[k] = cols_to_loops(tuple(k.split("-")), gathered[k][1], cis=True)
+        loops.extend(per_key[k])
     _log("Output %s loops to %s_loops.txt" % (len(loops), fout))
     loops2txt(loops, fout + "_loops.txt")
     if ucsc:

@@ -17,36 +17,36 @@ from .callCisLoops import cluster_pass, sweep_passes, cols_to_loops, selSigLoops
 
 
 def trans_pair(ctx, key, xy, eps, minPts, pts=None, exact=False):
-    """Whole per-pair path (sweep -> combine -> count -> test -> mark -> select); returns (final cols, stats)."""
+    """Whole per-pair path (sweep -> combine -> count -> test -> mark -> select) around one native call
+    (cl2_call_loops); returns (final cols, stats).  exact as in callCisLoops.cis_chromosome."""
     own = pts is None
     if own:
         pts = _lib.Points(ctx, xy, cut=0, mcut=-1)
     try:
-        stats = {"pets": pts.n, "candidates": 0, "tested": 0, "loops": 0}
+        stats = {"pets": pts.n, "candidates": 0, "tested": 0, "loops": 0, "first_pass": -1}
         if pts.n == 0:
             return hostops._empty_cols(), stats
-        per_pass = [c for c, _ in sweep_passes(pts, [(ep, mp) for ep in eps for mp in minPts], hic=False, cis=False)]
-        # combineLoops only (callTransLoops.py:230-234): coordinates already seen in an EARLIER pass are dropped,
-        # duplicates inside one pass survive.  As on the cis path the de-duplication is applied after the tests.
-        cands = np.concatenate(per_pass, axis=0) if len(per_pass) > 1 else per_pass[0]
-        pass_id = np.concatenate([np.full(len(c), i, dtype=np.int64) for i, c in enumerate(per_pass)])
-        stats["candidates"] = int(cands.shape[0])
-        if cands.shape[0] == 0:
-            pts.drop_cache()
+        passes = [(ep, mp) for ep in eps for mp in minPts]
+        ctx.set_pvalue_margin(0.0)                            # the trans estLoopSig has no cut on a tail probability
+        # combineLoops only (callTransLoops.py:230-234): coordinates already seen in an EARLIER run are dropped,
+        # duplicates inside one run survive; no cut / anchor-size / order filters (:58-79); countDiffCut 10 (:107)
+        res = pts.call_loops(passes, mode=_lib.MODE_TRANS, hic=False, cut=0, min_pts_test=max(minPts), countDiffCut=10)
+        stats["candidates"] = int(res["totals"][1])
+        nz = np.nonzero(res["pass_cand"])[0]
+        stats["first_pass"] = int(nz[0]) if len(nz) else -1
+        if stats["candidates"] == 0:
             return hostops._empty_cols(), stats
-        ext = pts.extent()
+        ext = res["totals"][4:8]
         span = float(int(ext[3]) - int(ext[0]))
-        index = _lib.Index(pts)
-        try:
-            cols = hostops.est_trans(index, cands, pts.n, span, max(minPts), pass_id=pass_id)
-        finally:
-            index.close()
-            pts.drop_cache()
-        cols = hostops.take(cols, hostops.first_occurrence(cols["coords"], cols.pop("pass_id")))
+        rpb = float(pts.n) / span
+        cols = hostops._cols_from_stats(res["coords"], res["core"], res["hyp"], res["stats"], 1, pts.n)
+        if exact:
+            cols = hostops.exact_cuts(cols, pts.n, rpb, cis=False)
         stats["tested"] = int(cols["coords"].shape[0])
         final = hostops.select_twice(cols, hostops.mark_sig_trans(cols))
-        if exact:
-            final = hostops.scipy_pvalues(final, pts.n, float(pts.n) / span, cis=False)
+        if exact and exact != "defer":
+            final = hostops.scipy_pvalues(final, pts.n, rpb, cis=False)
+        final["N"], final["rpb"] = pts.n, rpb
         stats["loops"] = int(final["coords"].shape[0])
         return final, stats
     finally:
@@ -123,27 +123,31 @@ def callTransLoops(predir, fout, logger, eps=[2000, 5000], minPts=[5, 10], cpu=1
     rank, world = shard.rank_world()
     mine = shard.assign(keys, [shard.ixy_rows(files[k]) for k in keys], world)[rank]
     ctxs = shard.worker_contexts()
-    ex = exact_default()
+    ex = "defer" if exact_default() else False
 
     def one(ctx, k):
-        return trans_pair(ctx, tuple(k.split("-")), loadIxy(files[k]), eps, minPts, exact=ex)
+        return trans_pair(ctx, tuple(k.split("-")), shard.load_pinned(ctx, files[k]), eps, minPts, exact=ex)
 
     results = {}
+    first = {}
     stats = np.zeros(4, dtype=np.int64)
     for k, (final, st) in zip(mine, shard.map_units(ctxs, mine, one)):
         stats += np.array([st["pets"], st["candidates"], st["tested"], st["loops"]], dtype=np.int64)
-        if st["candidates"] > 0:
+        if st["first_pass"] >= 0:
             results[k] = final
+            first[k] = st["first_pass"]
+    if ex:
+        hostops.scipy_pvalues_many([results[k] for k in results], cis=False)
     stats = shard.allreduce_stats(stats)
-    gathered = shard.gather_results(results)
+    gathered = shard.gather_results({k: (first[k], results[k]) for k in results})
     if rank != 0:
         return
     logger.info("Estimating loop statstical significance.")
     logger.info("Selecting the most significant loops of overlapped ones. ")
     loops = []
-    for k in keys:
-        if k in gathered:
-            loops.extend(cols_to_loops(tuple(k.split("-")), gathered[k], cis=False))
+    # dict order of the reference: a pair enters in the run that first finds a candidate for it (:100-103, geo.py:94-96)
+    for k in sorted((k for k in keys if k in gathered), key=lambda k: (gathered[k][0], keys.index(k))):
+        loops.extend(cols_to_loops(tuple(k.split("-")), gathered[k][1], cis=False))
     logger.info("Output %s loops to %s_loops.txt" % (len(loops), fout))
     loops2txt(loops, fout + "_trans_loops.txt")
     if washU:

@@ -75,6 +75,12 @@ extern "C" void cl2_ctx_destroy(cl2_ctx *ctx) {
 
 extern "C" const char *cl2_last_error(cl2_ctx *ctx) { return ctx ? ctx->err : "null context"; }
 
+extern "C" int cl2_set_pvalue_margin(cl2_ctx *ctx, double margin) {
+    if (!ctx || !(margin >= 0.0) || margin > 1.0) return CL2_ERR_ARG;
+    ctx->pvalue_margin = margin;
+    return CL2_OK;
+}
+
 extern "C" int cl2_ctx_sync(cl2_ctx *ctx) {
     if (!ctx) return CL2_ERR_ARG;
     CL2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

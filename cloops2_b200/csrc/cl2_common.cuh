@@ -82,6 +82,7 @@ struct cl2_ctx {
     int sm_count = 148;
     int no_pool = 0;            // CL2_NO_POOL=1: plain cudaMalloc/cudaFree (used when profiling under ncu)
     void *h_scratch = nullptr;  // small pinned buffer for scalar read-backs
+    double pvalue_margin = 0.0; // cl2_set_pvalue_margin
 };
 
 inline int cl2_fail(cl2_ctx *ctx, int code, const char *fmt, const char *a = "", const char *b = "") {

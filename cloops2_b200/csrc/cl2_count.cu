@@ -891,15 +891,16 @@ __device__ double warp_median(WarpVals &S, int m, int lane) {
 // Permuted-window background, enrichment tests and anchor tests of one loop (one warp); results into o[13] (shared):
 // mrabs, mbps, fdr, poisson sf, binomial sf, px, esx, py, esy, count_x, wide_x, count_y, wide_y
 // Background of one loop (one warp): permuted windows -> mrabs, mbps, fdr (callCisLoops.py:207-223, 315-321).
-// early_cut > 0 (cis): return false as soon as `mrabs >= rab or fdr >= 0.1` or `es < 1` (:322-327) is known.
+// bg_cut (cis): return false as soon as `mrabs >= rab or fdr >= 0.1` or `es < 1` (:322-327) is known; the reference
+// applies these cuts whatever `pseudo` is, which only enters the enrichment score.
 __device__ bool loop_background(const IdxView &ix, long long xs,
                                 long long xe, long long ys, long long ye, double rab, int win, int mode, WarpAcc &S,
-                                WarpVals &V, int lane, double early_cut, double *o_mrabs, double *o_mbps,
+                                WarpVals &V, int lane, bool bg_cut, double pseudo, double *o_mrabs, double *o_mbps,
                                 double *o_fdr, long long *g_scan) {
     const int W = 2 * win, m = W * W;
     // smallest number of window pairs above rab that makes fdr = gt / m >= 0.1 (the comparison the reference makes)
     int fdr_stop = 0;
-    if (early_cut > 0) {
+    if (bg_cut) {
         fdr_stop = m / 10;
         while ((double)fdr_stop / (double)m < 0.1) fdr_stop++;
         while (fdr_stop > 1 && (double)(fdr_stop - 1) / (double)m >= 0.1) fdr_stop--;
@@ -919,15 +920,15 @@ __device__ bool loop_background(const IdxView &ix, long long xs,
     // counts and for the densities alike (a density is 0 exactly where the count is 0) -- the common case
     const bool zero_median = mode == CL2_MODE_CIS && nzero >= m / 2 + 1;
     const double fdr = (double)gt / (double)m;
-    if (early_cut > 0 && fdr >= 0.1) return false;         // the cheap half of the background cut first
+    if (bg_cut && fdr >= 0.1) return false;                // the cheap half of the background cut first
     double mrabs, mbps;
     if (zero_median) mrabs = 0.0;
     else if (mode == CL2_MODE_CIS) mrabs = warp_median(V, m, lane);
     else mrabs = np_pairwise_sum(V.v, m) / (double)m;     // every lane computes the same value
     __syncwarp();
-    if (early_cut > 0) {
+    if (bg_cut) {
         if (mrabs >= rab || fdr >= 0.1) return false;
-        if (rab / (mrabs > early_cut ? mrabs : early_cut) < 1.0) return false;
+        if (rab / (mrabs > pseudo ? mrabs : pseudo) < 1.0) return false;
     }
     if (zero_median) {
         mbps = 0.0;
@@ -979,7 +980,7 @@ __device__ void loop_tests_warp(const IdxView &ix, long long xs,
                                 long long xe, long long ys, long long ye, double ra, double rb, double rab, int win,
                                 int mode, double rpb, WarpAcc &S, WarpVals &V, int lane, double *o, long long *g_scan) {
     double mrabs, mbps, fdr;
-    loop_background(ix, xs, xe, ys, ye, rab, win, mode, S, V, lane, 0.0, &mrabs, &mbps, &fdr, g_scan);
+    loop_background(ix, xs, xe, ys, ye, rab, win, mode, S, V, lane, false, 1.0, &mrabs, &mbps, &fdr, g_scan);
     if (lane == 0) { o[0] = mrabs; o[1] = mbps; o[2] = fdr; }
     loop_tail(ix, xs, xe, ys, ye, ra, rb, rab, mrabs, mbps, mode, rpb, lane, o, g_scan);
 }
@@ -1035,8 +1036,8 @@ __global__ void __launch_bounds__(CNT_WARPS * 32, MINB) k_est_bg(const IdxView i
         if (cis && hic && p2ll < 1.0) keep = false;                                    // :307
         if (keep) {
             double mrabs, mbps, fdr;
-            keep = loop_background(ix, xs, xe, ys, ye, rab, win, mode, acc[w], vals[w], lane,
-                                   cis ? pseudo : 0.0, &mrabs, &mbps, &fdr, &scanned);
+            keep = loop_background(ix, xs, xe, ys, ye, rab, win, mode, acc[w], vals[w], lane, cis, pseudo, &mrabs, &mbps,
+                                   &fdr, &scanned);
             if (keep && lane == 0) {
                 core_out[4 * k] = c[0]; core_out[4 * k + 1] = c[1]; core_out[4 * k + 2] = c[2]; core_out[4 * k + 3] = c[3];
                 stats_out[CL2_NSTAT * k] = mrabs; stats_out[CL2_NSTAT * k + 1] = mbps; stats_out[CL2_NSTAT * k + 2] = fdr;
@@ -1074,7 +1075,8 @@ __global__ void __launch_bounds__(CNT_WARPS * 32) k_est_anchor(const IdxView ix,
 
 #define EST_GROUP 8      // threads per survivor in k_est_stats
 __global__ void __launch_bounds__(256) k_est_stats(const longlong4 *__restrict__ loops, const long long *__restrict__ sel,
-                                                    int64_t K, int64_t n, int mode, int hic, double peakPcut, double rpb,
+                                                    int64_t K, int64_t n, int mode, int hic, double peakPcut, double slack,
+                                                    double rpb,
                                                     const long long *__restrict__ core, double *__restrict__ hyp,
                                                     double *__restrict__ stats, int32_t *__restrict__ flag2) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1116,8 +1118,10 @@ __global__ void __launch_bounds__(256) k_est_stats(const longlong4 *__restrict__
     else if (s == 3) { o[7] = v; o[8] = es; }
     if (s == 0) {
         bool keep = true;
-        if (cis && fmax(1e-300, h) > 1e-2) keep = false;                                  // :311
-        if (cis && !hic && !(fmax(1e-300, px) < peakPcut && fmax(1e-300, py) < peakPcut)) keep = false;   // :347
+        // slack = 1 + cl2_set_pvalue_margin: the cuts are widened by that factor for callers that take the final
+        // decision with another library's tail probabilities
+        if (cis && fmax(1e-300, h) > 1e-2 * slack) keep = false;                          // :311
+        if (cis && !hic && !(fmax(1e-300, px) < peakPcut * slack && fmax(1e-300, py) < peakPcut * slack)) keep = false;   // :347
         hyp[i] = h;
         flag2[i] = keep ? 1 : 0;
     }
@@ -1288,7 +1292,8 @@ extern "C" int cl2_est_loops(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops,
             k_est_anchor<<<cl2_grid(nk, CNT_WARPS), CNT_WARPS * 32, 0, ctx->stream>>>(cl2_view(idx), d_loops, d_sel, nk, d_stats_c,
                                                                                       (unsigned long long *)(d_total + 1));
             k_est_stats<<<cl2_grid(nk * EST_GROUP, 256), 256, 0, ctx->stream>>>(d_loops, d_sel, nk, idx->n, mode, hic, peakPcut,
-                                                                                rpb, d_core_c, d_hyp_c, d_stats_c, d_flag2);
+                                                                                1.0 + ctx->pvalue_margin, rpb, d_core_c,
+                                                                                d_hyp_c, d_stats_c, d_flag2);
         }
         f2.resize((size_t)nk);
         CL2_CUDA(ctx, cudaMemcpyAsync(sel, d_sel, (size_t)nk * 8, cudaMemcpyDeviceToHost, ctx->stream));

@@ -117,7 +117,7 @@ def _clamp(p):
 
 
 def est_cis(index, cands, N, span, tot, minPts, hic=False, pseudo=1, peakPcut=1e-5, win=5, countDiffCut=20,
-            exact=False):
+            exact=False, stepwise=None):
     """estLoopSig (callCisLoops.py:250-354) for one chromosome.  `index` is a device XY index; cands int64[L,4].
     Counting, the permuted-window statistics and the tail probabilities are computed on the device (two launches:
     every candidate, then the survivors of the first filters); the filter cascade itself is applied here in the
@@ -128,14 +128,25 @@ def est_cis(index, cands, N, span, tot, minPts, hic=False, pseudo=1, peakPcut=1e
     cols = _empty_cols()
     if L == 0:
         return cols
-    if hasattr(index, "est_loops"):
-        # fused device path: counting, statistics and the filter cascade below all run in one kernel; only the
-        # survivors come back (the step-by-step path that follows is the same arithmetic, kept for small inputs)
+    if stepwise is None:
+        stepwise = not hasattr(index, "est_loops")          # an index that only offers the phase-by-phase calls
+    if not stepwise:
+        # fused device path: counting, statistics and the filter cascade below all run on the device; only the
+        # survivors come back.  stepwise=True runs the same arithmetic phase by phase with the cascade applied here
+        # (tests/test_hostops.py drives it with an oracle-backed index, tests/test_gpu_pipeline.py with the device)
         rpb = float(N) / span
-        sel, core, hyp, st = index.est_loops(cands, rpb, minPts, mode=_lib.MODE_CIS, win=win, hic=hic,
-                                             countDiffCut=countDiffCut, pseudo=pseudo, peakPcut=peakPcut)
+        if exact:
+            index.ctx.set_pvalue_margin(PV_MARGIN)
+        try:
+            sel, core, hyp, st = index.est_loops(cands, rpb, minPts, mode=_lib.MODE_CIS, win=win, hic=hic,
+                                                 countDiffCut=countDiffCut, pseudo=pseudo, peakPcut=peakPcut)
+        finally:
+            if exact:
+                index.ctx.set_pvalue_margin(0.0)
         cols = _cols_from_stats(cands[sel], core, hyp, st, pseudo, tot)
-        return scipy_pvalues(cols, N, rpb, cis=True) if exact else cols
+        if exact:
+            cols = scipy_pvalues(exact_cuts(cols, N, rpb, cis=True, hic=hic, peakPcut=peakPcut, mark=False), N, rpb, cis=True)
+        return cols
     la = (cands[:, 1] - cands[:, 0])
     lb = (cands[:, 3] - cands[:, 2])
     keep = ~((la / lb > countDiffCut) | (lb / la > countDiffCut))                    # :282-286
@@ -176,7 +187,8 @@ def est_cis(index, cands, N, span, tot, minPts, hic=False, pseudo=1, peakPcut=1e
     return cols
 
 
-def est_trans(index, cands, N, span, minPts, pseudo=1, countDiffCut=10, win=5, exact=False, pass_id=None):
+def est_trans(index, cands, N, span, minPts, pseudo=1, countDiffCut=10, win=5, exact=False, pass_id=None,
+              stepwise=None):
     """trans estLoopSig (callTransLoops.py:106-193).  `pass_id` (optional, per candidate) is carried through the
     filters so the caller can apply combineLoops' cross-pass de-duplication afterwards."""
     L = cands.shape[0]
@@ -185,7 +197,9 @@ def est_trans(index, cands, N, span, minPts, pseudo=1, countDiffCut=10, win=5, e
         if pass_id is not None:
             cols["pass_id"] = np.zeros(0, dtype=np.int64)
         return cols
-    if hasattr(index, "est_loops"):
+    if stepwise is None:
+        stepwise = not hasattr(index, "est_loops")
+    if not stepwise:
         rpb = float(N) / span
         sel, core, hyp, st = index.est_loops(cands, rpb, minPts, mode=_lib.MODE_TRANS, win=win,
                                              countDiffCut=countDiffCut, pseudo=pseudo)
@@ -223,9 +237,13 @@ def est_trans(index, cands, N, span, minPts, pseudo=1, countDiffCut=10, win=5, e
 
 def _threaded(fn, *arrays):
     """Evaluate a scipy ufunc-backed function over chunks in host threads (the inner loops release the GIL);
-    hypergeom.sf costs ~150 us per element in scipy 1.18, so this is what bounds the exact mode."""
+    hypergeom.sf costs ~25 us per element in scipy 1.18, which is what bounds the exact mode."""
     n = arrays[0].shape[0]
-    nthr = min(os.cpu_count() or 1, max(1, n // 64))
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    nthr = min(cores, max(1, n // 256))
     if nthr <= 1:
         return fn(*arrays)
     from concurrent.futures import ThreadPoolExecutor
@@ -252,19 +270,95 @@ def _cols_from_stats(c, core, hyp, st, pseudo, tot):
 def scipy_pvalues(cols, N, rpb, cis=True):
     """Re-evaluate the tail probabilities of (few) surviving loops with scipy, argument for argument as the reference
     calls it (callCisLoops.py:246,310,329,332; callTransLoops.py:153,178,181), so the printed digits are the
-    reference's.  Everything else in `cols` is already bit-identical."""
-    if cols["coords"].shape[0] == 0:
+    reference's.  Everything else in `cols` is already bit-identical.  N and rpb may be per-row arrays (rows of
+    several files at once)."""
+    n = cols["coords"].shape[0]
+    if n == 0:
         return cols
     out = dict(cols)
     ra, rb, rab = cols["ra"], cols["rb"], cols["rab"]
-    out["hyp"] = _clamp(_threaded(lambda a, b, c: hypergeom.sf(a - 1.0, N, b, c), rab, ra, rb))
-    out["pop"] = _clamp(poisson.sf(rab - 1.0, cols["mrabs"]))
-    out["nbp"] = _clamp(binom.sf(rab - 1.0, ra * rb - rab if cis else ra * rb, cols["mbps"]))
+    Nv = np.broadcast_to(np.asarray(N, dtype=np.float64), (n,))
+    rv = np.broadcast_to(np.asarray(rpb, dtype=np.float64), (n,))
     c = cols["coords"]
     anc = cols["anc"]
-    out["px"], out["esx"] = anchor_sig(anc[:, 0].astype(np.int64), anc[:, 1].astype(np.int64), c[:, 1] - c[:, 0], rpb)
-    out["py"], out["esy"] = anchor_sig(anc[:, 2].astype(np.int64), anc[:, 3].astype(np.int64), c[:, 3] - c[:, 2], rpb)
+
+    def tails(rab, ra, rb, Nv, rv, mrabs, mbps, la, lb, a0, a1, a2, a3):
+        hyp = hypergeom.sf(rab - 1.0, Nv, ra, rb)
+        pop = poisson.sf(rab - 1.0, mrabs)
+        nbp = binom.sf(rab - 1.0, ra * rb - rab if cis else ra * rb, mbps)
+        px, esx = anchor_sig(a0, a1, la, rv)
+        py, esy = anchor_sig(a2, a3, lb, rv)
+        return np.stack([hyp, pop, nbp, px, esx, py, esy], axis=1)
+
+    t = _threaded(tails, rab, ra, rb, Nv, rv, cols["mrabs"], cols["mbps"], c[:, 1] - c[:, 0], c[:, 3] - c[:, 2],
+                  anc[:, 0].astype(np.int64), anc[:, 1].astype(np.int64), anc[:, 2].astype(np.int64),
+                  anc[:, 3].astype(np.int64))
+    out["hyp"], out["pop"], out["nbp"] = _clamp(t[:, 0]), _clamp(t[:, 1]), _clamp(t[:, 2])
+    out["px"], out["esx"], out["py"], out["esy"] = t[:, 3], t[:, 4], t[:, 5], t[:, 6]
     return out
+
+
+def scipy_pvalues_many(finals, cis=True):
+    """scipy_pvalues over the final loops of several files at once (one evaluation, one thread pool per rank instead
+    of one per file); every entry carries its own "N" and "rpb" (cis_chromosome / trans_pair).  In place."""
+    finals = [f for f in finals if f["coords"].shape[0] > 0]
+    if not finals:
+        return
+    names = [k for k in COLS if k in finals[0]]
+    cat = {k: np.concatenate([f[k] for f in finals], axis=0) for k in names}
+    Nv = np.concatenate([np.full(f["coords"].shape[0], float(f["N"])) for f in finals])
+    rv = np.concatenate([np.full(f["coords"].shape[0], float(f["rpb"])) for f in finals])
+    out = scipy_pvalues(cat, Nv, rv, cis=cis)
+    o = 0
+    for f in finals:
+        m = f["coords"].shape[0]
+        for k in ("hyp", "pop", "nbp", "px", "py", "esx", "esy"):
+            f[k] = out[k][o:o + m]
+        o += m
+
+
+# Relative distance from a cut below which a device tail probability is not trusted to decide like scipy's would: the
+# fp64 series of cl2_stats.cuh are accurate to ~1e-14, scipy 1.18 drifts up to ~1e-7 at bench-scale populations
+# (DESIGN.md section 2); rows that close to a threshold are decided with scipy's own value in the exact mode.
+PV_MARGIN = 1e-5
+
+
+def _near(v, thresholds):
+    near = np.zeros(v.shape[0], dtype=bool)
+    for t in thresholds:
+        near |= np.abs(v - t) <= 2.0 * PV_MARGIN * t
+    return near
+
+
+def exact_cuts(cols, N, rpb, cis=True, hic=False, peakPcut=1e-5, mark=True):
+    """Exact-mode decisions.  The device applied its p-value cuts widened by PV_MARGIN (cl2_set_pvalue_margin); rows
+    whose tails lie within the margin of any threshold the reference compares them with (estLoopSig :311, :347;
+    markSigLoops :364-372 when mark=True; trans :200) get scipy's values, then the cuts are applied as written."""
+    n = cols["coords"].shape[0]
+    if n == 0:
+        return cols
+    if cis:
+        near = _near(cols["hyp"], [1e-2] + ([1e-5] if mark else []))
+        if not hic:
+            near |= _near(cols["px"], [peakPcut]) | _near(cols["py"], [peakPcut])
+        if mark:
+            near |= _near(cols["pop"], [1e-5]) | _near(cols["nbp"], [1e-3 if hic else 1e-1])
+    else:
+        near = _near(cols["nbp"], [1e-10]) if mark else np.zeros(n, dtype=bool)
+    if near.any():
+        sub = scipy_pvalues(take(cols, near), N, rpb, cis=cis)
+        cols = dict(cols)
+        for k in ("hyp", "pop", "nbp", "px", "py", "esx", "esy"):
+            v = cols[k].copy()
+            v[near] = sub[k]
+            cols[k] = v
+    if cis:
+        keep = ~(cols["hyp"] > 1e-2)                                                  # :311
+        if not hic:
+            keep &= (cols["px"] < peakPcut) & (cols["py"] < peakPcut)                 # :347
+        if not keep.all():
+            cols = take(cols, keep)
+    return cols
 
 
 COLS = ["coords", "ra", "rb", "rab", "P2LL", "FDR", "ES", "density", "hyp", "pop", "nbp", "px", "py", "esx", "esy",

@@ -15,17 +15,23 @@ def ixyKey(f):
     return tuple(os.path.split(f)[1].replace(".ixy", "").split("-"))
 
 
-def loadIxy(f, out=None):
-    """Raw int64[N,2] of a `.ixy` (joblib pickle, io.py:55-67).  With `out` (e.g. a pinned buffer factory result)
-    the rows are copied into it from a memory map, avoiding an intermediate pageable copy."""
+def ixyMap(f):
+    """The [N,2] matrix of a `.ixy` (joblib pickle, io.py:55-67) as a read-only memory map where joblib can map it."""
     import joblib
     try:
         mat = joblib.load(f, mmap_mode="r")
     except Exception:
         mat = joblib.load(f)
-    mat = np.asarray(mat)
+    mat = np.asarray(mat) if not isinstance(mat, np.ndarray) else mat
     if mat.ndim != 2 or mat.shape[1] != 2:
         raise ValueError("%s does not hold an [N,2] matrix" % f)
+    return mat
+
+
+def loadIxy(f, out=None):
+    """Raw int64[N,2] of a `.ixy`.  With `out` (e.g. a pinned buffer) the rows are copied into it from the memory
+    map, avoiding an intermediate pageable copy."""
+    mat = ixyMap(f)
     if out is not None:
         np.copyto(out, mat, casting="unsafe")
         return out

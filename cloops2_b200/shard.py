@@ -74,6 +74,30 @@ def allreduce_stats(vals):
     return t.cpu().numpy()
 
 
+def broadcast_flag(v):
+    """Rank 0's integer, on every rank (decisions that every rank has to take the same way)."""
+    rank, world = rank_world()
+    if world == 1:
+        return int(v)
+    import torch
+    import torch.distributed as dist
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([int(v)], dtype=torch.int64, device=dev)
+    dist.broadcast(t, src=0)
+    return int(t.item())
+
+
+def load_pinned(ctx, f):
+    """Rows of a `.ixy` file in the worker's page-locked staging buffer, copied straight from the memory map joblib
+    opens (no pageable intermediate).  The buffer belongs to `ctx` and is reused by its next file: the upload
+    (cl2_points_upload) has finished with it when it returns."""
+    from .io import ixyMap
+    mat = ixyMap(f)
+    out = ctx.staging(mat.shape, np.int64)
+    np.copyto(out, mat, casting="unsafe")
+    return out
+
+
 def gather_results(results):
     """Per-chromosome result dicts of every rank merged on rank 0 (other ranks get {})."""
     rank, world = rank_world()
@@ -135,7 +159,15 @@ def worker_contexts(device=None, nthreads=None):
     _lib.load().cl2_set_sync_mode(1 if blocking else 0)
     nthreads = max(1, nthreads)
     first = _lib.default_context(device)
-    return [first] + [_lib.Context(first.device) for _ in range(nthreads - 1)]
+    # the workers of a device are kept for the life of the process: a second callCisLoops / callTransLoops call reuses
+    # their streams, scratch reservations and page-locked staging buffers
+    pool = _worker_pool.setdefault(first.device, [first])
+    while len(pool) < nthreads:
+        pool.append(_lib.Context(first.device))
+    return pool[:nthreads]
+
+
+_worker_pool = {}
 
 
 def map_units(ctxs, units, fn):

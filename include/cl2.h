@@ -145,6 +145,44 @@ int cl2_est_loops(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops, int64_t L,
                   int32_t minPts, int32_t hic, double countDiffCut, double pseudo, double peakPcut, double rpb,
                   int64_t *n_out, int64_t *sel, int64_t *core, double *hyp, double *stats);
 
+/*
+ * The device-side cuts on tail probabilities inside cl2_est_loops / cl2_call_loops (hypergeometric > 1e-2,
+ * callCisLoops.py:311; anchor peaks >= peakPcut, :347) are widened by the factor 1 + margin, so that a caller who
+ * re-evaluates the tails with another library (scipy, whose values differ from the fp64 series here in the 8th digit
+ * at large populations) receives every row its own decision could keep and takes that decision itself.  0 (default)
+ * = the cuts as the reference writes them.
+ */
+int cl2_set_pvalue_margin(cl2_ctx *ctx, double margin);
+
+/* ---- the per-file work unit ----------------------------------------------------------------------------- */
+/*
+ * What the reference hands to one joblib worker, for ONE chromosome (pair) file resident in HBM, in one call:
+ * runCisDBSCANLoops for every (eps[i], minPts[i]) of the sweep (callCisLoops.py:58-124 as driven by :529-551; trans:
+ * runTransDBSCANLoops, callTransLoops.py:33-84, :224-236) with its per-run candidate filters, filterLoopsByDis
+ * (distance > cut, callCisLoops.py:146-156, cis only), estLoopSig on the candidates (callCisLoops.py:250-354 /
+ * callTransLoops.py:106-193; arguments as in cl2_est_loops, min_pts_test = the minPts handed to estLoopSig,
+ * callCisLoops.py:557-568) and the de-duplication of combineLoops / filterDupLoops (geo.py:90-112,
+ * callCisLoops.py:159-169; trans keeps duplicates that arise inside one run).  mode = CL2_MODE_CIS | CL2_MODE_TRANS;
+ * hic != 0 clusters with cDBSCAN2 and applies the -hic rules (cis only).  The runs may be executed in any order
+ * (results are reported in the order given); the derived data cached on `pts` is dropped at the end.
+ * want_unique != 0 also counts the distinct candidate coordinates (the number logged at callCisLoops.py:564-566).
+ * The survivors wait in *out until cl2_loops_free.
+ */
+typedef struct cl2_loops cl2_loops;
+int cl2_call_loops(cl2_ctx *ctx, cl2_points *pts, int32_t mode, int32_t hic, int32_t npass, const int64_t *eps,
+                   const int32_t *minPts, int64_t cut, int32_t min_pts_test, int32_t win, double countDiffCut,
+                   double pseudo, double peakPcut, int32_t want_unique, cl2_loops **out);
+/* surviving loops, in candidate order (run by run as given, ascending cluster id inside a run) */
+int64_t cl2_loops_count(const cl2_loops *r);
+/* pass_cand[npass], pass_pets[npass]: candidates of every run after its filters and the PETs they hold (the numbers
+ * logged at callCisLoops.py:122); totals[8] = PETs of the file, candidates tested, distinct candidate coordinates
+ * (-1 unless want_unique), survivors, min X, max X, min Y, max Y; seconds[3] = host wall time of the clustering
+ * runs, the index build, the tests.  Any pointer may be NULL. */
+int cl2_loops_info(const cl2_loops *r, int64_t *pass_cand, int64_t *pass_pets, int64_t *totals, double *seconds);
+/* coords int64[K,4], pass_id int32[K] (index of the run a survivor came from), core / hyp / stats as cl2_est_loops */
+int cl2_loops_read(const cl2_loops *r, int64_t *coords, int32_t *pass_id, int64_t *core, double *hyp, double *stats);
+void cl2_loops_free(cl2_loops *r);
+
 /* ---- host-side selection (native, no GPU) ----------------------------------------------------------------- */
 /*
  * selSigLoops (callCisLoops.py:379-422) for the loops of ONE chromosome (pair), all already significant, in list
