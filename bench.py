@@ -400,8 +400,12 @@ def main():
 
     def step_e2e_exact():
         from cloops2_b200 import hostops
-        res = shard.map_units(ctxs, keys, lambda c, k: unit(c, k, pinned[k], None, exact="defer"))
-        hostops.scipy_pvalues_many([f for f, _ in res], cis=(kind == "cis"))
+        prev = shard.set_sync_mode(True)          # as callCisLoops does in this mode: waits sleep, the scipy pool gets the cores
+        try:
+            res = shard.map_units(ctxs, keys, lambda c, k: unit(c, k, pinned[k], None, exact="defer"))
+        finally:
+            shard.set_sync_mode(prev)
+        hostops.wait_pvalues([f for f, _ in res])
 
     def timed(fn, warmup, steps):
         for _ in range(warmup):

@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.path.join(_HERE, "libcl2.so")
-SOURCES = ["cl2_api.cu", "cl2_sort.cu", "cl2_block.cu", "cl2_cdbscan.cu", "cl2_count.cu", "cl2_driver.cu", "cl2_host.cu",
+SOURCES = ["cl2_api.cu", "cl2_sort.cu", "cl2_block.cu", "cl2_cdbscan.cu", "cl2_count.cu", "cl2_driver.cu", "cl2_comm.cu", "cl2_host.cu",
            "cl2_pre.cu"]
 HEADERS = ["cl2_common.cuh", "cl2_points.cuh", "cl2_stats.cuh", os.path.join("..", "..", "include", "cl2.h")]
 # -fmad=false: no FMA contraction, so the fp64 statistics give the same bits in every kernel they are inlined into
@@ -58,7 +58,7 @@ def build(force=False, verbose=False):
         out, _ = p.communicate()
         if p.returncode != 0:
             raise Cl2Error("nvcc failed: %s\n%s" % (" ".join(cmd), out.decode(errors="replace")))
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO_PATH] + objs + ["-lcudart"]
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO_PATH] + objs + ["-lcudart", "-ldl"]
     subprocess.check_call(cmd)
     return SO_PATH
 
@@ -116,6 +116,10 @@ SIGNATURES = {
     "cl2_loops_info": (ctypes.c_int, [_vp, _i64p, _i64p, _i64p, _f64p]),
     "cl2_loops_read": (ctypes.c_int, [_vp, _i64p, _i32p, _i64p, _f64p, _f64p]),
     "cl2_loops_free": (None, [_vp]),
+    "cl2_comm_unique_id": (ctypes.c_int, [_u8p]),
+    "cl2_comm_init": (ctypes.c_int, [_vp, _u8p, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(_vp)]),
+    "cl2_stats_allreduce": (ctypes.c_int, [_vp, _vp, _i64p, ctypes.c_int32]),
+    "cl2_comm_destroy": (None, [_vp]),
     "cl2_sel_sig_loops": (ctypes.c_int, [_i64p, _f64p, ctypes.c_int64, _i64p, _i64p]),
     "cl2_stat_poisson_sf": (ctypes.c_double, [ctypes.c_double, ctypes.c_double]),
     "cl2_stat_binom_sf": (ctypes.c_double, [ctypes.c_double, ctypes.c_double, ctypes.c_double]),

@@ -47,6 +47,8 @@ def trans_pair(ctx, key, xy, eps, minPts, pts=None, exact=False):
         if exact and exact != "defer":
             final = hostops.scipy_pvalues(final, pts.n, rpb, cis=False)
         final["N"], final["rpb"] = pts.n, rpb
+        if exact == "defer":
+            hostops.submit_pvalues(final, cis=False)          # evaluated by the process-wide pool while other files run
         stats["loops"] = int(final["coords"].shape[0])
         return final, stats
     finally:
@@ -131,13 +133,19 @@ def callTransLoops(predir, fout, logger, eps=[2000, 5000], minPts=[5, 10], cpu=1
     results = {}
     first = {}
     stats = np.zeros(4, dtype=np.int64)
-    for k, (final, st) in zip(mine, shard.map_units(ctxs, mine, one)):
+    prev_mode = shard.set_sync_mode(True) if ex else None      # sleeping waits leave the cores to the scipy pool
+    try:
+        done = shard.map_units(ctxs, mine, one)
+    finally:
+        if ex:
+            shard.set_sync_mode(prev_mode)
+    for k, (final, st) in zip(mine, done):
         stats += np.array([st["pets"], st["candidates"], st["tested"], st["loops"]], dtype=np.int64)
         if st["first_pass"] >= 0:
             results[k] = final
             first[k] = st["first_pass"]
     if ex:
-        hostops.scipy_pvalues_many([results[k] for k in results], cis=False)
+        hostops.wait_pvalues([results[k] for k in results])
     stats = shard.allreduce_stats(stats)
     gathered = shard.gather_results({k: (first[k], results[k]) for k in results})
     if rank != 0:

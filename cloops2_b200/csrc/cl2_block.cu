@@ -93,10 +93,8 @@ __device__ __forceinline__ int lb_backward(const uint64_t *__restrict__ ckey, in
 
 __global__ void __launch_bounds__(256) k_block_nbr(const uint64_t *__restrict__ ckey,
                                                     const int32_t *__restrict__ cstart, int32_t *__restrict__ nbr,
-                                                    int32_t *__restrict__ s3, int32_t *__restrict__ maxcnt,
-                                                    int32_t ncells, int by) {
+                                                    int32_t *__restrict__ s3, int32_t ncells, int by) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
-    int mycnt = 0;
     if (c < ncells) {
         const uint64_t k = ckey[c];
         const uint64_t ymask = (1ull << by) - 1;
@@ -136,8 +134,7 @@ __global__ void __launch_bounds__(256) k_block_nbr(const uint64_t *__restrict__ 
                 else break;
             }
         }
-        mycnt = cstart[c + 1] - cstart[c];
-        int s = mycnt;
+        int s = cstart[c + 1] - cstart[c];
 #pragma unroll
         for (int d = 0; d < 8; d++) {
             if (out[d] >= 0) s += cstart[out[d] + 1] - cstart[out[d]];
@@ -147,9 +144,6 @@ __global__ void __launch_bounds__(256) k_block_nbr(const uint64_t *__restrict__ 
         o[1] = make_int4(out[4], out[5], out[6], out[7]);
         s3[c] = s;
     }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) mycnt = max(mycnt, __shfl_xor_sync(0xffffffffu, mycnt, o));
-    if ((threadIdx.x & 31) == 0 && mycnt > 0) atomicMax(maxcnt, mycnt);
 }
 
 // ------------------------------------------------------------------------------------------------ K7 noise
@@ -328,10 +322,14 @@ __global__ void __launch_bounds__(HEAVY_THREADS) k_block_adj_heavy(const int2 *_
                                                                     const int32_t *__restrict__ cstart,
                                                                     const int32_t *__restrict__ nbr,
                                                                     const int2 *__restrict__ heavy,
+                                                                    const int32_t *__restrict__ nheavy,
                                                                     unsigned *__restrict__ adj, int64_t eps) {
     __shared__ int2 tile[HEAVY_TILE];
     __shared__ int found;
-    int2 h = heavy[blockIdx.x];
+    const int nh = *nheavy;
+    for (int hi = blockIdx.x; hi < nh; hi += gridDim.x) {
+    __syncthreads();                       // `found` and the tile of the previous pair are done with
+    int2 h = heavy[hi];
     int a = h.x, d = h.y;
     int b = nbr[8 * (int64_t)a + d];
     int a0 = cstart[a], a1 = cstart[a + 1], b0 = cstart[b], b1 = cstart[b + 1];
@@ -361,6 +359,7 @@ __global__ void __launch_bounds__(HEAVY_THREADS) k_block_adj_heavy(const int2 *_
         atomicOr(&adj[a], 1u << d);
         atomicOr(&adj[b], 1u << c_opp[d]);
     }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ K10 core
@@ -369,7 +368,7 @@ __global__ void __launch_bounds__(HEAVY_THREADS) k_block_adj_heavy(const int2 *_
 __global__ void __launch_bounds__(256) k_block_core(const int32_t *__restrict__ cstart, const int32_t *__restrict__ nbr,
                                                      const unsigned *__restrict__ adj, const uint32_t *__restrict__ first,
                                                      const int32_t *__restrict__ list, int32_t nkept, int minPts,
-                                                     int32_t maxcnt, uint8_t *__restrict__ core,
+                                                     uint8_t *__restrict__ core,
                                                      uint64_t *__restrict__ okey, int32_t *__restrict__ parent,
                                                      uint64_t *__restrict__ minkey) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -385,7 +384,7 @@ __global__ void __launch_bounds__(256) k_block_core(const int32_t *__restrict__ 
         near += cstart[b + 1] - cstart[b];
     }
     core[c] = near >= minPts ? 1 : 0;
-    okey[c] = ((uint64_t)(uint32_t)(maxcnt - cnt) << 32) | (uint64_t)first[c];
+    okey[c] = ((uint64_t)(uint32_t)(0x7fffffff - cnt) << 32) | (uint64_t)first[c];     // larger cells first, ties by dict position
     parent[c] = c;
     minkey[c] = ~0ull;
 }
@@ -664,14 +663,10 @@ int cl2_grid_build(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int kind, int32_t
         FamTimer t(ctx, FAM_CELLS, 20.0 * (double)n);
         k_cell_table<<<cl2_grid(n, 256), 256, 0, ctx->stream>>>(g.sxy, gen, g.row, g.cid, g.cstart, g.ckey, g.first, n, ncells);
     }
-    int32_t *d_max;
-    CL2_TRY(sc.get(&d_max, 1));
-    CL2_CUDA(ctx, cudaMemsetAsync(d_max, 0, 4, ctx->stream));
     {
         FamTimer t(ctx, FAM_NBR, 52.0 * (double)ncells);
-        k_block_nbr<<<cl2_grid(ncells, 256), 256, 0, ctx->stream>>>(g.ckey, g.cstart, g.nbr, g.s3, d_max, ncells, by);
+        k_block_nbr<<<cl2_grid(ncells, 256), 256, 0, ctx->stream>>>(g.ckey, g.cstart, g.nbr, g.s3, ncells, by);
     }
-    CL2_TRY(cl2_read_i32(ctx, d_max, &g.maxcnt));
     CL2_CUDA(ctx, cudaGetLastError());
     g.valid = true;
     g.kind = kind;
@@ -808,11 +803,20 @@ extern "C" int cl2_block_noise(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int32
 
 extern "C" int cl2_block_dbscan(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int32_t minPts, int32_t *labels_out,
                                 int32_t *n_clusters) {
+    return cl2_block_dbscan_impl(ctx, pts, eps, minPts, labels_out, n_clusters, true);
+}
+
+// ordered = false: the clusters are reported in cell-key order with pts->ckeys[i] the key that ranks cluster i in the
+// reference's numbering (no labels then)
+int cl2_block_dbscan_impl(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int32_t minPts, int32_t *labels_out,
+                          int32_t *n_clusters, bool ordered) {
     CL2_TRY(block_check_args(ctx, pts, eps, minPts));
+    if (labels_out) ordered = true;
     if (n_clusters) *n_clusters = 0;
     pts->ncl = 0;
     pts->bbox.clear();
     pts->size.clear();
+    pts->ckeys.clear();
     if (pts->n == 0) return CL2_OK;
     CL2_CUDA(ctx, cudaSetDevice(ctx->device));
     CL2_TRY(cl2_grid_build(ctx, pts, eps, 0, minPts));
@@ -868,14 +872,14 @@ extern "C" int cl2_block_dbscan(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int3
         CL2_TRY(sc.get(&compid, (size_t)ncells));
         CL2_TRY(sc.get(&heavy, (size_t)nkept * 4));
         CL2_TRY(sc.get(&nheavy, 2));                 // [0] heavy pairs, [1] crowded cells
-        if (g.maxcnt > CELLSTAT_SERIAL_MAX) CL2_TRY(sc.get(&crowd, (size_t)nkept));
+        CL2_TRY(sc.get(&crowd, (size_t)nkept));
         CL2_CUDA(ctx, cudaMemsetAsync(adj, 0, (size_t)ncells * 4, s));
         CL2_CUDA(ctx, cudaMemsetAsync(core, 0, (size_t)ncells, s));
         CL2_CUDA(ctx, cudaMemsetAsync(nheavy, 0, 8, s));
         {
             FamTimer t(ctx, FAM_CELLSTAT, 8.0 * (double)n, 2);
             k_block_cellstat_small<<<cl2_grid(nkept, 256), 256, 0, s>>>(g.sxy, g.cstart, list, st, nkept, crowd, nheavy + 1);
-            if (g.maxcnt > CELLSTAT_SERIAL_MAX) {
+            {
                 int64_t want = cl2_grid((int64_t)nkept * 32, 256), cap = (int64_t)ctx->sm_count * 8;
                 k_block_cellstat_list<<<(unsigned)(want < cap ? want : cap), 256, 0, s>>>(g.sxy, g.cstart, crowd, nheavy + 1, st);
             }
@@ -885,16 +889,17 @@ extern "C" int cl2_block_dbscan(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int3
             k_block_adj<<<cl2_grid((int64_t)nkept * 4, 128), 128, 0, s>>>(g.sxy, g.cstart, g.nbr, keep, st, list, nkept,
                                                                            adj, eps, heavy, nheavy);
         }
-        int32_t nh = 0;
-        CL2_TRY(cl2_read_i32(ctx, nheavy, &nh));
-        if (nh > 0) {
+        {
+            // heavy pairs (listed by k_block_adj, count on the device): blocks of a fixed-size grid stride over the list
             FamTimer t(ctx, FAM_ADJ, 0.0);
-            k_block_adj_heavy<<<nh, HEAVY_THREADS, 0, s>>>(g.sxy, g.cstart, g.nbr, heavy, adj, eps);
+            int64_t want = (int64_t)nkept * 4, cap = (int64_t)ctx->sm_count * 8;
+            k_block_adj_heavy<<<(unsigned)(want < cap ? want : cap), HEAVY_THREADS, 0, s>>>(g.sxy, g.cstart, g.nbr, heavy, nheavy,
+                                                                                           adj, eps);
         }
         {
             FamTimer t(ctx, FAM_CORE, 64.0 * (double)nkept);
-            k_block_core<<<cl2_grid(nkept, 256), 256, 0, s>>>(g.cstart, g.nbr, adj, g.first, list, nkept, minPts, g.maxcnt,
-                                                               core, okey, parent, minkey);
+            k_block_core<<<cl2_grid(nkept, 256), 256, 0, s>>>(g.cstart, g.nbr, adj, g.first, list, nkept, minPts, core, okey,
+                                                               parent, minkey);
         }
         {
             FamTimer t(ctx, FAM_UNION, 48.0 * (double)nkept, 2);
@@ -936,40 +941,22 @@ extern "C" int cl2_block_dbscan(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int3
     }
 
     // Cluster numbering = rank of the components' start-cell order keys (blockDBSCAN.py:146-152).  The component
-    // count is tiny next to n, so the keys and boxes go to the host and are ordered there (no device sort).
+    // count is small next to n, so the keys and boxes go to the host and are ordered there.  Callers that only need the
+    // boxes and sort a few survivors themselves (cl2_call_loops) take them unordered, each with its key.
     std::vector<ClusterBox> hb((size_t)ncomp);
     std::vector<uint64_t> hk((size_t)ncomp);
     if (ncomp > 0) {
         CL2_CUDA(ctx, cudaMemcpyAsync(hb.data(), box, (size_t)ncomp * sizeof(ClusterBox), cudaMemcpyDeviceToHost, s));
-        ctx->d2h_bytes += (int64_t)ncomp * (int64_t)sizeof(ClusterBox);
-        if (ncomp <= CL2_HOST_SORT_MAX) {
-            CL2_CUDA(ctx, cudaMemcpyAsync(hk.data(), ckeys, (size_t)ncomp * 8, cudaMemcpyDeviceToHost, s));
-            ctx->d2h_bytes += (int64_t)ncomp * 8;
-        }
+        CL2_CUDA(ctx, cudaMemcpyAsync(hk.data(), ckeys, (size_t)ncomp * 8, cudaMemcpyDeviceToHost, s));
+        ctx->d2h_bytes += (int64_t)ncomp * ((int64_t)sizeof(ClusterBox) + 8);
     }
     std::vector<int32_t> order((size_t)ncomp);
-    const bool device_sort = ncomp > CL2_HOST_SORT_MAX;
-    if (device_sort) {
-        // many components (large chromosomes): order the keys with the device radix sort, read back the permutation
-        uint64_t *ck1, *cks;
-        uint32_t *o0, *o1, *os;
-        CL2_TRY(sc.get(&ck1, (size_t)ncomp));
-        CL2_TRY(sc.get(&o0, (size_t)ncomp));
-        CL2_TRY(sc.get(&o1, (size_t)ncomp));
-        ctx->sort_family = FAM_COMP;   // a few thousand keys: part of the component ordering, not of the PET sorts
-        const int src = cl2_radix_sort_pairs(ctx, ckeys, ck1, o0, o1, ncomp, 32 + bits_for((uint64_t)g.maxcnt), &cks, &os);
-        ctx->sort_family = -1;
-        CL2_TRY(src);
-        (void)cks;
-        CL2_CUDA(ctx, cudaMemcpyAsync(order.data(), os, (size_t)ncomp * 4, cudaMemcpyDeviceToHost, s));
-        ctx->d2h_bytes += (int64_t)ncomp * 4;
-    }
     CL2_CUDA(ctx, cudaStreamSynchronize(s));
     CL2_CUDA(ctx, cudaGetLastError());
-    if (!device_sort) {
-        for (int32_t i = 0; i < ncomp; i++) order[i] = i;
-        std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return hk[a] < hk[b]; });
-    }
+    for (int32_t i = 0; i < ncomp; i++) order[i] = i;
+    if (ordered) std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return hk[a] < hk[b]; });
+    pts->ckeys.resize((size_t)ncomp);
+    for (int32_t i = 0; i < ncomp; i++) pts->ckeys[i] = hk[order[i]];
     pts->ncl = ncomp;
     pts->bbox.resize((size_t)ncomp * 4);
     pts->size.resize((size_t)ncomp);

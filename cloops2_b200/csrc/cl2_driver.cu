@@ -83,7 +83,10 @@ extern "C" int cl2_call_loops(cl2_ctx *ctx, cl2_points *pts, int32_t mode, int32
             if (eps[a] != eps[b]) return eps[a] > eps[b];
             return minPts[a] < minPts[b];
         });
-    std::vector<std::vector<int64_t>> cand((size_t)npass);   // per run: kept boxes, 4 values each, ascending cluster id
+    // per run: kept boxes, 4 values each, and the key that ranks each box in the reference's cluster numbering (the
+    // blockDBSCAN runs report their clusters unordered: only the few survivors are put in order, at the end)
+    std::vector<std::vector<int64_t>> cand((size_t)npass);
+    std::vector<std::vector<uint64_t>> ckey((size_t)npass);
     int rc = CL2_OK;
     for (int pos = 0; pos < npass && rc == CL2_OK; pos++) {
         const int i = order[pos];
@@ -94,10 +97,13 @@ extern "C" int cl2_call_loops(cl2_ctx *ctx, cl2_points *pts, int32_t mode, int32
             cl2_points_sweep_hint(ctx, pts, useful ? 1 : 2);
         }
         int32_t ncl = 0;
-        rc = use_c2 ? cl2_cdbscan2(ctx, pts, eps[i], minPts[i], nullptr, &ncl) : cl2_block_dbscan(ctx, pts, eps[i], minPts[i], nullptr, &ncl);
+        rc = use_c2 ? cl2_cdbscan2(ctx, pts, eps[i], minPts[i], nullptr, &ncl)
+                    : cl2_block_dbscan_impl(ctx, pts, eps[i], minPts[i], nullptr, &ncl, false);
         if (rc != CL2_OK) break;
         std::vector<int64_t> &c = cand[(size_t)i];
+        std::vector<uint64_t> &ck = ckey[(size_t)i];
         c.reserve((size_t)ncl * 4);
+        ck.reserve((size_t)ncl);
         int64_t pets = 0;
         for (int32_t k = 0; k < ncl; k++) {
             const int64_t x0 = pts->bbox[4 * (size_t)k], x1 = pts->bbox[4 * (size_t)k + 1];
@@ -108,6 +114,7 @@ extern "C" int cl2_call_loops(cl2_ctx *ctx, cl2_points *pts, int32_t mode, int32
                 if (!(x1 < y0)) continue;                    // :116
             }
             c.push_back(x0); c.push_back(x1); c.push_back(y0); c.push_back(y1);
+            ck.push_back(use_c2 ? (uint64_t)k : pts->ckeys[(size_t)k]);
             pets += pts->size[(size_t)k];
         }
         r->pass_cand[(size_t)i] = (int64_t)c.size() / 4;
@@ -118,6 +125,7 @@ extern "C" int cl2_call_loops(cl2_ctx *ctx, cl2_points *pts, int32_t mode, int32
     // centres as the reference computes them, (start + end) / 2 in floating point (:107-112)
     std::vector<int64_t> all;
     std::vector<int32_t> pid;
+    std::vector<uint64_t> akey;
     for (int i = 0; i < npass; i++) {
         const std::vector<int64_t> &c = cand[(size_t)i];
         for (size_t k = 0; k + 3 < c.size(); k += 4) {
@@ -128,6 +136,7 @@ extern "C" int cl2_call_loops(cl2_ctx *ctx, cl2_points *pts, int32_t mode, int32
             }
             all.insert(all.end(), c.begin() + k, c.begin() + k + 4);
             pid.push_back(i);
+            akey.push_back(ckey[(size_t)i][k / 4]);
         }
     }
     const int64_t L = (int64_t)pid.size();
@@ -164,9 +173,19 @@ extern "C" int cl2_call_loops(cl2_ctx *ctx, cl2_points *pts, int32_t mode, int32
     // combineLoops (geo.py:90-112) drops a candidate whose coordinates were already present from an EARLIER run;
     // the cis path then also applies filterDupLoops (callCisLoops.py:159-169: first position of every coordinate
     // tuple).  A candidate's test result depends on its coordinates only, so both are applied to the survivors.
+    // survivors in candidate order: run by run as given, ascending cluster id inside a run
+    std::vector<int64_t> sorder((size_t)nk);
+    for (int64_t q = 0; q < nk; q++) sorder[(size_t)q] = q;
+    std::sort(sorder.begin(), sorder.end(), [&](int64_t a, int64_t b) {
+        const int64_t ka = sel[(size_t)a], kb = sel[(size_t)b];
+        if (pid[(size_t)ka] != pid[(size_t)kb]) return pid[(size_t)ka] < pid[(size_t)kb];
+        if (akey[(size_t)ka] != akey[(size_t)kb]) return akey[(size_t)ka] < akey[(size_t)kb];
+        return ka < kb;
+    });
     std::unordered_map<Key4, int32_t, Key4Hash> first_pass;
     first_pass.reserve((size_t)nk * 2 + 1);
-    for (int64_t q = 0; q < nk; q++) {
+    for (int64_t qq = 0; qq < nk; qq++) {
+        const int64_t q = sorder[(size_t)qq];
         const int64_t k = sel[(size_t)q];
         Key4 key = {{all[4 * k], all[4 * k + 1], all[4 * k + 2], all[4 * k + 3]}};
         auto it = first_pass.find(key);

@@ -13,7 +13,6 @@ struct cl2_grid_cache {
     int sub_level = -1;       // which pts->subs[] entry it was built from (-1: every point)
     int32_t ncells = 0;
     int by = 0;               // bits of the low (gy) field of the packed key
-    int32_t maxcnt = 0;       // largest cell population
     uint32_t *row = nullptr;  // [n]   original row id of sorted position i
     int2 *sxy = nullptr;      // [n]   (x,y) of sorted position i   (cDBSCAN2 grid: (u,v) rotated, int64 pairs in suv)
     int32_t *cid = nullptr;   // [n]   cell id of sorted position i
@@ -52,6 +51,7 @@ struct cl2_points {
     int32_t ncl = 0;
     std::vector<int64_t> bbox;  // [ncl*4]
     std::vector<int64_t> size;  // [ncl]
+    std::vector<uint64_t> ckeys;  // [ncl] rank key of every cluster in the reference's numbering (blockDBSCAN runs)
 };
 
 struct cl2_index {
@@ -70,6 +70,8 @@ void cl2_subsets_free(cl2_ctx *ctx, cl2_points *pts, size_t keep_levels = 0);
 // minPts >= 0 allows a grid over the smallest pts->subs[] entry valid for (eps, minPts); -1 asks for every point.
 int cl2_grid_build(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int kind, int32_t minPts = -1);
 int cl2_points_yorder(cl2_ctx *ctx, cl2_points *pts);   // cl2_count.cu
+int cl2_block_dbscan_impl(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int32_t minPts, int32_t *labels_out,
+                          int32_t *n_clusters, bool ordered);    // cl2_block.cu
 int cl2_read_i64(cl2_ctx *ctx, const int64_t *d, int64_t *out);
 int cl2_read_i32(cl2_ctx *ctx, const int32_t *d, int32_t *out);
 

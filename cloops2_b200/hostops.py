@@ -267,7 +267,11 @@ def _cols_from_stats(c, core, hyp, st, pseudo, tot):
                 mrabs=mrabs, mbps=st[:, 1], anc=st[:, 9:13])
 
 
-def scipy_pvalues(cols, N, rpb, cis=True):
+def _scipy_serial(cols, N, rpb, cis):
+    return scipy_pvalues(cols, N, rpb, cis=cis, threads=False)
+
+
+def scipy_pvalues(cols, N, rpb, cis=True, threads=True):
     """Re-evaluate the tail probabilities of (few) surviving loops with scipy, argument for argument as the reference
     calls it (callCisLoops.py:246,310,329,332; callTransLoops.py:153,178,181), so the printed digits are the
     reference's.  Everything else in `cols` is already bit-identical.  N and rpb may be per-row arrays (rows of
@@ -290,31 +294,67 @@ def scipy_pvalues(cols, N, rpb, cis=True):
         py, esy = anchor_sig(a2, a3, lb, rv)
         return np.stack([hyp, pop, nbp, px, esx, py, esy], axis=1)
 
-    t = _threaded(tails, rab, ra, rb, Nv, rv, cols["mrabs"], cols["mbps"], c[:, 1] - c[:, 0], c[:, 3] - c[:, 2],
-                  anc[:, 0].astype(np.int64), anc[:, 1].astype(np.int64), anc[:, 2].astype(np.int64),
-                  anc[:, 3].astype(np.int64))
+    run = _threaded if threads else (lambda fn, *a: fn(*a))
+    t = run(tails, rab, ra, rb, Nv, rv, cols["mrabs"], cols["mbps"], c[:, 1] - c[:, 0], c[:, 3] - c[:, 2],
+            anc[:, 0].astype(np.int64), anc[:, 1].astype(np.int64), anc[:, 2].astype(np.int64),
+            anc[:, 3].astype(np.int64))
     out["hyp"], out["pop"], out["nbp"] = _clamp(t[:, 0]), _clamp(t[:, 1]), _clamp(t[:, 2])
     out["px"], out["esx"], out["py"], out["esy"] = t[:, 3], t[:, 4], t[:, 5], t[:, 6]
     return out
 
 
-def scipy_pvalues_many(finals, cis=True):
-    """scipy_pvalues over the final loops of several files at once (one evaluation, one thread pool per rank instead
-    of one per file); every entry carries its own "N" and "rpb" (cis_chromosome / trans_pair).  In place."""
-    finals = [f for f in finals if f["coords"].shape[0] > 0]
-    if not finals:
-        return
-    names = [k for k in COLS if k in finals[0]]
-    cat = {k: np.concatenate([f[k] for f in finals], axis=0) for k in names}
-    Nv = np.concatenate([np.full(f["coords"].shape[0], float(f["N"])) for f in finals])
-    rv = np.concatenate([np.full(f["coords"].shape[0], float(f["rpb"])) for f in finals])
-    out = scipy_pvalues(cat, Nv, rv, cis=cis)
-    o = 0
+_pv_pool = None
+
+
+def pvalue_pool():
+    """One pool of host threads per process for the scipy re-evaluation of the exact mode (the ufunc loops release the
+    GIL).  Work is handed to it file by file as soon as a file's final loops are known, so it overlaps the GPU work on
+    the remaining files."""
+    global _pv_pool
+    if _pv_pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except AttributeError:
+            cores = os.cpu_count() or 1
+        world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1)
+        _pv_pool = ThreadPoolExecutor(max(2, cores // max(1, world) - 1))
+    return _pv_pool
+
+
+def submit_pvalues(final, cis=True, chunk=1024):
+    """Queue scipy_pvalues for the rows of `final` (which carries its file's "N" and "rpb"); the futures are stored in
+    final["_pending"] and the columns are replaced by wait_pvalues().  (numpy only releases the GIL for ufunc loops of
+    more than 500 elements, so the chunks must not be small.)"""
+    n = final["coords"].shape[0]
+    if n == 0:
+        return final
+    pool = pvalue_pool()
+    names = [k for k in COLS if k in final]
+    futs = []
+    for o in range(0, n, chunk):
+        part = {k: final[k][o:o + chunk] for k in names}
+        futs.append(pool.submit(_scipy_serial, part, final["N"], final["rpb"], cis))
+    final["_pending"] = futs
+    return final
+
+
+def wait_pvalues(finals):
     for f in finals:
-        m = f["coords"].shape[0]
+        futs = f.pop("_pending", None)
+        if not futs:
+            continue
+        parts = [x.result() for x in futs]
         for k in ("hyp", "pop", "nbp", "px", "py", "esx", "esy"):
-            f[k] = out[k][o:o + m]
-        o += m
+            f[k] = np.concatenate([q[k] for q in parts])
+
+
+def scipy_pvalues_many(finals, cis=True):
+    """scipy_pvalues over the final loops of several files (every entry carries its own "N" and "rpb"), in place."""
+    for f in finals:
+        if "_pending" not in f:
+            submit_pvalues(f, cis=cis)
+    wait_pvalues(finals)
 
 
 # Relative distance from a cut below which a device tail probability is not trusted to decide like scipy's would: the

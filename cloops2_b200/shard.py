@@ -146,17 +146,17 @@ def worker_contexts(device=None, nthreads=None):
     except AttributeError:
         cores = os.cpu_count() or 8
     share = max(1, cores // max(1, world))                   # host cores this rank can count on
-    # Default: 8 workers that spin while they wait (measured per 100M-PET step with a core per worker: 4 workers 104 ms,
-    # 6: 96, 8: 93, 12: 97; sleeping waits cost ~12 % when cores are plentiful).  With 6-8 cores per rank: one worker
-    # per core but one, still spinning (4 GPUs on 32 cores: 7 workers, 99 ms).  Below that spinning workers starve each
-    # other, so the waits sleep (cl2_set_sync_mode) and the worker count stays at 8 (4 cores: 3 spinning workers 118 ms,
-    # 8 sleeping workers 114 ms).  CL2_THREADS / CL2_BLOCKING_SYNC override either choice.
-    blocking = share < 6
+    # Default: 8 workers that spin while they wait.  Since the per-file loop runs on the native side of the ABI
+    # (cl2_call_loops) the workers hold no interpreter lock while they wait, and measured on one B200 per 100M-PET step:
+    # 16 cores 66 ms (7 workers); confined to 4 cores: 8 spinning workers 77 ms, 8 sleeping workers 87 ms -- so the
+    # waits only sleep (cl2_set_sync_mode) below 4 cores per rank, or when the scipy pool of the exact mode needs the
+    # cores.  CL2_THREADS / CL2_BLOCKING_SYNC override either choice.
+    blocking = share < 4
     if nthreads is None:
-        nthreads = int(os.environ.get("CL2_THREADS", "8" if blocking else str(max(2, min(8, share - 1)))))
+        nthreads = int(os.environ.get("CL2_THREADS", "8" if share < 8 else str(max(2, min(8, share - 1)))))
     if os.environ.get("CL2_BLOCKING_SYNC") is not None:
         blocking = os.environ["CL2_BLOCKING_SYNC"] not in ("0", "")
-    _lib.load().cl2_set_sync_mode(1 if blocking else 0)
+    set_sync_mode(blocking)
     nthreads = max(1, nthreads)
     first = _lib.default_context(device)
     # the workers of a device are kept for the life of the process: a second callCisLoops / callTransLoops call reuses
@@ -168,6 +168,19 @@ def worker_contexts(device=None, nthreads=None):
 
 
 _worker_pool = {}
+
+
+_sync_mode = [0]
+
+
+def set_sync_mode(blocking):
+    """How worker threads wait for their streams (cl2_set_sync_mode): spinning (lowest latency) or sleeping (leaves the
+    cores to other host work, e.g. the scipy pool of the exact mode).  Returns the previous mode."""
+    from . import _lib
+    prev = _sync_mode[0]
+    _sync_mode[0] = 1 if blocking else 0
+    _lib.load().cl2_set_sync_mode(_sync_mode[0])
+    return prev
 
 
 def map_units(ctxs, units, fn):

@@ -183,6 +183,23 @@ int cl2_loops_info(const cl2_loops *r, int64_t *pass_cand, int64_t *pass_pets, i
 int cl2_loops_read(const cl2_loops *r, int64_t *coords, int32_t *pass_id, int64_t *core, double *hyp, double *stats);
 void cl2_loops_free(cl2_loops *r);
 
+/* ---- multi-GPU: the path's only collective ------------------------------------------------------------------ */
+/*
+ * One process per GPU, chromosome (pair) files sharded over the ranks (the reference fans the same units out over
+ * joblib workers, callCisLoops.py:134-137, 561-572); no data flows between units, so the only exchange is the sum of
+ * the per-rank counters (PETs, candidates, tested, loops) that the reference's single process simply accumulates.
+ * cl2_comm wraps an NCCL communicator (libnccl is loaded at run time): rank 0 calls cl2_comm_unique_id and hands the
+ * CL2_COMM_ID_BYTES bytes to the other ranks over any host channel (a file, MPI, the launcher's store), then every rank
+ * calls cl2_comm_init with the same id.  cl2_stats_allreduce sums vals[0..k) over the ranks in place (host buffer;
+ * ncclAllReduce of int64 on the context's stream).  Per-file loop lists are gathered by the host program.
+ */
+#define CL2_COMM_ID_BYTES 128
+typedef struct cl2_comm cl2_comm;
+int cl2_comm_unique_id(uint8_t *id_out);
+int cl2_comm_init(cl2_ctx *ctx, const uint8_t *id, int32_t rank, int32_t world, cl2_comm **out);
+int cl2_stats_allreduce(cl2_ctx *ctx, cl2_comm *comm, int64_t *vals, int32_t k);
+void cl2_comm_destroy(cl2_comm *comm);
+
 /* ---- host-side selection (native, no GPU) ----------------------------------------------------------------- */
 /*
  * selSigLoops (callCisLoops.py:379-422) for the loops of ONE chromosome (pair), all already significant, in list
