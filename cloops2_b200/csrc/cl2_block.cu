@@ -346,9 +346,11 @@ __global__ void __launch_bounds__(HEAVY_THREADS) k_block_adj_heavy(const int2 *_
                 int2 q = tile[j];
                 long long dist = (long long)abs(p.x - q.x) + (long long)abs(p.y - q.y);
                 if (dist <= eps) { hit = true; break; }
+                // another thread already found a pair: only shortens this thread's scan (any hit decides the pair)
+                if ((j & 63) == 63 && *(volatile int *)&found) break;
             }
             if (hit) { found = 1; break; }
-            if (found) break;   // another thread already found a pair (only shortens this thread's scan)
+            if (*(volatile int *)&found) break;
         }
         __syncthreads();
         int f = found;          // uniform: written only between the two barriers above
@@ -523,23 +525,40 @@ __global__ void __launch_bounds__(256) k_box_init(ClusterBox *__restrict__ box, 
         box[i] = b;
     }
 }
+// Cells are visited in key order, so the cells of a large cluster (a diagonal band of Hi-C-like data holds most of
+// them) arrive warp after warp with the same label: the lanes of a warp that share a label combine their boxes with a
+// masked warp reduction and their first lane issues the five atomics, instead of 32 atomics on one address.
 __global__ void __launch_bounds__(256) k_block_bbox(const int32_t *__restrict__ cstart,
                                                      const CellStat *__restrict__ st,
                                                      const int32_t *__restrict__ clabel,
                                                      const int32_t *__restrict__ list, int32_t nkept,
                                                      ClusterBox *__restrict__ box) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= nkept) return;
-    int c = list[k];
-    int lab = clabel[c];
-    if (lab < 0) return;
-    const CellStat s = st[c];
+    int lab = -1;
+    int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
+    unsigned size = 0;
+    if (k < nkept) {
+        int c = list[k];
+        lab = clabel[c];
+        if (lab >= 0) {
+            const CellStat s = st[c];
+            xmin = s.xmin; xmax = s.xmax; ymin = s.ymin; ymax = s.ymax;
+            size = (unsigned)(cstart[c + 1] - cstart[c]);
+        }
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, lab);
+    xmin = __reduce_min_sync(peers, xmin);
+    xmax = __reduce_max_sync(peers, xmax);
+    ymin = __reduce_min_sync(peers, ymin);
+    ymax = __reduce_max_sync(peers, ymax);
+    size = __reduce_add_sync(peers, size);
+    if (lab < 0 || (int)(threadIdx.x & 31) != __ffs(peers) - 1) return;
     ClusterBox *b = &box[lab];
-    atomicMin(&b->xmin, s.xmin);
-    atomicMax(&b->xmax, s.xmax);
-    atomicMin(&b->ymin, s.ymin);
-    atomicMax(&b->ymax, s.ymax);
-    atomicAdd(&b->size, (unsigned)(cstart[c + 1] - cstart[c]));
+    atomicMin(&b->xmin, xmin);
+    atomicMax(&b->xmax, xmax);
+    atomicMin(&b->ymin, ymin);
+    atomicMax(&b->ymax, ymax);
+    atomicAdd(&b->size, size);
 }
 
 __global__ void __launch_bounds__(256) k_fill_i32(int32_t *__restrict__ p, int32_t v, int64_t n) {

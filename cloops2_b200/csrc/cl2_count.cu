@@ -305,10 +305,39 @@ __device__ __forceinline__ long long ycount_both(const IvPos &U, const IvPos &V)
     return e > b ? e - b : 0;
 }
 
+// The warps that work on one candidate together.  Candidates whose regions hold few rows are handled by one warp each;
+// the rare large ones (a 1 Mb anchor of Hi-C-like data spans millions of rows) would leave that warp running long after
+// the rest of the grid has finished, so they are handed to a second kernel in which all warps of a block share the scan
+// of one candidate and combine their partial sums through shared memory.
+struct Coop {
+    int nw;      // warps sharing the candidate (1: no shared reduction, no block barrier)
+    int part;    // this warp's index among them
+    int *red;    // shared scratch of COOP_RED ints (nw > 1)
+    bool defer;  // a single warp may decline a large candidate (the caller has the cooperative kernel to hand it to)
+};
+__device__ __forceinline__ Coop coop_solo() { Coop c = {1, 0, nullptr, false}; return c; }
+#define COOP_RED 128
+#define BIG_ROWS 8192        // rows (X-range lengths) from which a candidate goes to the cooperative kernel
+// vals[0..k): warp-uniform partial sums on entry, the sums over the cooperating warps on return (all threads call)
+template <int K>
+__device__ __forceinline__ void coop_sum(const Coop &C, int (&vals)[K], int lane) {
+    if (C.nw == 1) return;
+    __syncthreads();
+    if ((int)threadIdx.x < K) C.red[threadIdx.x] = 0;
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < K; i++) atomicAdd(&C.red[i], vals[i]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < K; i++) vals[i] = C.red[i];
+}
+
 // sum over the rows with x in U | V:  cnt = [(x|y in U) and (x|y in V)] - [y in U and y in V],
 // eu = [x in U and y in U], ev = [x in V and y in V]
 __device__ __forceinline__ void pair_scan(const int2 *__restrict__ byx, const Iv32 U, const Iv32 V, const IvPos &PU,
-                                          const IvPos &PV, int lane, int &cnt, int &eu, int &ev) {
+                                          const IvPos &PV, int lane, const Coop &C, int &cnt, int &eu, int &ev) {
     uint32_t b0 = PU.xb, e0 = PU.xe, b1 = PV.xb, e1 = PV.xe;
     if (b0 <= e1 && b1 <= e0) {                              // overlapping or touching ranges: one scan
         b0 = b0 < b1 ? b0 : b1;
@@ -316,10 +345,11 @@ __device__ __forceinline__ void pair_scan(const int2 *__restrict__ byx, const Iv
         b1 = e1 = 0;
     }
     int c = 0, u = 0, v = 0;
+    const uint32_t stride = 32u * (uint32_t)C.nw;
 #pragma unroll 1
     for (int rr = 0; rr < 2; rr++) {
         const uint32_t b = rr ? b1 : b0, e = rr ? e1 : e0;
-        for (uint32_t p = b + lane; p < e; p += 32) {
+        for (uint32_t p = b + 32u * (uint32_t)C.part + lane; p < e; p += stride) {
             const int2 P = byx[p];
             const bool px = in32(U, P.x), qy = in32(U, P.y), rx = in32(V, P.x), sy = in32(V, P.y);
             c += (int)((px || qy) && (rx || sy)) - (int)(qy && sy);
@@ -327,15 +357,19 @@ __device__ __forceinline__ void pair_scan(const int2 *__restrict__ byx, const Iv
             v += (int)(rx && sy);
         }
     }
-    cnt = warp_sum(c);
-    eu = warp_sum(u);
-    ev = warp_sum(v);
+    int r[3] = {warp_sum(c), warp_sum(u), warp_sum(v)};
+    coop_sum(C, r, lane);
+    cnt = r[0];
+    eu = r[1];
+    ev = r[2];
 }
 // #{x in I and y in I} over the X range of I
-__device__ __forceinline__ int both_scan(const int2 *__restrict__ byx, const Iv32 I, const IvPos &P, int lane) {
+__device__ __forceinline__ int both_scan(const int2 *__restrict__ byx, const Iv32 I, const IvPos &P, int lane, const Coop &C) {
     int c = 0;
-    for (uint32_t p = P.xb + lane; p < P.xe; p += 32) c += (int)in32(I, byx[p].y);
-    return warp_sum(c);
+    for (uint32_t p = P.xb + 32u * (uint32_t)C.part + lane; p < P.xe; p += 32u * (uint32_t)C.nw) c += (int)in32(I, byx[p].y);
+    int r[1] = {warp_sum(c)};
+    coop_sum(C, r, lane);
+    return r[0];
 }
 
 struct WarpAcc {
@@ -405,8 +439,10 @@ __device__ __forceinline__ void window_accumulate(WarpAcc &A, int W, unsigned ma
 // queried, members counted from below as max(cX, cY), plus 2 arrays x 2 searches x ceil(log2 N) x 8 B per interval
 // query; every lane carries the same value.
 // queryLoop counts + the P2LL window (cis callCisLoops.py:287-289, 302-305; trans callTransLoops.py:124-126, 142-144)
-__device__ void loop_core(const IdxView &ix, long long xs, long long xe, long long ys, long long ye, int mode, int lane,
-                          int64_t out[4], long long *g_bytes) {
+// Returns false (nothing scanned, nothing counted) when a single warp is asked for a candidate with more than BIG_ROWS
+// rows to scan: the caller hands it to the cooperative kernel.
+__device__ bool loop_core(const IdxView &ix, long long xs, long long xe, long long ys, long long ye, int mode, int lane,
+                          const Coop &C, int64_t out[4], long long *g_bytes) {
     // intervals 0..3: A, B, the lower-left pair A2, B2; lane 4k + 2*list + end searches one bound of interval k
     const int k = (lane >> 2) & 3;
     long long lo, hi;
@@ -418,22 +454,24 @@ __device__ void loop_core(const IdxView &ix, long long xs, long long xe, long lo
     } else { lo = ys - (ye - ys); hi = ys; }
     const uint32_t pos = lane < 16 ? bound_task(ix, lo, hi, (lane >> 1) & 1, lane & 1) : 0u;
     const IvPos PA = gather_pos(pos, 0), PB = gather_pos(pos, 1), PA2 = gather_pos(pos, 2), PB2 = gather_pos(pos, 3);
+    if (C.defer && (long long)(PA.xe - PA.xb) + (PB.xe - PB.xb) + (PA2.xe - PA2.xb) + (PB2.xe - PB2.xb) > BIG_ROWS) return false;
     const Iv32 A = iv32(xs, xe), B = iv32(ys, ye);
     Iv32 A2 = mode == CL2_MODE_CIS ? iv32(xe, xe + (xe - xs)) : iv32(xs - (xe - xs), xs);
     const Iv32 B2 = iv32(ys - (ye - ys), ys);
     int cab, ea, eb, clow, t1, t2;
-    pair_scan(ix.byx, A, B, PA, PB, lane, cab, ea, eb);
-    pair_scan(ix.byx, A2, B2, PA2, PB2, lane, clow, t1, t2);
+    pair_scan(ix.byx, A, B, PA, PB, lane, C, cab, ea, eb);
+    pair_scan(ix.byx, A2, B2, PA2, PB2, lane, C, clow, t1, t2);
     out[0] = ((int64_t)PA.xe - PA.xb) + ((int64_t)PA.ye - PA.yb) - ea;
     out[1] = ((int64_t)PB.xe - PB.xb) + ((int64_t)PB.ye - PB.yb) - eb;
     out[2] = ycount_both(PA, PB) + cab;
     out[3] = ycount_both(PA2, PB2) + clow;
     *g_bytes += 16 * (pos_max(PA) + pos_max(PB) + pos_max(PA2) + pos_max(PB2)) + 4 * 32 * (long long)ix.lg;
+    return true;
 }
 
 // estAnchorSig counts of both anchors (callCisLoops.py:226-247): count = |P(l,r)|, wide = |P(max(0, m-5len), m+5len)|
 __device__ void loop_anchors(const IdxView &ix, long long xs, long long xe, long long ys, long long ye, int lane,
-                             int64_t *cx, int64_t *wx, int64_t *cy, int64_t *wy, long long *g_bytes) {
+                             const Coop &C, int64_t *cx, int64_t *wx, int64_t *cy, int64_t *wy, long long *g_bytes) {
     // intervals 0..3: anchor x, its wide window, anchor y, its wide window
     const int k = (lane >> 2) & 3;
     const long long l = k < 2 ? xs : ys, r = k < 2 ? xe : ye;
@@ -449,7 +487,7 @@ __device__ void loop_anchors(const IdxView &ix, long long xs, long long xe, long
     for (int q = 0; q < 4; q++) {
         const IvPos P = gather_pos(pos, q);
         const long long il = __shfl_sync(0xffffffffu, I.lo, 4 * q), ih = __shfl_sync(0xffffffffu, I.hi, 4 * q);
-        res[q] = ((int64_t)P.xe - P.xb) + ((int64_t)P.ye - P.yb) - both_scan(ix.byx, iv32(il, ih), P, lane);
+        res[q] = ((int64_t)P.xe - P.xb) + ((int64_t)P.ye - P.yb) - both_scan(ix.byx, iv32(il, ih), P, lane, C);
         if (q & 1) *g_bytes += 16 * pos_max(P) + 2 * 32 * (long long)ix.lg;
     }
     *cx = res[0]; *wx = res[1]; *cy = res[2]; *wy = res[3];
@@ -514,8 +552,10 @@ __device__ __forceinline__ unsigned div_mask(const FamDiv &F, const WinDiv &D, i
 // W*W pair counters in registers from shuffled columns -- no shared-memory atomics, no data-dependent loops.
 // fdr_stop > 0: the scan may stop as soon as fdr_stop window pairs are known to hold more than `rab` rows (the
 // counters only grow), which decides the reference's `fdr >= 0.1` cut (callCisLoops.py:322); returns false then.
-__device__ bool loop_windows10(const IdxView &ix, long long xs, long long xe, long long ys, long long ye, int win, int lane,
-                               WarpAcc &S, long long *g_bytes, int fdr_stop = 0, long long rab = 0) {
+// Returns 1 when the counts are complete, 0 when the fdr cut was decided early, -1 when a single warp was asked for more
+// than BIG_ROWS rows (nothing scanned: the candidate goes to the cooperative kernel).
+__device__ int loop_windows10(const IdxView &ix, long long xs, long long xe, long long ys, long long ye, int win, int lane,
+                              const Coop &C, WarpAcc &S, long long *g_bytes, int fdr_stop = 0, long long rab = 0) {
     const int W = 2 * win;
     bool regular = ix.small != 0;
     WinDiv D;
@@ -568,7 +608,6 @@ __device__ bool loop_windows10(const IdxView &ix, long long xs, long long xe, lo
     uint32_t b0 = S.pos[0][0], e0 = S.pos[1][W - 1], b1 = S.pos[0][W], e1 = S.pos[1][2 * W - 1];
     const long long span_rows = (long long)max(e0 > b0 ? e0 - b0 : 0u, S.pos[3][W - 1] > S.pos[2][0] ? S.pos[3][W - 1] - S.pos[2][0] : 0u) +
                                 (long long)max(e1 > b1 ? e1 - b1 : 0u, S.pos[3][2 * W - 1] > S.pos[2][W] ? S.pos[3][2 * W - 1] - S.pos[2][W] : 0u);
-    *g_bytes += (2 * W + 1) * 32 * (long long)ix.lg;
     if (e0 < b0) e0 = b0;
     if (e1 < b1) e1 = b1;
     if (b0 <= e1 && b1 <= e0) {
@@ -577,6 +616,9 @@ __device__ bool loop_windows10(const IdxView &ix, long long xs, long long xe, lo
         b1 = e1 = 0;
     }
     const long long scan_rows = (long long)(e0 - b0) + (long long)(e1 - b1);
+    if (C.defer && scan_rows > BIG_ROWS) return -1;
+    if (C.nw > 1) fdr_stop = 0;                              // the partial counters of one warp decide nothing
+    *g_bytes += (2 * W + 1) * 32 * (long long)ix.lg;
     // this lane's pairs: lanes 0..29 own a-window lane / 3 and up to four b-windows from 4 * (lane % 3)
     const int pi = lane / 3, pj0 = 4 * (lane - 3 * pi);
     const bool own = lane < 30 && pi < W;
@@ -600,12 +642,13 @@ __device__ bool loop_windows10(const IdxView &ix, long long xs, long long xe, lo
 #pragma unroll 1
     for (int rr = 0; rr < 2 && !stopped; rr++) {
         const uint32_t rb = rr ? b1 : b0, re = rr ? e1 : e0;
-        int2 pnext = (rb + lane < re) ? byx[rb + lane] : make_int2(0, 0);
+        const uint32_t first = rb + 32u * (uint32_t)C.part, stride = 32u * (uint32_t)C.nw;
+        int2 pnext = (first + lane < re) ? byx[first + lane] : make_int2(0, 0);
         int since = 0;
-        for (uint32_t p0 = rb; p0 < re; p0 += 32) {
+        for (uint32_t p0 = first; p0 < re; p0 += stride) {
             const bool valid = p0 + lane < re;
             const int2 P = pnext;
-            pnext = (p0 + 32 + lane < re) ? byx[p0 + 32 + lane] : make_int2(0, 0);
+            pnext = (p0 + stride + lane < re) ? byx[p0 + stride + lane] : make_int2(0, 0);
             unsigned ax, ay, bx, by;
             if (regular) {
                 ax = div_mask(D.a, D, P.x); ay = div_mask(D.a, D, P.y);
@@ -645,7 +688,24 @@ __device__ bool loop_windows10(const IdxView &ix, long long xs, long long xe, lo
     }
     // rows of the regions actually needed: all of them, or the part scanned before the fdr cut was decided
     *g_bytes += 16 * (stopped && scan_rows > 0 ? (span_rows * done_rows) / scan_rows : span_rows);
-    if (stopped) return false;
+    if (stopped) return 0;
+    if (C.nw > 1) {
+        // partial counters of the cooperating warps -> shared slots: pair (i, j) at i*10 + j, e_a at 100.., e_b at 110..
+        __syncthreads();
+        for (int t = threadIdx.x; t < COOP_RED; t += blockDim.x) C.red[t] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (own && pj0 + q < W && acc[q]) atomicAdd(&C.red[pi * 10 + pj0 + q], acc[q]);
+        if (lane >= 20 && lane < 20 + W) {
+            if (e_a) atomicAdd(&C.red[100 + lane - 20], e_a);
+            if (e_b) atomicAdd(&C.red[110 + lane - 20], e_b);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; q++) acc[q] = (own && pj0 + q < W) ? C.red[pi * 10 + pj0 + q] : 0;
+        if (lane >= 20 && lane < 30) { e_a = C.red[100 + lane - 20]; e_b = C.red[110 + lane - 20]; }
+    }
     const int src = 20 + (lane < W ? lane : 0);
     const int ea_i = __shfl_sync(0xffffffffu, e_a, src), eb_i = __shfl_sync(0xffffffffu, e_b, src);
     if (lane < W) {
@@ -657,7 +717,7 @@ __device__ bool loop_windows10(const IdxView &ix, long long xs, long long xe, lo
     for (int q = 0; q < 4; q++)
         if (own && pj0 + q < W) S.nab[pi * W + pj0 + q] = acc[q] + cy[q];
     __syncwarp();
-    return true;
+    return 1;
 }
 
 // ---- the same counts for 2*win > 10 (up to 16): four range scans with de-duplication --------------------------
@@ -755,12 +815,12 @@ __device__ void loop_windows_wide(const IdxView &ix, long long xs, long long xe,
     __syncwarp();
 }
 
-__device__ __forceinline__ bool loop_windows(const IdxView &ix, long long xs, long long xe, long long ys, long long ye,
-                                             int win, int lane, WarpAcc &S, long long *g_bytes, int fdr_stop = 0,
-                                             long long rab = 0) {
-    if (2 * win <= 10) return loop_windows10(ix, xs, xe, ys, ye, win, lane, S, g_bytes, fdr_stop, rab);
-    loop_windows_wide(ix, xs, xe, ys, ye, win, lane, S, g_bytes);
-    return true;
+__device__ __forceinline__ int loop_windows(const IdxView &ix, long long xs, long long xe, long long ys, long long ye,
+                                            int win, int lane, const Coop &C, WarpAcc &S, long long *g_bytes,
+                                            int fdr_stop = 0, long long rab = 0) {
+    if (2 * win <= 10) return loop_windows10(ix, xs, xe, ys, ye, win, lane, C, S, g_bytes, fdr_stop, rab);
+    if (C.part == 0) loop_windows_wide(ix, xs, xe, ys, ye, win, lane, S, g_bytes);       // not shared between warps
+    return 1;
 }
 
 // ---- raw counts (cl2_loop_counts) ---------------------------------------------------------------------------
@@ -778,18 +838,18 @@ __global__ void __launch_bounds__(CNT_WARPS * 32) k_loop_counts(const IdxView ix
     long long scanned = 0;
     if (core) {
         int64_t c[4];
-        loop_core(ix, xs, xe, ys, ye, mode, lane, c, &scanned);
+        loop_core(ix, xs, xe, ys, ye, mode, lane, coop_solo(), c, &scanned);
         if (lane == 0) { core[4 * k] = c[0]; core[4 * k + 1] = c[1]; core[4 * k + 2] = c[2]; core[4 * k + 3] = c[3]; }
     }
     if (anchors) {
         int64_t cx, wx, cy, wy;
-        loop_anchors(ix, xs, xe, ys, ye, lane, &cx, &wx, &cy, &wy, &scanned);
+        loop_anchors(ix, xs, xe, ys, ye, lane, coop_solo(), &cx, &wx, &cy, &wy, &scanned);
         if (lane == 0) { anchors[4 * k] = cx; anchors[4 * k + 1] = wx; anchors[4 * k + 2] = cy; anchors[4 * k + 3] = wy; }
     }
     if (na_out || nb_out || nab_out) {
         const int W = 2 * win;
         WarpAcc &S = acc[w];
-        loop_windows(ix, xs, xe, ys, ye, win, lane, S, &scanned);
+        loop_windows(ix, xs, xe, ys, ye, win, lane, coop_solo(), S, &scanned);
         if (na_out && lane < W) na_out[(int64_t)W * k + lane] = S.na[lane];
         if (nb_out && lane < W) nb_out[(int64_t)W * k + lane] = S.nb[lane];
         if (nab_out)
@@ -808,7 +868,7 @@ __global__ void __launch_bounds__(CNT_WARPS * 32) k_loop_core(const IdxView ix, 
     const longlong4 lp = loops[k];
     int64_t c[4];
     long long scanned = 0;
-    loop_core(ix, lp.x, lp.y, lp.z, lp.w, mode, lane, c, &scanned);
+    loop_core(ix, lp.x, lp.y, lp.z, lp.w, mode, lane, coop_solo(), c, &scanned);
     if (lane == 0) {
         core[4 * k] = c[0]; core[4 * k + 1] = c[1]; core[4 * k + 2] = c[2]; core[4 * k + 3] = c[3];
         hyp[k] = cl2_hypergeom_sf_ge((double)c[2], (double)ix.n, (double)c[0], (double)c[1]);
@@ -893,10 +953,12 @@ __device__ double warp_median(WarpVals &S, int m, int lane) {
 // Background of one loop (one warp): permuted windows -> mrabs, mbps, fdr (callCisLoops.py:207-223, 315-321).
 // bg_cut (cis): return false as soon as `mrabs >= rab or fdr >= 0.1` or `es < 1` (:322-327) is known; the reference
 // applies these cuts whatever `pseudo` is, which only enters the enrichment score.
-__device__ bool loop_background(const IdxView &ix, long long xs,
-                                long long xe, long long ys, long long ye, double rab, int win, int mode, WarpAcc &S,
-                                WarpVals &V, int lane, bool bg_cut, double pseudo, double *o_mrabs, double *o_mbps,
-                                double *o_fdr, long long *g_scan) {
+// Returns 1 keep, 0 drop, -1 hand the candidate to the cooperative kernel, -2 (cooperating warps other than the first)
+// nothing left to do for this warp.
+__device__ int loop_background(const IdxView &ix, long long xs,
+                               long long xe, long long ys, long long ye, double rab, int win, int mode, const Coop &C,
+                               WarpAcc &S, WarpVals &V, int lane, bool bg_cut, double pseudo, double *o_mrabs,
+                               double *o_mbps, double *o_fdr, long long *g_scan) {
     const int W = 2 * win, m = W * W;
     // smallest number of window pairs above rab that makes fdr = gt / m >= 0.1 (the comparison the reference makes)
     int fdr_stop = 0;
@@ -905,7 +967,12 @@ __device__ bool loop_background(const IdxView &ix, long long xs,
         while ((double)fdr_stop / (double)m < 0.1) fdr_stop++;
         while (fdr_stop > 1 && (double)(fdr_stop - 1) / (double)m >= 0.1) fdr_stop--;
     }
-    if (!loop_windows(ix, xs, xe, ys, ye, win, lane, S, g_scan, fdr_stop, (long long)rab)) return false;
+    const int wr = loop_windows(ix, xs, xe, ys, ye, win, lane, C, S, g_scan, fdr_stop, (long long)rab);
+    if (wr <= 0) return wr;
+    if (C.nw > 1) {
+        __syncthreads();                                   // the counters in S are complete for every warp
+        if (C.part != 0) return -2;                        // the medians are one warp's work
+    }
     // rabs: counts of the 4*win^2 window pairs; fdr = #{rabs > rab} / m
     int gt = 0, nzero = 0;
     for (int t = lane; t < m; t += 32) {
@@ -920,15 +987,15 @@ __device__ bool loop_background(const IdxView &ix, long long xs,
     // counts and for the densities alike (a density is 0 exactly where the count is 0) -- the common case
     const bool zero_median = mode == CL2_MODE_CIS && nzero >= m / 2 + 1;
     const double fdr = (double)gt / (double)m;
-    if (bg_cut && fdr >= 0.1) return false;                // the cheap half of the background cut first
+    if (bg_cut && fdr >= 0.1) return 0;                    // the cheap half of the background cut first
     double mrabs, mbps;
     if (zero_median) mrabs = 0.0;
     else if (mode == CL2_MODE_CIS) mrabs = warp_median(V, m, lane);
     else mrabs = np_pairwise_sum(V.v, m) / (double)m;     // every lane computes the same value
     __syncwarp();
     if (bg_cut) {
-        if (mrabs >= rab || fdr >= 0.1) return false;
-        if (rab / (mrabs > pseudo ? mrabs : pseudo) < 1.0) return false;
+        if (mrabs >= rab || fdr >= 0.1) return 0;
+        if (rab / (mrabs > pseudo ? mrabs : pseudo) < 1.0) return 0;
     }
     if (zero_median) {
         mbps = 0.0;
@@ -947,7 +1014,7 @@ __device__ bool loop_background(const IdxView &ix, long long xs,
         __syncwarp();
     }
     *o_mrabs = mrabs; *o_mbps = mbps; *o_fdr = fdr;
-    return true;
+    return 1;
 }
 
 // Anchor windows and the tail probabilities of one loop (one warp): o[3..12] = poisson sf, binomial sf, px, esx, py,
@@ -956,7 +1023,7 @@ __device__ void loop_tail(const IdxView &ix, long long xs,
                           long long xe, long long ys, long long ye, double ra, double rb, double rab, double mrabs,
                           double mbps, int mode, double rpb, int lane, double *o, long long *g_scan) {
     int64_t cx, wx, cy, wy;
-    loop_anchors(ix, xs, xe, ys, ye, lane, &cx, &wx, &cy, &wy, g_scan);
+    loop_anchors(ix, xs, xe, ys, ye, lane, coop_solo(), &cx, &wx, &cy, &wy, g_scan);
     if (lane == 0) {
         o[3] = cl2_poisson_sf_ge(rab, mrabs);                                            // :329
         o[9] = (double)cx; o[10] = (double)wx; o[11] = (double)cy; o[12] = (double)wy;
@@ -980,7 +1047,7 @@ __device__ void loop_tests_warp(const IdxView &ix, long long xs,
                                 long long xe, long long ys, long long ye, double ra, double rb, double rab, int win,
                                 int mode, double rpb, WarpAcc &S, WarpVals &V, int lane, double *o, long long *g_scan) {
     double mrabs, mbps, fdr;
-    loop_background(ix, xs, xe, ys, ye, rab, win, mode, S, V, lane, false, 1.0, &mrabs, &mbps, &fdr, g_scan);
+    loop_background(ix, xs, xe, ys, ye, rab, win, mode, coop_solo(), S, V, lane, false, 1.0, &mrabs, &mbps, &fdr, g_scan);
     if (lane == 0) { o[0] = mrabs; o[1] = mbps; o[2] = fdr; }
     loop_tail(ix, xs, xe, ys, ye, ra, rb, rab, mrabs, mbps, mode, rpb, lane, o, g_scan);
 }
@@ -1007,69 +1074,112 @@ __global__ void __launch_bounds__(CNT_WARPS * 32) k_loop_tests(const IdxView ix,
 // 127-139), the permuted-window background and, for cis, the background cut (:322-327).  Survivors get flag = 1 and
 // core[4], stats[0..2] = mrabs, mbps, fdr.  The hypergeometric cut (:311) is applied by kernel B: the cascade is a
 // conjunction, so the order of the tests does not change which candidates survive.
+// One candidate by the warps of C: returns 1 keep, 0 drop, -1 too large for a single warp (nothing was counted).
+__device__ int est_candidate(const IdxView &ix, const longlong4 lp, int win, int mode, int minPts, int hic, double cdc,
+                             double pseudo, const Coop &C, WarpAcc &S, WarpVals &V, int lane, int64_t c[4], double st[3],
+                             long long *bytes) {
+    const long long xs = lp.x, xe = lp.y, ys = lp.z, ye = lp.w;
+    const double la = (double)(xe - xs), lb = (double)(ye - ys);
+    const bool cis = mode == CL2_MODE_CIS;
+    if (la / lb > cdc || lb / la > cdc) return 0;                                      // :282-286 / trans :135-139
+    if (!loop_core(ix, xs, xe, ys, ye, mode, lane, C, c, bytes)) return -1;
+    const double ra = (double)c[0], rb = (double)c[1], rab = (double)c[2];
+    if (c[2] < minPts) return 0;                                                       // :290 / trans :127
+    if (cis && (c[0] == c[2] || c[1] == c[2])) return 0;                               // :293
+    if (ra / rb > cdc || rb / ra > cdc) return 0;                                      // :296 / trans :133
+    const double lower = (double)c[3];
+    const double p2ll = rab / (lower > pseudo ? lower : pseudo);                       // :306
+    if (cis && hic && p2ll < 1.0) return 0;                                            // :307
+    return loop_background(ix, xs, xe, ys, ye, rab, win, mode, C, S, V, lane, cis, pseudo, &st[0], &st[1], &st[2], bytes);
+}
+
 template <int MINB>
 __global__ void __launch_bounds__(CNT_WARPS * 32, MINB) k_est_bg(const IdxView ix, const longlong4 *__restrict__ loops, int64_t L,
                                                             int win, int mode, int minPts, int hic, double cdc,
                                                             double pseudo, long long *__restrict__ core_out,
                                                             double *__restrict__ stats_out, int32_t *__restrict__ flag,
-                                                            unsigned long long *__restrict__ scanned_total) {
+                                                            unsigned long long *__restrict__ scanned_total,
+                                                            int32_t *__restrict__ biglist, int32_t *__restrict__ nbig) {
     __shared__ WarpAcc acc[CNT_WARPS];
     __shared__ WarpVals vals[CNT_WARPS];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t k = (int64_t)blockIdx.x * CNT_WARPS + w;
     if (k >= L) return;
     long long scanned = 0;
-    const longlong4 lp = loops[k];
-    const long long xs = lp.x, xe = lp.y, ys = lp.z, ye = lp.w;
-    const double la = (double)(xe - xs), lb = (double)(ye - ys);
-    const bool cis = mode == CL2_MODE_CIS;
-    bool keep = !(la / lb > cdc || lb / la > cdc);                                      // :282-286 / trans :135-139
-    if (keep) {
-        int64_t c[4];
-        loop_core(ix, xs, xe, ys, ye, mode, lane, c, &scanned);
-        const double ra = (double)c[0], rb = (double)c[1], rab = (double)c[2];
-        if (c[2] < minPts) keep = false;                                               // :290 / trans :127
-        if (cis && (c[0] == c[2] || c[1] == c[2])) keep = false;                       // :293
-        if (ra / rb > cdc || rb / ra > cdc) keep = false;                              // :296 / trans :133
-        double lower = (double)c[3];
-        double p2ll = rab / (lower > pseudo ? lower : pseudo);                         // :306
-        if (cis && hic && p2ll < 1.0) keep = false;                                    // :307
-        if (keep) {
-            double mrabs, mbps, fdr;
-            keep = loop_background(ix, xs, xe, ys, ye, rab, win, mode, acc[w], vals[w], lane, cis, pseudo, &mrabs, &mbps,
-                                   &fdr, &scanned);
-            if (keep && lane == 0) {
-                core_out[4 * k] = c[0]; core_out[4 * k + 1] = c[1]; core_out[4 * k + 2] = c[2]; core_out[4 * k + 3] = c[3];
-                stats_out[CL2_NSTAT * k] = mrabs; stats_out[CL2_NSTAT * k + 1] = mbps; stats_out[CL2_NSTAT * k + 2] = fdr;
-            }
-        }
-    }
+    int64_t c[4];
+    double st[3];
+    const Coop C = {1, 0, nullptr, true};
+    const int r = est_candidate(ix, loops[k], win, mode, minPts, hic, cdc, pseudo, C, acc[w], vals[w], lane, c, st, &scanned);
     if (lane == 0) {
-        flag[k] = keep ? 1 : 0;
-        if (scanned) atomicAdd(scanned_total, (unsigned long long)scanned);
+        if (r == 1) {
+            core_out[4 * k] = c[0]; core_out[4 * k + 1] = c[1]; core_out[4 * k + 2] = c[2]; core_out[4 * k + 3] = c[3];
+            stats_out[CL2_NSTAT * k] = st[0]; stats_out[CL2_NSTAT * k + 1] = st[1]; stats_out[CL2_NSTAT * k + 2] = st[2];
+        }
+        flag[k] = r == 1 ? 1 : 0;
+        if (r < 0) biglist[atomicAdd(nbig, 1)] = (int32_t)k;        // decided by k_est_bg_big
+        else if (scanned) atomicAdd(scanned_total, (unsigned long long)scanned);
+    }
+}
+
+// The candidates kernel A declined (regions with more than BIG_ROWS rows), one block each: its warps share every scan.
+// The blocks of a fixed-size grid stride over the list, whose length stays on the device.
+template <int BIG_THREADS, int MINB>
+__global__ void __launch_bounds__(BIG_THREADS, MINB) k_est_bg_big(const IdxView ix, const longlong4 *__restrict__ loops, int win, int mode,
+                                                            int minPts, int hic, double cdc, double pseudo,
+                                                            long long *__restrict__ core_out, double *__restrict__ stats_out,
+                                                            int32_t *__restrict__ flag,
+                                                            unsigned long long *__restrict__ scanned_total,
+                                                            const int32_t *__restrict__ biglist,
+                                                            const int32_t *__restrict__ nbig) {
+    __shared__ WarpAcc acc;
+    __shared__ WarpVals vals;
+    __shared__ int red[COOP_RED];
+    const int lane = threadIdx.x & 31;
+    const Coop C = {BIG_THREADS / 32, (int)(threadIdx.x >> 5), red, false};
+    const int n = *nbig;
+    for (int b = blockIdx.x; b < n; b += gridDim.x) {
+        __syncthreads();                                   // the shared accumulators of the previous candidate are free
+        const int64_t k = biglist[b];
+        long long scanned = 0;
+        int64_t c[4];
+        double st[3];
+        const int r = est_candidate(ix, loops[k], win, mode, minPts, hic, cdc, pseudo, C, acc, vals, lane, c, st, &scanned);
+        // every warp sees the same outcome except in loop_background, where warps 1.. leave with -2 once the counting is
+        // done: the first warp reports
+        if (threadIdx.x == 0) {
+            if (r == 1) {
+                core_out[4 * k] = c[0]; core_out[4 * k + 1] = c[1]; core_out[4 * k + 2] = c[2]; core_out[4 * k + 3] = c[3];
+                stats_out[CL2_NSTAT * k] = st[0]; stats_out[CL2_NSTAT * k + 1] = st[1]; stats_out[CL2_NSTAT * k + 2] = st[2];
+            }
+            flag[k] = r == 1 ? 1 : 0;
+            if (scanned) atomicAdd(scanned_total, (unsigned long long)scanned);
+        }
     }
 }
 
 // kernel B (survivors of kernel A, compacted): hypergeometric / Poisson / binomial tails, anchor
 // windows and tests, and the remaining cuts (:311 hypergeometric > 1e-2, :347 anchor peaks unless -hic).
 // Kernel B runs in two launches so that the fp64 series of the five tests do not run one after the other on a single
-// lane: B1 (one warp per survivor) counts the anchor windows, B2 gives every survivor eight threads, five of which
-// evaluate one tail probability each (same routines, same arguments as loop_tail()).
+// lane: B1 (one block per survivor, its warps sharing the scans: the wide anchor windows of a large loop hold millions
+// of rows) counts the anchor windows, B2 gives every survivor eight threads, five of which evaluate one tail
+// probability each (same routines, same arguments as loop_tail()).
 __global__ void __launch_bounds__(CNT_WARPS * 32) k_est_anchor(const IdxView ix, const longlong4 *__restrict__ loops,
                                                                 const long long *__restrict__ sel, int64_t K,
                                                                 double *__restrict__ stats,
                                                                 unsigned long long *__restrict__ scanned_total) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t i = (int64_t)blockIdx.x * CNT_WARPS + w;
-    if (i >= K) return;
-    long long scanned = 0;
-    const longlong4 lp = loops[sel[i]];
-    int64_t cx, wx, cy, wy;
-    loop_anchors(ix, lp.x, lp.y, lp.z, lp.w, lane, &cx, &wx, &cy, &wy, &scanned);
-    if (lane == 0) {
-        double *o = stats + CL2_NSTAT * i;
-        o[9] = (double)cx; o[10] = (double)wx; o[11] = (double)cy; o[12] = (double)wy;
-        if (scanned) atomicAdd(scanned_total, (unsigned long long)scanned);
+    __shared__ int red[COOP_RED];
+    const int lane = threadIdx.x & 31;
+    const Coop C = {CNT_WARPS, (int)(threadIdx.x >> 5), red, false};
+    for (int64_t i = blockIdx.x; i < K; i += gridDim.x) {
+        long long scanned = 0;
+        const longlong4 lp = loops[sel[i]];
+        int64_t cx, wx, cy, wy;
+        loop_anchors(ix, lp.x, lp.y, lp.z, lp.w, lane, C, &cx, &wx, &cy, &wy, &scanned);
+        if (threadIdx.x == 0) {
+            double *o = stats + CL2_NSTAT * i;
+            o[9] = (double)cx; o[10] = (double)wx; o[11] = (double)cy; o[12] = (double)wy;
+            if (scanned) atomicAdd(scanned_total, (unsigned long long)scanned);
+        }
     }
 }
 
@@ -1255,6 +1365,9 @@ extern "C" int cl2_est_loops(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops,
     CL2_TRY(sc.get(&d_core, (size_t)L * 4));
     CL2_TRY(sc.get(&d_stats, (size_t)L * CL2_NSTAT));
     CL2_TRY(sc.get(&d_flag, (size_t)L));
+    int32_t *d_big;                                          // candidates for the cooperative kernel + their number
+    CL2_TRY(sc.get(&d_big, (size_t)L + 1));
+    CL2_CUDA(ctx, cudaMemsetAsync(d_big + L, 0, 4, ctx->stream));
     CL2_TRY(sc.get(&d_total, 2));
     CL2_CUDA(ctx, cudaMemsetAsync(d_total, 0, 16, ctx->stream));
     CL2_CUDA(ctx, cudaMemcpyAsync(d_loops, loops, (size_t)L * 32, cudaMemcpyHostToDevice, ctx->stream));
@@ -1265,7 +1378,23 @@ extern "C" int cl2_est_loops(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops,
         auto kern = occ == 3 ? k_est_bg<3> : (occ == 2 ? k_est_bg<2> : k_est_bg<4>);
         kern<<<cl2_grid(L, CNT_WARPS), CNT_WARPS * 32, 0, ctx->stream>>>(cl2_view(idx), d_loops, L, win, mode, minPts, hic,
                                                                          countDiffCut, pseudo, d_core, d_stats, d_flag,
-                                                                         (unsigned long long *)(d_total + 1));
+                                                                         (unsigned long long *)(d_total + 1), d_big, d_big + L);
+        static const int bigcfg = getenv("CL2_BIG_CFG") ? atoi(getenv("CL2_BIG_CFG")) : 1;
+        const int64_t cap = (int64_t)ctx->sm_count * (bigcfg == 0 ? 2 : 8);
+        const unsigned bgrid = (unsigned)(L < cap ? L : cap);
+        if (bigcfg == 0)
+            k_est_bg_big<512, 1><<<bgrid, 512, 0, ctx->stream>>>(cl2_view(idx), d_loops, win, mode, minPts, hic, countDiffCut, pseudo,
+                                                                 d_core, d_stats, d_flag, (unsigned long long *)(d_total + 1), d_big,
+                                                                 d_big + L);
+        else if (bigcfg == 2)
+            k_est_bg_big<256, 4><<<bgrid, 256, 0, ctx->stream>>>(cl2_view(idx), d_loops, win, mode, minPts, hic, countDiffCut, pseudo,
+                                                                 d_core, d_stats, d_flag, (unsigned long long *)(d_total + 1), d_big,
+                                                                 d_big + L);
+        else
+            k_est_bg_big<256, 3><<<bgrid, 256, 0, ctx->stream>>>(cl2_view(idx), d_loops, win, mode, minPts, hic, countDiffCut, pseudo,
+                                                                 d_core, d_stats, d_flag, (unsigned long long *)(d_total + 1), d_big,
+                                                                 d_big + L);
+        ctx->launches++;
     }
     CL2_TRY(cl2_exclusive_scan_i32(ctx, d_flag, L, d_total));
     int64_t nk = 0;
@@ -1289,8 +1418,9 @@ extern "C" int cl2_est_loops(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops,
         }
         {
             FamTimer t(ctx, FAM_COUNT, 0.0, 2);
-            k_est_anchor<<<cl2_grid(nk, CNT_WARPS), CNT_WARPS * 32, 0, ctx->stream>>>(cl2_view(idx), d_loops, d_sel, nk, d_stats_c,
-                                                                                      (unsigned long long *)(d_total + 1));
+            const int64_t acap = (int64_t)ctx->sm_count * 16;
+            k_est_anchor<<<(unsigned)(nk < acap ? nk : acap), CNT_WARPS * 32, 0, ctx->stream>>>(cl2_view(idx), d_loops, d_sel, nk, d_stats_c,
+                                                                                                (unsigned long long *)(d_total + 1));
             k_est_stats<<<cl2_grid(nk * EST_GROUP, 256), 256, 0, ctx->stream>>>(d_loops, d_sel, nk, idx->n, mode, hic, peakPcut,
                                                                                 1.0 + ctx->pvalue_margin, rpb, d_core_c,
                                                                                 d_hyp_c, d_stats_c, d_flag2);
