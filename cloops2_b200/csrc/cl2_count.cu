@@ -617,7 +617,6 @@ __device__ int loop_windows10(const IdxView &ix, long long xs, long long xe, lon
     }
     const long long scan_rows = (long long)(e0 - b0) + (long long)(e1 - b1);
     if (C.defer && scan_rows > BIG_ROWS) return -1;
-    if (C.nw > 1) fdr_stop = 0;                              // the partial counters of one warp decide nothing
     *g_bytes += (2 * W + 1) * 32 * (long long)ix.lg;
     // this lane's pairs: lanes 0..29 own a-window lane / 3 and up to four b-windows from 4 * (lane % 3)
     const int pi = lane / 3, pj0 = 4 * (lane - 3 * pi);
@@ -639,13 +638,25 @@ __device__ int loop_windows10(const IdxView &ix, long long xs, long long xe, lon
     const int2 *__restrict__ byx = ix.byx;
     bool stopped = false;
     long long done_rows = 0;
+    // cooperating warps: C.red[i*10 + j] collects the pair counters (what each warp has already added is in sent[]),
+    // C.red[100..] / [110..] the e_a / e_b sums at the end, C.red[127] the stop flag
+    int sent[4] = {0, 0, 0, 0};
+    if (C.nw > 1) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < COOP_RED; t += blockDim.x) C.red[t] = 0;
+        __syncthreads();
+    }
 #pragma unroll 1
     for (int rr = 0; rr < 2 && !stopped; rr++) {
         const uint32_t rb = rr ? b1 : b0, re = rr ? e1 : e0;
-        const uint32_t first = rb + 32u * (uint32_t)C.part, stride = 32u * (uint32_t)C.nw;
+        const uint32_t stride = 32u * (uint32_t)C.nw;
+        const uint32_t nbatch = (re - rb + 31u) >> 5;
+        const uint32_t iters = (nbatch + (uint32_t)C.nw - 1u) / (uint32_t)C.nw;      // the same for every cooperating warp
+        const uint32_t first = rb + 32u * (uint32_t)C.part;
         int2 pnext = (first + lane < re) ? byx[first + lane] : make_int2(0, 0);
         int since = 0;
-        for (uint32_t p0 = first; p0 < re; p0 += stride) {
+        for (uint32_t it = 0; it < iters; it++) {
+            const uint32_t p0 = first + it * stride;
             const bool valid = p0 + lane < re;
             const int2 P = pnext;
             pnext = (p0 + stride + lane < re) ? byx[p0 + stride + lane] : make_int2(0, 0);
@@ -659,27 +670,54 @@ __device__ int loop_windows10(const IdxView &ix, long long xs, long long xe, lon
             }
             unsigned w1 = (ax | ay) | ((bx | by) << 10) | ((ax & ay) << 20);
             w1 = valid ? w1 : 0u;
-            if (!__any_sync(0xffffffffu, w1 != 0)) continue; // rows in the gaps between windows
-            unsigned w2 = ay | (by << 10) | ((bx & by) << 20);
-            w2 = valid ? w2 : 0u;
-            const unsigned c1 = warp_transpose32(w1, lane), c2 = warp_transpose32(w2, lane);
-            e_a += __popc(c1);                               // meaningful in lanes 20..29 only
-            e_b += __popc(c2);
-            const unsigned A = __shfl_sync(0xffffffffu, c1, srca), C = __shfl_sync(0xffffffffu, c2, srca);
+            if (__any_sync(0xffffffffu, w1 != 0)) {          // else: rows in the gaps between windows
+                unsigned w2 = ay | (by << 10) | ((bx & by) << 20);
+                w2 = valid ? w2 : 0u;
+                const unsigned c1 = warp_transpose32(w1, lane), c2 = warp_transpose32(w2, lane);
+                e_a += __popc(c1);                           // meaningful in lanes 20..29 only
+                e_b += __popc(c2);
+                const unsigned A = __shfl_sync(0xffffffffu, c1, srca), Cc = __shfl_sync(0xffffffffu, c2, srca);
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int sj = 10 + ((pj0 + q) < 10 ? pj0 + q : 9);
-                const unsigned B = __shfl_sync(0xffffffffu, c1, sj), Dd = __shfl_sync(0xffffffffu, c2, sj);
-                acc[q] += __popc(A & B & ~(C & Dd));
+                for (int q = 0; q < 4; q++) {
+                    const int sj = 10 + ((pj0 + q) < 10 ? pj0 + q : 9);
+                    const unsigned B = __shfl_sync(0xffffffffu, c1, sj), Dd = __shfl_sync(0xffffffffu, c2, sj);
+                    acc[q] += __popc(A & B & ~(Cc & Dd));
+                }
             }
-            if (fdr_stop > 0 && ++since == 4) {
-                since = 0;
-                int over = 0;
+            if (fdr_stop <= 0) continue;
+            if (C.nw == 1) {
+                if (++since == 4) {
+                    since = 0;
+                    int over = 0;
 #pragma unroll
-                for (int q = 0; q < 4; q++) over += (own && pj0 + q < W && (long long)acc[q] + cy[q] > rab) ? 1 : 0;
-                if (warp_sum(over) >= fdr_stop) {
+                    for (int q = 0; q < 4; q++) over += (own && pj0 + q < W && (long long)acc[q] + cy[q] > rab) ? 1 : 0;
+                    if (warp_sum(over) >= fdr_stop) {
+                        stopped = true;
+                        done_rows += (long long)(p0 + 32 - rb);
+                        break;
+                    }
+                }
+            } else if ((it & 63u) == 63u) {
+                // every warp is at the same iteration: pool what was counted since the last check and let the totals decide
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (own && pj0 + q < W && acc[q] != sent[q]) {
+                        atomicAdd(&C.red[pi * 10 + pj0 + q], acc[q] - sent[q]);
+                        sent[q] = acc[q];
+                    }
+                __syncthreads();
+                if (C.part == 0) {
+                    int over = 0;
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        over += (own && pj0 + q < W && (long long)C.red[pi * 10 + pj0 + q] + cy[q] > rab) ? 1 : 0;
+                    if (warp_sum(over) >= fdr_stop && lane == 0) C.red[127] = 1;
+                }
+                __syncthreads();
+                if (C.red[127]) {
                     stopped = true;
-                    done_rows += (long long)(p0 + 32 - rb);
+                    const long long d = (long long)(it + 1) * stride;
+                    done_rows += d < (long long)(re - rb) ? d : (long long)(re - rb);
                     break;
                 }
             }
@@ -690,13 +728,10 @@ __device__ int loop_windows10(const IdxView &ix, long long xs, long long xe, lon
     *g_bytes += 16 * (stopped && scan_rows > 0 ? (span_rows * done_rows) / scan_rows : span_rows);
     if (stopped) return 0;
     if (C.nw > 1) {
-        // partial counters of the cooperating warps -> shared slots: pair (i, j) at i*10 + j, e_a at 100.., e_b at 110..
-        __syncthreads();
-        for (int t = threadIdx.x; t < COOP_RED; t += blockDim.x) C.red[t] = 0;
-        __syncthreads();
+        // what is left of the partial counters -> shared slots, then every warp takes the totals
 #pragma unroll
         for (int q = 0; q < 4; q++)
-            if (own && pj0 + q < W && acc[q]) atomicAdd(&C.red[pi * 10 + pj0 + q], acc[q]);
+            if (own && pj0 + q < W && acc[q] != sent[q]) atomicAdd(&C.red[pi * 10 + pj0 + q], acc[q] - sent[q]);
         if (lane >= 20 && lane < 20 + W) {
             if (e_a) atomicAdd(&C.red[100 + lane - 20], e_a);
             if (e_b) atomicAdd(&C.red[110 + lane - 20], e_b);

@@ -243,3 +243,18 @@ def test_filter_option_files_match_golden(gpu_ctx, tmp_path):
         assert np.array_equal(joblib.load(out + "_filtered/%s.ixy" % k), g["filter_" + k.replace("-", "_")]), k
     fmeta = json.load(open(out + "_filtered/petMeta.json"))
     assert fmeta["Unique PETs"] == int(g["filter_tot"]) and sorted(fmeta["data"]["cis"]) == sorted(files)
+
+
+@pytest.mark.parametrize("hic", [False, True])
+def test_dense_hic_like_vs_oracle(gpu_ctx, hic):
+    """BASELINE configs[2] density (324 k PETs/Mb, Hi-C-like clusters), eps 5000,10000 x minPts 50,20, blockDBSCAN and
+    cDBSCAN2: candidates whose windows hold tens of thousands of rows (the cooperative counting kernel), crowded cells
+    (heavy cell pairs), one diagonal component holding most cells.  Same loops, same text as the oracle."""
+    files = {"chr21-chr21": synth.cis_chrom(4_600_000, 1_500_000, 33, "hic")}
+    tot = len(files["chr21-chr21"])
+    want, _ = oracle.call_cis_loops(files, tot, [5000, 10000], [50, 20], hic=hic)
+    final, st = cis_chromosome(gpu_ctx, ("chr21", "chr21"), files["chr21-chr21"], tot, [5000, 10000], [50, 20], hic=hic,
+                               exact=True)
+    got = cols_to_loops(("chr21", "chr21"), final)
+    assert st["candidates"] > 500 and len(want) > 10
+    assert _rows(got) == _rows(want)
