@@ -1198,14 +1198,58 @@ __global__ void __launch_bounds__(BIG_THREADS, MINB) k_est_bg_big(const IdxView 
 // lane: B1 (one block per survivor, its warps sharing the scans: the wide anchor windows of a large loop hold millions
 // of rows) counts the anchor windows, B2 gives every survivor eight threads, five of which evaluate one tail
 // probability each (same routines, same arguments as loop_tail()).
+// rows the anchor counts of one loop have to scan (the X ranges of both anchors and their wide windows)
+__device__ __forceinline__ long long anchor_rows(const IdxView &ix, const longlong4 lp, int lane) {
+    const int k = (lane >> 1) & 3;                           // lanes 0..7: interval k, lower / upper bound in the X list
+    const long long l = k < 2 ? lp.x : lp.z, r = k < 2 ? lp.y : lp.w;
+    const long long m4 = 2 * (l + r), len = r - l;
+    long long s4 = m4 - 20 * len;
+    if (s4 < 0) s4 = 0;
+    const Iv Wd = iv4(s4, m4 + 20 * len);
+    Iv I;
+    if (k & 1) I = Wd; else { I.lo = l; I.hi = r; }
+    const uint32_t pos = lane < 8 ? bound_task(ix, I.lo, I.hi, 0, lane & 1) : 0u;
+    long long rows = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) rows += (long long)__shfl_sync(0xffffffffu, pos, 2 * q + 1) - (long long)__shfl_sync(0xffffffffu, pos, 2 * q);
+    return rows;
+}
 __global__ void __launch_bounds__(CNT_WARPS * 32) k_est_anchor(const IdxView ix, const longlong4 *__restrict__ loops,
                                                                 const long long *__restrict__ sel, int64_t K,
                                                                 double *__restrict__ stats,
-                                                                unsigned long long *__restrict__ scanned_total) {
+                                                                unsigned long long *__restrict__ scanned_total,
+                                                                int32_t *__restrict__ biglist, int32_t *__restrict__ nbig) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * CNT_WARPS + w;
+    if (i >= K) return;
+    long long scanned = 0;
+    const longlong4 lp = loops[sel[i]];
+    if (anchor_rows(ix, lp, lane) > BIG_ROWS) {              // k_est_anchor_big's work
+        if (lane == 0) biglist[atomicAdd(nbig, 1)] = (int32_t)i;
+        return;
+    }
+    int64_t cx, wx, cy, wy;
+    loop_anchors(ix, lp.x, lp.y, lp.z, lp.w, lane, coop_solo(), &cx, &wx, &cy, &wy, &scanned);
+    if (lane == 0) {
+        double *o = stats + CL2_NSTAT * i;
+        o[9] = (double)cx; o[10] = (double)wx; o[11] = (double)cy; o[12] = (double)wy;
+        if (scanned) atomicAdd(scanned_total, (unsigned long long)scanned);
+    }
+}
+// the survivors with large anchor windows (the wide window of a 100 kb anchor of Hi-C-like data holds 10^5 rows), one
+// block each, its warps sharing the scans
+__global__ void __launch_bounds__(CNT_WARPS * 32) k_est_anchor_big(const IdxView ix, const longlong4 *__restrict__ loops,
+                                                                    const long long *__restrict__ sel,
+                                                                    double *__restrict__ stats,
+                                                                    unsigned long long *__restrict__ scanned_total,
+                                                                    const int32_t *__restrict__ biglist,
+                                                                    const int32_t *__restrict__ nbig) {
     __shared__ int red[COOP_RED];
     const int lane = threadIdx.x & 31;
     const Coop C = {CNT_WARPS, (int)(threadIdx.x >> 5), red, false};
-    for (int64_t i = blockIdx.x; i < K; i += gridDim.x) {
+    const int n = *nbig;
+    for (int b = blockIdx.x; b < n; b += gridDim.x) {
+        const int64_t i = biglist[b];
         long long scanned = 0;
         const longlong4 lp = loops[sel[i]];
         int64_t cx, wx, cy, wy;
@@ -1453,9 +1497,14 @@ extern "C" int cl2_est_loops(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops,
         }
         {
             FamTimer t(ctx, FAM_COUNT, 0.0, 2);
-            const int64_t acap = (int64_t)ctx->sm_count * 16;
-            k_est_anchor<<<(unsigned)(nk < acap ? nk : acap), CNT_WARPS * 32, 0, ctx->stream>>>(cl2_view(idx), d_loops, d_sel, nk, d_stats_c,
-                                                                                                (unsigned long long *)(d_total + 1));
+            CL2_CUDA(ctx, cudaMemsetAsync(d_big + L, 0, 4, ctx->stream));       // the list is reused for the anchor stage
+            k_est_anchor<<<cl2_grid(nk, CNT_WARPS), CNT_WARPS * 32, 0, ctx->stream>>>(cl2_view(idx), d_loops, d_sel, nk, d_stats_c,
+                                                                                      (unsigned long long *)(d_total + 1), d_big,
+                                                                                      d_big + L);
+            const int64_t acap = (int64_t)ctx->sm_count * 8;
+            k_est_anchor_big<<<(unsigned)(nk < acap ? nk : acap), CNT_WARPS * 32, 0, ctx->stream>>>(
+                cl2_view(idx), d_loops, d_sel, d_stats_c, (unsigned long long *)(d_total + 1), d_big, d_big + L);
+            ctx->launches++;
             k_est_stats<<<cl2_grid(nk * EST_GROUP, 256), 256, 0, ctx->stream>>>(d_loops, d_sel, nk, idx->n, mode, hic, peakPcut,
                                                                                 1.0 + ctx->pvalue_margin, rpb, d_core_c,
                                                                                 d_hyp_c, d_stats_c, d_flag2);

@@ -60,18 +60,48 @@ def assign(keys, weights, world):
     return [[keys[i] for i in range(len(keys)) if owner[i] == r] for r in range(world)]
 
 
+_comm = {}
+
+
+def _library_comm():
+    """The library's own NCCL communicator (cl2_comm_init), created on first use.  Rank 0's unique id travels over the
+    launcher's process group -- any host channel would do; a C caller would use a file or MPI."""
+    if "h" not in _comm:
+        import ctypes
+        import torch.distributed as dist
+        from . import _lib
+        rank, world = rank_world()
+        ctx = _lib.default_context()
+        idb = np.zeros(128, dtype=np.uint8)
+        if rank == 0:
+            ctx.check(ctx.lib.cl2_comm_unique_id(idb.ctypes.data_as(_lib._u8p)), "cl2_comm_unique_id")
+        box = [idb.tobytes()]
+        dist.broadcast_object_list(box, src=0)
+        idb = np.frombuffer(box[0], dtype=np.uint8).copy()
+        h = ctypes.c_void_p()
+        ctx.check(ctx.lib.cl2_comm_init(ctx.h, idb.ctypes.data_as(_lib._u8p), rank, world, ctypes.byref(h)), "cl2_comm_init")
+        _comm["h"], _comm["ctx"] = h, ctx
+    return _comm["ctx"], _comm["h"]
+
+
 def allreduce_stats(vals):
-    """Sum an int64 vector over ranks (the path's only collective)."""
+    """Sum an int64 vector over ranks (the path's only collective): cl2_stats_allreduce (NCCL inside libcl2.so) when
+    the ranks own GPUs, the launcher's gloo group in the CPU tests."""
     rank, world = rank_world()
-    vals = np.asarray(vals, dtype=np.int64)
+    vals = np.ascontiguousarray(vals, dtype=np.int64).copy()
     if world == 1:
         return vals
-    import torch
     import torch.distributed as dist
-    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
-    t = torch.from_numpy(vals.copy()).to(dev)
+    if dist.get_backend() == "nccl":
+        from . import _lib
+        ctx, h = _library_comm()
+        ctx.check(ctx.lib.cl2_stats_allreduce(ctx.h, h, vals.ctypes.data_as(_lib._i64p), int(vals.shape[0])),
+                  "cl2_stats_allreduce")
+        return vals
+    import torch
+    t = torch.from_numpy(vals)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    return t.cpu().numpy()
+    return t.numpy()
 
 
 def broadcast_flag(v):

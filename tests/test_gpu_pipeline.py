@@ -258,3 +258,39 @@ def test_dense_hic_like_vs_oracle(gpu_ctx, hic):
     got = cols_to_loops(("chr21", "chr21"), final)
     assert st["candidates"] > 500 and len(want) > 10
     assert _rows(got) == _rows(want)
+
+
+def test_repeatable_across_streams_and_runs(gpu_ctx):
+    """compute-sanitizer is closed on this pool, so the lock-free pieces (union-find with path halving, decoupled
+    look-back of the sort, shared-memory reductions of the cooperative counting kernel) are checked the way that is
+    left: the same files through four contexts at once, five times over, must give bit-identical labels, boxes and
+    loop tables every time (a data race that mattered would show as a difference sooner or later), and equal the
+    oracle's."""
+    import threading
+    from cloops2_b200 import _lib as L
+    sparse = synth.cis_chrom(6_000_000, 200_000, 41, "hitrac")
+    dense = synth.cis_chrom(1_500_000, 500_000, 42, "hic")
+    want_lab, want_n = oracle.block_dbscan(dense, 5000, 20)
+    ctxs = [gpu_ctx] + [L.Context(0) for _ in range(3)]
+    out = [[] for _ in ctxs]
+
+    def work(i):
+        c = ctxs[i]
+        for _ in range(5):
+            p = L.Points(c, dense)
+            lab, n = p.block_dbscan(5000, 20)
+            lab2, n2 = p.cdbscan2(5000, 20)
+            p.close()
+            f1, _ = cis_chromosome(c, ("chr1", "chr1"), sparse, len(sparse), [200, 500, 1000], [5])
+            f2, _ = cis_chromosome(c, ("chr2", "chr2"), dense, len(dense), [5000, 10000], [50, 20])
+            out[i].append((lab.tobytes(), n, lab2.tobytes(), n2, f1["coords"].tobytes(), f1["hyp"].tobytes(),
+                           f2["coords"].tobytes(), f2["nbp"].tobytes(), f2["rab"].tobytes()))
+
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(len(ctxs))]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    first = out[0][0]
+    assert all(r == first for o in out for r in o)
+    assert first[1] == want_n and first[0] == want_lab.tobytes()
