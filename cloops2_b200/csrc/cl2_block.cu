@@ -257,7 +257,12 @@ __global__ void __launch_bounds__(256) k_block_cellstat_list(const int2 *__restr
 }
 
 // ------------------------------------------------------------------------------------------------ K9 adjacency
-#define ADJ_LIGHT_MAX 2048   // |a|*|b| up to this is tested by one thread; larger pairs go to the block-per-pair kernel
+// Three tiers by the number of point pairs |a|*|b| of a cell pair: up to ADJ_LIGHT_MAX one thread tests them (the bulk
+// of sparse data: cells of 1-5 points); up to ADJ_WARP_MAX one warp does (k_block_adj_warp: the cells of a loop's own
+// cluster hold tens of points each, and a thread working through 1600 pairs alone keeps its whole warp waiting);
+// beyond that a block with shared-memory tiles (k_block_adj_heavy: crowded cells of Hi-C-like data).
+#define ADJ_LIGHT_MAX 48
+#define ADJ_WARP_MAX 65536
 
 __device__ __forceinline__ bool centroid_close(const CellStat &a, int na, const CellStat &b, int nb, double eps) {
     // blockDBSCAN.py:136-137 (x / len) and :46,:227 (abs(dx)+abs(dy) <= eps), fp64, no contraction possible
@@ -267,51 +272,100 @@ __device__ __forceinline__ bool centroid_close(const CellStat &a, int na, const 
 }
 
 // forward directions (neighbour index > own index in key order): (0,+1)=1, (+1,-1)=6, (+1,0)=3, (+1,+1)=7
-__global__ void __launch_bounds__(128, 10) k_block_adj(const int2 *__restrict__ sxy, const int32_t *__restrict__ cstart,
-                                                    const int32_t *__restrict__ nbr, const uint8_t *__restrict__ keep,
-                                                    const CellStat *__restrict__ st, const int32_t *__restrict__ list,
-                                                    int32_t nkept, unsigned *__restrict__ adj, int64_t eps,
-                                                    int2 *__restrict__ heavy, int32_t *__restrict__ nheavy) {
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int k = (int)(t >> 2);
+// One thread per kept cell tests its four forward neighbours.  The kernel waits on chains of dependent loads (list ->
+// neighbour ids -> the neighbours' tables -> their points; ncu: 72 % of the stall samples are long-scoreboard), so the
+// loads of every level are issued for all four neighbours before the first is used.
+__global__ void __launch_bounds__(128, 6) k_block_adj(const int2 *__restrict__ sxy, const int32_t *__restrict__ cstart,
+                                                   const int32_t *__restrict__ nbr, const uint8_t *__restrict__ keep,
+                                                   const CellStat *__restrict__ st, const int32_t *__restrict__ list,
+                                                   int32_t nkept, unsigned *__restrict__ adj, int64_t eps,
+                                                   int2 *__restrict__ heavy, int32_t *__restrict__ nheavy,
+                                                   int2 *__restrict__ medium, int32_t *__restrict__ nmedium) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nkept) return;
     const int fdir[4] = {1, 6, 3, 7};
-    int d = fdir[t & 3];
-    int a = list[k];
-    int b = nbr[8 * (int64_t)a + d];
-    // the kernel waits on memory: everything that only needs `a`, then everything that only needs `b`, is requested
-    // before the first use (b clamped so the loads are unconditional)
+    const int a = list[k];
+    const int4 *nb4 = reinterpret_cast<const int4 *>(nbr + 8 * (int64_t)a);
+    const int4 n0 = nb4[0], n1 = nb4[1];
     const int a0 = cstart[a], a1 = cstart[a + 1];
     const CellStat A = st[a];
-    const int bb = b < 0 ? a : b;
-    const uint8_t kb = keep[bb];
-    const int b0 = cstart[bb], b1 = cstart[bb + 1];
-    const CellStat B = st[bb];
-    if (b < 0 || !kb) return;
-    int na = a1 - a0, nb = b1 - b0;
-    bool close = centroid_close(A, na, B, nb, (double)eps);
-    if (!close) {
-        // bounding boxes further apart than eps in L1 can hold no close pair
-        long long gx = max(0, max(A.xmin - B.xmax, B.xmin - A.xmax));
-        long long gy = max(0, max(A.ymin - B.ymax, B.ymin - A.ymax));
-        if (gx + gy > eps) return;
-        if ((long long)na * nb > ADJ_LIGHT_MAX) {
-            int slot = atomicAdd(nheavy, 1);
-            heavy[slot] = make_int2(a, d);
-            return;
-        }
-        for (int i = a0; i < a1 && !close; i++) {
-            int2 p = sxy[i];
-            for (int j = b0; j < b1; j++) {
-                int2 q = sxy[j];
-                long long dist = (long long)abs(p.x - q.x) + (long long)abs(p.y - q.y);
-                if (dist <= eps) { close = true; break; }
+    const int bq[4] = {n0.y, n1.z, n0.w, n1.w};              // directions 1, 6, 3, 7
+    int b0[4], b1[4];
+    uint8_t kb[4];
+    CellStat B[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int bb = bq[q] < 0 ? a : bq[q];                // clamped so the loads are unconditional
+        kb[q] = keep[bb];
+        b0[q] = cstart[bb];
+        b1[q] = cstart[bb + 1];
+        B[q] = st[bb];
+    }
+    const int na = a1 - a0;
+    unsigned mine = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int b = bq[q], d = fdir[q];
+        if (b < 0 || !kb[q]) continue;
+        const int nb = b1[q] - b0[q];
+        bool close = centroid_close(A, na, B[q], nb, (double)eps);
+        if (!close) {
+            // bounding boxes further apart than eps in L1 can hold no close pair
+            long long gx = max(0, max(A.xmin - B[q].xmax, B[q].xmin - A.xmax));
+            long long gy = max(0, max(A.ymin - B[q].ymax, B[q].ymin - A.ymax));
+            if (gx + gy > eps) continue;
+            if ((long long)na * nb > ADJ_LIGHT_MAX) {
+                if ((long long)na * nb > ADJ_WARP_MAX) heavy[atomicAdd(nheavy, 1)] = make_int2(a, d);
+                else medium[atomicAdd(nmedium, 1)] = make_int2(a, d);
+                continue;
+            }
+            for (int i = a0; i < a1 && !close; i++) {
+                int2 p = sxy[i];
+                for (int j = b0[q]; j < b1[q]; j++) {
+                    int2 qq = sxy[j];
+                    long long dist = (long long)abs(p.x - qq.x) + (long long)abs(p.y - qq.y);
+                    if (dist <= eps) { close = true; break; }
+                }
             }
         }
+        if (close) {
+            mine |= 1u << d;
+            atomicOr(&adj[b], 1u << c_opp[d]);
+        }
     }
-    if (close) {
-        atomicOr(&adj[a], 1u << d);
-        atomicOr(&adj[b], 1u << c_opp[d]);
+    if (mine) atomicOr(&adj[a], mine);
+}
+
+// one warp per listed pair (the warps of a fixed-size grid stride over the list, whose length stays on the device): the
+// lanes hold points of the larger cell, the points of the smaller one are read by all lanes together (one broadcast
+// load each) and a ballot ends the pair on the first hit
+__device__ __forceinline__ void adj_warp_pairs(const int2 *__restrict__ sxy, const int32_t *__restrict__ cstart,
+                                               const int32_t *__restrict__ nbr, const int2 *__restrict__ medium,
+                                               const int32_t *__restrict__ nmedium, unsigned *__restrict__ adj,
+                                               int64_t eps) {
+    const int lane = threadIdx.x & 31;
+    const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+    const int n = *nmedium;
+    for (int h = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); h < n; h += nwarps) {
+        const int2 pr = medium[h];
+        const int a = pr.x, d = pr.y;
+        const int b = nbr[8 * (int64_t)a + d];
+        int l0 = cstart[a], l1 = cstart[a + 1], s0 = cstart[b], s1 = cstart[b + 1];
+        if (l1 - l0 < s1 - s0) { int t0 = l0, t1 = l1; l0 = s0; l1 = s1; s0 = t0; s1 = t1; }     // lanes take the larger cell
+        bool found = false;
+        for (int i0 = l0; i0 < l1 && !found; i0 += 32) {
+            const bool valid = i0 + lane < l1;
+            const int2 p = valid ? sxy[i0 + lane] : make_int2(0, 0);
+            for (int j = s0; j < s1; j++) {
+                const int2 q = sxy[j];
+                const long long dist = (long long)abs(p.x - q.x) + (long long)abs(p.y - q.y);
+                if (__any_sync(0xffffffffu, valid && dist <= eps)) { found = true; break; }
+            }
+        }
+        if (found && lane == 0) {
+            atomicOr(&adj[a], 1u << d);
+            atomicOr(&adj[b], 1u << c_opp[d]);
+        }
     }
 }
 
@@ -323,9 +377,12 @@ __global__ void __launch_bounds__(HEAVY_THREADS) k_block_adj_heavy(const int2 *_
                                                                     const int32_t *__restrict__ nbr,
                                                                     const int2 *__restrict__ heavy,
                                                                     const int32_t *__restrict__ nheavy,
+                                                                    const int2 *__restrict__ medium,
+                                                                    const int32_t *__restrict__ nmedium,
                                                                     unsigned *__restrict__ adj, int64_t eps) {
     __shared__ int2 tile[HEAVY_TILE];
     __shared__ int found;
+    adj_warp_pairs(sxy, cstart, nbr, medium, nmedium, adj, eps);          // the medium pairs, one warp each
     const int nh = *nheavy;
     for (int hi = blockIdx.x; hi < nh; hi += gridDim.x) {
     __syncthreads();                       // `found` and the tile of the previous pair are done with
@@ -879,7 +936,7 @@ int cl2_block_dbscan_impl(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int32_t mi
         uint8_t *core;
         uint64_t *okey, *minkey;
         int32_t *parent, *root, *compid, *nheavy, *crowd = nullptr;
-        int2 *heavy;
+        int2 *heavy, *medium;
         // cell-indexed arrays are sized by ncells but only touched at kept cells
         CL2_TRY(sc.get(&st, (size_t)ncells));
         CL2_TRY(sc.get(&adj, (size_t)ncells));
@@ -890,11 +947,12 @@ int cl2_block_dbscan_impl(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int32_t mi
         CL2_TRY(sc.get(&root, (size_t)ncells));
         CL2_TRY(sc.get(&compid, (size_t)ncells));
         CL2_TRY(sc.get(&heavy, (size_t)nkept * 4));
-        CL2_TRY(sc.get(&nheavy, 2));                 // [0] heavy pairs, [1] crowded cells
+        CL2_TRY(sc.get(&medium, (size_t)nkept * 4));
+        CL2_TRY(sc.get(&nheavy, 4));                 // [0] heavy pairs, [1] crowded cells, [2] medium pairs
         CL2_TRY(sc.get(&crowd, (size_t)nkept));
         CL2_CUDA(ctx, cudaMemsetAsync(adj, 0, (size_t)ncells * 4, s));
         CL2_CUDA(ctx, cudaMemsetAsync(core, 0, (size_t)ncells, s));
-        CL2_CUDA(ctx, cudaMemsetAsync(nheavy, 0, 8, s));
+        CL2_CUDA(ctx, cudaMemsetAsync(nheavy, 0, 16, s));
         {
             FamTimer t(ctx, FAM_CELLSTAT, 8.0 * (double)n, 2);
             k_block_cellstat_small<<<cl2_grid(nkept, 256), 256, 0, s>>>(g.sxy, g.cstart, list, st, nkept, crowd, nheavy + 1);
@@ -905,15 +963,16 @@ int cl2_block_dbscan_impl(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int32_t mi
         }
         {
             FamTimer t(ctx, FAM_ADJ, 8.0 * (double)n);
-            k_block_adj<<<cl2_grid((int64_t)nkept * 4, 128), 128, 0, s>>>(g.sxy, g.cstart, g.nbr, keep, st, list, nkept,
-                                                                           adj, eps, heavy, nheavy);
+            k_block_adj<<<cl2_grid(nkept, 128), 128, 0, s>>>(g.sxy, g.cstart, g.nbr, keep, st, list, nkept,
+                                                                           adj, eps, heavy, nheavy, medium, nheavy + 2);
         }
         {
-            // heavy pairs (listed by k_block_adj, count on the device): blocks of a fixed-size grid stride over the list
+            // medium and heavy pairs (listed by k_block_adj, counts on the device): the warps / blocks of one fixed-size
+            // grid stride over the two lists
             FamTimer t(ctx, FAM_ADJ, 0.0);
             int64_t want = (int64_t)nkept * 4, cap = (int64_t)ctx->sm_count * 8;
             k_block_adj_heavy<<<(unsigned)(want < cap ? want : cap), HEAVY_THREADS, 0, s>>>(g.sxy, g.cstart, g.nbr, heavy, nheavy,
-                                                                                           adj, eps);
+                                                                                           medium, nheavy + 2, adj, eps);
         }
         {
             FamTimer t(ctx, FAM_CORE, 64.0 * (double)nkept);

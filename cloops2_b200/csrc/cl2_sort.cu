@@ -383,17 +383,21 @@ __global__ void __launch_bounds__(OS_THREADS, MINB) k_os_pass(const K *__restric
         __syncwarp();
     }
     __syncthreads();
+    // per digit: the warps' counts (kept in registers until the block scan has placed the digit inside the tile), the
+    // look-back for the digit's base over earlier tiles, and the two offsets the later phases add to an element's rank:
+    // warp_cnt[w][d] := position inside the tile of warp w's first element with digit d; gbase[d] := global position
+    // of the tile's first element with digit d minus its position inside the tile
     int off = 0;
+    int wc[OS_WARPS];
+    unsigned excl = 0;
     if (threadIdx.x < 256) {
         const int d = threadIdx.x;
 #pragma unroll
         for (int k = 0; k < OS_WARPS; k++) {
-            int c = S.warp_cnt[k][d];
-            S.warp_cnt[k][d] = off;
-            off += c;
+            wc[k] = S.warp_cnt[k][d];
+            off += wc[k];
         }
         // look back for the exclusive prefix over earlier tiles, four descriptors per round trip
-        unsigned excl = 0;
         long long t = (long long)tile - 1;
         while (t >= 0) {
             unsigned v[4];
@@ -409,12 +413,20 @@ __global__ void __launch_bounds__(OS_THREADS, MINB) k_os_pass(const K *__restric
             }
         }
         os_st(&desc[(size_t)tile * 256 + d], (excl + (unsigned)off) | OS_INC);
-        S.gbase[d] = (int)(gprefix[d] + excl);
     }
     {
         int tot;
-        int ex = block_excl_scan<OS_THREADS>(off, &tot);
-        if (threadIdx.x < 256) S.dprefix[threadIdx.x] = ex;
+        const int ex = block_excl_scan<OS_THREADS>(off, &tot);
+        if (threadIdx.x < 256) {
+            const int d = threadIdx.x;
+            int run = ex;
+#pragma unroll
+            for (int k = 0; k < OS_WARPS; k++) {
+                S.warp_cnt[k][d] = run;
+                run += wc[k];
+            }
+            S.gbase[d] = (int)(gprefix[d] + excl) - ex;
+        }
     }
     __syncthreads();
 #pragma unroll
@@ -422,7 +434,7 @@ __global__ void __launch_bounds__(OS_THREADS, MINB) k_os_pass(const K *__restric
         int64_t i = wbase + r * 32 + lane;
         if (i < n) {
             int d = (int)((key[r] >> shift) & 255);
-            int pos = S.dprefix[d] + S.warp_cnt[w][d] + rank[r];
+            int pos = S.warp_cnt[w][d] + rank[r];
             S.keys[pos] = key[r];
             S.vals[pos] = val[r];
         }
@@ -433,7 +445,7 @@ __global__ void __launch_bounds__(OS_THREADS, MINB) k_os_pass(const K *__restric
     for (int j = threadIdx.x; j < cnt; j += OS_THREADS) {
         K k = S.keys[j];
         int d = (int)((k >> shift) & 255);
-        int64_t dst = (int64_t)S.gbase[d] + (j - S.dprefix[d]);
+        const uint32_t dst = (uint32_t)(S.gbase[d] + j);
         if (put_keys) kout[dst] = k;
         vout[dst] = S.vals[j];
     }
