@@ -85,6 +85,7 @@ extern "C" int cl2_index_build(cl2_ctx *ctx, cl2_points *pts, cl2_index **out) {
     const int64_t n = pts->n;
     ix->n = n;
     ix->small = (pts->ext[1] < (1ll << 29) && pts->ext[3] < (1ll << 29)) ? 1 : 0;
+    ix->ymax = pts->ext[3];
     int rc = CL2_OK;
     if (n > 0) {
         Scratch sc(ctx);
@@ -136,6 +137,7 @@ extern "C" void cl2_index_free(cl2_ctx *ctx, cl2_index *idx) {
     cl2_dev_free(ctx, idx->byy);
     cl2_dev_free(ctx, idx->tx);
     cl2_dev_free(ctx, idx->ty);
+    cl2_dev_free(ctx, idx->wm);
     delete idx;
 }
 
@@ -153,6 +155,10 @@ struct IdxView {
     int sx, sy, nbx, nby;
     int lg;               // ceil(log2 n): depth of one binary search in SURVEY.md 8d's byte count
     int small;            // every coordinate is below 2^29 (4 * c fits an int: closed-form window masks)
+    const uint2 *wm;      // wavelet matrix over y in x order (null until built), see cl2_index
+    int wm_L;
+    uint32_t wm_nw;
+    uint32_t wm_z[32];
 };
 struct Arr {
     const int2 *a;
@@ -160,7 +166,9 @@ struct Arr {
     int shift, nb;
 };
 static IdxView cl2_view(const cl2_index *idx) {
-    IdxView v = {idx->byx, idx->byy, idx->tx, idx->ty, idx->n, idx->sx, idx->sy, idx->nbx, idx->nby, 1, idx->small};
+    IdxView v = {idx->byx, idx->byy, idx->tx, idx->ty, idx->n, idx->sx, idx->sy, idx->nbx, idx->nby, 1, idx->small,
+                 idx->wm, idx->wm_L, (uint32_t)idx->wm_nw, {0}};
+    for (int l = 0; l < 32; l++) v.wm_z[l] = idx->wm_z[l];
     while (((int64_t)1 << v.lg) < idx->n) v.lg++;
     return v;
 }
@@ -543,22 +551,13 @@ __device__ __forceinline__ unsigned div_mask(const FamDiv &F, const WinDiv &D, i
     return (m & D.lowmask) | ((m >> (D.win + 1)) << D.win);
 }
 
-// getPerRegions + getLoopNearbyPETs counts into the warp's accumulator (callCisLoops.py:173-223), W = 2*win <= 10.
-// With ax / ay / bx / by the masks of the a- and b-windows holding a row's x and y (ma = ax | ay, mb = bx | by):
-//     na[i]     = cX(a_i) + cY(a_i) - sum [ax_i and ay_i]
-//     nab[i][j] = cY(a_i & b_j) + sum ([ma_i and mb_j] - [ay_i and by_j])       sums over the rows with x in any window
-// One X-range scan; per batch of 32 rows the three 10-bit fields (ma, mb, ax & ay) and (ay, by, bx & by) are
-// transposed across the warp so that lane t owns the ballot of bit t, and every lane accumulates its share of the
-// W*W pair counters in registers from shuffled columns -- no shared-memory atomics, no data-dependent loops.
-// fdr_stop > 0: the scan may stop as soon as fdr_stop window pairs are known to hold more than `rab` rows (the
-// counters only grow), which decides the reference's `fdr >= 0.1` cut (callCisLoops.py:322); returns false then.
-// Returns 1 when the counts are complete, 0 when the fdr cut was decided early, -1 when a single warp was asked for more
-// than BIG_ROWS rows (nothing scanned: the candidate goes to the cooperative kernel).
-__device__ int loop_windows10(const IdxView &ix, long long xs, long long xe, long long ys, long long ye, int win, int lane,
-                              const Coop &C, WarpAcc &S, long long *g_bytes, int fdr_stop = 0, long long rab = 0) {
+// The 2*win permuted windows of both anchors (callCisLoops.py:179-198): bounds into S.aw / S.bw / S.wlo / S.whi, their
+// positions in the two sorted lists into S.pos (one search per lane and round), the closed-form mask parameters into D;
+// returns whether the closed form may be used.
+__device__ __forceinline__ bool windows_setup(const IdxView &ix, long long xs, long long xe, long long ys, long long ye, int win,
+                                              int lane, WarpAcc &S, WinDiv &D) {
     const int W = 2 * win;
     bool regular = ix.small != 0;
-    WinDiv D;
     {
         const long long ca4 = 2 * (xs + xe), cb4 = 2 * (ys + ye), sa4 = 2 * (xe - xs), sb4 = 2 * (ye - ys);
         const long long step4 = (xe - xs) + (ye - ys);
@@ -604,6 +603,25 @@ __device__ int loop_windows10(const IdxView &ix, long long xs, long long xe, lon
         S.pos[t & 3][w] = bound_task(ix, S.wlo[w], S.whi[w], (t >> 1) & 1, t & 1);
     }
     __syncwarp();
+    return regular;
+}
+
+// getPerRegions + getLoopNearbyPETs counts into the warp's accumulator (callCisLoops.py:173-223), W = 2*win <= 10.
+// With ax / ay / bx / by the masks of the a- and b-windows holding a row's x and y (ma = ax | ay, mb = bx | by):
+//     na[i]     = cX(a_i) + cY(a_i) - sum [ax_i and ay_i]
+//     nab[i][j] = cY(a_i & b_j) + sum ([ma_i and mb_j] - [ay_i and by_j])       sums over the rows with x in any window
+// One X-range scan; per batch of 32 rows the three 10-bit fields (ma, mb, ax & ay) and (ay, by, bx & by) are
+// transposed across the warp so that lane t owns the ballot of bit t, and every lane accumulates its share of the
+// W*W pair counters in registers from shuffled columns -- no shared-memory atomics, no data-dependent loops.
+// fdr_stop > 0: the scan may stop as soon as fdr_stop window pairs are known to hold more than `rab` rows (the
+// counters only grow), which decides the reference's `fdr >= 0.1` cut (callCisLoops.py:322); returns false then.
+// Returns 1 when the counts are complete, 0 when the fdr cut was decided early, -1 when a single warp was asked for more
+// than BIG_ROWS rows (nothing scanned: the candidate goes to the cooperative kernel).
+__device__ int loop_windows10(const IdxView &ix, long long xs, long long xe, long long ys, long long ye, int win, int lane,
+                              const Coop &C, WarpAcc &S, long long *g_bytes, int fdr_stop = 0, long long rab = 0) {
+    const int W = 2 * win;
+    WinDiv D;
+    const bool regular = windows_setup(ix, xs, xe, ys, ye, win, lane, S, D);
     // X ranges of the two spans (window centres are monotone in i, so are the positions)
     uint32_t b0 = S.pos[0][0], e0 = S.pos[1][W - 1], b1 = S.pos[0][W], e1 = S.pos[1][2 * W - 1];
     const long long span_rows = (long long)max(e0 > b0 ? e0 - b0 : 0u, S.pos[3][W - 1] > S.pos[2][0] ? S.pos[3][W - 1] - S.pos[2][0] : 0u) +
@@ -858,6 +876,247 @@ __device__ __forceinline__ int loop_windows(const IdxView &ix, long long xs, lon
     return 1;
 }
 
+// ---- wavelet matrix: 2-D range counts without scanning ---------------------------------------------------------
+// Every count of the path is a combination of 1-D range counts and rectangle counts R(I, J) = #{x in I and y in J}
+// (checked against the oracle for ordered, unordered, overlapping and clipped intervals):
+//     |P(I)|        = cX(I) + cY(I) - R(I, I)
+//     |P(U) & P(V)| = cX(UV) + cY(UV) + R(U,V) + R(V,U) - R(U,UV) - R(V,UV) - R(UV,U) - R(UV,V) + R(UV,UV),  UV = U & V
+// The scans above find R by visiting the rows of an X range, which is the cheapest way while a range holds a few
+// hundred rows (Hi-TrAC / ChIA-PET like data).  In Hi-C like data a 10 kb window holds thousands of rows and the +-5
+// step region of a candidate 10^5: there R(I, J) = F(p, q, J.hi + 1) - F(p, q, J.lo) with [p, q) the X range of I and
+// F(p, q, v) = #{rows in [p, q) with y < v} comes from a wavelet matrix over the y values in x order in wm_L steps,
+// each two 8-byte reads -- independent of the number of rows.
+__global__ void __launch_bounds__(256) k_wm_init(const int2 *__restrict__ byx, uint32_t *__restrict__ cur, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) cur[i] = (uint32_t)byx[i].y;
+}
+// ones per word of 32 rows (input of the prefix scan)
+__global__ void __launch_bounds__(256) k_wm_ones(const uint32_t *__restrict__ cur, int64_t n, int shift, int64_t nw,
+                                                  int32_t *__restrict__ ones) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((i >> 5) >= nw) return;
+    const unsigned word = __ballot_sync(0xffffffffu, i < n && ((cur[i < n ? i : 0] >> shift) & 1u));
+    if ((threadIdx.x & 31) == 0) ones[i >> 5] = __popc(word);
+}
+// stable partition by the bit (zeros first) + the level's {bits, ones before} table; pre = exclusive scan of `ones`,
+// total[0] = number of ones
+__global__ void __launch_bounds__(256) k_wm_partition(const uint32_t *__restrict__ cur, uint32_t *__restrict__ nxt, int64_t n,
+                                                       int shift, int64_t nw, const int32_t *__restrict__ pre,
+                                                       const int64_t *__restrict__ total, uint2 *__restrict__ level) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((i >> 5) >= nw) return;
+    const int lane = threadIdx.x & 31;
+    const bool valid = i < n;
+    const uint32_t v = valid ? cur[i] : 0u;
+    const bool bit = valid && ((v >> shift) & 1u);
+    const unsigned word = __ballot_sync(0xffffffffu, bit);
+    const uint32_t before = (uint32_t)pre[i >> 5];
+    if (lane == 0) level[i >> 5] = make_uint2(word, before);
+    if (!valid) return;
+    const uint32_t r1 = before + __popc(word & ((1u << lane) - 1u));
+    const uint32_t z = (uint32_t)(n - *total);
+    nxt[bit ? z + r1 : (uint32_t)i - r1] = v;
+}
+
+static int cl2_index_wavelet(cl2_ctx *ctx, cl2_index *idx) {
+    if (idx->wm || idx->n <= 0) return CL2_OK;
+    const int64_t n = idx->n;
+    const int L = bits_for((uint64_t)idx->ymax);
+    const int64_t nw = n / 32 + 1;
+    if (L > 32 || n >= (int64_t)INT32_MAX) return cl2_fail(ctx, CL2_ERR_RANGE, "wavelet matrix: too many rows");
+    Scratch sc(ctx);
+    uint32_t *cur, *nxt;
+    int32_t *ones;
+    int64_t *tot;
+    CL2_TRY(sc.get(&cur, (size_t)n));
+    CL2_TRY(sc.get(&nxt, (size_t)n));
+    CL2_TRY(sc.get(&ones, (size_t)nw));
+    CL2_TRY(sc.get(&tot, (size_t)L));
+    uint2 *wm;
+    CL2_TRY(cl2_dev_alloc(ctx, &wm, (size_t)L * (size_t)nw));
+    {
+        FamTimer t(ctx, FAM_INDEX, 12.0 * (double)n);
+        k_wm_init<<<cl2_grid(n, 256), 256, 0, ctx->stream>>>(idx->byx, cur, n);
+    }
+    for (int l = 0; l < L; l++) {
+        const int shift = L - 1 - l;
+        {
+            FamTimer t(ctx, FAM_INDEX, 4.0 * (double)n);
+            k_wm_ones<<<cl2_grid(nw * 32, 256), 256, 0, ctx->stream>>>(cur, n, shift, nw, ones);
+        }
+        CL2_TRY(cl2_exclusive_scan_i32(ctx, ones, nw, tot + l));
+        {
+            FamTimer t(ctx, FAM_INDEX, 8.25 * (double)n);
+            k_wm_partition<<<cl2_grid(nw * 32, 256), 256, 0, ctx->stream>>>(cur, nxt, n, shift, nw, ones, tot + l,
+                                                                            wm + (size_t)l * (size_t)nw);
+        }
+        uint32_t *t2 = cur; cur = nxt; nxt = t2;
+    }
+    std::vector<int64_t> ht((size_t)L);
+    CL2_CUDA(ctx, cudaMemcpyAsync(ht.data(), tot, (size_t)L * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CL2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CL2_CUDA(ctx, cudaGetLastError());
+    for (int l = 0; l < L; l++) idx->wm_z[l] = (uint32_t)(n - ht[(size_t)l]);
+    idx->wm = wm;
+    idx->wm_L = L;
+    idx->wm_nw = nw;
+    return CL2_OK;
+}
+
+// F(p, q, vv) = #{rows at x positions [p, q) with y < vv}, one lane on its own query
+__device__ __forceinline__ int wm_less(const IdxView &ix, uint32_t p, uint32_t q, long long vv) {
+    if (q <= p || vv <= 0) return 0;
+    const int L = ix.wm_L;
+    if (vv >= (1ll << L)) return (int)(q - p);
+    const uint32_t v = (uint32_t)vv;
+    int cnt = 0;
+    const uint2 *lev = ix.wm;
+    for (int l = 0; l < L; l++, lev += ix.wm_nw) {
+        const uint2 ep = lev[p >> 5], eq = lev[q >> 5];
+        const uint32_t r1p = ep.y + __popc(ep.x & ((1u << (p & 31)) - 1u));
+        const uint32_t r1q = eq.y + __popc(eq.x & ((1u << (q & 31)) - 1u));
+        if ((v >> (L - 1 - l)) & 1u) {
+            cnt += (int)((q - r1q) - (p - r1p));             // the rows with a 0 here are smaller
+            p = ix.wm_z[l] + r1p;
+            q = ix.wm_z[l] + r1q;
+        } else {
+            p -= r1p;
+            q -= r1q;
+        }
+        if (p == q) break;
+    }
+    return cnt;
+}
+
+struct WmTab {                 // per-warp tables of the wavelet form of the window counts
+    int T[2 * 10][4 * 10];     // T[w][t] = F(X range of window w, threshold t); t < 2W: lo of window t, else hi + 1 of t - 2W
+    int O[100][4];             // per window pair (i, j): F(X range of a_i & b_j, {a.lo, a.hi + 1, b.lo, b.hi + 1})
+};
+
+// |P(U)|, |P(V)|-style terms for the four core intervals A, B, A2, B2 in one round of 32 queries:
+// lanes 0-1 R(A,A), 2-3 R(B,B), 4-17 the seven rectangles of (A, B), 18-31 those of (A2, B2)
+__device__ void core_wm(const IdxView &ix, long long xs, long long xe, long long ys, long long ye, int mode, int lane,
+                        int64_t out[4], long long *g_bytes) {
+    const int k = (lane >> 2) & 3;
+    long long lo, hi;
+    if (k == 0) { lo = xs; hi = xe; }
+    else if (k == 1) { lo = ys; hi = ye; }
+    else if (k == 2) {
+        if (mode == CL2_MODE_CIS) { lo = xe; hi = xe + (xe - xs); }
+        else { lo = xs - (xe - xs); hi = xs; }
+    } else { lo = ys - (ye - ys); hi = ys; }
+    const uint32_t pos = lane < 16 ? bound_task(ix, lo, hi, (lane >> 1) & 1, lane & 1) : 0u;
+    IvPos P[4];
+    Iv I[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        P[q] = gather_pos(pos, q);
+        I[q].lo = __shfl_sync(0xffffffffu, lo, 4 * q);
+        I[q].hi = __shfl_sync(0xffffffffu, hi, 4 * q);
+    }
+    // this lane's query: X range [p, q), threshold, sign, destination (0 R(A,A), 1 R(B,B), 2 pair(A,B), 3 pair(A2,B2))
+    uint32_t p = 0, q = 0;
+    long long thr = 0;
+    int sign = 0, dst = 0;
+    if (lane < 4) {
+        const int w = lane >> 1;
+        p = P[w].xb; q = P[w].xe;
+        thr = (lane & 1) ? I[w].hi + 1 : I[w].lo;
+        sign = (lane & 1) ? 1 : -1;
+        dst = w;
+    } else {
+        const int g = lane < 18 ? 0 : 1, r = ((lane - 4) % 14) >> 1, side = (lane - 4) & 1;
+        const Iv U = I[2 * g], V = I[2 * g + 1];
+        const IvPos PU = P[2 * g], PV = P[2 * g + 1];
+        Iv UV;
+        UV.lo = U.lo > V.lo ? U.lo : V.lo;
+        UV.hi = U.hi < V.hi ? U.hi : V.hi;
+        IvPos PUV;
+        PUV.xb = PU.xb > PV.xb ? PU.xb : PV.xb;
+        PUV.xe = PU.xe < PV.xe ? PU.xe : PV.xe;
+        // rectangles: 0 R(U,V) 1 R(V,U) 2 R(U,UV) 3 R(V,UV) 4 R(UV,U) 5 R(UV,V) 6 R(UV,UV); signs + + - - - - +
+        const IvPos X = (r == 0 || r == 2) ? PU : ((r == 1 || r == 3) ? PV : PUV);
+        const Iv J = (r == 0 || r == 5) ? V : ((r == 1 || r == 4) ? U : UV);
+        p = X.xb; q = X.xe;
+        const bool empty = J.lo > J.hi || (r >= 2 && UV.lo > UV.hi);
+        if (empty) q = p;
+        thr = side ? J.hi + 1 : J.lo;
+        sign = (side ? 1 : -1) * ((r == 0 || r == 1 || r == 6) ? 1 : -1);
+        dst = 2 + g;
+    }
+    const int f = sign * wm_less(ix, p, q, thr);
+    int r4[4];
+#pragma unroll
+    for (int d = 0; d < 4; d++) r4[d] = warp_sum(dst == d ? f : 0);
+    out[0] = ((int64_t)P[0].xe - P[0].xb) + ((int64_t)P[0].ye - P[0].yb) - r4[0];
+    out[1] = ((int64_t)P[1].xe - P[1].xb) + ((int64_t)P[1].ye - P[1].yb) - r4[1];
+#pragma unroll
+    for (int g = 0; g < 2; g++) {
+        const IvPos PU = P[2 * g], PV = P[2 * g + 1];
+        const long long xb = PU.xb > PV.xb ? PU.xb : PV.xb, xe_ = PU.xe < PV.xe ? PU.xe : PV.xe;
+        out[2 + g] = (xe_ > xb ? xe_ - xb : 0) + ycount_both(PU, PV) + r4[2 + g];
+    }
+    *g_bytes += 16 * (pos_max(P[0]) + pos_max(P[1]) + pos_max(P[2]) + pos_max(P[3])) + 4 * 32 * (long long)ix.lg;
+}
+
+// The window counts of loop_windows10 from rectangle counts: S.na, S.nb, S.nab as that function leaves them.
+__device__ void windows_wm(const IdxView &ix, long long xs, long long xe, long long ys, long long ye, int win, int lane,
+                           WarpAcc &S, WmTab &Tb, long long *g_bytes) {
+    const int W = 2 * win;
+    WinDiv D;
+    windows_setup(ix, xs, xe, ys, ye, win, lane, S, D);
+    {
+        const uint32_t b0 = S.pos[0][0], e0 = S.pos[1][W - 1], b1 = S.pos[0][W], e1 = S.pos[1][2 * W - 1];
+        const long long span_rows = (long long)max(e0 > b0 ? e0 - b0 : 0u, S.pos[3][W - 1] > S.pos[2][0] ? S.pos[3][W - 1] - S.pos[2][0] : 0u) +
+                                    (long long)max(e1 > b1 ? e1 - b1 : 0u, S.pos[3][2 * W - 1] > S.pos[2][W] ? S.pos[3][2 * W - 1] - S.pos[2][W] : 0u);
+        *g_bytes += 16 * span_rows + (2 * W + 1) * 32 * (long long)ix.lg;
+    }
+    // T[w][t]: 2W windows x 4W thresholds
+    for (int q = lane; q < 2 * W * 4 * W; q += 32) {
+        const int w = q / (4 * W), t = q - w * 4 * W;
+        const long long thr = t < 2 * W ? S.wlo[t] : S.whi[t - 2 * W] + 1;
+        Tb.T[w][t] = wm_less(ix, S.pos[0][w], S.pos[1][w], thr);
+    }
+    // O[pair][k]: the X range of a_i & b_j against the four bounds of the pair (empty intersection: zeros)
+    for (int q = lane; q < W * W * 4; q += 32) {
+        const int pr = q >> 2, kk = q & 3, i = pr / W, j = W + pr % W;
+        const uint32_t p = S.pos[0][i] > S.pos[0][j] ? S.pos[0][i] : S.pos[0][j];
+        const uint32_t e = S.pos[1][i] < S.pos[1][j] ? S.pos[1][i] : S.pos[1][j];
+        const long long thr = kk == 0 ? S.wlo[i] : kk == 1 ? S.whi[i] + 1 : kk == 2 ? S.wlo[j] : S.whi[j] + 1;
+        Tb.O[pr][kk] = wm_less(ix, p, e > p ? e : p, thr);
+    }
+    __syncwarp();
+    if (lane < W) {
+        const int i = lane, j = W + lane;
+        S.na[lane] = (int)(((long long)S.pos[1][i] - S.pos[0][i]) + ((long long)S.pos[3][i] - S.pos[2][i]) -
+                           (Tb.T[i][2 * W + i] - Tb.T[i][i]));
+        S.nb[lane] = (int)(((long long)S.pos[1][j] - S.pos[0][j]) + ((long long)S.pos[3][j] - S.pos[2][j]) -
+                           (Tb.T[j][2 * W + j] - Tb.T[j][j]));
+    }
+    for (int pr = lane; pr < W * W; pr += 32) {
+        const int i = pr / W, j = W + pr % W;
+        // a = window i, b = window j; ab = a & b
+        const long long alo = S.wlo[i], ahi = S.whi[i], blo = S.wlo[j], bhi = S.whi[j];
+        const bool lo_from_a = alo >= blo, hi_from_a = ahi <= bhi;
+        const long long ablo = lo_from_a ? alo : blo, abhi = hi_from_a ? ahi : bhi;
+        const int tlo = lo_from_a ? i : j, thi = 2 * W + (hi_from_a ? i : j);          // thresholds of ab in T's columns
+        long long v = (Tb.T[i][2 * W + j] - Tb.T[i][j]) + (Tb.T[j][2 * W + i] - Tb.T[j][i]);     // R(a,b) + R(b,a)
+        if (ablo <= abhi) {
+            const uint32_t xb = S.pos[0][i] > S.pos[0][j] ? S.pos[0][i] : S.pos[0][j];
+            const uint32_t xe_ = S.pos[1][i] < S.pos[1][j] ? S.pos[1][i] : S.pos[1][j];
+            const uint32_t yb = S.pos[2][i] > S.pos[2][j] ? S.pos[2][i] : S.pos[2][j];
+            const uint32_t ye_ = S.pos[3][i] < S.pos[3][j] ? S.pos[3][i] : S.pos[3][j];
+            v += (xe_ > xb ? (long long)(xe_ - xb) : 0) + (ye_ > yb ? (long long)(ye_ - yb) : 0);      // cX(ab) + cY(ab)
+            v -= (Tb.T[i][thi] - Tb.T[i][tlo]) + (Tb.T[j][thi] - Tb.T[j][tlo]);                        // R(a,ab) + R(b,ab)
+            const int *o = Tb.O[pr];
+            v -= (o[1] - o[0]) + (o[3] - o[2]);                                                        // R(ab,a) + R(ab,b)
+            v += (hi_from_a ? o[1] : o[3]) - (lo_from_a ? o[0] : o[2]);                                // R(ab,ab)
+        }
+        S.nab[pr] = (int)v;
+    }
+    __syncwarp();
+}
+
 // ---- raw counts (cl2_loop_counts) ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(CNT_WARPS * 32) k_loop_counts(const IdxView ix, const longlong4 *__restrict__ loops, int64_t L,
                                                                  int win, int mode, long long *__restrict__ core,
@@ -985,29 +1244,11 @@ __device__ double warp_median(WarpVals &S, int m, int lane) {
 #define CL2_NSTAT 13
 // Permuted-window background, enrichment tests and anchor tests of one loop (one warp); results into o[13] (shared):
 // mrabs, mbps, fdr, poisson sf, binomial sf, px, esx, py, esy, count_x, wide_x, count_y, wide_y
-// Background of one loop (one warp): permuted windows -> mrabs, mbps, fdr (callCisLoops.py:207-223, 315-321).
-// bg_cut (cis): return false as soon as `mrabs >= rab or fdr >= 0.1` or `es < 1` (:322-327) is known; the reference
-// applies these cuts whatever `pseudo` is, which only enters the enrichment score.
-// Returns 1 keep, 0 drop, -1 hand the candidate to the cooperative kernel, -2 (cooperating warps other than the first)
-// nothing left to do for this warp.
-__device__ int loop_background(const IdxView &ix, long long xs,
-                               long long xe, long long ys, long long ye, double rab, int win, int mode, const Coop &C,
-                               WarpAcc &S, WarpVals &V, int lane, bool bg_cut, double pseudo, double *o_mrabs,
-                               double *o_mbps, double *o_fdr, long long *g_scan) {
+// From the window counts in S (na, nb, nab) to mrabs, mbps, fdr and the background cut: the part of loop_background
+// after the counting.  Returns 1 keep, 0 drop.
+__device__ int background_finish(double rab, int win, int mode, WarpAcc &S, WarpVals &V, int lane, bool bg_cut, double pseudo,
+                                 double *o_mrabs, double *o_mbps, double *o_fdr) {
     const int W = 2 * win, m = W * W;
-    // smallest number of window pairs above rab that makes fdr = gt / m >= 0.1 (the comparison the reference makes)
-    int fdr_stop = 0;
-    if (bg_cut) {
-        fdr_stop = m / 10;
-        while ((double)fdr_stop / (double)m < 0.1) fdr_stop++;
-        while (fdr_stop > 1 && (double)(fdr_stop - 1) / (double)m >= 0.1) fdr_stop--;
-    }
-    const int wr = loop_windows(ix, xs, xe, ys, ye, win, lane, C, S, g_scan, fdr_stop, (long long)rab);
-    if (wr <= 0) return wr;
-    if (C.nw > 1) {
-        __syncthreads();                                   // the counters in S are complete for every warp
-        if (C.part != 0) return -2;                        // the medians are one warp's work
-    }
     // rabs: counts of the 4*win^2 window pairs; fdr = #{rabs > rab} / m
     int gt = 0, nzero = 0;
     for (int t = lane; t < m; t += 32) {
@@ -1050,6 +1291,33 @@ __device__ int loop_background(const IdxView &ix, long long xs,
     }
     *o_mrabs = mrabs; *o_mbps = mbps; *o_fdr = fdr;
     return 1;
+}
+
+
+// Background of one loop (one warp): permuted windows -> mrabs, mbps, fdr (callCisLoops.py:207-223, 315-321).
+// bg_cut (cis): return false as soon as `mrabs >= rab or fdr >= 0.1` or `es < 1` (:322-327) is known; the reference
+// applies these cuts whatever `pseudo` is, which only enters the enrichment score.
+// Returns 1 keep, 0 drop, -1 hand the candidate to the cooperative kernel, -2 (cooperating warps other than the first)
+// nothing left to do for this warp.
+__device__ int loop_background(const IdxView &ix, long long xs,
+                               long long xe, long long ys, long long ye, double rab, int win, int mode, const Coop &C,
+                               WarpAcc &S, WarpVals &V, int lane, bool bg_cut, double pseudo, double *o_mrabs,
+                               double *o_mbps, double *o_fdr, long long *g_scan) {
+    const int W = 2 * win, m = W * W;
+    // smallest number of window pairs above rab that makes fdr = gt / m >= 0.1 (the comparison the reference makes)
+    int fdr_stop = 0;
+    if (bg_cut) {
+        fdr_stop = m / 10;
+        while ((double)fdr_stop / (double)m < 0.1) fdr_stop++;
+        while (fdr_stop > 1 && (double)(fdr_stop - 1) / (double)m >= 0.1) fdr_stop--;
+    }
+    const int wr = loop_windows(ix, xs, xe, ys, ye, win, lane, C, S, g_scan, fdr_stop, (long long)rab);
+    if (wr <= 0) return wr;
+    if (C.nw > 1) {
+        __syncthreads();                                   // the counters in S are complete for every warp
+        if (C.part != 0) return -2;                        // the medians are one warp's work
+    }
+    return background_finish(rab, win, mode, S, V, lane, bg_cut, pseudo, o_mrabs, o_mbps, o_fdr);
 }
 
 // Anchor windows and the tail probabilities of one loop (one warp): o[3..12] = poisson sf, binomial sf, px, esx, py,
@@ -1192,6 +1460,59 @@ __global__ void __launch_bounds__(BIG_THREADS, MINB) k_est_bg_big(const IdxView 
     }
 }
 
+// The candidates kernel A declined, wavelet form: one warp each, the lanes working on different range counts; the cost
+// of a candidate no longer depends on how many rows its regions hold.
+#define WM_WARPS 4
+__global__ void __launch_bounds__(WM_WARPS * 32) k_est_bg_wm(const IdxView ix, const longlong4 *__restrict__ loops, int win, int mode,
+                                                             int minPts, int hic, double cdc, double pseudo,
+                                                             long long *__restrict__ core_out, double *__restrict__ stats_out,
+                                                             int32_t *__restrict__ flag,
+                                                             unsigned long long *__restrict__ scanned_total,
+                                                             const int32_t *__restrict__ biglist,
+                                                             const int32_t *__restrict__ nbig) {
+    __shared__ WarpAcc acc[WM_WARPS];
+    __shared__ WarpVals vals[WM_WARPS];
+    __shared__ WmTab tab[WM_WARPS];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+    const int n = *nbig;
+    const bool cis = mode == CL2_MODE_CIS;
+    for (int b = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); b < n; b += nwarps) {
+        const int64_t k = biglist[b];
+        const longlong4 lp = loops[k];
+        const long long xs = lp.x, xe = lp.y, ys = lp.z, ye = lp.w;
+        const double la = (double)(xe - xs), lb = (double)(ye - ys);
+        long long scanned = 0;
+        int64_t c[4];
+        double st[3] = {0.0, 0.0, 0.0};
+        int r = 1;
+        if (la / lb > cdc || lb / la > cdc) r = 0;                                         // :282-286 / trans :135-139
+        if (r) {
+            core_wm(ix, xs, xe, ys, ye, mode, lane, c, &scanned);
+            const double ra = (double)c[0], rb = (double)c[1], rab = (double)c[2];
+            if (c[2] < minPts) r = 0;                                                      // :290 / trans :127
+            if (cis && (c[0] == c[2] || c[1] == c[2])) r = 0;                              // :293
+            if (ra / rb > cdc || rb / ra > cdc) r = 0;                                     // :296 / trans :133
+            const double lower = (double)c[3];
+            const double p2ll = rab / (lower > pseudo ? lower : pseudo);                   // :306
+            if (cis && hic && p2ll < 1.0) r = 0;                                           // :307
+            if (r) {
+                windows_wm(ix, xs, xe, ys, ye, win, lane, acc[w], tab[w], &scanned);
+                r = background_finish(rab, win, mode, acc[w], vals[w], lane, cis, pseudo, &st[0], &st[1], &st[2]);
+            }
+        }
+        if (lane == 0) {
+            if (r == 1) {
+                core_out[4 * k] = c[0]; core_out[4 * k + 1] = c[1]; core_out[4 * k + 2] = c[2]; core_out[4 * k + 3] = c[3];
+                stats_out[CL2_NSTAT * k] = st[0]; stats_out[CL2_NSTAT * k + 1] = st[1]; stats_out[CL2_NSTAT * k + 2] = st[2];
+            }
+            flag[k] = r == 1 ? 1 : 0;
+            if (scanned) atomicAdd(scanned_total, (unsigned long long)scanned);
+        }
+        __syncwarp();
+    }
+}
+
 // kernel B (survivors of kernel A, compacted): hypergeometric / Poisson / binomial tails, anchor
 // windows and tests, and the remaining cuts (:311 hypergeometric > 1e-2, :347 anchor peaks unless -hic).
 // Kernel B runs in two launches so that the fp64 series of the five tests do not run one after the other on a single
@@ -1258,6 +1579,51 @@ __global__ void __launch_bounds__(CNT_WARPS * 32) k_est_anchor_big(const IdxView
             double *o = stats + CL2_NSTAT * i;
             o[9] = (double)cx; o[10] = (double)wx; o[11] = (double)cy; o[12] = (double)wy;
             if (scanned) atomicAdd(scanned_total, (unsigned long long)scanned);
+        }
+    }
+}
+
+// the same survivors from rectangle counts: |P(I)| = cX(I) + cY(I) - R(I, I), eight range counts per survivor
+__global__ void __launch_bounds__(CNT_WARPS * 32) k_est_anchor_wm(const IdxView ix, const longlong4 *__restrict__ loops,
+                                                                   const long long *__restrict__ sel,
+                                                                   double *__restrict__ stats,
+                                                                   unsigned long long *__restrict__ scanned_total,
+                                                                   const int32_t *__restrict__ biglist,
+                                                                   const int32_t *__restrict__ nbig) {
+    const int lane = threadIdx.x & 31;
+    const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+    const int n = *nbig;
+    for (int b = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); b < n; b += nwarps) {
+        const int64_t i = biglist[b];
+        const longlong4 lp = loops[sel[i]];
+        // intervals 0..3: anchor x, its wide window, anchor y, its wide window; lane 4k + 2*list + end searches a bound
+        const int k = (lane >> 2) & 3;
+        const long long l = k < 2 ? lp.x : lp.z, r = k < 2 ? lp.y : lp.w;
+        const long long m4 = 2 * (l + r), len = r - l;
+        long long s4 = m4 - 20 * len;
+        if (s4 < 0) s4 = 0;
+        const Iv Wd = iv4(s4, m4 + 20 * len);
+        Iv I;
+        if (k & 1) I = Wd; else { I.lo = l; I.hi = r; }
+        const uint32_t pos = lane < 16 ? bound_task(ix, I.lo, I.hi, (lane >> 1) & 1, lane & 1) : 0u;
+        // lanes 0..7: interval lane >> 1, lower / upper threshold
+        const int q = (lane >> 1) & 3;
+        const IvPos P = gather_pos(pos, q);
+        const long long ilo = __shfl_sync(0xffffffffu, I.lo, 4 * q), ihi = __shfl_sync(0xffffffffu, I.hi, 4 * q);
+        int f = 0;
+        if (lane < 8) f = ((lane & 1) ? 1 : -1) * wm_less(ix, P.xb, P.xe, (lane & 1) ? ihi + 1 : ilo);
+        long long res[4], bytes = 0;
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+            const int rr = warp_sum((lane < 8 && q == d) ? f : 0);
+            const IvPos Pd = gather_pos(pos, d);
+            res[d] = ((long long)Pd.xe - Pd.xb) + ((long long)Pd.ye - Pd.yb) - rr;
+            if (d & 1) bytes += 16 * pos_max(Pd) + 2 * 32 * (long long)ix.lg;
+        }
+        if (lane == 0) {
+            double *o = stats + CL2_NSTAT * i;
+            o[9] = (double)res[0]; o[10] = (double)res[1]; o[11] = (double)res[2]; o[12] = (double)res[3];
+            atomicAdd(scanned_total, (unsigned long long)bytes);
         }
     }
 }
@@ -1458,22 +1824,30 @@ extern "C" int cl2_est_loops(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops,
         kern<<<cl2_grid(L, CNT_WARPS), CNT_WARPS * 32, 0, ctx->stream>>>(cl2_view(idx), d_loops, L, win, mode, minPts, hic,
                                                                          countDiffCut, pseudo, d_core, d_stats, d_flag,
                                                                          (unsigned long long *)(d_total + 1), d_big, d_big + L);
-        static const int bigcfg = getenv("CL2_BIG_CFG") ? atoi(getenv("CL2_BIG_CFG")) : 1;
-        const int64_t cap = (int64_t)ctx->sm_count * (bigcfg == 0 ? 2 : 8);
-        const unsigned bgrid = (unsigned)(L < cap ? L : cap);
-        if (bigcfg == 0)
-            k_est_bg_big<512, 1><<<bgrid, 512, 0, ctx->stream>>>(cl2_view(idx), d_loops, win, mode, minPts, hic, countDiffCut, pseudo,
-                                                                 d_core, d_stats, d_flag, (unsigned long long *)(d_total + 1), d_big,
-                                                                 d_big + L);
-        else if (bigcfg == 2)
-            k_est_bg_big<256, 4><<<bgrid, 256, 0, ctx->stream>>>(cl2_view(idx), d_loops, win, mode, minPts, hic, countDiffCut, pseudo,
-                                                                 d_core, d_stats, d_flag, (unsigned long long *)(d_total + 1), d_big,
-                                                                 d_big + L);
-        else
-            k_est_bg_big<256, 3><<<bgrid, 256, 0, ctx->stream>>>(cl2_view(idx), d_loops, win, mode, minPts, hic, countDiffCut, pseudo,
-                                                                 d_core, d_stats, d_flag, (unsigned long long *)(d_total + 1), d_big,
-                                                                 d_big + L);
-        ctx->launches++;
+    }
+    // The candidates kernel A declined (regions of more than BIG_ROWS rows).  A few of them: a block each shares the
+    // scans (k_est_bg_big).  Many of them (Hi-C like data, where nearly every candidate is one): range counts from the
+    // wavelet matrix, built once per index, cost the same whatever the regions hold.  CL2_WM=0 / 1 forces either.
+    int32_t nbig = 0;
+    CL2_TRY(cl2_read_i32(ctx, d_big + L, &nbig));
+    bool use_wm = false;
+    if (nbig > 0) {
+        const int wmcfg = getenv("CL2_WM") ? atoi(getenv("CL2_WM")) : -1;      // read per call: the tests switch it
+        use_wm = 2 * win <= 10 && idx->n < (int64_t)INT32_MAX && idx->ymax < (1ll << 31) &&
+                 (wmcfg == 1 || (wmcfg != 0 && (int64_t)nbig * BIG_ROWS >= idx->n));
+        if (use_wm) CL2_TRY(cl2_index_wavelet(ctx, idx));
+        FamTimer t(ctx, FAM_COUNT, 0.0);
+        if (use_wm) {
+            const int64_t cap = (int64_t)ctx->sm_count * 16, want = cl2_grid(nbig, WM_WARPS);
+            k_est_bg_wm<<<(unsigned)(want < cap ? want : cap), WM_WARPS * 32, 0, ctx->stream>>>(
+                cl2_view(idx), d_loops, win, mode, minPts, hic, countDiffCut, pseudo, d_core, d_stats, d_flag,
+                (unsigned long long *)(d_total + 1), d_big, d_big + L);
+        } else {
+            const int64_t cap = (int64_t)ctx->sm_count * 8;
+            k_est_bg_big<256, 3><<<(unsigned)(nbig < cap ? nbig : cap), 256, 0, ctx->stream>>>(
+                cl2_view(idx), d_loops, win, mode, minPts, hic, countDiffCut, pseudo, d_core, d_stats, d_flag,
+                (unsigned long long *)(d_total + 1), d_big, d_big + L);
+        }
     }
     CL2_TRY(cl2_exclusive_scan_i32(ctx, d_flag, L, d_total));
     int64_t nk = 0;
@@ -1502,8 +1876,12 @@ extern "C" int cl2_est_loops(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops,
                                                                                       (unsigned long long *)(d_total + 1), d_big,
                                                                                       d_big + L);
             const int64_t acap = (int64_t)ctx->sm_count * 8;
-            k_est_anchor_big<<<(unsigned)(nk < acap ? nk : acap), CNT_WARPS * 32, 0, ctx->stream>>>(
-                cl2_view(idx), d_loops, d_sel, d_stats_c, (unsigned long long *)(d_total + 1), d_big, d_big + L);
+            if (idx->wm)
+                k_est_anchor_wm<<<(unsigned)(cl2_grid(nk, CNT_WARPS) < acap ? cl2_grid(nk, CNT_WARPS) : acap), CNT_WARPS * 32, 0, ctx->stream>>>(
+                    cl2_view(idx), d_loops, d_sel, d_stats_c, (unsigned long long *)(d_total + 1), d_big, d_big + L);
+            else
+                k_est_anchor_big<<<(unsigned)(nk < acap ? nk : acap), CNT_WARPS * 32, 0, ctx->stream>>>(
+                    cl2_view(idx), d_loops, d_sel, d_stats_c, (unsigned long long *)(d_total + 1), d_big, d_big + L);
             ctx->launches++;
             k_est_stats<<<cl2_grid(nk * EST_GROUP, 256), 256, 0, ctx->stream>>>(d_loops, d_sel, nk, idx->n, mode, hic, peakPcut,
                                                                                 1.0 + ctx->pvalue_margin, rpb, d_core_c,

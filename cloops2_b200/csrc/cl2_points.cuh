@@ -62,6 +62,14 @@ struct cl2_index {
     uint32_t *tx = nullptr, *ty = nullptr;
     int sx = 0, sy = 0, nbx = 0, nby = 0;
     int small = 0;        // every coordinate < 2^29
+    // Wavelet matrix over the y values in x order (built on demand, cl2_count.cu): level l holds, for every 32 rows in
+    // the order after l stable partitions, the bits at position wm_L-1-l of their y and the number of ones before them;
+    // wm_z[l] = zeros of level l.  Answers "rows at x positions [p, q) with y < v" in wm_L steps.
+    uint2 *wm = nullptr;
+    int wm_L = 0;
+    int64_t wm_nw = 0;
+    uint32_t wm_z[32] = {0};
+    int64_t ymax = 0;
 };
 
 void cl2_grid_free(cl2_ctx *ctx, cl2_grid_cache &g);

@@ -246,51 +246,52 @@ def test_filter_option_files_match_golden(gpu_ctx, tmp_path):
 
 
 @pytest.mark.parametrize("hic", [False, True])
-def test_dense_hic_like_vs_oracle(gpu_ctx, hic):
+def test_dense_hic_like_vs_oracle(gpu_ctx, hic, monkeypatch):
     """BASELINE configs[2] density (324 k PETs/Mb, Hi-C-like clusters), eps 5000,10000 x minPts 50,20, blockDBSCAN and
-    cDBSCAN2: candidates whose windows hold tens of thousands of rows (the cooperative counting kernel), crowded cells
-    (heavy cell pairs), one diagonal component holding most cells.  Same loops, same text as the oracle."""
+    cDBSCAN2: candidates whose windows hold tens of thousands of rows, counted both ways the library has for them (the
+    cooperative scan kernel, CL2_WM=0, and the wavelet-matrix range counts, CL2_WM=1), crowded cells (heavy cell
+    pairs), one diagonal component holding most cells.  Same loops, same text as the oracle."""
     files = {"chr21-chr21": synth.cis_chrom(4_600_000, 1_500_000, 33, "hic")}
     tot = len(files["chr21-chr21"])
     want, _ = oracle.call_cis_loops(files, tot, [5000, 10000], [50, 20], hic=hic)
-    final, st = cis_chromosome(gpu_ctx, ("chr21", "chr21"), files["chr21-chr21"], tot, [5000, 10000], [50, 20], hic=hic,
-                               exact=True)
-    got = cols_to_loops(("chr21", "chr21"), final)
-    assert st["candidates"] > 500 and len(want) > 10
-    assert _rows(got) == _rows(want)
+    assert len(want) > 10
+    for wm in ("0", "1"):
+        monkeypatch.setenv("CL2_WM", wm)
+        final, st = cis_chromosome(gpu_ctx, ("chr21", "chr21"), files["chr21-chr21"], tot, [5000, 10000], [50, 20], hic=hic,
+                                   exact=True)
+        got = cols_to_loops(("chr21", "chr21"), final)
+        assert st["candidates"] > 500
+        assert _rows(got) == _rows(want), wm
 
 
-def test_repeatable_across_streams_and_runs(gpu_ctx):
-    """compute-sanitizer is closed on this pool, so the lock-free pieces (union-find with path halving, decoupled
-    look-back of the sort, shared-memory reductions of the cooperative counting kernel) are checked the way that is
-    left: the same files through four contexts at once, five times over, must give bit-identical labels, boxes and
-    loop tables every time (a data race that mattered would show as a difference sooner or later), and equal the
-    oracle's."""
-    import threading
-    from cloops2_b200 import _lib as L
-    sparse = synth.cis_chrom(6_000_000, 200_000, 41, "hitrac")
-    dense = synth.cis_chrom(1_500_000, 500_000, 42, "hic")
-    want_lab, want_n = oracle.block_dbscan(dense, 5000, 20)
-    ctxs = [gpu_ctx] + [L.Context(0) for _ in range(3)]
-    out = [[] for _ in ctxs]
-
-    def work(i):
-        c = ctxs[i]
-        for _ in range(5):
-            p = L.Points(c, dense)
-            lab, n = p.block_dbscan(5000, 20)
-            lab2, n2 = p.cdbscan2(5000, 20)
-            p.close()
-            f1, _ = cis_chromosome(c, ("chr1", "chr1"), sparse, len(sparse), [200, 500, 1000], [5])
-            f2, _ = cis_chromosome(c, ("chr2", "chr2"), dense, len(dense), [5000, 10000], [50, 20])
-            out[i].append((lab.tobytes(), n, lab2.tobytes(), n2, f1["coords"].tobytes(), f1["hyp"].tobytes(),
-                           f2["coords"].tobytes(), f2["nbp"].tobytes(), f2["rab"].tobytes()))
-
-    ths = [threading.Thread(target=work, args=(i,)) for i in range(len(ctxs))]
-    for t in ths:
-        t.start()
-    for t in ths:
-        t.join()
-    first = out[0][0]
-    assert all(r == first for o in out for r in o)
-    assert first[1] == want_n and first[0] == want_lab.tobytes()
+def test_wavelet_counts_on_unordered_and_clipped_loops(gpu_ctx, monkeypatch):
+    """The wavelet form of estLoopSig's counts on what the pipeline never produces but the drop-in estLoopSig may be
+    handed: overlapping anchors, windows clipped at 0, trans-like rows with X > Y -- against the scan form."""
+    from cloops2_b200 import hostops
+    rng = np.random.default_rng(12)
+    n = 400_000
+    x = rng.integers(0, 600_000, n)
+    xy = np.stack([x, x + np.exp(rng.uniform(0, np.log(200_000), n)).astype(np.int64)], 1)
+    xy2 = np.stack([rng.integers(0, 500_000, n), rng.integers(0, 500_000, n)], 1)
+    a = rng.integers(0, 400_000, size=(300, 1))
+    la, lb, gap = rng.integers(2_000, 40_000, size=(300, 1)), rng.integers(2_000, 40_000, size=(300, 1)), rng.integers(-30_000, 90_000, size=(300, 1))
+    loops = np.concatenate([a, a + la, np.maximum(0, a + la + gap), np.maximum(0, a + la + gap) + lb], 1)
+    loops[:40, 0] = rng.integers(0, 3_000, 40)                      # windows hanging over position 0
+    loops[:40, 1] = loops[:40, 0] + la[:40, 0]
+    for mode, data in ((0, xy), (1, xy2)):
+        core, na, nb, nab, anc = oracle.XYIndex(data).loop_counts(loops, win=5, mode=mode)
+        mr, mb, fdr = hostops.permuted_stats(na, nb, nab, core[:, 2], cis=(mode == 0))
+        pts = _lib.Points(gpu_ctx, data)
+        idx = _lib.Index(pts)
+        out = {}
+        for wm in ("0", "1"):
+            monkeypatch.setenv("CL2_WM", wm)
+            out[wm] = sel, c, hyp, st = idx.est_loops(loops, 0.7, 3, mode=mode)
+            assert len(sel) >= (3 if mode == 0 else 100)
+            assert np.array_equal(c, core[sel])                              # ra, rb, rab, lower as the oracle counts them
+            assert np.array_equal(st[:, 0], mr[sel]) and np.array_equal(st[:, 2], fdr[sel])
+            assert np.array_equal(st[:, 9:13], anc[sel].astype(np.float64))
+        idx.close()
+        pts.close()
+        for u, v in zip(out["0"], out["1"]):
+            assert np.array_equal(u, v)
