@@ -371,7 +371,7 @@ __device__ __forceinline__ void adj_warp_pairs(const int2 *__restrict__ sxy, con
 
 // one block per heavy pair: tile b's points through shared memory, all threads scan a's points against the tile
 #define HEAVY_THREADS 256
-#define HEAVY_TILE 1024
+#define HEAVY_TILE 512
 __global__ void __launch_bounds__(HEAVY_THREADS) k_block_adj_heavy(const int2 *__restrict__ sxy,
                                                                     const int32_t *__restrict__ cstart,
                                                                     const int32_t *__restrict__ nbr,
@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(HEAVY_THREADS) k_block_adj_heavy(const int2 *_
                 long long dist = (long long)abs(p.x - q.x) + (long long)abs(p.y - q.y);
                 if (dist <= eps) { hit = true; break; }
                 // another thread already found a pair: only shortens this thread's scan (any hit decides the pair)
-                if ((j & 63) == 63 && *(volatile int *)&found) break;
+                if ((j & 7) == 7 && *(volatile int *)&found) break;
             }
             if (hit) { found = 1; break; }
             if (*(volatile int *)&found) break;
