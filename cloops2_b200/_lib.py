@@ -121,6 +121,10 @@ SIGNATURES = {
     "cl2_stats_allreduce": (ctypes.c_int, [_vp, _vp, _i64p, ctypes.c_int32]),
     "cl2_comm_destroy": (None, [_vp]),
     "cl2_sel_sig_loops": (ctypes.c_int, [_i64p, _f64p, ctypes.c_int64, _i64p, _i64p]),
+    "cl2_loops_text": (ctypes.c_int64, [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, _i64p,
+                                        _i64p, _i64p, _i64p, _f64p, _f64p, _f64p, _f64p, _f64p, _f64p, _f64p, _f64p, _f64p,
+                                        ctypes.c_char_p, ctypes.c_int64]),
+    "cl2_format_floats": (ctypes.c_int64, [_f64p, ctypes.c_int64, ctypes.c_char_p, ctypes.c_int64]),
     "cl2_stat_poisson_sf": (ctypes.c_double, [ctypes.c_double, ctypes.c_double]),
     "cl2_stat_binom_sf": (ctypes.c_double, [ctypes.c_double, ctypes.c_double, ctypes.c_double]),
     "cl2_stat_hypergeom_sf": (ctypes.c_double, [ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double]),

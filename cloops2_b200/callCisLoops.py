@@ -16,8 +16,8 @@ import numpy as np
 
 from . import _lib, hostops, shard
 from .ds import Loop
-from .io import (ixyKey, loadIxy, parseIxy, updateJson, loops2txt, loops2ucscTxt, loops2juiceTxt, loops2washuTxt,
-                 loops2NewWashuTxt)
+from .io import (ixyKey, loadIxy, parseIxy, updateJson, loops2txt, cols2txt, loops2ucscTxt, loops2juiceTxt,  # noqa: F401
+                 loops2washuTxt, loops2NewWashuTxt)
 
 logger = None
 
@@ -337,11 +337,15 @@ def callCisLoops(predir, fout, log, eps=[2000, 5000], minPts=[5, 10], cpu=1, cut
     # the reference's dict order: chromosomes enter `loops` in the run that first finds a candidate for them, in meta
     # key order within a run (parallelRunCisDBSCANLoops :140-143 skips empty results, combineLoops appends new keys)
     order = sorted((k for k in keys if k in gathered), key=lambda k: (gathered[k][0], keys.index(k)))
-    for k in order:
-        per_key[k] = cols_to_loops(tuple(k.split("-")), gathered[k][1], cis=True)
-        loops.extend(per_key[k])
-    _log("Output %s loops to %s_loops.txt" % (len(loops), fout))
-    loops2txt(loops, fout + "_loops.txt")
+    nloops = sum(int(gathered[k][1]["coords"].shape[0]) for k in order)
+    _log("Output %s loops to %s_loops.txt" % (nloops, fout))
+    # the loop table straight from the column arrays (same bytes as loops2txt on Loop objects, tests/test_text_format.py);
+    # Loop objects are only built for the track writers and -filter
+    cols2txt([(tuple(k.split("-")), gathered[k][1]) for k in order], fout + "_loops.txt", cis=True)
+    if ucsc or juicebox or washU or filter:
+        for k in order:
+            per_key[k] = cols_to_loops(tuple(k.split("-")), gathered[k][1], cis=True)
+            loops.extend(per_key[k])
     if ucsc:
         loops2ucscTxt(loops, fout + "_loops_ucsc.interact")
     if juicebox:

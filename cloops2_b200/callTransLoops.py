@@ -12,7 +12,7 @@ import numpy as np
 
 from . import _lib, hostops, shard
 from .ds import Loop
-from .io import ixyKey, loadIxy, loops2txt, loops2juiceTxt, loops2washuTxt
+from .io import ixyKey, loadIxy, loops2txt, cols2txt, loops2juiceTxt, loops2washuTxt  # noqa: F401
 from .callCisLoops import cluster_pass, sweep_passes, cols_to_loops, selSigLoops, _loops_to_cands, exact_default  # noqa: F401
 
 
@@ -154,10 +154,12 @@ def callTransLoops(predir, fout, logger, eps=[2000, 5000], minPts=[5, 10], cpu=1
     logger.info("Selecting the most significant loops of overlapped ones. ")
     loops = []
     # dict order of the reference: a pair enters in the run that first finds a candidate for it (:100-103, geo.py:94-96)
-    for k in sorted((k for k in keys if k in gathered), key=lambda k: (gathered[k][0], keys.index(k))):
-        loops.extend(cols_to_loops(tuple(k.split("-")), gathered[k][1], cis=False))
-    logger.info("Output %s loops to %s_loops.txt" % (len(loops), fout))
-    loops2txt(loops, fout + "_trans_loops.txt")
+    order = sorted((k for k in keys if k in gathered), key=lambda k: (gathered[k][0], keys.index(k)))
+    logger.info("Output %s loops to %s_loops.txt" % (sum(int(gathered[k][1]["coords"].shape[0]) for k in order), fout))
+    cols2txt([(tuple(k.split("-")), gathered[k][1]) for k in order], fout + "_trans_loops.txt", cis=False)
+    if washU or juicebox:
+        for k in order:
+            loops.extend(cols_to_loops(tuple(k.split("-")), gathered[k][1], cis=False))
     if washU:
         loops2washuTxt(loops, fout + "_trans_loops_washU.txt")
     if juicebox:

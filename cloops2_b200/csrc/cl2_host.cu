@@ -83,3 +83,124 @@ extern "C" double cl2_stat_binom_sf(double k, double n, double p) { return cl2_b
 extern "C" double cl2_stat_hypergeom_sf(double k, double M, double n, double N) {
     return cl2_hypergeom_sf_ge(floor(k) + 1.0, M, n, N);
 }
+
+// ---- text of the loop table -----------------------------------------------------------------------------------
+// loops2txt (cLoops2/io.py:517-561) writes every field through Python's str().  For floats that is repr(): the
+// shortest digit string that round-trips, in fixed notation with at least one decimal for 1e-4 <= |x| < 1e16 and as
+// d.ddde-XX (two exponent digits at least) otherwise.  std::to_chars yields the same shortest digits; the layout is
+// redone here to Python's rules so the file is byte-identical without a Python-level loop over 24 fields per row.
+#include <charconv>
+
+static char *put_str(char *o, const char *s) {
+    while (*s) *o++ = *s++;
+    return o;
+}
+static char *put_i64(char *o, int64_t v) {
+    auto r = std::to_chars(o, o + 24, v);
+    return r.ptr;
+}
+// Python's repr(float)
+static char *put_pyfloat(char *o, double x) {
+    if (x != x) return put_str(o, "nan");
+    if (x == HUGE_VAL) return put_str(o, "inf");
+    if (x == -HUGE_VAL) return put_str(o, "-inf");
+    if (x == 0.0) return put_str(o, std::signbit(x) ? "-0.0" : "0.0");
+    char buf[48];
+    auto r = std::to_chars(buf, buf + sizeof(buf), x, std::chars_format::scientific);     // [-]d[.ddd]e[+-]XX, shortest
+    const char *p = buf, *end = r.ptr;
+    if (*p == '-') *o++ = *p++;
+    char digits[24];
+    int nd = 0;
+    while (p < end && *p != 'e') {
+        if (*p != '.') digits[nd++] = *p;
+        p++;
+    }
+    int exp10 = 0;
+    if (p < end) {
+        p++;                                                   // 'e'
+        bool neg = *p == '-';
+        if (*p == '-' || *p == '+') p++;
+        while (p < end) exp10 = exp10 * 10 + (*p++ - '0');
+        if (neg) exp10 = -exp10;
+    }
+    const int decpt = exp10 + 1;                               // position of the decimal point relative to the digits
+    if (decpt > 16 || decpt < -3) {                            // exponent form: d[.ddd]e+XX
+        *o++ = digits[0];
+        if (nd > 1) {
+            *o++ = '.';
+            for (int i = 1; i < nd; i++) *o++ = digits[i];
+        }
+        *o++ = 'e';
+        int e = decpt - 1;
+        *o++ = e < 0 ? '-' : '+';
+        if (e < 0) e = -e;
+        if (e < 10) *o++ = '0';
+        auto r2 = std::to_chars(o, o + 8, e);
+        return r2.ptr;
+    }
+    if (decpt <= 0) {                                          // 0.000ddd
+        *o++ = '0';
+        *o++ = '.';
+        for (int i = 0; i < -decpt; i++) *o++ = '0';
+        for (int i = 0; i < nd; i++) *o++ = digits[i];
+        return o;
+    }
+    for (int i = 0; i < decpt; i++) *o++ = i < nd ? digits[i] : '0';
+    *o++ = '.';
+    if (nd > decpt) {
+        for (int i = decpt; i < nd; i++) *o++ = digits[i];
+    } else {
+        *o++ = '0';
+    }
+    return o;
+}
+
+extern "C" int64_t cl2_format_floats(const double *v, int64_t n, char *out, int64_t cap) {
+    if (n < 0 || (n > 0 && (!v || !out))) return CL2_ERR_ARG;
+    char *o = out;
+    for (int64_t i = 0; i < n; i++) {
+        if (o - out + 40 > cap) return CL2_ERR_RANGE;
+        o = put_pyfloat(o, v[i]);
+        *o++ = '\n';
+    }
+    return o - out;
+}
+
+extern "C" int64_t cl2_loops_text(const char *chrA, const char *chrB, int64_t first_id, int64_t n, int32_t cis,
+                                  const int64_t *coords, const int64_t *ra, const int64_t *rb, const int64_t *rab,
+                                  const double *density, const double *es, const double *p2ll, const double *fdr,
+                                  const double *nbp, const double *hyp, const double *pop, const double *px,
+                                  const double *py, char *out, int64_t cap) {
+    if (!chrA || !chrB || n < 0 || (n > 0 && (!coords || !ra || !rb || !rab || !density || !es || !p2ll || !fdr || !nbp ||
+                                               !hyp || !pop || !px || !py || !out)))
+        return CL2_ERR_ARG;
+    const int64_t need = 2 * ((int64_t)strlen(chrA) + (int64_t)strlen(chrB)) + 640;
+    char *o = out;
+    for (int64_t i = 0; i < n; i++) {
+        if (o - out + need > cap) return CL2_ERR_RANGE;
+        const int64_t xs = coords[4 * i], xe = coords[4 * i + 1], ys = coords[4 * i + 2], ye = coords[4 * i + 3];
+        o = put_str(o, "loop_"); o = put_str(o, chrA); *o++ = '-'; o = put_str(o, chrB); *o++ = '-';
+        o = put_i64(o, first_id + i); *o++ = '\t';
+        o = put_str(o, chrA); *o++ = '\t';
+        o = put_i64(o, xs); *o++ = '\t';
+        o = put_i64(o, xe); *o++ = '\t';
+        o = put_str(o, chrB); *o++ = '\t';
+        o = put_i64(o, ys); *o++ = '\t';
+        o = put_i64(o, ye); *o++ = '\t';
+        const double xc = (double)(xs + xe) / 2.0, yc = (double)(ys + ye) / 2.0;      // callCisLoops.py:107-112
+        if (cis) { const double d = yc - xc; o = put_pyfloat(o, d < 0 ? -d : d); }
+        else o = put_str(o, "-1");                                                   // callTransLoops.py:78
+        *o++ = '\t';
+        o = put_pyfloat(o, xc); *o++ = '\t';
+        o = put_pyfloat(o, yc); *o++ = '\t';
+        o = put_i64(o, ra[i]); *o++ = '\t';
+        o = put_i64(o, rb[i]); *o++ = '\t';
+        o = put_str(o, cis ? "True" : "False"); *o++ = '\t';
+        o = put_i64(o, rab[i]); *o++ = '\t';
+        const double *cols[9] = {density, es, p2ll, fdr, nbp, hyp, pop, px, py};
+        for (int k = 0; k < 9; k++) { o = put_pyfloat(o, cols[k][i]); *o++ = '\t'; }
+        *o++ = '1';
+        *o++ = '\n';
+    }
+    return o - out;
+}

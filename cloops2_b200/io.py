@@ -83,6 +83,34 @@ def loops2txt(loops, fout):
             fo.write("\t".join(map(str, line)) + "\n")
 
 
+def cols2txt(items, fout, cis=True):
+    """The same file as loops2txt(cols_to_loops(...)) straight from the column arrays of the per-file results, without
+    a Loop object and 24 str() calls per row: items = [((chrA, chrB), cols), ...] in output order.  The rows are
+    formatted by cl2_loops_text (native; floats laid out as Python's repr() does)."""
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    with open(fout, "wb") as fo:
+        fo.write(("\t".join(LOOP_HEADER) + "\n").encode())
+        base = 0
+        for key, cols in items:
+            n = int(cols["coords"].shape[0])
+            if n == 0:
+                continue
+            a = [np.ascontiguousarray(cols[k], dtype=np.int64) for k in ("coords", "ra", "rb", "rab")]
+            f = [np.ascontiguousarray(cols[k], dtype=np.float64) for k in ("density", "ES", "P2LL", "FDR", "nbp", "hyp", "pop",
+                                                                          "px", "py")]
+            cap = n * (640 + 2 * (len(key[0]) + len(key[1])))
+            buf = ctypes.create_string_buffer(cap)
+            m = lib.cl2_loops_text(key[0].encode(), key[1].encode(), base, n, 1 if cis else 0,
+                                   *[x.ctypes.data_as(_lib._i64p) for x in a], *[x.ctypes.data_as(_lib._f64p) for x in f],
+                                   buf, cap)
+            if m < 0:
+                raise _lib.Cl2Error("cl2_loops_text failed rc=%d" % m)
+            fo.write(buf.raw[:m])
+            base += n
+
+
 def loops2ucscTxt(loops, fout, significant=1):
     """UCSC interact track (io.py:564-608)."""
     print("Converting %s loops to UCSC interact track." % (len(loops)))

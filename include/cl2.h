@@ -210,6 +210,20 @@ void cl2_comm_destroy(cl2_comm *comm);
 int cl2_sel_sig_loops(const int64_t *coords, const double *es, int64_t L, int64_t *out_idx, int64_t *out_n);
 
 /*
+ * Rows of loops2txt (cLoops2/io.py:517-561) for n loops of one chromosome pair, header excluded, every field as
+ * Python's str() prints it (ints as ints, floats in repr() form -- shortest round-trip digits, fixed notation with at
+ * least one decimal for 1e-4 <= |x| < 1e16, d.ddde-XX otherwise --, `True` / `False`, significant = 1).  Ids are
+ * loop_<chrA>-<chrB>-<first_id + i>.  Returns the bytes written to out[0, cap) or a negative error code
+ * (CL2_ERR_RANGE: cap too small; 640 bytes per row plus the names are enough).  cl2_format_floats writes repr(v[i])
+ * followed by a newline for every value (the building block, exposed for tests).
+ */
+int64_t cl2_loops_text(const char *chrA, const char *chrB, int64_t first_id, int64_t n, int32_t cis, const int64_t *coords,
+                       const int64_t *ra, const int64_t *rb, const int64_t *rab, const double *density, const double *es,
+                       const double *p2ll, const double *fdr, const double *nbp, const double *hyp, const double *pop,
+                       const double *px, const double *py, char *out, int64_t cap);
+int64_t cl2_format_floats(const double *v, int64_t n, char *out, int64_t cap);
+
+/*
  * Host copies of the fp64 tail probabilities the device evaluates (scipy argument convention, sf(k) = P(X > k)):
  * scipy.stats.poisson.sf / binom.sf / hypergeom.sf as called at callCisLoops.py:246,310,329,332.
  */
