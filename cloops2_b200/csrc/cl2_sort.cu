@@ -304,77 +304,61 @@ __global__ void __launch_bounds__(256) k_os_prefix(unsigned *__restrict__ ghist)
     ghist[blockIdx.x * 256 + threadIdx.x] = (unsigned)ex;
 }
 
-#define OS_THREADS 512
-#define OS_WARPS (OS_THREADS / 32)
-#define OS_IPT 8
-#define OS_TILE (OS_THREADS * OS_IPT)
-
-template <typename K>
+// One tile of one pass.  NT threads x IPT items; FULL tiles (all but the last) carry no bounds checks, GEN = the keys of
+// this pass are generated from the coordinates (first pass of a sort) instead of read from the key buffer.
+template <typename K, int NT, int IPT>
 struct OsSmem {
-    K keys[OS_TILE];
-    uint32_t vals[OS_TILE];
-    int warp_cnt[OS_WARPS][256];
+    K keys[NT * IPT];
+    uint32_t vals[NT * IPT];
+    int warp_cnt[NT / 32][256];
     int hist[256];
-    int dprefix[256];
     int gbase[256];
 };
 
-template <typename K, int MINB>
-__global__ void __launch_bounds__(OS_THREADS, MINB) k_os_pass(const K *__restrict__ kin, const cl2_keygen gen,
-                                                           const uint32_t *__restrict__ vin,
-                                                           K *__restrict__ kout, uint32_t *__restrict__ vout,
-                                                           int64_t n, int shift, const unsigned *__restrict__ gprefix,
-                                                           unsigned *__restrict__ desc, unsigned *__restrict__ ticket,
-                                                           int flags) {
-    const int iota = flags & 1;
-    const bool put_keys = !(flags & 2);   // the last pass of a sort whose caller only wants the row order
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    OsSmem<K> &S = *reinterpret_cast<OsSmem<K> *>(smem_raw);
-    __shared__ unsigned s_tile;
+template <typename K, int NT, int IPT, bool GEN, bool FULL>
+__device__ __forceinline__ void os_tile(OsSmem<K, NT, IPT> &S, const K *__restrict__ kin, const cl2_keygen &gen,
+                                        const uint32_t *__restrict__ vin, K *__restrict__ kout, uint32_t *__restrict__ vout,
+                                        const uint32_t n, const int shift, const unsigned *__restrict__ gprefix,
+                                        unsigned *__restrict__ desc, const unsigned tile, const bool iota, const bool put_keys) {
+    constexpr int TILE = NT * IPT, NW = NT / 32;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-    for (int i = threadIdx.x; i < OS_WARPS * 256 + 256; i += OS_THREADS) (&S.warp_cnt[0][0])[i] = 0;   // + hist
-    __syncthreads();
-    const unsigned tile = s_tile;
-    const int64_t tbase = (int64_t)tile * OS_TILE;
-    const int64_t wbase = tbase + (int64_t)w * (32 * OS_IPT);
-    K key[OS_IPT];
-    uint32_t val[OS_IPT];
-    unsigned short rank[OS_IPT];
+    const uint32_t tbase = tile * (uint32_t)TILE;
+    const uint32_t i0 = tbase + (uint32_t)w * (32 * IPT) + lane;
+    K key[IPT];
+    uint32_t val[IPT];
+    unsigned short rank[IPT];
+    unsigned peers_of[IPT];
     const unsigned lt = (1u << lane) - 1u;
     // all global loads of the tile are issued up front (keys and row ids) so their latency overlaps the ranking
 #pragma unroll
-    for (int r = 0; r < OS_IPT; r++) {
-        int64_t i = wbase + r * 32 + lane;
-        key[r] = (i < n) ? (gen.kind == CL2_KEY_ARRAY ? kin[i] : (K)os_key(gen, nullptr, i)) : (K)~(K)0;
+    for (int r = 0; r < IPT; r++) {
+        const uint32_t i = i0 + r * 32;
+        if (FULL || i < n) key[r] = GEN ? (K)os_key(gen, nullptr, i) : kin[i];
+        else key[r] = (K) ~(K)0;
     }
 #pragma unroll
-    for (int r = 0; r < OS_IPT; r++) {
-        int64_t i = wbase + r * 32 + lane;
-        val[r] = iota ? (uint32_t)i : ((i < n) ? vin[i] : 0u);
+    for (int r = 0; r < IPT; r++) {
+        const uint32_t i = i0 + r * 32;
+        val[r] = iota ? i : ((FULL || i < n) ? vin[i] : 0u);
     }
-    // tile histogram first, so the tile's digit counts are published (AGGREGATE) before the longer ranking phase:
-    // by the time this tile looks back, its predecessors have usually published their inclusive prefixes
-    // (one shared atomic per group of equal digits in the warp: sorted-ish input, e.g. the column digit of y-ordered
-    // PETs, would otherwise serialise on a few hot bins)
-    unsigned peers_of[OS_IPT];
+    // tile histogram first, so the tile's digit counts are published (AGGREGATE) before the longer ranking phase: by the
+    // time this tile looks back, its predecessors have usually published their inclusive prefixes (one shared atomic
+    // per group of equal digits in the warp)
 #pragma unroll
-    for (int r = 0; r < OS_IPT; r++) {
-        int64_t i = wbase + r * 32 + lane;
-        bool valid = i < n;
-        unsigned d = valid ? (unsigned)((key[r] >> shift) & 255) : (0x10000u | lane);
-        unsigned peers = __match_any_sync(0xffffffffu, d);
+    for (int r = 0; r < IPT; r++) {
+        const bool valid = FULL || (i0 + r * 32 < n);
+        const unsigned d = valid ? (unsigned)((key[r] >> shift) & 255) : (0x10000u | lane);
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
         peers_of[r] = peers;
         if (valid && (peers & lt) == 0) atomicAdd(&S.hist[d], __popc(peers));
     }
     __syncthreads();
     if (threadIdx.x < 256) os_st(&desc[(size_t)tile * 256 + threadIdx.x], (unsigned)S.hist[threadIdx.x] | OS_AGG);
 #pragma unroll
-    for (int r = 0; r < OS_IPT; r++) {
-        int64_t i = wbase + r * 32 + lane;
-        bool valid = i < n;
-        unsigned d = valid ? (unsigned)((key[r] >> shift) & 255) : (0x10000u | lane);
-        unsigned peers = peers_of[r];
+    for (int r = 0; r < IPT; r++) {
+        const bool valid = FULL || (i0 + r * 32 < n);
+        const unsigned d = (unsigned)((key[r] >> shift) & 255);
+        const unsigned peers = peers_of[r];
         int before = 0;
         if (valid) before = S.warp_cnt[w][d];
         __syncwarp();
@@ -388,17 +372,17 @@ __global__ void __launch_bounds__(OS_THREADS, MINB) k_os_pass(const K *__restric
     // warp_cnt[w][d] := position inside the tile of warp w's first element with digit d; gbase[d] := global position
     // of the tile's first element with digit d minus its position inside the tile
     int off = 0;
-    int wc[OS_WARPS];
+    int wc[NW];
     unsigned excl = 0;
-    if (threadIdx.x < 256) {
+    if (NT == 256 || threadIdx.x < 256) {
         const int d = threadIdx.x;
 #pragma unroll
-        for (int k = 0; k < OS_WARPS; k++) {
+        for (int k = 0; k < NW; k++) {
             wc[k] = S.warp_cnt[k][d];
             off += wc[k];
         }
         // look back for the exclusive prefix over earlier tiles, four descriptors per round trip
-        long long t = (long long)tile - 1;
+        int t = (int)tile - 1;
         while (t >= 0) {
             unsigned v[4];
 #pragma unroll
@@ -416,12 +400,12 @@ __global__ void __launch_bounds__(OS_THREADS, MINB) k_os_pass(const K *__restric
     }
     {
         int tot;
-        const int ex = block_excl_scan<OS_THREADS>(off, &tot);
-        if (threadIdx.x < 256) {
+        const int ex = block_excl_scan<NT>(off, &tot);
+        if (NT == 256 || threadIdx.x < 256) {
             const int d = threadIdx.x;
             int run = ex;
 #pragma unroll
-            for (int k = 0; k < OS_WARPS; k++) {
+            for (int k = 0; k < NW; k++) {
                 S.warp_cnt[k][d] = run;
                 run += wc[k];
             }
@@ -430,56 +414,60 @@ __global__ void __launch_bounds__(OS_THREADS, MINB) k_os_pass(const K *__restric
     }
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < OS_IPT; r++) {
-        int64_t i = wbase + r * 32 + lane;
-        if (i < n) {
-            int d = (int)((key[r] >> shift) & 255);
-            int pos = S.warp_cnt[w][d] + rank[r];
+    for (int r = 0; r < IPT; r++) {
+        if (FULL || i0 + r * 32 < n) {
+            const int d = (int)((key[r] >> shift) & 255);
+            const int pos = S.warp_cnt[w][d] + rank[r];
             S.keys[pos] = key[r];
             S.vals[pos] = val[r];
         }
     }
     __syncthreads();
-    int cnt = (int)((n - tbase) < OS_TILE ? (n - tbase) : OS_TILE);
+    const int cnt = FULL ? TILE : (int)(n - tbase);
 #pragma unroll 4
-    for (int j = threadIdx.x; j < cnt; j += OS_THREADS) {
-        K k = S.keys[j];
-        int d = (int)((k >> shift) & 255);
+    for (int j = threadIdx.x; j < cnt; j += NT) {
+        const K k = S.keys[j];
+        const int d = (int)((k >> shift) & 255);
         const uint32_t dst = (uint32_t)(S.gbase[d] + j);
         if (put_keys) kout[dst] = k;
         vout[dst] = S.vals[j];
     }
 }
 
-template <typename K>
-static int radix_sort_onesweep(cl2_ctx *ctx, const cl2_keygen &gen, K *keys0, K *keys1, uint32_t *vals0,
-                               uint32_t *vals1, int64_t n, int passes, K **kout, uint32_t **vout,
-                               const uint32_t *vals_first) {
-    int ntiles = (int)((n + OS_TILE - 1) / OS_TILE);
-    Scratch sc(ctx);
-    unsigned *ghist, *desc, *ticket;
-    CL2_TRY(sc.get(&ghist, (size_t)OS_MAXPASS * 256 + OS_MAXPASS));
-    CL2_TRY(sc.get(&desc, (size_t)passes * ntiles * 256));
-    ticket = ghist + OS_MAXPASS * 256;
-    CL2_CUDA(ctx, cudaMemsetAsync(ghist, 0, ((size_t)OS_MAXPASS * 256 + OS_MAXPASS) * 4, ctx->stream));
-    CL2_CUDA(ctx, cudaMemsetAsync(desc, 0, (size_t)passes * ntiles * 256 * 4, ctx->stream));
+template <typename K, int NT, int IPT, int MINB, bool GEN>
+__global__ void __launch_bounds__(NT, MINB) k_os_pass(const K *__restrict__ kin, const cl2_keygen gen,
+                                                   const uint32_t *__restrict__ vin, K *__restrict__ kout,
+                                                   uint32_t *__restrict__ vout, uint32_t n, int shift,
+                                                   const unsigned *__restrict__ gprefix, unsigned *__restrict__ desc,
+                                                   unsigned *__restrict__ ticket, int flags) {
+    const bool iota = flags & 1;
+    const bool put_keys = !(flags & 2);   // the last pass of a sort whose caller only wants the row order
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    OsSmem<K, NT, IPT> &S = *reinterpret_cast<OsSmem<K, NT, IPT> *>(smem_raw);
+    __shared__ unsigned s_tile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int i = threadIdx.x; i < (NT / 32) * 256 + 256; i += NT) (&S.warp_cnt[0][0])[i] = 0;   // + hist
+    __syncthreads();
+    const unsigned tile = s_tile;
+    if ((tile + 1u) * (uint32_t)(NT * IPT) <= n)
+        os_tile<K, NT, IPT, GEN, true>(S, kin, gen, vin, kout, vout, n, shift, gprefix, desc, tile, iota, put_keys);
+    else
+        os_tile<K, NT, IPT, GEN, false>(S, kin, gen, vin, kout, vout, n, shift, gprefix, desc, tile, iota, put_keys);
+}
+
+template <typename K, int NT, int IPT, int MINB>
+static int onesweep_passes(cl2_ctx *ctx, const cl2_keygen &gen, K *keys0, K *keys1, uint32_t *vals0, uint32_t *vals1, int64_t n,
+                           int passes, K **kout, uint32_t **vout, const uint32_t *vals_first, unsigned *ghist,
+                           unsigned *desc, unsigned *ticket, int ntiles) {
     static bool attr_set = false;      // one flag per instantiation
     if (!attr_set) {
-        CL2_CUDA(ctx, cudaFuncSetAttribute(k_os_pass<K, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)sizeof(OsSmem<K>)));
-        CL2_CUDA(ctx, cudaFuncSetAttribute(k_os_pass<K, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)sizeof(OsSmem<K>)));
+        CL2_CUDA(ctx, cudaFuncSetAttribute(k_os_pass<K, NT, IPT, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sizeof(OsSmem<K, NT, IPT>)));
+        CL2_CUDA(ctx, cudaFuncSetAttribute(k_os_pass<K, NT, IPT, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sizeof(OsSmem<K, NT, IPT>)));
         attr_set = true;
     }
-    {
-        FamTimer t(ctx, ctx->sort_family >= 0 ? ctx->sort_family : FAM_SORT_HIST, 8.0 * (double)n, 2);
-        int grid = ctx->sm_count * 8;
-        int need = cl2_grid(n, 256);
-        k_os_hist<K><<<need < grid ? need : grid, 256, 0, ctx->stream>>>(keys0, gen, n, passes, ghist);
-        k_os_prefix<<<passes, 256, 0, ctx->stream>>>(ghist);
-    }
     const bool want_keys = kout != nullptr;
-    static const bool occ3 = sizeof(K) == 4 && getenv("CL2_SORT_OCC3") != nullptr;
     K *kin = keys0, *ko = keys1;
     uint32_t *vi = vals0, *vo = vals1;
     cl2_keygen none;
@@ -490,10 +478,11 @@ static int radix_sort_onesweep(cl2_ctx *ctx, const cl2_keygen &gen, K *keys0, K 
                        ((p == passes - 1 && !want_keys ? 1.0 : 2.0) * sizeof(K) + 8.0) * (double)n);
             const uint32_t *vin = (p == 0 && vals_first) ? vals_first : vi;
             const int flags = ((p == 0 && !vals_first) ? 1 : 0) | ((p == passes - 1 && !want_keys) ? 2 : 0);
-            auto kern = occ3 ? k_os_pass<K, 3> : k_os_pass<K, 2>;
-            kern<<<ntiles, OS_THREADS, sizeof(OsSmem<K>), ctx->stream>>>(kin, p == 0 ? gen : none, vin, ko, vo, n, p * 8,
-                                                                         ghist + p * 256, desc + (size_t)p * ntiles * 256,
-                                                                         ticket + p, flags);
+            const bool generated = p == 0 && gen.kind != CL2_KEY_ARRAY;
+            auto kern = generated ? k_os_pass<K, NT, IPT, MINB, true> : k_os_pass<K, NT, IPT, MINB, false>;
+            kern<<<ntiles, NT, sizeof(OsSmem<K, NT, IPT>), ctx->stream>>>(kin, generated ? gen : none, vin, ko, vo, (uint32_t)n, p * 8,
+                                                                          ghist + p * 256, desc + (size_t)p * ntiles * 256,
+                                                                          ticket + p, flags);
         }
         K *tk = kin; kin = ko; ko = tk;
         uint32_t *tv = vi; vi = vo; vo = tv;
@@ -502,6 +491,39 @@ static int radix_sort_onesweep(cl2_ctx *ctx, const cl2_keygen &gen, K *keys0, K 
     if (kout) *kout = kin;
     *vout = vi;
     return CL2_OK;
+}
+
+template <typename K>
+static int radix_sort_onesweep(cl2_ctx *ctx, const cl2_keygen &gen, K *keys0, K *keys1, uint32_t *vals0,
+                               uint32_t *vals1, int64_t n, int passes, K **kout, uint32_t **vout,
+                               const uint32_t *vals_first) {
+    // tile shape: 512 threads x 8 items (2 resident blocks per SM) by default; CL2_SORT_CFG=1: 256 x 8 (4 blocks),
+    // 2: 256 x 16 (2 blocks)
+    static const int cfg = getenv("CL2_SORT_CFG") ? atoi(getenv("CL2_SORT_CFG")) : 0;
+    const int tile = cfg == 1 ? 256 * 8 : 512 * 8;
+    int ntiles = (int)((n + tile - 1) / tile);
+    Scratch sc(ctx);
+    unsigned *ghist, *desc, *ticket;
+    CL2_TRY(sc.get(&ghist, (size_t)OS_MAXPASS * 256 + OS_MAXPASS));
+    CL2_TRY(sc.get(&desc, (size_t)passes * ntiles * 256));
+    ticket = ghist + OS_MAXPASS * 256;
+    CL2_CUDA(ctx, cudaMemsetAsync(ghist, 0, ((size_t)OS_MAXPASS * 256 + OS_MAXPASS) * 4, ctx->stream));
+    CL2_CUDA(ctx, cudaMemsetAsync(desc, 0, (size_t)passes * ntiles * 256 * 4, ctx->stream));
+    {
+        FamTimer t(ctx, ctx->sort_family >= 0 ? ctx->sort_family : FAM_SORT_HIST, 8.0 * (double)n, 2);
+        int grid = ctx->sm_count * 8;
+        int need = cl2_grid(n, 256);
+        k_os_hist<K><<<need < grid ? need : grid, 256, 0, ctx->stream>>>(keys0, gen, n, passes, ghist);
+        k_os_prefix<<<passes, 256, 0, ctx->stream>>>(ghist);
+    }
+    if (cfg == 1)
+        return onesweep_passes<K, 256, 8, 4>(ctx, gen, keys0, keys1, vals0, vals1, n, passes, kout, vout, vals_first, ghist, desc,
+                                             ticket, ntiles);
+    if (cfg == 2)
+        return onesweep_passes<K, 256, 16, 2>(ctx, gen, keys0, keys1, vals0, vals1, n, passes, kout, vout, vals_first, ghist, desc,
+                                              ticket, ntiles);
+    return onesweep_passes<K, 512, 8, 2>(ctx, gen, keys0, keys1, vals0, vals1, n, passes, kout, vout, vals_first, ghist, desc,
+                                         ticket, ntiles);
 }
 
 __global__ void __launch_bounds__(256) k_os_materialise(const cl2_keygen gen, uint64_t *__restrict__ keys, int64_t n) {
