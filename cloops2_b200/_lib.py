@@ -378,7 +378,7 @@ class Points:
                    "core": np.empty((k, 4), dtype=np.int64), "hyp": np.empty(k, dtype=np.float64),
                    "stats": np.empty((k, 13), dtype=np.float64), "pass_cand": np.zeros(npass, dtype=np.int64),
                    "pass_pets": np.zeros(npass, dtype=np.int64), "totals": np.zeros(8, dtype=np.int64),
-                   "seconds": np.zeros(3, dtype=np.float64)}
+                   "seconds": np.zeros(6, dtype=np.float64)}
             ctx.check(lib.cl2_loops_info(h, _ptr(out["pass_cand"], _i64p), _ptr(out["pass_pets"], _i64p),
                                          _ptr(out["totals"], _i64p), _ptr(out["seconds"], _f64p)), "cl2_loops_info")
             ctx.check(lib.cl2_loops_read(h, _ptr(out["coords"], _i64p), _ptr(out["pass_id"], _i32p), _ptr(out["core"], _i64p),

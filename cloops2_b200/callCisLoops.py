@@ -105,7 +105,8 @@ def cis_chromosome(ctx, key, xy, tot, eps, minPts, cut=0, mcut=-1, hic=False, em
         stats["candidates"] = unique if unique >= 0 else tested
         nz = np.nonzero(res["pass_cand"])[0]
         stats["first_pass"] = int(nz[0]) if len(nz) else -1     # the reference's dicts list a chromosome from that run on
-        stats["host_s"] = dict(zip(("cluster", "index", "test"), (float(v) for v in res["seconds"])))
+        stats["host_s"] = dict(zip(("cluster", "index", "test", "cluster_cpu", "index_cpu", "test_cpu"),
+                                   (float(v) for v in res["seconds"])))
         if tested == 0:
             return hostops._empty_cols(), stats
         ext = res["totals"][4:8]
@@ -114,7 +115,7 @@ def cis_chromosome(ctx, key, xy, tot, eps, minPts, cut=0, mcut=-1, hic=False, em
         _log("Estimate significance for %s candidate interactions in %s with %s PETs distance > =%s and <=%s,requiring minPts >=%s."
              % (stats["candidates"], "-".join(key), pts.n, cut, mcut, mm))
         import time
-        t3 = time.perf_counter()
+        t3, c3 = time.perf_counter(), time.thread_time()
         cols = hostops._cols_from_stats(res["coords"], res["core"], res["hyp"], res["stats"], 1, tot)
         if exact:
             cols = hostops.exact_cuts(cols, pts.n, rpb, cis=True, hic=hic)
@@ -127,6 +128,7 @@ def cis_chromosome(ctx, key, xy, tot, eps, minPts, cut=0, mcut=-1, hic=False, em
         if exact == "defer":
             hostops.submit_pvalues(final, cis=True)          # evaluated by the process-wide pool while other files run
         stats["host_s"]["select"] = time.perf_counter() - t3
+        stats["host_s"]["select_cpu"] = time.thread_time() - c3
         stats["loops"] = int(final["coords"].shape[0])
         return final, stats
     finally:

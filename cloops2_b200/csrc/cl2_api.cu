@@ -325,7 +325,7 @@ extern "C" int cl2_points_sweep_hint(cl2_ctx *ctx, cl2_points *pts, int32_t enab
 }
 
 int g_cl2_sync_mode = 0;
-extern "C" void cl2_set_sync_mode(int32_t blocking) { g_cl2_sync_mode = blocking ? 1 : 0; }
+extern "C" void cl2_set_sync_mode(int32_t mode) { g_cl2_sync_mode = (mode == 1 || mode == 2) ? mode : 0; }
 
 extern "C" void cl2_points_drop_cache(cl2_ctx *ctx, cl2_points *pts) {
     if (!ctx || !pts) return;

@@ -885,7 +885,7 @@ extern "C" int cl2_block_dbscan(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int3
 // ordered = false: the clusters are reported in cell-key order with pts->ckeys[i] the key that ranks cluster i in the
 // reference's numbering (no labels then)
 int cl2_block_dbscan_impl(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int32_t minPts, int32_t *labels_out,
-                          int32_t *n_clusters, bool ordered) {
+                          int32_t *n_clusters, bool ordered, cl2_cand_sink *sink) {
     CL2_TRY(block_check_args(ctx, pts, eps, minPts));
     if (labels_out) ordered = true;
     if (n_clusters) *n_clusters = 0;
@@ -1018,6 +1018,15 @@ int cl2_block_dbscan_impl(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int32_t mi
         ctx->launches++;
     }
 
+    if (sink && !labels_out) {
+        // the boxes go straight into the device-resident candidate list of cl2_call_loops (filters applied there)
+        static_assert(sizeof(ClusterBox) == 5 * sizeof(int), "box record");
+        if (ncomp > 0) CL2_TRY(cl2_sink_emit(ctx, sink, reinterpret_cast<const int *>(box), ckeys, ncomp));
+        CL2_CUDA(ctx, cudaGetLastError());
+        pts->ncl = ncomp;
+        if (n_clusters) *n_clusters = ncomp;
+        return CL2_OK;
+    }
     // Cluster numbering = rank of the components' start-cell order keys (blockDBSCAN.py:146-152).  The component
     // count is small next to n, so the keys and boxes go to the host and are ordered there.  Callers that only need the
     // boxes and sort a few survivors themselves (cl2_call_loops) take them unordered, each with its key.

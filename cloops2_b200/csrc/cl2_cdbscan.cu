@@ -454,6 +454,11 @@ __global__ void __launch_bounds__(256) k_c2_labels(const int2 *__restrict__ sxy,
 // ================================================================================================ host driver
 extern "C" int cl2_cdbscan2(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int32_t minPts, int32_t *labels_out,
                             int32_t *n_clusters) {
+    return cl2_cdbscan2_impl(ctx, pts, eps, minPts, labels_out, n_clusters, nullptr);
+}
+
+int cl2_cdbscan2_impl(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int32_t minPts, int32_t *labels_out,
+                      int32_t *n_clusters, cl2_cand_sink *sink) {
     if (!ctx || !pts) return CL2_ERR_ARG;
     if (eps <= 0) return cl2_fail(ctx, CL2_ERR_ARG, "eps must be > 0");
     if (n_clusters) *n_clusters = 0;
@@ -623,6 +628,18 @@ extern "C" int cl2_cdbscan2(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int32_t 
     if (labels_out) {
         CL2_CUDA(ctx, cudaMemcpyAsync(labels_out, dl, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
         ctx->d2h_bytes += n * 4;
+    }
+    if (sink && !labels_out) {
+        // clusters are in their final order here: the record index is the rank key
+        static_assert(sizeof(C2Box) == 5 * sizeof(int), "box record");
+        if (ncomp > 0) CL2_TRY(cl2_sink_emit(ctx, sink, reinterpret_cast<const int *>(box), nullptr, ncomp));
+        CL2_CUDA(ctx, cudaStreamSynchronize(s));
+        CL2_CUDA(ctx, cudaGetLastError());
+        pts->ncl = ncomp;
+        pts->bbox.clear();
+        pts->size.clear();
+        if (n_clusters) *n_clusters = ncomp;
+        return CL2_OK;
     }
     std::vector<C2Box> hb((size_t)ncomp);
     if (ncomp > 0) CL2_CUDA(ctx, cudaMemcpyAsync(hb.data(), box, (size_t)ncomp * sizeof(C2Box), cudaMemcpyDeviceToHost, s));

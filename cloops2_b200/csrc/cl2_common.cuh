@@ -3,11 +3,21 @@
 #include <cuda_runtime.h>
 
 // Every wait on a stream goes through here.  Mode 0: cudaStreamSynchronize (the runtime spins: lowest latency, one
-// busy host core per waiting thread).  Mode 1: record a blocking-sync event and sleep on it, for hosts with fewer
-// cores than worker threads (cl2_set_sync_mode; 8 ranks x several workers on a 32-core box).
+// busy host core per waiting thread).  Mode 1: record a blocking-sync event and sleep on it.  Mode 2: poll the stream
+// and give the core away between polls (sched_yield): as quick as spinning while cores are idle, but a waiting thread
+// no longer keeps a runnable one -- of this rank or another -- off the core when there are more workers than cores
+// (8 ranks x 8 workers on a 32-core box).
+#include <sched.h>
 extern int g_cl2_sync_mode;
 inline cudaError_t cl2_sync_stream(cudaStream_t s) {
     if (g_cl2_sync_mode == 0) return cudaStreamSynchronize(s);
+    if (g_cl2_sync_mode == 2) {
+        for (;;) {
+            cudaError_t e = cudaStreamQuery(s);
+            if (e != cudaErrorNotReady) return e;
+            sched_yield();
+        }
+    }
     thread_local cudaEvent_t ev = nullptr;
     thread_local int ev_dev = -1;
     int dev = 0;

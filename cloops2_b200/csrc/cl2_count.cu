@@ -886,36 +886,112 @@ __device__ __forceinline__ int loop_windows(const IdxView &ix, long long xs, lon
 // step region of a candidate 10^5: there R(I, J) = F(p, q, J.hi + 1) - F(p, q, J.lo) with [p, q) the X range of I and
 // F(p, q, v) = #{rows in [p, q) with y < v} comes from a wavelet matrix over the y values in x order in wm_L steps,
 // each two 8-byte reads -- independent of the number of rows.
-__global__ void __launch_bounds__(256) k_wm_init(const int2 *__restrict__ byx, uint32_t *__restrict__ cur, int64_t n) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) cur[i] = (uint32_t)byx[i].y;
+// gpu-scope descriptor access for the chained scan below (coherent in L2, never served from L1)
+__device__ __forceinline__ unsigned wm_ld(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
-// ones per word of 32 rows (input of the prefix scan)
-__global__ void __launch_bounds__(256) k_wm_ones(const uint32_t *__restrict__ cur, int64_t n, int shift, int64_t nw,
-                                                  int32_t *__restrict__ ones) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if ((i >> 5) >= nw) return;
-    const unsigned word = __ballot_sync(0xffffffffu, i < n && ((cur[i < n ? i : 0] >> shift) & 1u));
-    if ((threadIdx.x & 31) == 0) ones[i >> 5] = __popc(word);
+__device__ __forceinline__ void wm_st(unsigned *p, unsigned v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// stable partition by the bit (zeros first) + the level's {bits, ones before} table; pre = exclusive scan of `ones`,
-// total[0] = number of ones
-__global__ void __launch_bounds__(256) k_wm_partition(const uint32_t *__restrict__ cur, uint32_t *__restrict__ nxt, int64_t n,
-                                                       int shift, int64_t nw, const int32_t *__restrict__ pre,
-                                                       const int64_t *__restrict__ total, uint2 *__restrict__ level) {
+#define WM_AGG 0x40000000u
+#define WM_INC 0x80000000u
+#define WM_VAL 0x3FFFFFFFu
+#define WM_NT 256
+#define WM_IPT 8
+#define WM_TILE (WM_NT * WM_IPT)
+
+// y values in x order + the number of ones of the top level
+__global__ void __launch_bounds__(256) k_wm_init(const int2 *__restrict__ byx, uint32_t *__restrict__ cur, int64_t n, int shift,
+                                                  unsigned long long *__restrict__ ones0) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if ((i >> 5) >= nw) return;
-    const int lane = threadIdx.x & 31;
-    const bool valid = i < n;
-    const uint32_t v = valid ? cur[i] : 0u;
-    const bool bit = valid && ((v >> shift) & 1u);
-    const unsigned word = __ballot_sync(0xffffffffu, bit);
-    const uint32_t before = (uint32_t)pre[i >> 5];
-    if (lane == 0) level[i >> 5] = make_uint2(word, before);
-    if (!valid) return;
-    const uint32_t r1 = before + __popc(word & ((1u << lane) - 1u));
-    const uint32_t z = (uint32_t)(n - *total);
-    nxt[bit ? z + r1 : (uint32_t)i - r1] = v;
+    unsigned bit = 0;
+    if (i < n) {
+        const uint32_t y = (uint32_t)byx[i].y;
+        cur[i] = y;
+        bit = (y >> shift) & 1u;
+    }
+    const int c = __popc(__ballot_sync(0xffffffffu, bit));
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(ones0, (unsigned long long)c);
+}
+// One level in one pass: the level's {bits, ones before} table, the stable partition by the bit (zeros first) and the
+// number of ones of the NEXT level (counted while the values pass through).  The ones before a tile come from a chained
+// scan over the tiles (ticket order, decoupled look-back by the first warp); ones_here = this level's total, known from
+// the previous pass, gives the start of the ones.
+__global__ void __launch_bounds__(WM_NT) k_wm_level(const uint32_t *__restrict__ cur, uint32_t *__restrict__ nxt, uint32_t n,
+                                                     int shift, uint32_t nw, uint2 *__restrict__ level,
+                                                     const unsigned long long *__restrict__ ones_here,
+                                                     unsigned long long *__restrict__ ones_next, unsigned *__restrict__ desc,
+                                                     unsigned *__restrict__ ticket) {
+    __shared__ unsigned s_tile, s_excl;
+    __shared__ int wtot[WM_NT / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const unsigned tile = s_tile;
+    const uint32_t i0 = tile * (uint32_t)WM_TILE + (uint32_t)w * (32 * WM_IPT) + lane;
+    uint32_t v[WM_IPT];
+    unsigned word[WM_IPT];
+    int mine = 0;
+#pragma unroll
+    for (int r = 0; r < WM_IPT; r++) {
+        const uint32_t i = i0 + r * 32;
+        v[r] = i < n ? cur[i] : 0u;
+    }
+#pragma unroll
+    for (int r = 0; r < WM_IPT; r++) {
+        word[r] = __ballot_sync(0xffffffffu, (i0 + r * 32 < n) && ((v[r] >> shift) & 1u));
+        mine += __popc(word[r]);
+    }
+    if (lane == 0) wtot[w] = mine;
+    __syncthreads();
+    if (w == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int k = 0; k < WM_NT / 32; k++) tot += wtot[k];
+        if (lane == 0) wm_st(&desc[tile], (unsigned)tot | WM_AGG);
+        // look back: lane j reads the descriptor of tile t - j; the nearest tiles are summed up to the first inclusive one
+        unsigned excl = 0;
+        int t = (int)tile - 1;
+        while (t >= 0) {
+            const int tt = t - lane;
+            const unsigned d = tt >= 0 ? wm_ld(&desc[tt]) : WM_INC;
+            const unsigned inc = __ballot_sync(0xffffffffu, (d & WM_INC) != 0);
+            const unsigned nr = __ballot_sync(0xffffffffu, (d & (WM_INC | WM_AGG)) == 0);
+            const int first_inc = inc ? __ffs(inc) - 1 : 32, first_nr = nr ? __ffs(nr) - 1 : 32;
+            const int upto = first_inc < first_nr ? first_inc : first_nr;          // lanes below `upto` hold aggregates
+            const bool take = lane < upto || (lane == upto && first_inc == upto);
+            excl += __reduce_add_sync(0xffffffffu, take ? (d & WM_VAL) : 0u);
+            if (first_inc == upto && upto < 32) break;                             // reached an inclusive prefix
+            t -= upto;                                                             // not published yet: read again from there
+        }
+        if (lane == 0) {
+            wm_st(&desc[tile], (excl + (unsigned)tot) | WM_INC);
+            s_excl = excl;
+        }
+    }
+    __syncthreads();
+    unsigned before = s_excl;
+    for (int k = 0; k < w; k++) before += (unsigned)wtot[k];
+    const uint32_t z = n - (uint32_t)*ones_here;
+    const unsigned lt = (1u << lane) - 1u;
+    int nb = 0;
+#pragma unroll
+    for (int r = 0; r < WM_IPT; r++) {
+        const uint32_t i = i0 + r * 32;
+        if (lane == 0 && (i >> 5) < nw) level[i >> 5] = make_uint2(word[r], before);
+        if (i < n) {
+            const uint32_t r1 = before + __popc(word[r] & lt);
+            nxt[((word[r] >> lane) & 1u) ? z + r1 : i - r1] = v[r];
+            if (shift > 0) nb += (v[r] >> (shift - 1)) & 1u;
+        }
+        before += __popc(word[r]);
+    }
+    if (shift > 0) {
+        nb = __reduce_add_sync(0xffffffffu, nb);
+        if (lane == 0 && nb) atomicAdd(ones_next, (unsigned long long)nb);
+    }
 }
 
 static int cl2_index_wavelet(cl2_ctx *ctx, cl2_index *idx) {
@@ -923,40 +999,36 @@ static int cl2_index_wavelet(cl2_ctx *ctx, cl2_index *idx) {
     const int64_t n = idx->n;
     const int L = bits_for((uint64_t)idx->ymax);
     const int64_t nw = n / 32 + 1;
-    if (L > 32 || n >= (int64_t)INT32_MAX) return cl2_fail(ctx, CL2_ERR_RANGE, "wavelet matrix: too many rows");
+    if (L > 32 || n >= (int64_t)WM_VAL) return cl2_fail(ctx, CL2_ERR_RANGE, "wavelet matrix: too many rows");
+    const int ntiles = (int)((nw * 32 + WM_TILE - 1) / WM_TILE);
     Scratch sc(ctx);
     uint32_t *cur, *nxt;
-    int32_t *ones;
-    int64_t *tot;
+    unsigned long long *tot;          // ones of every level
+    unsigned *desc, *ticket;
     CL2_TRY(sc.get(&cur, (size_t)n));
     CL2_TRY(sc.get(&nxt, (size_t)n));
-    CL2_TRY(sc.get(&ones, (size_t)nw));
-    CL2_TRY(sc.get(&tot, (size_t)L));
+    CL2_TRY(sc.get(&tot, (size_t)L + 1));
+    CL2_TRY(sc.get(&desc, (size_t)L * (size_t)ntiles + (size_t)L));
+    ticket = desc + (size_t)L * (size_t)ntiles;
     uint2 *wm;
     CL2_TRY(cl2_dev_alloc(ctx, &wm, (size_t)L * (size_t)nw));
+    CL2_CUDA(ctx, cudaMemsetAsync(tot, 0, ((size_t)L + 1) * 8, ctx->stream));
+    CL2_CUDA(ctx, cudaMemsetAsync(desc, 0, ((size_t)L * (size_t)ntiles + (size_t)L) * 4, ctx->stream));
     {
         FamTimer t(ctx, FAM_INDEX, 12.0 * (double)n);
-        k_wm_init<<<cl2_grid(n, 256), 256, 0, ctx->stream>>>(idx->byx, cur, n);
+        k_wm_init<<<cl2_grid(n, 256), 256, 0, ctx->stream>>>(idx->byx, cur, n, L - 1, tot);
     }
     for (int l = 0; l < L; l++) {
-        const int shift = L - 1 - l;
-        {
-            FamTimer t(ctx, FAM_INDEX, 4.0 * (double)n);
-            k_wm_ones<<<cl2_grid(nw * 32, 256), 256, 0, ctx->stream>>>(cur, n, shift, nw, ones);
-        }
-        CL2_TRY(cl2_exclusive_scan_i32(ctx, ones, nw, tot + l));
-        {
-            FamTimer t(ctx, FAM_INDEX, 8.25 * (double)n);
-            k_wm_partition<<<cl2_grid(nw * 32, 256), 256, 0, ctx->stream>>>(cur, nxt, n, shift, nw, ones, tot + l,
-                                                                            wm + (size_t)l * (size_t)nw);
-        }
+        FamTimer t(ctx, FAM_INDEX, 8.25 * (double)n);
+        k_wm_level<<<ntiles, WM_NT, 0, ctx->stream>>>(cur, nxt, (uint32_t)n, L - 1 - l, (uint32_t)nw, wm + (size_t)l * (size_t)nw,
+                                                       tot + l, tot + l + 1, desc + (size_t)l * (size_t)ntiles, ticket + l);
         uint32_t *t2 = cur; cur = nxt; nxt = t2;
     }
-    std::vector<int64_t> ht((size_t)L);
+    std::vector<unsigned long long> ht((size_t)L);
     CL2_CUDA(ctx, cudaMemcpyAsync(ht.data(), tot, (size_t)L * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CL2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     CL2_CUDA(ctx, cudaGetLastError());
-    for (int l = 0; l < L; l++) idx->wm_z[l] = (uint32_t)(n - ht[(size_t)l]);
+    for (int l = 0; l < L; l++) idx->wm_z[l] = (uint32_t)(n - (int64_t)ht[(size_t)l]);
     idx->wm = wm;
     idx->wm_L = L;
     idx->wm_nw = nw;
@@ -1789,24 +1861,60 @@ extern "C" int cl2_loop_tests(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops
     return CL2_OK;
 }
 
+__global__ void __launch_bounds__(256) k_est_gather(const long long *__restrict__ sel, int64_t K, const longlong4 *__restrict__ loops,
+                                                     const int32_t *__restrict__ pid, const uint64_t *__restrict__ key,
+                                                     longlong4 *__restrict__ oc, int32_t *__restrict__ op,
+                                                     uint64_t *__restrict__ ok) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K) return;
+    const long long k = sel[i];
+    if (oc) oc[i] = loops[k];
+    if (op) op[i] = pid[k];
+    if (ok) ok[i] = key[k];
+}
+
 extern "C" int cl2_est_loops(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops, int64_t L, int32_t win, int32_t mode,
                              int32_t minPts, int32_t hic, double countDiffCut, double pseudo, double peakPcut,
                              double rpb, int64_t *n_out, int64_t *sel, int64_t *core, double *hyp, double *stats) {
     if (!ctx || !idx || !n_out || L < 0 || (L > 0 && (!loops || !sel || !core || !hyp || !stats)))
         return cl2_fail(ctx, CL2_ERR_ARG, "cl2_est_loops: bad argument");
+    *n_out = 0;
+    if (L == 0) return CL2_OK;
+    CL2_CUDA(ctx, cudaSetDevice(ctx->device));
+    Scratch sc(ctx);
+    longlong4 *d_loops;
+    CL2_TRY(sc.get(&d_loops, (size_t)L));
+    CL2_CUDA(ctx, cudaMemcpyAsync(d_loops, loops, (size_t)L * 32, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h2d_bytes += L * 32;
+    cl2_est_out out;
+    CL2_TRY(cl2_est_loops_device(ctx, idx, d_loops, L, win, mode, minPts, hic, countDiffCut, pseudo, peakPcut, rpb, nullptr,
+                                 nullptr, false, out));
+    const size_t m = out.sel.size();
+    if (m) {
+        memcpy(sel, out.sel.data(), m * 8);
+        memcpy(core, out.core.data(), m * 32);
+        memcpy(hyp, out.hyp.data(), m * 8);
+        memcpy(stats, out.stats.data(), m * CL2_NSTAT * 8);
+    }
+    *n_out = (int64_t)m;
+    return CL2_OK;
+}
+
+int cl2_est_loops_device(cl2_ctx *ctx, cl2_index *idx, const longlong4 *d_loops, int64_t L, int32_t win, int32_t mode,
+                         int32_t minPts, int32_t hic, double countDiffCut, double pseudo, double peakPcut, double rpb,
+                         const int32_t *aux_pid, const uint64_t *aux_key, bool want_coords, cl2_est_out &out) {
+    out.sel.clear(); out.core.clear(); out.coords.clear(); out.hyp.clear(); out.stats.clear(); out.pid.clear(); out.key.clear();
+    if (!ctx || !idx || L < 0 || (L > 0 && !d_loops)) return cl2_fail(ctx, CL2_ERR_ARG, "cl2_est_loops: bad argument");
     if (win < 1 || 2 * win > CNT_MAXW) return cl2_fail(ctx, CL2_ERR_ARG, "cl2_est_loops: win must be in 1..8");
     if (mode != CL2_MODE_CIS && mode != CL2_MODE_TRANS) return cl2_fail(ctx, CL2_ERR_ARG, "cl2_est_loops: bad mode");
-    *n_out = 0;
     if (L == 0) return CL2_OK;
     if (L >= (int64_t)INT32_MAX) return cl2_fail(ctx, CL2_ERR_RANGE, "cl2_est_loops: too many loops in one call");
     CL2_CUDA(ctx, cudaSetDevice(ctx->device));
     Scratch sc(ctx);
-    longlong4 *d_loops;
     long long *d_core;
     double *d_stats;
     int32_t *d_flag;
     int64_t *d_total;
-    CL2_TRY(sc.get(&d_loops, (size_t)L));
     CL2_TRY(sc.get(&d_core, (size_t)L * 4));
     CL2_TRY(sc.get(&d_stats, (size_t)L * CL2_NSTAT));
     CL2_TRY(sc.get(&d_flag, (size_t)L));
@@ -1815,8 +1923,6 @@ extern "C" int cl2_est_loops(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops,
     CL2_CUDA(ctx, cudaMemsetAsync(d_big + L, 0, 4, ctx->stream));
     CL2_TRY(sc.get(&d_total, 2));
     CL2_CUDA(ctx, cudaMemsetAsync(d_total, 0, 16, ctx->stream));
-    CL2_CUDA(ctx, cudaMemcpyAsync(d_loops, loops, (size_t)L * 32, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->h2d_bytes += L * 32;
     {
         FamTimer t(ctx, FAM_COUNT, 0.0);
         static const int occ = getenv("CL2_EST_OCC") ? atoi(getenv("CL2_EST_OCC")) : 4;
@@ -1888,12 +1994,40 @@ extern "C" int cl2_est_loops(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops,
                                                                                 d_hyp_c, d_stats_c, d_flag2);
         }
         f2.resize((size_t)nk);
-        CL2_CUDA(ctx, cudaMemcpyAsync(sel, d_sel, (size_t)nk * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CL2_CUDA(ctx, cudaMemcpyAsync(core, d_core_c, (size_t)nk * 32, cudaMemcpyDeviceToHost, ctx->stream));
-        CL2_CUDA(ctx, cudaMemcpyAsync(hyp, d_hyp_c, (size_t)nk * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CL2_CUDA(ctx, cudaMemcpyAsync(stats, d_stats_c, (size_t)nk * CL2_NSTAT * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        out.sel.resize((size_t)nk);
+        out.core.resize((size_t)nk * 4);
+        out.hyp.resize((size_t)nk);
+        out.stats.resize((size_t)nk * CL2_NSTAT);
+        CL2_CUDA(ctx, cudaMemcpyAsync(out.sel.data(), d_sel, (size_t)nk * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CL2_CUDA(ctx, cudaMemcpyAsync(out.core.data(), d_core_c, (size_t)nk * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        CL2_CUDA(ctx, cudaMemcpyAsync(out.hyp.data(), d_hyp_c, (size_t)nk * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CL2_CUDA(ctx, cudaMemcpyAsync(out.stats.data(), d_stats_c, (size_t)nk * CL2_NSTAT * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CL2_CUDA(ctx, cudaMemcpyAsync(f2.data(), d_flag2, (size_t)nk * 4, cudaMemcpyDeviceToHost, ctx->stream));
         ctx->d2h_bytes += nk * (8 + 32 + 8 + CL2_NSTAT * 8 + 4);
+        if (want_coords || aux_pid || aux_key) {
+            // the survivors' own rows (candidates that live on the device only)
+            longlong4 *g_c = nullptr;
+            int32_t *g_p = nullptr;
+            uint64_t *g_k = nullptr;
+            if (want_coords) CL2_TRY(sc.get(&g_c, (size_t)nk));
+            if (aux_pid) CL2_TRY(sc.get(&g_p, (size_t)nk));
+            if (aux_key) CL2_TRY(sc.get(&g_k, (size_t)nk));
+            k_est_gather<<<cl2_grid(nk, 256), 256, 0, ctx->stream>>>(d_sel, nk, d_loops, aux_pid, aux_key, g_c, g_p, g_k);
+            ctx->launches++;
+            if (want_coords) {
+                out.coords.resize((size_t)nk * 4);
+                CL2_CUDA(ctx, cudaMemcpyAsync(out.coords.data(), g_c, (size_t)nk * 32, cudaMemcpyDeviceToHost, ctx->stream));
+            }
+            if (aux_pid) {
+                out.pid.resize((size_t)nk);
+                CL2_CUDA(ctx, cudaMemcpyAsync(out.pid.data(), g_p, (size_t)nk * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            }
+            if (aux_key) {
+                out.key.resize((size_t)nk);
+                CL2_CUDA(ctx, cudaMemcpyAsync(out.key.data(), g_k, (size_t)nk * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            }
+            ctx->d2h_bytes += nk * ((want_coords ? 32 : 0) + (aux_pid ? 4 : 0) + (aux_key ? 8 : 0));
+        }
         CL2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     if (ctx->timing) {
@@ -1909,13 +2043,22 @@ extern "C" int cl2_est_loops(cl2_ctx *ctx, cl2_index *idx, const int64_t *loops,
     for (int64_t i = 0; i < nk; i++) {
         if (!f2[i]) continue;
         if (m != i) {
-            sel[m] = sel[i];
-            memcpy(core + 4 * m, core + 4 * i, 32);
-            hyp[m] = hyp[i];
-            memcpy(stats + CL2_NSTAT * m, stats + CL2_NSTAT * i, CL2_NSTAT * 8);
+            out.sel[m] = out.sel[i];
+            memcpy(&out.core[4 * m], &out.core[4 * i], 32);
+            out.hyp[m] = out.hyp[i];
+            memcpy(&out.stats[CL2_NSTAT * m], &out.stats[CL2_NSTAT * i], CL2_NSTAT * 8);
+            if (!out.coords.empty()) memcpy(&out.coords[4 * m], &out.coords[4 * i], 32);
+            if (!out.pid.empty()) out.pid[m] = out.pid[i];
+            if (!out.key.empty()) out.key[m] = out.key[i];
         }
         m++;
     }
-    *n_out = m;
+    out.sel.resize((size_t)m);
+    out.core.resize((size_t)m * 4);
+    out.hyp.resize((size_t)m);
+    out.stats.resize((size_t)m * CL2_NSTAT);
+    if (!out.coords.empty()) out.coords.resize((size_t)m * 4);
+    if (!out.pid.empty()) out.pid.resize((size_t)m);
+    if (!out.key.empty()) out.key.resize((size_t)m);
     return CL2_OK;
 }

@@ -20,11 +20,17 @@ struct cl2_loops {
     std::vector<int64_t> coords, core;
     std::vector<int32_t> pass_id;
     std::vector<double> hyp, stats;
-    double seconds[3] = {0, 0, 0};               // clustering runs, index build, tests
+    double seconds[6] = {0, 0, 0, 0, 0, 0};      // clustering runs, index build, tests: host wall time, then thread CPU time
 };
 
 static inline double now_s() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+#include <time.h>
+static inline double cpu_s() {              // CPU time of the calling thread (waits that spin count, waits that sleep do not)
+    struct timespec ts;
+    clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
 
 static int64_t gcd_i64(int64_t a, int64_t b) {
@@ -50,6 +56,214 @@ struct Key4Hash {
     }
 };
 
+// ---- device-resident candidate list ------------------------------------------------------------------------------
+// per cluster box of one run: the per-run candidate filters (cis: callCisLoops.py:97-99, :114, :116; trans:
+// callTransLoops.py:62-64), the run's counters as runCisDBSCANLoops logs them (:122), then filterLoopsByDis (distance
+// > cut, callCisLoops.py:146-156; centres as the reference computes them, (start + end) / 2 in floating point,
+// :107-112) and the append
+__global__ void __launch_bounds__(256) k_cand_emit(const int *__restrict__ boxes, const uint64_t *__restrict__ keys, int32_t ncomp,
+                                                    int mode, long long cut, int pass, longlong4 *__restrict__ cand,
+                                                    uint64_t *__restrict__ key, int32_t *__restrict__ pid,
+                                                    int32_t *__restrict__ cursor, long long *__restrict__ pass_stat) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    bool cnt = false, keep = false;
+    long long x0 = 0, x1 = 0, y0 = 0, y1 = 0, size = 0;
+    if (k < ncomp) {
+        x0 = boxes[5 * (size_t)k]; x1 = boxes[5 * (size_t)k + 1]; y0 = boxes[5 * (size_t)k + 2]; y1 = boxes[5 * (size_t)k + 3];
+        size = (unsigned)boxes[5 * (size_t)k + 4];
+        cnt = !(x0 == x1 || y0 == y1);
+        if (cnt && mode == CL2_MODE_CIS) {
+            if ((x1 - x0) + (y1 - y0) < 200) cnt = false;
+            if (!(x1 < y0)) cnt = false;
+        }
+        keep = cnt;
+        if (keep && mode == CL2_MODE_CIS) {
+            const double xc = (double)(x0 + x1) / 2.0, yc = (double)(y0 + y1) / 2.0;
+            const double d = yc - xc;
+            keep = (d < 0 ? -d : d) > (double)cut;
+        }
+    }
+    // the run's counters: one atomic pair per warp
+    const unsigned mc = __ballot_sync(0xffffffffu, cnt);
+    long long sz = cnt ? size : 0;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sz += __shfl_xor_sync(0xffffffffu, sz, o);
+    if ((threadIdx.x & 31) == 0 && mc) {
+        atomicAdd((unsigned long long *)&pass_stat[2 * pass], (unsigned long long)__popc(mc));
+        atomicAdd((unsigned long long *)&pass_stat[2 * pass + 1], (unsigned long long)sz);
+    }
+    // the append: one cursor bump per warp
+    const unsigned mk = __ballot_sync(0xffffffffu, keep);
+    int base = 0;
+    if ((threadIdx.x & 31) == 0 && mk) base = atomicAdd(cursor, __popc(mk));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (keep) {
+        const int slot = base + __popc(mk & ((1u << (threadIdx.x & 31)) - 1u));
+        cand[slot] = make_longlong4(x0, x1, y0, y1);
+        key[slot] = keys ? keys[k] : (uint64_t)k;
+        pid[slot] = pass;
+    }
+}
+
+int cl2_sink_emit(cl2_ctx *ctx, cl2_cand_sink *sink, const int *boxes, const uint64_t *keys, int32_t ncomp) {
+    if (ncomp <= 0) return CL2_OK;
+    if (sink->bound + ncomp > sink->cap) {
+        // grow (the rows used so far are at most `bound`)
+        int64_t cap = sink->cap ? sink->cap : 1 << 16;
+        while (cap < sink->bound + ncomp) cap *= 2;
+        longlong4 *c2 = nullptr;
+        uint64_t *k2 = nullptr;
+        int32_t *p2 = nullptr;
+        CL2_TRY(cl2_dev_alloc(ctx, &c2, (size_t)cap));
+        CL2_TRY(cl2_dev_alloc(ctx, &k2, (size_t)cap));
+        CL2_TRY(cl2_dev_alloc(ctx, &p2, (size_t)cap));
+        if (sink->bound > 0) {
+            CL2_CUDA(ctx, cudaMemcpyAsync(c2, sink->cand, (size_t)sink->bound * 32, cudaMemcpyDeviceToDevice, ctx->stream));
+            CL2_CUDA(ctx, cudaMemcpyAsync(k2, sink->key, (size_t)sink->bound * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+            CL2_CUDA(ctx, cudaMemcpyAsync(p2, sink->pid, (size_t)sink->bound * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        cl2_dev_free(ctx, sink->cand);
+        cl2_dev_free(ctx, sink->key);
+        cl2_dev_free(ctx, sink->pid);
+        sink->cand = c2;
+        sink->key = k2;
+        sink->pid = p2;
+        sink->cap = cap;
+    }
+    k_cand_emit<<<cl2_grid(ncomp, 256), 256, 0, ctx->stream>>>(boxes, keys, ncomp, sink->mode, (long long)sink->cut, sink->pass,
+                                                               sink->cand, sink->key, sink->pid, sink->cursor, sink->pass_stat);
+    ctx->launches++;
+    sink->bound += ncomp;
+    return CL2_OK;
+}
+
+void cl2_sink_free(cl2_ctx *ctx, cl2_cand_sink *sink) {
+    cl2_dev_free(ctx, sink->cand);
+    cl2_dev_free(ctx, sink->key);
+    cl2_dev_free(ctx, sink->pid);
+    cl2_dev_free(ctx, sink->cursor);
+    *sink = cl2_cand_sink();
+}
+
+static int call_loops_body(cl2_ctx *ctx, cl2_points *pts, int32_t mode, int32_t hic, int32_t npass, const int64_t *eps,
+                           const int32_t *minPts, int64_t cut, int32_t min_pts_test, int32_t win, double countDiffCut,
+                           double pseudo, double peakPcut, int32_t want_unique, cl2_loops *r, cl2_cand_sink &sink) {
+    const bool cis = mode == CL2_MODE_CIS;
+    const bool use_c2 = cis && hic;                          // trans always clusters with blockDBSCAN (callTransLoops.py:29)
+    double t0 = now_s(), c0 = cpu_s();
+    // cursor + the runs' counters in one small device block
+    CL2_TRY(cl2_dev_alloc(ctx, &sink.cursor, (size_t)4 * ((size_t)npass + 1)));
+    CL2_CUDA(ctx, cudaMemsetAsync(sink.cursor, 0, (size_t)16 * ((size_t)npass + 1), ctx->stream));
+    sink.pass_stat = reinterpret_cast<long long *>(sink.cursor + 4);
+    sink.mode = mode;
+    sink.cut = cut;
+
+    // Order of execution.  The result of a run does not depend on it; the blockDBSCAN runs go from the largest eps down
+    // (smallest minPts first) so that each tells the later ones which rows sit in noise cells it removed.
+    std::vector<int> order((size_t)npass);
+    for (int i = 0; i < npass; i++) order[i] = i;
+    bool hint = false;
+    if (!use_c2)
+        for (int i = 1; i < npass; i++)
+            if (eps[i] != eps[0]) hint = true;
+    if (hint)
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            if (eps[a] != eps[b]) return eps[a] > eps[b];
+            return minPts[a] < minPts[b];
+        });
+    for (int pos = 0; pos < npass; pos++) {
+        const int i = order[pos];
+        if (hint) {
+            bool useful = false;                             // remembering rows costs a pass over the points
+            for (int q = pos + 1; q < npass; q++)
+                if (rows_carry_over(eps[i], minPts[i], eps[order[q]], minPts[order[q]])) useful = true;
+            cl2_points_sweep_hint(ctx, pts, useful ? 1 : 2);
+        }
+        int32_t ncl = 0;
+        sink.pass = i;
+        // the clusters of the run go straight into the device-resident list (blockDBSCAN: unordered, each with the key
+        // that ranks it in the reference's numbering; only the few survivors are put in order, at the end)
+        CL2_TRY(use_c2 ? cl2_cdbscan2_impl(ctx, pts, eps[i], minPts[i], nullptr, &ncl, &sink)
+                       : cl2_block_dbscan_impl(ctx, pts, eps[i], minPts[i], nullptr, &ncl, false, &sink));
+    }
+    // one read-back for all runs: the rows in the list and the runs' counters
+    std::vector<long long> hs((size_t)2 * (size_t)npass + 2);
+    CL2_CUDA(ctx, cudaMemcpyAsync(hs.data(), sink.cursor, hs.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CL2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->d2h_bytes += (int64_t)hs.size() * 8;
+    const int64_t L = (int64_t)(int32_t)(hs[0] & 0xffffffffll);
+    for (int i = 0; i < npass; i++) {
+        r->pass_cand[(size_t)i] = hs[2 + 2 * (size_t)i];
+        r->pass_pets[(size_t)i] = hs[3 + 2 * (size_t)i];
+    }
+    r->n_tested = L;
+    if (want_unique && L > 0) {
+        std::vector<int64_t> all((size_t)L * 4);
+        CL2_CUDA(ctx, cudaMemcpyAsync(all.data(), sink.cand, (size_t)L * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        CL2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->d2h_bytes += L * 32;
+        std::unordered_map<Key4, int, Key4Hash> seen;
+        seen.reserve((size_t)L * 2);
+        for (int64_t k = 0; k < L; k++) {
+            Key4 key = {{all[4 * k], all[4 * k + 1], all[4 * k + 2], all[4 * k + 3]}};
+            seen.emplace(key, 0);
+        }
+        r->n_unique = (int64_t)seen.size();
+    }
+    double t1 = now_s(), c1 = cpu_s();
+    r->seconds[0] = t1 - t0;
+    r->seconds[3] = c1 - c0;
+    if (L == 0) {
+        cl2_points_drop_cache(ctx, pts);
+        return CL2_OK;
+    }
+    cl2_index *idx = nullptr;
+    CL2_TRY(cl2_index_build(ctx, pts, &idx));
+    double t2 = now_s(), c2 = cpu_s();
+    r->seconds[1] = t2 - t1;
+    r->seconds[4] = c2 - c1;
+    cl2_est_out eo;
+    const double rpb = (double)pts->n / (double)(pts->ext[3] - pts->ext[0]);       // callCisLoops.py:231
+    int rc = cl2_est_loops_device(ctx, idx, sink.cand, L, win, mode, min_pts_test, hic, countDiffCut, pseudo, peakPcut, rpb,
+                                  sink.pid, sink.key, true, eo);
+    cl2_index_free(ctx, idx);
+    cl2_points_drop_cache(ctx, pts);                          // eps grid + y-order: derived data, rebuilt by the next call
+    if (rc != CL2_OK) return rc;
+    const int64_t nk = (int64_t)eo.sel.size();
+    // survivors in candidate order: run by run as given, ascending cluster id inside a run
+    std::vector<int64_t> sorder((size_t)nk);
+    for (int64_t q = 0; q < nk; q++) sorder[(size_t)q] = q;
+    std::sort(sorder.begin(), sorder.end(), [&](int64_t a, int64_t b) {
+        if (eo.pid[(size_t)a] != eo.pid[(size_t)b]) return eo.pid[(size_t)a] < eo.pid[(size_t)b];
+        if (eo.key[(size_t)a] != eo.key[(size_t)b]) return eo.key[(size_t)a] < eo.key[(size_t)b];
+        return eo.sel[(size_t)a] < eo.sel[(size_t)b];
+    });
+    // combineLoops (geo.py:90-112) drops a candidate whose coordinates were already present from an EARLIER run;
+    // the cis path then also applies filterDupLoops (callCisLoops.py:159-169: first position of every coordinate
+    // tuple).  A candidate's test result depends on its coordinates only, so both are applied to the survivors.
+    std::unordered_map<Key4, int32_t, Key4Hash> first_pass;
+    first_pass.reserve((size_t)nk * 2 + 1);
+    for (int64_t qq = 0; qq < nk; qq++) {
+        const size_t q = (size_t)sorder[(size_t)qq];
+        Key4 key = {{eo.coords[4 * q], eo.coords[4 * q + 1], eo.coords[4 * q + 2], eo.coords[4 * q + 3]}};
+        auto it = first_pass.find(key);
+        if (it != first_pass.end()) {
+            if (cis || it->second != eo.pid[q]) continue;
+        } else {
+            first_pass.emplace(key, eo.pid[q]);
+        }
+        r->coords.insert(r->coords.end(), eo.coords.begin() + 4 * q, eo.coords.begin() + 4 * q + 4);
+        r->pass_id.push_back(eo.pid[q]);
+        r->core.insert(r->core.end(), eo.core.begin() + 4 * q, eo.core.begin() + 4 * q + 4);
+        r->hyp.push_back(eo.hyp[q]);
+        r->stats.insert(r->stats.end(), eo.stats.begin() + 13 * q, eo.stats.begin() + 13 * q + 13);
+    }
+    r->n = (int64_t)r->pass_id.size();
+    r->seconds[2] = now_s() - t2;
+    r->seconds[5] = cpu_s() - c2;
+    return CL2_OK;
+}
+
 extern "C" int cl2_call_loops(cl2_ctx *ctx, cl2_points *pts, int32_t mode, int32_t hic, int32_t npass, const int64_t *eps,
                               const int32_t *minPts, int64_t cut, int32_t min_pts_test, int32_t win, double countDiffCut,
                               double pseudo, double peakPcut, int32_t want_unique, cl2_loops **out) {
@@ -66,143 +280,12 @@ extern "C" int cl2_call_loops(cl2_ctx *ctx, cl2_points *pts, int32_t mode, int32
     for (int i = 0; i < 4; i++) r->ext[i] = pts->ext[i];
     *out = r;
     if (pts->n == 0 || npass == 0) return CL2_OK;
-    const bool cis = mode == CL2_MODE_CIS;
-    const bool use_c2 = cis && hic;                          // trans always clusters with blockDBSCAN (callTransLoops.py:29)
-    double t0 = now_s();
-
-    // Order of execution.  The result of a run does not depend on it; the blockDBSCAN runs go from the largest eps down
-    // (smallest minPts first) so that each tells the later ones which rows sit in noise cells it removed.
-    std::vector<int> order((size_t)npass);
-    for (int i = 0; i < npass; i++) order[i] = i;
-    bool hint = false;
-    if (!use_c2)
-        for (int i = 1; i < npass; i++)
-            if (eps[i] != eps[0]) hint = true;
-    if (hint)
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-            if (eps[a] != eps[b]) return eps[a] > eps[b];
-            return minPts[a] < minPts[b];
-        });
-    // per run: kept boxes, 4 values each, and the key that ranks each box in the reference's cluster numbering (the
-    // blockDBSCAN runs report their clusters unordered: only the few survivors are put in order, at the end)
-    std::vector<std::vector<int64_t>> cand((size_t)npass);
-    std::vector<std::vector<uint64_t>> ckey((size_t)npass);
-    int rc = CL2_OK;
-    for (int pos = 0; pos < npass && rc == CL2_OK; pos++) {
-        const int i = order[pos];
-        if (hint) {
-            bool useful = false;                             // remembering rows costs a pass over the points
-            for (int q = pos + 1; q < npass; q++)
-                if (rows_carry_over(eps[i], minPts[i], eps[order[q]], minPts[order[q]])) useful = true;
-            cl2_points_sweep_hint(ctx, pts, useful ? 1 : 2);
-        }
-        int32_t ncl = 0;
-        rc = use_c2 ? cl2_cdbscan2(ctx, pts, eps[i], minPts[i], nullptr, &ncl)
-                    : cl2_block_dbscan_impl(ctx, pts, eps[i], minPts[i], nullptr, &ncl, false);
-        if (rc != CL2_OK) break;
-        std::vector<int64_t> &c = cand[(size_t)i];
-        std::vector<uint64_t> &ck = ckey[(size_t)i];
-        c.reserve((size_t)ncl * 4);
-        ck.reserve((size_t)ncl);
-        int64_t pets = 0;
-        for (int32_t k = 0; k < ncl; k++) {
-            const int64_t x0 = pts->bbox[4 * (size_t)k], x1 = pts->bbox[4 * (size_t)k + 1];
-            const int64_t y0 = pts->bbox[4 * (size_t)k + 2], y1 = pts->bbox[4 * (size_t)k + 3];
-            if (x0 == x1 || y0 == y1) continue;              // callCisLoops.py:97-99 / callTransLoops.py:62-64
-            if (cis) {
-                if ((x1 - x0) + (y1 - y0) < 200) continue;   // :114
-                if (!(x1 < y0)) continue;                    // :116
-            }
-            c.push_back(x0); c.push_back(x1); c.push_back(y0); c.push_back(y1);
-            ck.push_back(use_c2 ? (uint64_t)k : pts->ckeys[(size_t)k]);
-            pets += pts->size[(size_t)k];
-        }
-        r->pass_cand[(size_t)i] = (int64_t)c.size() / 4;
-        r->pass_pets[(size_t)i] = pets;
-    }
-    if (rc != CL2_OK) return rc;
-    // candidates of all runs in sweep order; filterLoopsByDis (callCisLoops.py:146-156) keeps distance > cut, with the
-    // centres as the reference computes them, (start + end) / 2 in floating point (:107-112)
-    std::vector<int64_t> all;
-    std::vector<int32_t> pid;
-    std::vector<uint64_t> akey;
-    for (int i = 0; i < npass; i++) {
-        const std::vector<int64_t> &c = cand[(size_t)i];
-        for (size_t k = 0; k + 3 < c.size(); k += 4) {
-            if (cis) {
-                const double xc = (double)(c[k] + c[k + 1]) / 2.0, yc = (double)(c[k + 2] + c[k + 3]) / 2.0;
-                const double d = yc - xc;
-                if (!((d < 0 ? -d : d) > (double)cut)) continue;
-            }
-            all.insert(all.end(), c.begin() + k, c.begin() + k + 4);
-            pid.push_back(i);
-            akey.push_back(ckey[(size_t)i][k / 4]);
-        }
-    }
-    const int64_t L = (int64_t)pid.size();
-    r->n_tested = L;
-    if (want_unique) {
-        std::unordered_map<Key4, int, Key4Hash> seen;
-        seen.reserve((size_t)L * 2);
-        for (int64_t k = 0; k < L; k++) {
-            Key4 key = {{all[4 * k], all[4 * k + 1], all[4 * k + 2], all[4 * k + 3]}};
-            seen.emplace(key, 0);
-        }
-        r->n_unique = (int64_t)seen.size();
-    }
-    double t1 = now_s();
-    r->seconds[0] = t1 - t0;
-    if (L == 0) {
-        cl2_points_drop_cache(ctx, pts);
-        return CL2_OK;
-    }
-    cl2_index *idx = nullptr;
-    rc = cl2_index_build(ctx, pts, &idx);
-    if (rc != CL2_OK) return rc;
-    double t2 = now_s();
-    r->seconds[1] = t2 - t1;
-    std::vector<int64_t> sel((size_t)L), core((size_t)L * 4);
-    std::vector<double> hyp((size_t)L), stats((size_t)L * 13);
-    int64_t nk = 0;
-    const double rpb = (double)pts->n / (double)(pts->ext[3] - pts->ext[0]);       // callCisLoops.py:231
-    rc = cl2_est_loops(ctx, idx, all.data(), L, win, mode, min_pts_test, hic, countDiffCut, pseudo, peakPcut, rpb, &nk,
-                       sel.data(), core.data(), hyp.data(), stats.data());
-    cl2_index_free(ctx, idx);
-    cl2_points_drop_cache(ctx, pts);                          // eps grid + y-order: derived data, rebuilt by the next call
-    if (rc != CL2_OK) return rc;
-    // combineLoops (geo.py:90-112) drops a candidate whose coordinates were already present from an EARLIER run;
-    // the cis path then also applies filterDupLoops (callCisLoops.py:159-169: first position of every coordinate
-    // tuple).  A candidate's test result depends on its coordinates only, so both are applied to the survivors.
-    // survivors in candidate order: run by run as given, ascending cluster id inside a run
-    std::vector<int64_t> sorder((size_t)nk);
-    for (int64_t q = 0; q < nk; q++) sorder[(size_t)q] = q;
-    std::sort(sorder.begin(), sorder.end(), [&](int64_t a, int64_t b) {
-        const int64_t ka = sel[(size_t)a], kb = sel[(size_t)b];
-        if (pid[(size_t)ka] != pid[(size_t)kb]) return pid[(size_t)ka] < pid[(size_t)kb];
-        if (akey[(size_t)ka] != akey[(size_t)kb]) return akey[(size_t)ka] < akey[(size_t)kb];
-        return ka < kb;
-    });
-    std::unordered_map<Key4, int32_t, Key4Hash> first_pass;
-    first_pass.reserve((size_t)nk * 2 + 1);
-    for (int64_t qq = 0; qq < nk; qq++) {
-        const int64_t q = sorder[(size_t)qq];
-        const int64_t k = sel[(size_t)q];
-        Key4 key = {{all[4 * k], all[4 * k + 1], all[4 * k + 2], all[4 * k + 3]}};
-        auto it = first_pass.find(key);
-        if (it != first_pass.end()) {
-            if (cis || it->second != pid[(size_t)k]) continue;
-        } else {
-            first_pass.emplace(key, pid[(size_t)k]);
-        }
-        r->coords.insert(r->coords.end(), all.begin() + 4 * k, all.begin() + 4 * k + 4);
-        r->pass_id.push_back(pid[(size_t)k]);
-        r->core.insert(r->core.end(), core.begin() + 4 * q, core.begin() + 4 * q + 4);
-        r->hyp.push_back(hyp[(size_t)q]);
-        r->stats.insert(r->stats.end(), stats.begin() + 13 * q, stats.begin() + 13 * q + 13);
-    }
-    r->n = (int64_t)r->pass_id.size();
-    r->seconds[2] = now_s() - t2;
-    return CL2_OK;
+    CL2_CUDA(ctx, cudaSetDevice(ctx->device));
+    cl2_cand_sink sink;
+    const int rc = call_loops_body(ctx, pts, mode, hic, npass, eps, minPts, cut, min_pts_test, win, countDiffCut, pseudo,
+                                   peakPcut, want_unique, r, sink);
+    cl2_sink_free(ctx, &sink);
+    return rc;
 }
 
 extern "C" int64_t cl2_loops_count(const cl2_loops *r) { return r ? r->n : -1; }
@@ -221,7 +304,7 @@ extern "C" int cl2_loops_info(const cl2_loops *r, int64_t *pass_cand, int64_t *p
         for (int i = 0; i < 4; i++) totals[4 + i] = r->ext[i];
     }
     if (seconds)
-        for (int i = 0; i < 3; i++) seconds[i] = r->seconds[i];
+        for (int i = 0; i < 6; i++) seconds[i] = r->seconds[i];
     return CL2_OK;
 }
 

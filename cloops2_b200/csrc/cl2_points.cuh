@@ -72,6 +72,26 @@ struct cl2_index {
     int64_t ymax = 0;
 };
 
+// Device-resident candidate list of one cl2_call_loops: every clustering run appends the boxes that pass the per-run
+// candidate filters (and, cis, filterLoopsByDis), each with the index of its run and the key that ranks it in the
+// reference's cluster numbering.  The boxes never visit the host: estLoopSig reads them where they are and only the
+// few survivors are copied back (cl2_driver.cu).
+struct cl2_cand_sink {
+    longlong4 *cand = nullptr;     // [cap] x_start, x_end, y_start, y_end
+    uint64_t *key = nullptr;       // [cap]
+    int32_t *pid = nullptr;        // [cap]
+    int64_t cap = 0;
+    int64_t bound = 0;             // host-side upper bound of the rows used (sum of the cluster counts emitted so far)
+    int32_t *cursor = nullptr;     // device: rows used
+    long long *pass_stat = nullptr;  // device [2 * npass]: candidates of the run (before the distance filter), PETs in them
+    int32_t mode = 0;              // CL2_MODE_CIS | CL2_MODE_TRANS: which per-run filters apply
+    int64_t cut = 0;               // filterLoopsByDis keeps distance > cut (cis)
+    int32_t pass = 0;              // index of the run that is emitting
+};
+// boxes: ncomp records of 5 ints (xmin, xmax, ymin, ymax, size) on the device; keys may be null (key = record index)
+int cl2_sink_emit(cl2_ctx *ctx, cl2_cand_sink *sink, const int *boxes, const uint64_t *keys, int32_t ncomp);   // cl2_driver.cu
+void cl2_sink_free(cl2_ctx *ctx, cl2_cand_sink *sink);
+
 void cl2_grid_free(cl2_ctx *ctx, cl2_grid_cache &g);
 void cl2_subsets_free(cl2_ctx *ctx, cl2_points *pts, size_t keep_levels = 0);
 // keygen -> radix sort -> gather -> cell table -> neighbours + 3x3 sums (cl2_block.cu); cached per (eps, kind).
@@ -79,7 +99,20 @@ void cl2_subsets_free(cl2_ctx *ctx, cl2_points *pts, size_t keep_levels = 0);
 int cl2_grid_build(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int kind, int32_t minPts = -1);
 int cl2_points_yorder(cl2_ctx *ctx, cl2_points *pts);   // cl2_count.cu
 int cl2_block_dbscan_impl(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int32_t minPts, int32_t *labels_out,
-                          int32_t *n_clusters, bool ordered);    // cl2_block.cu
+                          int32_t *n_clusters, bool ordered, cl2_cand_sink *sink = nullptr);    // cl2_block.cu
+int cl2_cdbscan2_impl(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int32_t minPts, int32_t *labels_out,
+                      int32_t *n_clusters, cl2_cand_sink *sink);                                // cl2_cdbscan.cu
+// estLoopSig on candidates that already live on the device (cl2_count.cu).  aux_pid / aux_key (device, may be null)
+// are gathered for the survivors along with their coordinates.
+struct cl2_est_out {
+    std::vector<int64_t> sel, core, coords;
+    std::vector<double> hyp, stats;
+    std::vector<int32_t> pid;
+    std::vector<uint64_t> key;
+};
+int cl2_est_loops_device(cl2_ctx *ctx, cl2_index *idx, const longlong4 *d_loops, int64_t L, int32_t win, int32_t mode,
+                         int32_t minPts, int32_t hic, double countDiffCut, double pseudo, double peakPcut, double rpb,
+                         const int32_t *aux_pid, const uint64_t *aux_key, bool want_coords, cl2_est_out &out);
 int cl2_read_i64(cl2_ctx *ctx, const int64_t *d, int64_t *out);
 int cl2_read_i32(cl2_ctx *ctx, const int32_t *d, int32_t *out);
 

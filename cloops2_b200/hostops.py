@@ -313,12 +313,8 @@ def pvalue_pool():
     global _pv_pool
     if _pv_pool is None:
         from concurrent.futures import ThreadPoolExecutor
-        try:
-            cores = len(os.sched_getaffinity(0))
-        except AttributeError:
-            cores = os.cpu_count() or 1
-        world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1)
-        _pv_pool = ThreadPoolExecutor(max(2, cores // max(1, world) - 1))
+        from . import shard
+        _pv_pool = ThreadPoolExecutor(max(2, shard.rank_cores() - 1))
     return _pv_pool
 
 

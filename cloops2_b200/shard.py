@@ -35,7 +35,41 @@ def init_from_env(backend=None):
             torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group(backend=backend)
+        pin_rank_cores()
     return dist.get_rank(), dist.get_world_size()
+
+
+_pinned = [False]
+
+
+def rank_cores():
+    """Host cores this rank can count on: its own share once pinned, else an equal split of what the process may use."""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 8
+    if _pinned[0]:
+        return max(1, cores)
+    world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1)
+    return max(1, cores // max(1, world))
+
+
+def pin_rank_cores():
+    """Give every rank of a node its own share of the host cores (CL2_PIN=0 leaves the affinity alone).  The ranks'
+    worker threads wait actively; left to roam over all cores they keep displacing each other's launching threads,
+    which a 32-core host with 8 ranks shows as a third of the throughput lost."""
+    if os.environ.get("CL2_PIN", "1") in ("0", ""):
+        return
+    try:
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        nlocal = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1)
+        cores = sorted(os.sched_getaffinity(0))
+        per = len(cores) // max(1, nlocal)
+        if nlocal > 1 and per >= 2:
+            os.sched_setaffinity(0, cores[local * per:(local + 1) * per])
+            _pinned[0] = True
+    except (AttributeError, OSError, ValueError):
+        pass
 
 
 def ixy_rows(f):
@@ -170,23 +204,18 @@ def worker_contexts(device=None, nthreads=None):
     host-side bookkeeping (ctypes calls and numpy release the GIL).  CL2_THREADS overrides the number of workers,
     CL2_BLOCKING_SYNC=0/1 how they wait."""
     from . import _lib
-    world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1)
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except AttributeError:
-        cores = os.cpu_count() or 8
-    share = max(1, cores // max(1, world))                   # host cores this rank can count on
+    share = rank_cores()                                     # host cores this rank can count on
     # Default: 8 workers that spin while they wait.  Since the per-file loop runs on the native side of the ABI
     # (cl2_call_loops) the workers hold no interpreter lock while they wait, and measured on one B200 per 100M-PET step:
     # 16 cores 66 ms (7 workers); confined to 4 cores: 8 spinning workers 77 ms, 8 sleeping workers 87 ms -- so the
     # waits only sleep (cl2_set_sync_mode) below 4 cores per rank, or when the scipy pool of the exact mode needs the
     # cores.  CL2_THREADS / CL2_BLOCKING_SYNC override either choice.
-    blocking = share < 4
+    mode = 0 if share >= 8 else 2                            # fewer cores than workers: waiting threads yield the core
     if nthreads is None:
         nthreads = int(os.environ.get("CL2_THREADS", "8" if share < 8 else str(max(2, min(8, share - 1)))))
     if os.environ.get("CL2_BLOCKING_SYNC") is not None:
-        blocking = os.environ["CL2_BLOCKING_SYNC"] not in ("0", "")
-    set_sync_mode(blocking)
+        mode = int(os.environ["CL2_BLOCKING_SYNC"] or 0)
+    set_sync_mode(mode)
     nthreads = max(1, nthreads)
     first = _lib.default_context(device)
     # the workers of a device are kept for the life of the process: a second callCisLoops / callTransLoops call reuses
@@ -203,12 +232,13 @@ _worker_pool = {}
 _sync_mode = [0]
 
 
-def set_sync_mode(blocking):
-    """How worker threads wait for their streams (cl2_set_sync_mode): spinning (lowest latency) or sleeping (leaves the
-    cores to other host work, e.g. the scipy pool of the exact mode).  Returns the previous mode."""
+def set_sync_mode(mode):
+    """How worker threads wait for their streams (cl2_set_sync_mode): 0 spinning (lowest latency), 1 / True sleeping
+    (leaves the cores to other host work, e.g. the scipy pool of the exact mode), 2 polling with a yield between polls
+    (more workers than cores).  Returns the previous mode."""
     from . import _lib
     prev = _sync_mode[0]
-    _sync_mode[0] = 1 if blocking else 0
+    _sync_mode[0] = 1 if mode is True else (int(mode) if int(mode) in (1, 2) else 0)
     _lib.load().cl2_set_sync_mode(_sync_mode[0])
     return prev
 

@@ -176,8 +176,8 @@ int cl2_call_loops(cl2_ctx *ctx, cl2_points *pts, int32_t mode, int32_t hic, int
 int64_t cl2_loops_count(const cl2_loops *r);
 /* pass_cand[npass], pass_pets[npass]: candidates of every run after its filters and the PETs they hold (the numbers
  * logged at callCisLoops.py:122); totals[8] = PETs of the file, candidates tested, distinct candidate coordinates
- * (-1 unless want_unique), survivors, min X, max X, min Y, max Y; seconds[3] = host wall time of the clustering
- * runs, the index build, the tests.  Any pointer may be NULL. */
+ * (-1 unless want_unique), survivors, min X, max X, min Y, max Y; seconds[6] = host wall time of the clustering
+ * runs, the index build, the tests, then the calling thread's CPU time of the same three.  Any pointer may be NULL. */
 int cl2_loops_info(const cl2_loops *r, int64_t *pass_cand, int64_t *pass_pets, int64_t *totals, double *seconds);
 /* coords int64[K,4], pass_id int32[K] (index of the run a survivor came from), core / hyp / stats as cl2_est_loops */
 int cl2_loops_read(const cl2_loops *r, int64_t *coords, int32_t *pass_id, int64_t *core, double *hyp, double *stats);
@@ -256,8 +256,9 @@ int64_t cl2_pairs_parse(cl2_bedpe *p, const char *buf, int64_t len, int64_t cap,
 const char *cl2_bedpe_names(cl2_bedpe *p, int32_t *count);
 
 /* How the library waits for its streams, process wide: 0 (default) spin in cudaStreamSynchronize, 1 sleep on a
- * blocking-sync event -- for hosts with fewer cores than worker threads (several ranks x several contexts). */
-void cl2_set_sync_mode(int32_t blocking);
+ * blocking-sync event, 2 poll the stream and yield the core between polls -- for hosts with fewer cores than worker
+ * threads (several ranks x several contexts). */
+void cl2_set_sync_mode(int32_t mode);
 
 /* ---- measurement -------------------------------------------------------------------------------------- */
 /* Kernel launches issued by this context since creation (or since the last reset). */
