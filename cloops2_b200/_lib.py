@@ -29,15 +29,28 @@ class Cl2Error(RuntimeError):
     pass
 
 
-def _stale():
-    if not os.path.exists(SO_PATH):
-        return True
-    t = os.path.getmtime(SO_PATH)
+def source_hash():
+    """sha256 over the CUDA sources, headers and compiler flags of libcl2.so (first 16 hex digits)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
     for f in SOURCES + HEADERS:
-        p = os.path.join(_CSRC, f)
-        if os.path.exists(p) and os.path.getmtime(p) > t:
-            return True
-    return False
+        with open(os.path.join(_CSRC, f), "rb") as fh:
+            h.update(f.encode() + b"\0" + fh.read())
+    return h.hexdigest()[:16]
+
+
+HASH_PATH = SO_PATH + ".hash"
+
+
+def _stale():
+    """Does the shipped libcl2.so come from these sources?  Decided by content (the hash written beside the library
+    when it was built, also compiled into cl2_version()), not by file times: a snapshot copy does not keep them."""
+    if not os.path.exists(SO_PATH) or not os.path.exists(HASH_PATH):
+        return True
+    try:
+        return open(HASH_PATH).read().strip() != source_hash()
+    except OSError:
+        return True
 
 
 def build(force=False, verbose=False):
@@ -45,11 +58,12 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return SO_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
+    digest = source_hash()
     objs = []
     procs = []
     for src in SOURCES:
         obj = os.path.join(_CSRC, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", "-o", obj, os.path.join(_CSRC, src)]
+        cmd = [nvcc] + NVCC_FLAGS + ['-DCL2_SRC_HASH="%s"' % digest, "-c", "-o", obj, os.path.join(_CSRC, src)]
         if verbose:
             print(" ".join(cmd))
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
@@ -60,6 +74,8 @@ def build(force=False, verbose=False):
             raise Cl2Error("nvcc failed: %s\n%s" % (" ".join(cmd), out.decode(errors="replace")))
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO_PATH] + objs + ["-lcudart", "-ldl"]
     subprocess.check_call(cmd)
+    with open(HASH_PATH, "w") as fh:
+        fh.write(digest + "\n")
     return SO_PATH
 
 
@@ -85,6 +101,7 @@ SIGNATURES = {
     "cl2_points_free": (None, [_vp, _vp]),
     "cl2_points_drop_cache": (None, [_vp, _vp]),
     "cl2_points_sweep_hint": (ctypes.c_int, [_vp, _vp, ctypes.c_int32]),
+    "cl2_points_index_hint": (ctypes.c_int, [_vp, _vp, ctypes.c_int32]),
     "cl2_points_unique": (ctypes.c_int, [_vp, _vp, _i64p, ctypes.POINTER(ctypes.c_int64)]),
     "cl2_set_sync_mode": (None, [ctypes.c_int32]),
     "cl2_bedpe_create": (ctypes.c_int, [ctypes.POINTER(_vp)]),
@@ -326,6 +343,11 @@ class Points:
         noise for them (cl2_points_sweep_hint); results do not change.  enable: False/0 off, True/1 remember and
         use, 2 use only."""
         self.ctx.check(self.ctx.lib.cl2_points_sweep_hint(self.ctx.h, self.h, int(enable)), "cl2_points_sweep_hint")
+
+    def index_hint(self, enable=True):
+        """Announce that an index build follows the next blockDBSCAN runs: the first run over every row then leaves the
+        x-order of the points behind for it (cl2_points_index_hint); the index is the same either way."""
+        self.ctx.check(self.ctx.lib.cl2_points_index_hint(self.ctx.h, self.h, int(bool(enable))), "cl2_points_index_hint")
 
     def extent(self):
         ext = np.zeros(4, dtype=np.int64)

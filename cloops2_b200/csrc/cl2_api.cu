@@ -4,7 +4,11 @@
 #include <new>
 #include <stdlib.h>
 
-extern "C" const char *cl2_version(void) { return "cl2-b200 0.1 sm_100a"; }
+#ifndef CL2_SRC_HASH
+#define CL2_SRC_HASH "unknown"
+#endif
+// the hash of the sources this library was compiled from (cloops2_b200/_lib.py: source_hash)
+extern "C" const char *cl2_version(void) { return "cl2-b200 0.2 sm_100a src:" CL2_SRC_HASH; }
 
 extern "C" int cl2_ctx_create(int device, cl2_ctx **out) {
     if (!out) return CL2_ERR_ARG;
@@ -324,6 +328,16 @@ extern "C" int cl2_points_sweep_hint(cl2_ctx *ctx, cl2_points *pts, int32_t enab
     return CL2_OK;
 }
 
+extern "C" int cl2_points_index_hint(cl2_ctx *ctx, cl2_points *pts, int32_t enable) {
+    if (!ctx || !pts) return CL2_ERR_ARG;
+    pts->want_xorder = enable ? 1 : 0;
+    if (!enable) {
+        cudaSetDevice(ctx->device);
+        cl2_points_drop_xorder(ctx, pts);
+    }
+    return CL2_OK;
+}
+
 int g_cl2_sync_mode = 0;
 extern "C" void cl2_set_sync_mode(int32_t mode) { g_cl2_sync_mode = (mode == 1 || mode == 2) ? mode : 0; }
 
@@ -336,6 +350,14 @@ extern "C" void cl2_points_drop_cache(cl2_ctx *ctx, cl2_points *pts) {
     cl2_dev_free(ctx, pts->rowy);
     pts->byy = nullptr;
     pts->rowy = nullptr;
+    cl2_points_drop_xorder(ctx, pts);
+}
+
+void cl2_points_drop_xorder(cl2_ctx *ctx, cl2_points *pts) {
+    cl2_dev_free(ctx, pts->byx);
+    cl2_dev_free(ctx, pts->xorder_bad);
+    pts->byx = nullptr;
+    pts->xorder_bad = nullptr;
 }
 
 extern "C" void cl2_points_free(cl2_ctx *ctx, cl2_points *pts) {
@@ -345,6 +367,7 @@ extern "C" void cl2_points_free(cl2_ctx *ctx, cl2_points *pts) {
     cl2_subsets_free(ctx, pts);
     cl2_dev_free(ctx, pts->byy);
     cl2_dev_free(ctx, pts->rowy);
+    cl2_points_drop_xorder(ctx, pts);
     cl2_dev_free(ctx, pts->xy);
     delete pts;
 }

@@ -29,6 +29,42 @@ __global__ void __launch_bounds__(256) k_gather_xy(const int2 *__restrict__ xy, 
     if (i < n) sxy[i] = __ldg(&xy[row[i]]);
 }
 
+// ------------------------------------------------------------------------------------------------ x-order from the grid
+// The rows of a blockDBSCAN grid are stored column by column (column = (x - minX) / eps, ascending), so the x-order of
+// all points -- the first array of the XY index, ds.py:147 -- is the grid order with every column sorted by x.  One
+// thread per point ranks it inside its column by walking to both ends of the column:
+//     rank = #{earlier rows of the column with x' <= x} + #{later rows with x' < x}
+// (stable: equal x keep the grid's y order).  Columns of sparse data hold tens of rows and neighbouring threads walk
+// the same rows, so this is one read and one write of the coordinates instead of a 4-pass radix sort plus a gather.
+// A walk longer than XORDER_WALK_MAX gives up and raises *bad; cl2_index_build then sorts by radix.
+#define XORDER_WALK_MAX 4096
+#define XORDER_AVG_MAX 64      // attempted only when the average column holds at most this many rows
+__global__ void __launch_bounds__(256) k_xorder_from_grid(const int2 *__restrict__ sxy, int64_t n, int minx, unsigned eps,
+                                                           int2 *__restrict__ out, int32_t *__restrict__ bad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (*(volatile int32_t *)bad) return;                    // the result is void already
+    const int2 p = sxy[i];
+    const unsigned rel = (unsigned)(p.x - minx);
+    const int lo = minx + (int)(rel - rel % eps);            // smallest x of the column; the column is [lo, lo + eps)
+    int before = 0;
+    int64_t j = i - 1;
+    for (; j >= 0; j--) {
+        const int qx = sxy[j].x;
+        if ((unsigned)(qx - lo) >= eps) break;
+        if (i - j > XORDER_WALK_MAX) { atomicExch(bad, 1); return; }
+        before += qx <= p.x ? 1 : 0;
+    }
+    const int64_t start = j + 1;                             // first row of the column
+    for (j = i + 1; j < n; j++) {
+        const int qx = sxy[j].x;
+        if ((unsigned)(qx - lo) >= eps) break;
+        if (j - i > XORDER_WALK_MAX) { atomicExch(bad, 1); return; }
+        before += qx < p.x ? 1 : 0;
+    }
+    out[start + before] = p;
+}
+
 // ------------------------------------------------------------------------------------------------ K4 cells
 // Cells are the runs of equal packed key in the sorted order; the key is recomputed from the sorted coordinates.
 __global__ void __launch_bounds__(256) k_head_flags(const int2 *__restrict__ sxy, const cl2_keygen gen,
@@ -718,6 +754,18 @@ int cl2_grid_build(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int kind, int32_t
     {
         FamTimer t(ctx, FAM_GATHER, 20.0 * (double)n);
         k_gather_xy<<<cl2_grid(n, 256), 256, 0, ctx->stream>>>(pts->xy, g.row, g.sxy, n);
+    }
+    // an index build was announced (cl2_points_index_hint, cl2_call_loops): leave the x-order behind while the grid
+    // order of every row is at hand.  CL2_XGRID=0 switches this off (the index then sorts by radix as before).
+    static const bool xgrid_on = !(getenv("CL2_XGRID") && atoi(getenv("CL2_XGRID")) == 0);
+    if (kind == 0 && !use_sub && pts->want_xorder && !pts->byx && xgrid_on && n == pts->n &&
+        (uint64_t)n <= (uint64_t)XORDER_AVG_MAX * (gxmax + 1)) {
+        CL2_TRY(cl2_dev_alloc(ctx, &pts->byx, (size_t)n));
+        CL2_TRY(cl2_dev_alloc(ctx, &pts->xorder_bad, 1));
+        CL2_CUDA(ctx, cudaMemsetAsync(pts->xorder_bad, 0, 4, ctx->stream));
+        FamTimer t(ctx, FAM_INDEX, 16.0 * (double)n);
+        k_xorder_from_grid<<<cl2_grid(n, 256), 256, 0, ctx->stream>>>(g.sxy, n, (int)pts->ext[0], e32, pts->byx,
+                                                                     pts->xorder_bad);
     }
     int64_t *d_total;
     CL2_TRY(sc.get(&d_total, 1));

@@ -93,21 +93,32 @@ extern "C" int cl2_index_build(cl2_ctx *ctx, cl2_points *pts, cl2_index **out) {
         uint32_t *v0 = nullptr, *v1 = nullptr, *vs;
         do {
             if ((rc = cl2_points_yorder(ctx, pts))) break;
-            if ((rc = sc.get(&k0, (size_t)n)) || (rc = sc.get(&k1, (size_t)n)) || (rc = sc.get(&v0, (size_t)n)) ||
-                (rc = sc.get(&v1, (size_t)n)))
-                break;
-            if ((rc = cl2_dev_alloc(ctx, &ix->byx, (size_t)n)) || (rc = cl2_dev_alloc(ctx, &ix->byy, (size_t)n))) break;
+            // the x-order a clustering run left behind (cl2_block.cu: k_xorder_from_grid), unless a column was too long
+            if (pts->byx) {
+                int32_t bad = 1;
+                if ((rc = cl2_read_i32(ctx, pts->xorder_bad, &bad))) break;
+                if (bad == 0) {
+                    ix->byx = pts->byx;
+                    pts->byx = nullptr;
+                }
+                cl2_points_drop_xorder(ctx, pts);
+            }
+            if ((rc = cl2_dev_alloc(ctx, &ix->byy, (size_t)n))) break;
             // the index owns a copy of the y-order so it may outlive the points object
             if (cudaMemcpyAsync(ix->byy, pts->byy, (size_t)n * sizeof(int2), cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) {
                 rc = cl2_fail(ctx, CL2_ERR_CUDA, "cl2_index_build: copy failed");
                 break;
             }
-            cl2_keygen gen;
-            gen.kind = CL2_KEY_X;
-            gen.xy = pts->xy;
-            rc = cl2_radix_sort_gen(ctx, gen, k0, k1, v0, v1, n, bits_for((uint64_t)pts->ext[1]), &ks, &vs);
-            if (rc) break;
-            {
+            if (!ix->byx) {
+                if ((rc = sc.get(&k0, (size_t)n)) || (rc = sc.get(&k1, (size_t)n)) || (rc = sc.get(&v0, (size_t)n)) ||
+                    (rc = sc.get(&v1, (size_t)n)))
+                    break;
+                if ((rc = cl2_dev_alloc(ctx, &ix->byx, (size_t)n))) break;
+                cl2_keygen gen;
+                gen.kind = CL2_KEY_X;
+                gen.xy = pts->xy;
+                rc = cl2_radix_sort_gen(ctx, gen, k0, k1, v0, v1, n, bits_for((uint64_t)pts->ext[1]), &ks, &vs);
+                if (rc) break;
                 FamTimer t(ctx, FAM_INDEX, 20.0 * (double)n);
                 k_index_gather<<<cl2_grid(n, 256), 256, 0, ctx->stream>>>(pts->xy, vs, ix->byx, n, 0);
             }

@@ -282,8 +282,10 @@ extern "C" int cl2_call_loops(cl2_ctx *ctx, cl2_points *pts, int32_t mode, int32
     if (pts->n == 0 || npass == 0) return CL2_OK;
     CL2_CUDA(ctx, cudaSetDevice(ctx->device));
     cl2_cand_sink sink;
+    pts->want_xorder = 1;              // the first blockDBSCAN grid over every row also leaves the x-order for the index
     const int rc = call_loops_body(ctx, pts, mode, hic, npass, eps, minPts, cut, min_pts_test, win, countDiffCut, pseudo,
                                    peakPcut, want_unique, r, sink);
+    pts->want_xorder = 0;
     cl2_sink_free(ctx, &sink);
     return rc;
 }

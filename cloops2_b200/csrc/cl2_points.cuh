@@ -44,6 +44,13 @@ struct cl2_points {
     // sort of the y-sorted rows by column index alone yields (column, row-of-grid) order in 3 passes instead of 5-6)
     int2 *byy = nullptr;        // [n] (y, x) sorted by y
     uint32_t *rowy = nullptr;   // [n] file row of y-sorted position
+    // x-order of the points derived from a blockDBSCAN grid over every row (cl2_block.cu: the grid's columns are x
+    // intervals in ascending order, so sorting each column locally by x yields the global order -- one pass instead of
+    // a radix sort).  Built only when the caller announced an index build (want_xorder); cl2_index_build takes it over
+    // if xorder_bad (device flag: some column was too long for the local sort) stayed 0.
+    int2 *byx = nullptr;        // [n] (x, y) sorted by x
+    int32_t *xorder_bad = nullptr;
+    int want_xorder = 0;
     cl2_grid_cache grid;
     std::vector<cl2_subset> subs;   // nested subsets, subs[k+1] derived from subs[k]; only kept when sweep_hint is set
     int sweep_hint = 0;         // cl2_points_sweep_hint: 0 off, 1 remember rows and use them, 2 use only
@@ -98,6 +105,7 @@ void cl2_subsets_free(cl2_ctx *ctx, cl2_points *pts, size_t keep_levels = 0);
 // minPts >= 0 allows a grid over the smallest pts->subs[] entry valid for (eps, minPts); -1 asks for every point.
 int cl2_grid_build(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int kind, int32_t minPts = -1);
 int cl2_points_yorder(cl2_ctx *ctx, cl2_points *pts);   // cl2_count.cu
+void cl2_points_drop_xorder(cl2_ctx *ctx, cl2_points *pts);   // cl2_api.cu
 int cl2_block_dbscan_impl(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int32_t minPts, int32_t *labels_out,
                           int32_t *n_clusters, bool ordered, cl2_cand_sink *sink = nullptr);    // cl2_block.cu
 int cl2_cdbscan2_impl(cl2_ctx *ctx, cl2_points *pts, int64_t eps, int32_t minPts, int32_t *labels_out,

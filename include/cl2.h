@@ -72,6 +72,12 @@ void cl2_points_drop_cache(cl2_ctx *ctx, cl2_points *pts);
  * remembered rows.  enable = 2 keeps using what is remembered without remembering more (the runs at the smallest eps
  * of a sweep).  Results are identical with and without the hint; 0 disables it and frees the remembered rows. */
 int cl2_points_sweep_hint(cl2_ctx *ctx, cl2_points *pts, int32_t enable);
+/* Announce (enable != 0) that a cl2_index_build follows the next cl2_block_dbscan runs on `pts`, as estLoopSig
+ * follows the clustering runs of a file (callCisLoops.py:561-572 after :541-551).  The first run whose grid holds
+ * every row then also leaves the x-order of the points behind (the grid's columns are x intervals, so sorting each
+ * column locally by x gives ds.py:147's `xs`), and cl2_index_build takes it over instead of sorting again.  The index
+ * is the same either way; cl2_call_loops does this by itself. */
+int cl2_points_index_hint(cl2_ctx *ctx, cl2_points *pts, int32_t enable);
 /* Rows of `pts` without exact duplicates, ascending by (X, Y) -- the de-duplication of `cLoops2 pre` (getUniqueTxt,
  * cLoops2/io.py:40-52, which keeps a Python set of the text rows of one chromosome pair).  xy_out: int64[n,2] host
  * buffer with n = cl2_points_count(pts); *n_out rows are written. */

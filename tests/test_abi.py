@@ -25,7 +25,9 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_lib.SO_PATH)
     for name in declared_symbols():
         assert hasattr(lib, name), name
-    assert b"sm_100a" in ctypes.cast(_lib.load().cl2_version(), ctypes.c_char_p).value
+    version = ctypes.cast(_lib.load().cl2_version(), ctypes.c_char_p).value
+    assert b"sm_100a" in version
+    assert ("src:" + _lib.source_hash()).encode() in version      # the shipped library was compiled from these sources
 
 
 def test_context_creation_fails_loudly_without_gpu():

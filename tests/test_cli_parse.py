@@ -32,7 +32,8 @@ def test_pre_and_quant_flag_surface():
     assert (q.cmd, q.predir, q.loops, q.fnOut, q.offp) == ("quant", "D", "L.txt", "Q", True)
 
 
-def test_pre_refuses_missing_input_and_non_empty_output(tmp_path):
+def test_pre_refuses_missing_input_and_non_empty_output(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)                # the CLI appends to ./cLoops2.log like the reference: keep it out of the checkout
     out = tmp_path / "out"
     out.mkdir()
     (out / "something").write_text("x")

@@ -42,6 +42,51 @@ def test_counts_match_oracle(gpu_ctx, mode):
         assert np.array_equal(g, w), name
 
 
+@pytest.mark.parametrize("case", ["cis", "trans", "hot_column", "dense"])
+def test_counts_with_x_order_left_by_the_grid(gpu_ctx, case):
+    """cl2_points_index_hint: the blockDBSCAN run before the index build leaves the x-order (columns of the grid sorted
+    locally); the counts must be those of the oracle whether the local sort applies (cis, trans), gives up on a column
+    longer than its walk limit (hot_column -> radix sort) or is not attempted at all (dense: > 64 rows per column)."""
+    rng = np.random.default_rng(23)
+    mode, eps = 0, 1000
+    if case == "cis":
+        xy = synth.cis_chrom(3_000_000, 80_000, 3, "hitrac")
+    elif case == "trans":
+        xy, mode, eps = synth.trans_pair(2_000_000, 2_500_000, 60_000, 4, per=1500), 1, 5000
+    elif case == "hot_column":
+        x = rng.integers(0, 10_000_000, size=200_000)
+        hx = rng.integers(5_000_000, 5_000_500, size=6000)
+        x = np.concatenate([x, hx])
+        xy = np.stack([x, x + rng.integers(100, 2_000_000, size=len(x))], 1).astype(np.int64)
+        xy = xy[rng.permutation(len(xy))]
+    else:
+        x = rng.integers(0, 200_000, size=60_000)
+        xy = np.stack([x, x + rng.integers(100, 100_000, size=len(x))], 1).astype(np.int64)
+    cands = _cands(xy, rng, 300)
+    pts = _lib.Points(gpu_ctx, xy)
+    try:
+        pts.index_hint(True)
+        pts.block_dbscan(eps, 5, want_labels=False)
+        idx = _lib.Index(pts)
+        try:
+            got = idx.loop_counts(cands, win=5, mode=mode)
+        finally:
+            idx.close()
+        # a second index on the same points (nothing left behind now) must agree with the first
+        pts.index_hint(False)
+        idx = _lib.Index(pts)
+        try:
+            again = idx.loop_counts(cands, win=5, mode=mode)
+        finally:
+            idx.close()
+    finally:
+        pts.close()
+    want = oracle.XYIndex(xy).loop_counts(cands, win=5, mode=mode)
+    for name, g, a, w in zip(("core", "na", "nb", "nab", "anchors"), got, again, want):
+        assert np.array_equal(g, w), name
+        assert np.array_equal(a, w), name
+
+
 def test_counts_other_window_sizes_and_partial_outputs(gpu_ctx):
     rng = np.random.default_rng(5)
     xy = synth.cis_chrom(1_000_000, 30_000, 6, "hitrac")
