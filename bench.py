@@ -72,6 +72,9 @@ def parse_args():
     ap.add_argument("--no-kernel-timing", action="store_true", help="skip the instrumented single-stream pass")
     ap.add_argument("--no-exact", action="store_true", help="skip the e2e_exact_scipy leg")
     ap.add_argument("--no-files", action="store_true", help="skip the e2e_files leg")
+    ap.add_argument("--host-cores", type=int, default=0,
+                    help="confine the process to this many host cores once the workload is generated (emulates the "
+                         "per-rank share of a multi-GPU node, e.g. 4 = 8 ranks on 32 cores); 0 = leave the affinity alone")
     return ap.parse_args()
 
 
@@ -330,6 +333,10 @@ def main():
     t0 = time.time()
     files = generate(my_jobs, cores)              # fork happens before CUDA / NCCL initialisation
     gen_s = time.time() - t0
+    if args.host_cores > 0 and world == 1:
+        avail = sorted(os.sched_getaffinity(0))
+        os.sched_setaffinity(0, avail[:max(1, min(args.host_cores, len(avail)))])
+        host_cores = len(os.sched_getaffinity(0))
     kind = cfg["kind"]
     eps, minPts, hic = sorted(cfg["eps"]), sorted(cfg["minPts"], reverse=True), cfg["hic"]     # cLoops2.py:69-70, 83-84
 
@@ -577,7 +584,7 @@ def main():
         "kernels": kernels,
         "kernels_note": "per-kernel-family CUDA-event times of one resident step run on a single stream (see bench.py)",
         "stage_wall_ms_per_step": counters.get("stats_host_ms"),
-        "host_threads": len(ctxs), "host_cores": host_cores,
+        "host_threads": len(ctxs), "host_cores": host_cores, "host_sync_mode": shard._sync_mode[0],
         "job": {"pets": job_tot, "candidates": int(stats[1]), "tested": int(stats[2]), "loops": int(stats[3]),
                 "device_event_ms_per_step": dev_ms / args.steps, "generate_s": gen_s},
     }

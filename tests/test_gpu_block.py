@@ -68,6 +68,19 @@ def test_synthetic_chromosomes(gpu_ctx, profile, n, length, eps, minPts):
     assert np.array_equal(bbox, wb) and np.array_equal(size, ws)
 
 
+def test_dense_5m_labels(gpu_ctx):
+    """5 M Hi-C-like PETs at the density of BASELINE configs[2] (324 k PETs/Mb; eps 5000 / 10000, minPts 20 / 50): cells
+    of thousands of points, the heavy-pair tiers of the adjacency kernel, a diagonal component holding most cells.
+    Labels (numbering included) and boxes identical to the oracle."""
+    xy = synth.cis_chrom(15_432_098, 5_000_000, 33, "hic")
+    for eps, minPts in ((5000, 20), (10000, 50)):
+        want, wn = oracle.block_dbscan(xy, eps, minPts)
+        lab, ncl, bbox, size = gpu_block(gpu_ctx, xy, eps, minPts)
+        assert ncl == wn and np.array_equal(lab, want), (eps, minPts)
+        wb, ws = oracle.cluster_bbox(xy, want, wn)
+        assert np.array_equal(bbox, wb) and np.array_equal(size, ws), (eps, minPts)
+
+
 def test_minpts_sweep_reuses_grid(gpu_ctx):
     """eps-major sweep: the cached grid of one eps must give the same labels as a fresh build."""
     xy = synth.cis_chrom(10_000_000, 120_000, 77, "hitrac")

@@ -55,6 +55,17 @@ def test_synthetic_chromosomes(gpu_ctx, profile, n, length, eps, minPts):
     assert np.array_equal(bbox, wb) and np.array_equal(size, ws)
 
 
+def test_dense_5m_labels(gpu_ctx):
+    """-hic on 5 M Hi-C-like PETs at the density of BASELINE configs[2] (324 k PETs/Mb), eps 5000, minPts 20: crowded
+    cells (core counting with early exit, heavy cell pairs, border release rounds).  Labels identical to the oracle."""
+    xy = synth.cis_chrom(15_432_098, 5_000_000, 33, "hic")
+    want, wn = oracle.cdbscan2(xy, 5000, 20)
+    lab, ncl, bbox, size = gpu_c2(gpu_ctx, xy, 5000, 20)
+    assert ncl == wn and np.array_equal(lab, want)
+    wb, ws = oracle.cluster_bbox(xy, want, wn)
+    assert np.array_equal(bbox, wb) and np.array_equal(size, ws)
+
+
 def test_hic_golden_rows(gpu_ctx):
     g, files = golden_cis_files()
     loops = []
