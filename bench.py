@@ -72,6 +72,9 @@ def parse_args():
     ap.add_argument("--no-kernel-timing", action="store_true", help="skip the instrumented single-stream pass")
     ap.add_argument("--no-exact", action="store_true", help="skip the e2e_exact_scipy leg")
     ap.add_argument("--no-files", action="store_true", help="skip the e2e_files leg")
+    ap.add_argument("--extra-sync-modes", default="",
+                    help="comma list of wait modes (0 spin, 1 sleep, 2 poll + yield) to time the resident arm with once "
+                         "more each, after the default one (reported as sync_modes_ms_per_step)")
     ap.add_argument("--host-cores", type=int, default=0,
                     help="confine the process to this many host cores once the workload is generated (emulates the "
                          "per-rank share of a multi-GPU node, e.g. 4 = 8 ranks on 32 cores); 0 = leave the affinity alone")
@@ -456,6 +459,14 @@ def main():
     steps_ms, cpu_ms = timed.last_step_ms, timed.last_cpu_ms
     wall_e, _, clocks_e, _, xfer = timed(step_e2e, args.warmup, args.steps)
     steps_ms_e, cpu_ms_e = timed.last_step_ms, timed.last_cpu_ms
+    sync_ab = {}
+    for m in [int(v) for v in args.extra_sync_modes.split(",") if v.strip() != ""]:
+        prev = shard.set_sync_mode(m)
+        try:
+            w = timed(step_resident, 1, args.steps)[0]
+            sync_ab[str(m)] = {"ms_per_step": round(1e3 * w / args.steps, 2), "host_cpu_ms_per_step": timed.last_cpu_ms}
+        finally:
+            shard.set_sync_mode(prev)
 
     # parity of the benched configuration itself: the oracle's loops for the cpu_baseline sample vs the GPU arm's loops
     # for the same files (the oracle ran them as a job of their own, so the GPU arm repeats them with that job's total)
@@ -585,6 +596,7 @@ def main():
         "kernels_note": "per-kernel-family CUDA-event times of one resident step run on a single stream (see bench.py)",
         "stage_wall_ms_per_step": counters.get("stats_host_ms"),
         "host_threads": len(ctxs), "host_cores": host_cores, "host_sync_mode": shard._sync_mode[0],
+        "sync_modes_ms_per_step": sync_ab or None,
         "job": {"pets": job_tot, "candidates": int(stats[1]), "tested": int(stats[2]), "loops": int(stats[3]),
                 "device_event_ms_per_step": dev_ms / args.steps, "generate_s": gen_s},
     }

@@ -25,6 +25,8 @@ extern "C" int cl2_ctx_create(int device, cl2_ctx **out) {
     }
     const char *np = getenv("CL2_NO_POOL");
     ctx->no_pool = (np && np[0] == '1') ? 1 : 0;
+    const char *ar = getenv("CL2_ARENA");
+    ctx->use_arena = (ar && ar[0] == '0') ? 0 : 1;
     cudaDeviceGetDefaultMemPool(&ctx->pool, device);
     if (ctx->pool) {
         uint64_t thr = UINT64_MAX;  // keep freed scratch in the pool: steady-state calls never reach the driver allocator
@@ -72,6 +74,8 @@ extern "C" void cl2_ctx_destroy(cl2_ctx *ctx) {
         cudaEventDestroy(p.b);
     }
     for (auto e : ctx->evpool) cudaEventDestroy(e);
+    cl2_arena_release(ctx);
+    cudaStreamSynchronize(ctx->stream);
     if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
     cudaStreamDestroy(ctx->stream);
     delete ctx;

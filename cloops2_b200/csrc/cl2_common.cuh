@@ -38,6 +38,7 @@ inline cudaError_t cl2_sync_stream(cudaStream_t s) {
 #include <string.h>
 #include <vector>
 #include <string>
+#include <map>
 #include "../../include/cl2.h"
 
 #define CL2_NFAM 32
@@ -75,6 +76,47 @@ struct cl2_evpair {
     int fam;
 };
 
+// Scope-bound scratch of one context comes from an arena kept by the context instead of one cudaMallocAsync /
+// cudaFreeAsync pair per buffer: a clustering run asks for ~35 short-lived arrays, and with several worker threads
+// driving one device the runtime calls -- not the kernels -- are what a rank with few host cores runs out of.  All work
+// of a context is ordered on its one stream, so a block handed back by a scope may be handed out again at once (the
+// same guarantee the stream-ordered pool gives).  Blocks are carved first-fit from chunks taken from that pool; requests
+// above CL2_ARENA_MAX_REQ, and everything when CL2_ARENA=0 or CL2_NO_POOL=1, go to the pool / cudaMalloc directly.
+#define CL2_ARENA_ALIGN ((size_t)512)
+#define CL2_ARENA_MAX_REQ ((size_t)128 << 20)
+#define CL2_ARENA_CHUNK ((size_t)256 << 20)
+struct cl2_arena {
+    std::map<char *, size_t> free_blocks;      // address -> bytes, neighbours coalesced
+    std::vector<void *> chunks;
+    size_t held = 0;
+    void put(char *p, size_t bytes) {
+        auto nx = free_blocks.lower_bound(p);
+        if (nx != free_blocks.end() && p + bytes == nx->first) {
+            bytes += nx->second;
+            nx = free_blocks.erase(nx);
+        }
+        if (nx != free_blocks.begin()) {
+            auto pv = std::prev(nx);
+            if (pv->first + pv->second == p) {
+                pv->second += bytes;
+                return;
+            }
+        }
+        free_blocks.emplace(p, bytes);
+    }
+    char *take(size_t bytes) {
+        for (auto it = free_blocks.begin(); it != free_blocks.end(); ++it) {
+            if (it->second < bytes) continue;
+            char *p = it->first;
+            const size_t rest = it->second - bytes;
+            free_blocks.erase(it);
+            if (rest) free_blocks.emplace(p + bytes, rest);
+            return p;
+        }
+        return nullptr;
+    }
+};
+
 struct cl2_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -93,7 +135,36 @@ struct cl2_ctx {
     int no_pool = 0;            // CL2_NO_POOL=1: plain cudaMalloc/cudaFree (used when profiling under ncu)
     void *h_scratch = nullptr;  // small pinned buffer for scalar read-backs
     double pvalue_margin = 0.0; // cl2_set_pvalue_margin
+    cl2_arena arena;
+    int use_arena = 1;          // CL2_ARENA=0: every scratch buffer straight from the pool
 };
+
+// a block of the context's arena (null: none to be had -- the caller then asks the pool)
+inline void *cl2_arena_alloc(cl2_ctx *ctx, size_t bytes) {
+    bytes = (bytes + CL2_ARENA_ALIGN - 1) / CL2_ARENA_ALIGN * CL2_ARENA_ALIGN;
+    char *p = ctx->arena.take(bytes);
+    if (p) return p;
+    const size_t chunk = bytes > CL2_ARENA_CHUNK ? bytes : CL2_ARENA_CHUNK;
+    void *c = nullptr;
+    if (cudaMallocAsync(&c, chunk, ctx->stream) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    ctx->arena.chunks.push_back(c);
+    ctx->arena.held += chunk;
+    ctx->arena.put((char *)c, chunk);
+    return ctx->arena.take(bytes);
+}
+inline void cl2_arena_free(cl2_ctx *ctx, void *p, size_t bytes) {
+    bytes = (bytes + CL2_ARENA_ALIGN - 1) / CL2_ARENA_ALIGN * CL2_ARENA_ALIGN;
+    ctx->arena.put((char *)p, bytes);
+}
+inline void cl2_arena_release(cl2_ctx *ctx) {          // context teardown
+    for (void *c : ctx->arena.chunks) cudaFreeAsync(c, ctx->stream);
+    ctx->arena.chunks.clear();
+    ctx->arena.free_blocks.clear();
+    ctx->arena.held = 0;
+}
 
 inline int cl2_fail(cl2_ctx *ctx, int code, const char *fmt, const char *a = "", const char *b = "") {
     if (ctx) snprintf(ctx->err, sizeof(ctx->err), fmt, a, b);
@@ -116,13 +187,17 @@ inline int cl2_fail(cl2_ctx *ctx, int code, const char *fmt, const char *a = "",
         if (rc_ != CL2_OK) return rc_; \
     } while (0)
 
-// Stream-ordered scratch allocations released when the scope ends (cudaMallocAsync on the context's pool; the pool
+// Scratch allocations released when the scope ends: blocks of the context's arena (no runtime call), or -- large
+// requests, get_pool(), CL2_ARENA=0 -- stream-ordered allocations on the context's pool (cudaMallocAsync; the pool
 // keeps freed blocks, so steady-state calls do not touch the driver allocator).
 struct Scratch {
     cl2_ctx *ctx;
-    std::vector<void *> ptrs;
+    std::vector<void *> ptrs;                          // pool allocations
+    struct Blk { void *p; size_t bytes; };
+    std::vector<Blk> blks;                             // arena blocks
     explicit Scratch(cl2_ctx *c) : ctx(c) {}
     ~Scratch() {
+        for (const Blk &b : blks) cl2_arena_free(ctx, b.p, b.bytes);
         if (ctx->no_pool && !ptrs.empty()) cudaStreamSynchronize(ctx->stream);
         for (void *p : ptrs) {
             if (ctx->no_pool) cudaFree(p); else cudaFreeAsync(p, ctx->stream);
@@ -130,6 +205,20 @@ struct Scratch {
     }
     template <typename T>
     int get(T **out, size_t count) {
+        const size_t bytes = (count ? count : 1) * sizeof(T);
+        if (ctx->use_arena && !ctx->no_pool && bytes <= CL2_ARENA_MAX_REQ) {
+            void *p = cl2_arena_alloc(ctx, bytes);
+            if (p) {
+                blks.push_back({p, bytes});
+                *out = (T *)p;
+                return CL2_OK;
+            }
+        }
+        return get_pool(out, count);
+    }
+    // always a pool allocation: buffers whose ownership may be handed on with release()
+    template <typename T>
+    int get_pool(T **out, size_t count) {
         void *p = nullptr;
         size_t bytes = (count ? count : 1) * sizeof(T);
         cudaError_t e = ctx->no_pool ? cudaMalloc(&p, bytes) : cudaMallocAsync(&p, bytes, ctx->stream);
@@ -142,7 +231,7 @@ struct Scratch {
         *out = (T *)p;
         return CL2_OK;
     }
-    // hand ownership to the caller (long-lived buffers)
+    // hand ownership to the caller (long-lived buffers; must come from get_pool)
     void release(void *p) {
         for (size_t i = 0; i < ptrs.size(); i++)
             if (ptrs[i] == p) {

@@ -59,8 +59,8 @@ int cl2_points_yorder(cl2_ctx *ctx, cl2_points *pts) {
     uint32_t *v0, *v1, *vs;
     CL2_TRY(sc.get(&k0, (size_t)n));
     CL2_TRY(sc.get(&k1, (size_t)n));
-    CL2_TRY(sc.get(&v0, (size_t)n));
-    CL2_TRY(sc.get(&v1, (size_t)n));
+    CL2_TRY(sc.get_pool(&v0, (size_t)n));           // one of the two is kept as pts->rowy
+    CL2_TRY(sc.get_pool(&v1, (size_t)n));
     cl2_keygen gen;
     gen.kind = CL2_KEY_Y;
     gen.xy = pts->xy;

@@ -205,12 +205,16 @@ def worker_contexts(device=None, nthreads=None):
     CL2_BLOCKING_SYNC=0/1 how they wait."""
     from . import _lib
     share = rank_cores()                                     # host cores this rank can count on
-    # Default: 8 workers that spin while they wait.  Since the per-file loop runs on the native side of the ABI
-    # (cl2_call_loops) the workers hold no interpreter lock while they wait, and measured on one B200 per 100M-PET step:
-    # 16 cores 66 ms (7 workers); confined to 4 cores: 8 spinning workers 77 ms, 8 sleeping workers 87 ms -- so the
-    # waits only sleep (cl2_set_sync_mode) below 4 cores per rank, or when the scipy pool of the exact mode needs the
-    # cores.  CL2_THREADS / CL2_BLOCKING_SYNC override either choice.
-    mode = 0 if share >= 8 else 2                            # fewer cores than workers: waiting threads yield the core
+    # Default: 8 workers.  Since the per-file loop runs on the native side of the ABI (cl2_call_loops) the workers hold
+    # no interpreter lock while they wait.  How they wait, measured on one B200 per 100 M-PET step (bench.py
+    # --host-cores 4 confines the process like one of 8 ranks on a 32-core node): 16 cores, spinning 61 ms; 4 cores:
+    # polling with a yield 61.5 ms at 218 ms of host CPU per step, sleeping 68 ms at 115 ms.  A lone rank short of cores
+    # therefore polls and yields.  Eight ranks polling together measured 109 ms per step on a 32-core node where one
+    # confined rank measures 61.5, so that loss comes from the ranks competing for the node (64 busy threads on 32
+    # cores); several ranks short of cores therefore sleep, which needs half the CPU time.
+    # CL2_THREADS / CL2_BLOCKING_SYNC override either choice.
+    nlocal = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1)
+    mode = 0 if share >= 8 else (1 if nlocal > 1 else 2)
     if nthreads is None:
         nthreads = int(os.environ.get("CL2_THREADS", "8" if share < 8 else str(max(2, min(8, share - 1)))))
     if os.environ.get("CL2_BLOCKING_SYNC") is not None:
