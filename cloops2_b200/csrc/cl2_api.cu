@@ -77,6 +77,7 @@ extern "C" void cl2_ctx_destroy(cl2_ctx *ctx) {
     cl2_arena_release(ctx);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
+    cl2_sync_forget(ctx->stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -344,6 +345,47 @@ extern "C" int cl2_points_index_hint(cl2_ctx *ctx, cl2_points *pts, int32_t enab
 
 int g_cl2_sync_mode = 0;
 extern "C" void cl2_set_sync_mode(int32_t mode) { g_cl2_sync_mode = (mode == 1 || mode == 2) ? mode : 0; }
+
+// The blocking-sync event of every stream that was ever waited on in mode 1: one per stream for the life of the stream
+// (worker threads come and go with every job; an event per thread would be created again and again).
+#include <mutex>
+#include <unordered_map>
+#undef cudaStreamSynchronize
+static std::mutex g_sync_mu;
+static std::unordered_map<cudaStream_t, cudaEvent_t> g_sync_ev;
+cudaError_t cl2_sync_stream(cudaStream_t s) {
+    if (g_cl2_sync_mode == 0) return cudaStreamSynchronize(s);
+    if (g_cl2_sync_mode == 2) {
+        for (;;) {
+            cudaError_t e = cudaStreamQuery(s);
+            if (e != cudaErrorNotReady) return e;
+            sched_yield();
+        }
+    }
+    cudaEvent_t ev = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_sync_mu);
+        auto it = g_sync_ev.find(s);
+        if (it != g_sync_ev.end()) {
+            ev = it->second;
+        } else {
+            cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+            g_sync_ev.emplace(s, ev);
+        }
+    }
+    cudaError_t e = cudaEventRecord(ev, s);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(ev);
+}
+void cl2_sync_forget(cudaStream_t s) {
+    std::lock_guard<std::mutex> lk(g_sync_mu);
+    auto it = g_sync_ev.find(s);
+    if (it == g_sync_ev.end()) return;
+    cudaEventDestroy(it->second);
+    g_sync_ev.erase(it);
+}
+#define cudaStreamSynchronize(s) cl2_sync_stream(s)
 
 extern "C" void cl2_points_drop_cache(cl2_ctx *ctx, cl2_points *pts) {
     if (!ctx || !pts) return;

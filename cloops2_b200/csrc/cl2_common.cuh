@@ -9,29 +9,8 @@
 // (8 ranks x 8 workers on a 32-core box).
 #include <sched.h>
 extern int g_cl2_sync_mode;
-inline cudaError_t cl2_sync_stream(cudaStream_t s) {
-    if (g_cl2_sync_mode == 0) return cudaStreamSynchronize(s);
-    if (g_cl2_sync_mode == 2) {
-        for (;;) {
-            cudaError_t e = cudaStreamQuery(s);
-            if (e != cudaErrorNotReady) return e;
-            sched_yield();
-        }
-    }
-    thread_local cudaEvent_t ev = nullptr;
-    thread_local int ev_dev = -1;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!ev || ev_dev != dev) {
-        if (ev) cudaEventDestroy(ev);
-        cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming);
-        if (e != cudaSuccess) { ev = nullptr; return e; }
-        ev_dev = dev;
-    }
-    cudaError_t e = cudaEventRecord(ev, s);
-    if (e != cudaSuccess) return e;
-    return cudaEventSynchronize(ev);
-}
+cudaError_t cl2_sync_stream(cudaStream_t s);               // cl2_api.cu
+void cl2_sync_forget(cudaStream_t s);                       // the stream is about to be destroyed
 #define cudaStreamSynchronize(s) cl2_sync_stream(s)
 #include <stdint.h>
 #include <stdio.h>
@@ -39,6 +18,7 @@ inline cudaError_t cl2_sync_stream(cudaStream_t s) {
 #include <vector>
 #include <string>
 #include <map>
+#include <set>
 #include "../../include/cl2.h"
 
 #define CL2_NFAM 32
@@ -86,16 +66,24 @@ struct cl2_evpair {
 #define CL2_ARENA_MAX_REQ ((size_t)128 << 20)
 #define CL2_ARENA_CHUNK ((size_t)256 << 20)
 struct cl2_arena {
-    std::map<char *, size_t> free_blocks;      // address -> bytes, neighbours coalesced
+    std::map<char *, size_t> free_blocks;      // address -> bytes, neighbours inside one chunk coalesced
     std::vector<void *> chunks;
+    std::set<char *> chunk_base;               // a block never spans two chunks: cudaMemsetAsync / cudaMemcpyAsync
+                                               // reject a range that is not inside ONE allocation, adjacent or not
     size_t held = 0;
+    void add_chunk(char *c, size_t bytes) {
+        chunks.push_back(c);
+        chunk_base.insert(c);
+        held += bytes;
+        put(c, bytes);
+    }
     void put(char *p, size_t bytes) {
         auto nx = free_blocks.lower_bound(p);
-        if (nx != free_blocks.end() && p + bytes == nx->first) {
+        if (nx != free_blocks.end() && p + bytes == nx->first && !chunk_base.count(nx->first)) {
             bytes += nx->second;
             nx = free_blocks.erase(nx);
         }
-        if (nx != free_blocks.begin()) {
+        if (nx != free_blocks.begin() && !chunk_base.count(p)) {
             auto pv = std::prev(nx);
             if (pv->first + pv->second == p) {
                 pv->second += bytes;
@@ -150,9 +138,7 @@ inline void *cl2_arena_alloc(cl2_ctx *ctx, size_t bytes) {
         cudaGetLastError();
         return nullptr;
     }
-    ctx->arena.chunks.push_back(c);
-    ctx->arena.held += chunk;
-    ctx->arena.put((char *)c, chunk);
+    ctx->arena.add_chunk((char *)c, chunk);
     return ctx->arena.take(bytes);
 }
 inline void cl2_arena_free(cl2_ctx *ctx, void *p, size_t bytes) {
@@ -162,6 +148,7 @@ inline void cl2_arena_free(cl2_ctx *ctx, void *p, size_t bytes) {
 inline void cl2_arena_release(cl2_ctx *ctx) {          // context teardown
     for (void *c : ctx->arena.chunks) cudaFreeAsync(c, ctx->stream);
     ctx->arena.chunks.clear();
+    ctx->arena.chunk_base.clear();
     ctx->arena.free_blocks.clear();
     ctx->arena.held = 0;
 }
