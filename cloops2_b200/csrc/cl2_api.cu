@@ -27,6 +27,8 @@ extern "C" int cl2_ctx_create(int device, cl2_ctx **out) {
     ctx->no_pool = (np && np[0] == '1') ? 1 : 0;
     const char *ar = getenv("CL2_ARENA");
     ctx->use_arena = (ar && ar[0] == '0') ? 0 : 1;
+    const char *ac = getenv("CL2_ARENA_CHUNK_MB");
+    if (ac && atoi(ac) > 0) ctx->arena.chunk_bytes = (size_t)atoi(ac) << 20;
     cudaDeviceGetDefaultMemPool(&ctx->pool, device);
     if (ctx->pool) {
         uint64_t thr = UINT64_MAX;  // keep freed scratch in the pool: steady-state calls never reach the driver allocator

@@ -71,6 +71,7 @@ struct cl2_arena {
     std::set<char *> chunk_base;               // a block never spans two chunks: cudaMemsetAsync / cudaMemcpyAsync
                                                // reject a range that is not inside ONE allocation, adjacent or not
     size_t held = 0;
+    size_t chunk_bytes = CL2_ARENA_CHUNK;      // CL2_ARENA_CHUNK_MB (tests use small chunks to get many of them)
     void add_chunk(char *c, size_t bytes) {
         chunks.push_back(c);
         chunk_base.insert(c);
@@ -132,7 +133,7 @@ inline void *cl2_arena_alloc(cl2_ctx *ctx, size_t bytes) {
     bytes = (bytes + CL2_ARENA_ALIGN - 1) / CL2_ARENA_ALIGN * CL2_ARENA_ALIGN;
     char *p = ctx->arena.take(bytes);
     if (p) return p;
-    const size_t chunk = bytes > CL2_ARENA_CHUNK ? bytes : CL2_ARENA_CHUNK;
+    const size_t chunk = bytes > ctx->arena.chunk_bytes ? bytes : ctx->arena.chunk_bytes;
     void *c = nullptr;
     if (cudaMallocAsync(&c, chunk, ctx->stream) != cudaSuccess) {
         cudaGetLastError();

@@ -55,6 +55,29 @@ def test_synthetic_chromosomes(gpu_ctx, profile, n, length, eps, minPts):
     assert np.array_equal(bbox, wb) and np.array_equal(size, ws)
 
 
+def test_scratch_arena_with_many_small_chunks(monkeypatch):
+    """A context whose scratch arena grows in 1 MB chunks (CL2_ARENA_CHUNK_MB): dozens of chunks, many of them adjacent
+    in the address space.  A block must stay inside one chunk (the runtime's memset / memcpy reject a range that spans
+    two allocations), so both clusterings and the counting path must run and give the oracle's results."""
+    monkeypatch.setenv("CL2_ARENA_CHUNK_MB", "1")
+    ctx = _lib.Context(0)
+    try:
+        xy = synth.cis_chrom(6_000_000, 600_000, 5, "hic")
+        for eps, minPts in ((5000, 20), (2000, 10)):
+            want, wn = oracle.cdbscan2(xy, eps, minPts)
+            lab, ncl, _, _ = gpu_c2(ctx, xy, eps, minPts)
+            assert ncl == wn and np.array_equal(lab, want), (eps, minPts)
+            pts = _lib.Points(ctx, xy)
+            try:
+                lab, ncl = pts.block_dbscan(eps, minPts)
+            finally:
+                pts.close()
+            want, wn = oracle.block_dbscan(xy, eps, minPts)
+            assert ncl == wn and np.array_equal(lab, want), (eps, minPts)
+    finally:
+        ctx.close()
+
+
 def test_dense_5m_labels(gpu_ctx):
     """-hic on 5 M Hi-C-like PETs at the density of BASELINE configs[2] (324 k PETs/Mb), eps 5000, minPts 20: crowded
     cells (core counting with early exit, heavy cell pairs, border release rounds).  Labels identical to the oracle."""
