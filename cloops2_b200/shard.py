@@ -198,25 +198,30 @@ def barrier():
         dist.barrier()
 
 
+def wait_policy(share):
+    """(worker threads, wait mode) for a rank that can count on `share` host cores.  8 workers that spin while they
+    wait (mode 0) from 4 cores up; below that they sleep (mode 1).  Measured per 100 M-PET step (bench.py
+    --extra-sync-modes; --host-cores 4 confines one rank like one of 8 on a 32-core node):
+        1 GPU, 16 cores           spin 57-59 ms
+        1 GPU, 4 cores            spin 59.1   poll + yield 63.3   sleep 66.2 (102 ms of host CPU per step instead of 210)
+        8 GPUs, 4 cores per rank  spin 58.4   poll + yield 61.4   sleep 67.7
+    (Before scope-bound scratch moved into the context's arena, eight ranks took 109 ms per step whichever way they
+    waited: the ranks' cudaMallocAsync / cudaFreeAsync calls, not their waits, were what the node ran out of.)"""
+    share = max(1, int(share))
+    nthreads = 8 if share < 8 else max(2, min(8, share - 1))
+    return nthreads, (0 if share >= 4 else 1)
+
+
 def worker_contexts(device=None, nthreads=None):
     """One cl2 context (= CUDA stream + scratch) per host worker thread of this rank.  Chromosome files are
     independent units, so a rank processes several at once: while one thread's kernels run, another thread does its
-    host-side bookkeeping (ctypes calls and numpy release the GIL).  CL2_THREADS overrides the number of workers,
-    CL2_BLOCKING_SYNC=0/1 how they wait."""
+    host-side bookkeeping (the per-file loop runs on the native side of the ABI, cl2_call_loops, so the workers hold no
+    interpreter lock while they wait).  CL2_THREADS overrides the number of workers, CL2_BLOCKING_SYNC=0/1/2 how they
+    wait (wait_policy)."""
     from . import _lib
-    share = rank_cores()                                     # host cores this rank can count on
-    # Default: 8 workers.  Since the per-file loop runs on the native side of the ABI (cl2_call_loops) the workers hold
-    # no interpreter lock while they wait.  How they wait, measured on one B200 per 100 M-PET step (bench.py
-    # --host-cores 4 confines the process like one of 8 ranks on a 32-core node): 16 cores, spinning 61 ms; 4 cores:
-    # polling with a yield 61.5 ms at 218 ms of host CPU per step, sleeping 68 ms at 115 ms.  A lone rank short of cores
-    # therefore polls and yields.  Eight ranks polling together measured 109 ms per step on a 32-core node where one
-    # confined rank measures 61.5, so that loss comes from the ranks competing for the node (64 busy threads on 32
-    # cores); several ranks short of cores therefore sleep, which needs half the CPU time.
-    # CL2_THREADS / CL2_BLOCKING_SYNC override either choice.
-    nlocal = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1)
-    mode = 0 if share >= 8 else (1 if nlocal > 1 else 2)
+    dflt_threads, mode = wait_policy(rank_cores())
     if nthreads is None:
-        nthreads = int(os.environ.get("CL2_THREADS", "8" if share < 8 else str(max(2, min(8, share - 1)))))
+        nthreads = int(os.environ.get("CL2_THREADS", str(dflt_threads)))
     if os.environ.get("CL2_BLOCKING_SYNC") is not None:
         mode = int(os.environ["CL2_BLOCKING_SYNC"] or 0)
     set_sync_mode(mode)

@@ -44,6 +44,17 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def test_wait_policy_by_core_share():
+    """Workers and how they wait, by the host cores a rank can count on (shard.wait_policy): 8 spinning workers from 4
+    cores up (16-core single-GPU box, 4 cores per rank on an 8-GPU node), one worker fewer than cores above 8, sleeping
+    waits only for a rank that is truly short of cores."""
+    assert shard.wait_policy(16) == (8, 0)
+    assert shard.wait_policy(8) == (7, 0)
+    assert shard.wait_policy(4) == (8, 0)
+    assert shard.wait_policy(2) == (8, 1)
+    assert shard.wait_policy(0) == (8, 1)
+
+
 def test_two_rank_gloo_roundtrip():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
