@@ -562,14 +562,16 @@ def main():
         top = max(fam.items(), key=lambda kv: kv[1]["ms"])
         nm, v = top
         ach = (v["bytes"] / 1e9) / (v["ms"] / 1e3) if v["ms"] > 0 else 0.0
-        traffic, traffic_note = None, None
+        traffic, traffic_note, traffic_alg = None, None, None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(nm)
             traffic, traffic_note = tj["dram_bytes_per_launch"], tj["note"]
+            traffic_alg = tj.get("capture_algorithmic_bytes")
         except Exception:
             pass
         roof = {"bound": "hbm", "kernel": nm, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
+                "traffic": traffic, "traffic_note": traffic_note, "traffic_capture_algorithmic_bytes": traffic_alg,
+                "peak_source": peak_src,
                 "measured_in": "single-stream instrumented pass of the resident step (kernels_note)",
                 "avg_launch_ms": v["ms"] / max(1, v["launches"]),
                 "algorithmic_bytes_per_launch": v["bytes"] / max(1, v["launches"])}
