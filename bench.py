@@ -588,7 +588,8 @@ def main():
         "e2e_exact_scipy": None if wall_x is None else {
             "value": job_tot / (wall_x / ex_steps), "unit": "PETs/s", "steps": ex_steps,
             "note": "same call in the byte-identical mode: cuts decided with scipy's value wherever the device value is "
-                    "within 1e-5 of a threshold, the final loops' tail probabilities re-evaluated by scipy once per rank"},
+                    "within 1e-5 of a threshold, the final loops' tail probabilities re-evaluated by scipy in the rank's worker "
+                    "processes (hostops.pvalue_pool) while other files are on the GPU"},
         "e2e_files": e2e_files,
         "parity_check": parity,
         "gpu_launches": int(launches),

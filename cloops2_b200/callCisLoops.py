@@ -305,8 +305,10 @@ def callCisLoops(predir, fout, log, eps=[2000, 5000], minPts=[5, 10], cpu=1, cut
     keys = list(meta["data"]["cis"].keys())
     files = {k: meta["data"]["cis"][k]["ixy"] for k in keys}
     mine = shard.assign(keys, [shard.ixy_rows(files[k]) for k in keys], world)[rank]
-    ctxs = shard.worker_contexts()
     ex = "defer" if exact_default() else False
+    if ex:
+        hostops.pvalue_pool()              # the scipy workers start (and import scipy) while the files are loaded
+    ctxs = shard.worker_contexts()
 
     def one(ctx, k):
         return cis_chromosome(ctx, tuple(k.split("-")), shard.load_pinned(ctx, files[k]), tot, eps, minPts, cut=cut, mcut=mcut,

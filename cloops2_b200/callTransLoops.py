@@ -124,8 +124,10 @@ def callTransLoops(predir, fout, logger, eps=[2000, 5000], minPts=[5, 10], cpu=1
     files = {k: meta["data"]["trans"][k]["ixy"] for k in keys}
     rank, world = shard.rank_world()
     mine = shard.assign(keys, [shard.ixy_rows(files[k]) for k in keys], world)[rank]
-    ctxs = shard.worker_contexts()
     ex = "defer" if exact_default() else False
+    if ex:
+        hostops.pvalue_pool()              # the scipy workers start (and import scipy) while the files are loaded
+    ctxs = shard.worker_contexts()
 
     def one(ctx, k):
         return trans_pair(ctx, tuple(k.split("-")), shard.load_pinned(ctx, files[k]), eps, minPts, exact=ex)

@@ -8,9 +8,7 @@ import ctypes
 import os
 
 import numpy as np
-from scipy.stats import hypergeom, binom, poisson
-
-from . import _lib
+from . import _lib, pvalues
 
 
 # ---------------------------------------------------------------------------------------------- candidates
@@ -79,16 +77,8 @@ def cis_distance(c):
 
 
 # ---------------------------------------------------------------------------------------------- statistics
-def _floor300(p):
-    return np.maximum(1e-300, p)
-
-
-def anchor_sig(count, wide, length, rpb):
-    """estAnchorSig (callCisLoops.py:226-247) from the two counts: returns (p, es)."""
-    r = (wide - count) / 5 / 2
-    c = np.maximum(np.maximum(r, rpb * length), 1.0)
-    p = _floor300(poisson.sf(count - 1.0, c))
-    return p, count / c
+_floor300 = pvalues.floor300
+anchor_sig = pvalues.anchor_sig          # estAnchorSig (callCisLoops.py:226-247)
 
 
 def permuted_stats(na, nb, nab, rab, cis=True):
@@ -235,22 +225,38 @@ def est_trans(index, cands, N, span, minPts, pseudo=1, countDiffCut=10, win=5, e
     return cols
 
 
-def _threaded(fn, *arrays):
-    """Evaluate a scipy ufunc-backed function over chunks in host threads (the inner loops release the GIL);
-    hypergeom.sf costs ~25 us per element in scipy 1.18, which is what bounds the exact mode."""
-    n = arrays[0].shape[0]
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except AttributeError:
-        cores = os.cpu_count() or 1
-    nthr = min(cores, max(1, n // 256))
-    if nthr <= 1:
-        return fn(*arrays)
-    from concurrent.futures import ThreadPoolExecutor
-    cuts = np.linspace(0, n, nthr + 1).astype(int)
-    with ThreadPoolExecutor(nthr) as ex:
-        parts = list(ex.map(lambda i: fn(*[a[cuts[i]:cuts[i + 1]] for a in arrays]), range(nthr)))
-    return np.concatenate(parts)
+PV_CHUNK = 256        # rows per task of the p-value pool (hypergeom.sf: 5-40 ms of work each)
+
+
+def _tails_chunks(args, cis, pool=None):
+    """pvalues.tails over row chunks of `args` (a tuple of equally long arrays), as futures of the p-value pool (or,
+    without a pool, as already evaluated results behind the same interface)."""
+    n = args[0].shape[0]
+    out = []
+    for o in range(0, n, PV_CHUNK):
+        part = tuple(np.ascontiguousarray(a[o:o + PV_CHUNK]) for a in args)
+        out.append(pool.submit(pvalues.tails, *part, cis=cis) if pool is not None else _Done(pvalues.tails(*part, cis=cis)))
+    return out, args
+
+
+class _Done:
+    def __init__(self, v):
+        self.v = v
+
+    def result(self):
+        return self.v
+
+
+def _gather_tails(futs, args, cis):
+    """Results of _tails_chunks in row order; a task whose worker process died is evaluated here instead."""
+    parts = []
+    for i, f in enumerate(futs):
+        try:
+            parts.append(f.result())
+        except Exception:
+            o = i * PV_CHUNK
+            parts.append(pvalues.tails(*[a[o:o + PV_CHUNK] for a in args], cis=cis))
+    return np.concatenate(parts, axis=0) if parts else np.zeros((0, 7))
 
 
 def _cols_from_stats(c, core, hyp, st, pseudo, tot):
@@ -267,10 +273,6 @@ def _cols_from_stats(c, core, hyp, st, pseudo, tot):
                 mrabs=mrabs, mbps=st[:, 1], anc=st[:, 9:13])
 
 
-def _scipy_serial(cols, N, rpb, cis):
-    return scipy_pvalues(cols, N, rpb, cis=cis, threads=False)
-
-
 def scipy_pvalues(cols, N, rpb, cis=True, threads=True):
     """Re-evaluate the tail probabilities of (few) surviving loops with scipy, argument for argument as the reference
     calls it (callCisLoops.py:246,310,329,332; callTransLoops.py:153,178,181), so the printed digits are the
@@ -280,69 +282,155 @@ def scipy_pvalues(cols, N, rpb, cis=True, threads=True):
     if n == 0:
         return cols
     out = dict(cols)
-    ra, rb, rab = cols["ra"], cols["rb"], cols["rab"]
     Nv = np.broadcast_to(np.asarray(N, dtype=np.float64), (n,))
     rv = np.broadcast_to(np.asarray(rpb, dtype=np.float64), (n,))
-    c = cols["coords"]
-    anc = cols["anc"]
-
-    def tails(rab, ra, rb, Nv, rv, mrabs, mbps, la, lb, a0, a1, a2, a3):
-        hyp = hypergeom.sf(rab - 1.0, Nv, ra, rb)
-        pop = poisson.sf(rab - 1.0, mrabs)
-        nbp = binom.sf(rab - 1.0, ra * rb - rab if cis else ra * rb, mbps)
-        px, esx = anchor_sig(a0, a1, la, rv)
-        py, esy = anchor_sig(a2, a3, lb, rv)
-        return np.stack([hyp, pop, nbp, px, esx, py, esy], axis=1)
-
-    run = _threaded if threads else (lambda fn, *a: fn(*a))
-    t = run(tails, rab, ra, rb, Nv, rv, cols["mrabs"], cols["mbps"], c[:, 1] - c[:, 0], c[:, 3] - c[:, 2],
-            anc[:, 0].astype(np.int64), anc[:, 1].astype(np.int64), anc[:, 2].astype(np.int64),
-            anc[:, 3].astype(np.int64))
+    args = _tail_args(cols, Nv, rv)
+    pool = pvalue_pool() if (threads and n >= 2 * PV_CHUNK) else None
+    futs, args = _tails_chunks(args, cis, pool)
+    t = _gather_tails(futs, args, cis)
     out["hyp"], out["pop"], out["nbp"] = _clamp(t[:, 0]), _clamp(t[:, 1]), _clamp(t[:, 2])
     out["px"], out["esx"], out["py"], out["esy"] = t[:, 3], t[:, 4], t[:, 5], t[:, 6]
     return out
 
 
+def _tail_args(cols, Nv, rv):
+    c, anc = cols["coords"], cols["anc"]
+    return (cols["rab"], cols["ra"], cols["rb"], Nv, rv, cols["mrabs"], cols["mbps"], c[:, 1] - c[:, 0], c[:, 3] - c[:, 2],
+            anc[:, 0].astype(np.int64), anc[:, 1].astype(np.int64), anc[:, 2].astype(np.int64), anc[:, 3].astype(np.int64))
+
+
 _pv_pool = None
 
 
+class _PvPool:
+    """Worker processes running `python -m cloops2_b200.pvalues --worker`, one feeder thread per process (blocked on
+    the pipes, so the interpreter lock is free while a worker computes).  A task whose worker fails gets an exception
+    (its caller then evaluates the chunk itself, _gather_tails); when no worker is left every task does."""
+
+    def __init__(self, workers):
+        import queue
+        import subprocess
+        import sys
+        import threading
+        self.q = queue.Queue()
+        self.procs = []
+        self.lock = threading.Lock()
+        self.alive = 0
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        env = dict(os.environ)
+        env["PYTHONPATH"] = root + (os.pathsep + env["PYTHONPATH"] if env.get("PYTHONPATH") else "")
+        for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+            env[k] = "1"
+        for _ in range(workers):
+            p = subprocess.Popen([sys.executable, "-m", "cloops2_b200.pvalues", "--worker"], stdin=subprocess.PIPE,
+                                 stdout=subprocess.PIPE, env=env, cwd=root)
+            self.procs.append(p)
+            self.alive += 1
+            threading.Thread(target=self._feed, args=(p,), daemon=True).start()
+        import atexit
+        atexit.register(self.close)
+
+    def _feed(self, p):
+        try:
+            while True:
+                item = self.q.get()
+                if item is None:
+                    return
+                fut, args, cis = item
+                if not fut.set_running_or_notify_cancel():
+                    continue
+                try:
+                    pvalues.send_msg(p.stdin, (args, cis))
+                    ans = pvalues.recv_msg(p.stdout)
+                    if ans is None or ans[0] != "ok":
+                        raise RuntimeError("p-value worker failed: %r" % (ans,))
+                    fut.set_result(ans[1])
+                except Exception as e:
+                    fut.set_exception(e)
+                    if p.poll() is not None or isinstance(e, (OSError, ValueError)):
+                        return                   # the process is gone: its share goes to the other feeders
+        finally:
+            with self.lock:
+                self.alive -= 1
+                last = self.alive <= 0
+            if last:                             # nobody left to serve the queue
+                self._fail_pending()
+
+    def _fail_pending(self):
+        import queue
+        while True:
+            try:
+                item = self.q.get_nowait()
+            except queue.Empty:
+                return
+            if item is not None and item[0].set_running_or_notify_cancel():
+                item[0].set_exception(RuntimeError("no p-value worker left"))
+
+    def submit(self, fn, *args, cis=True):
+        from concurrent.futures import Future
+        assert fn is pvalues.tails
+        fut = Future()
+        with self.lock:
+            dead = self.alive <= 0
+            if not dead:
+                self.q.put((fut, args, cis))
+        if dead:
+            fut.set_exception(RuntimeError("no p-value worker left"))
+        return fut
+
+    def close(self):
+        with self.lock:
+            n = self.alive
+        for _ in range(n):
+            self.q.put(None)
+        for p in self.procs:
+            try:
+                p.stdin.close()
+            except Exception:
+                pass
+        self.procs = []
+
+
 def pvalue_pool():
-    """One pool of host threads per process for the scipy re-evaluation of the exact mode (the ufunc loops release the
-    GIL).  Work is handed to it file by file as soon as a file's final loops are known, so it overlaps the GPU work on
-    the remaining files."""
+    """One pool of worker PROCESSES per rank for the scipy evaluations of the exact mode (pvalues.py: the Boost-backed
+    ufuncs keep the interpreter lock, so threads gain nothing).  The workers are plain child processes -- fresh
+    interpreters with numpy / scipy only, which inherit the rank's core affinity and nothing else.  Work is handed
+    over file by file as soon as a file's final loops are known, so it overlaps the GPU work on the remaining files.
+    CL2_PV_WORKERS overrides the number of workers (0: evaluate in the calling thread)."""
     global _pv_pool
     if _pv_pool is None:
-        from concurrent.futures import ThreadPoolExecutor
         from . import shard
-        _pv_pool = ThreadPoolExecutor(max(2, shard.rank_cores() - 1))
-    return _pv_pool
+        want = os.environ.get("CL2_PV_WORKERS")
+        workers = int(want) if want not in (None, "") else max(2, shard.rank_cores() - 1)
+        try:
+            _pv_pool = _PvPool(workers) if workers > 0 else False
+        except Exception:                          # no child processes to be had: the calling thread does the work
+            _pv_pool = False
+    return _pv_pool or None
 
 
-def submit_pvalues(final, cis=True, chunk=1024):
-    """Queue scipy_pvalues for the rows of `final` (which carries its file's "N" and "rpb"); the futures are stored in
-    final["_pending"] and the columns are replaced by wait_pvalues().  (numpy only releases the GIL for ufunc loops of
-    more than 500 elements, so the chunks must not be small.)"""
+def submit_pvalues(final, cis=True):
+    """Queue the scipy tails of the rows of `final` (which carries its file's "N" and "rpb"); the futures are stored in
+    final["_pending"] and the columns are replaced by wait_pvalues()."""
     n = final["coords"].shape[0]
     if n == 0:
         return final
-    pool = pvalue_pool()
-    names = [k for k in COLS if k in final]
-    futs = []
-    for o in range(0, n, chunk):
-        part = {k: final[k][o:o + chunk] for k in names}
-        futs.append(pool.submit(_scipy_serial, part, final["N"], final["rpb"], cis))
-    final["_pending"] = futs
+    Nv = np.full(n, float(final["N"]))
+    rv = np.full(n, float(final["rpb"]))
+    futs, args = _tails_chunks(_tail_args(final, Nv, rv), cis, pvalue_pool())
+    final["_pending"] = (futs, args, cis)
     return final
 
 
 def wait_pvalues(finals):
     for f in finals:
-        futs = f.pop("_pending", None)
-        if not futs:
+        pend = f.pop("_pending", None)
+        if not pend:
             continue
-        parts = [x.result() for x in futs]
-        for k in ("hyp", "pop", "nbp", "px", "py", "esx", "esy"):
-            f[k] = np.concatenate([q[k] for q in parts])
+        futs, args, cis = pend
+        t = _gather_tails(futs, args, cis)
+        f["hyp"], f["pop"], f["nbp"] = _clamp(t[:, 0]), _clamp(t[:, 1]), _clamp(t[:, 2])
+        f["px"], f["esx"], f["py"], f["esy"] = t[:, 3], t[:, 4], t[:, 5], t[:, 6]
 
 
 def scipy_pvalues_many(finals, cis=True):

@@ -219,3 +219,67 @@ def test_filter_pets_matches_reference_rows_and_order(tmp_path):
         assert np.array_equal(got, g["filter_" + k.replace("-", "_")]), k
         tot += len(got)
     assert tot == int(g["filter_tot"])
+
+
+def _fake_final(rng, n, N, length):
+    """Columns shaped like the final loops of one file (only what the tail probabilities read)."""
+    ra = rng.integers(200, 3000, size=n).astype(np.int64)
+    rb = rng.integers(200, 3000, size=n).astype(np.int64)
+    rab = rng.integers(10, 80, size=n).astype(np.int64)
+    xs = rng.integers(0, length - 200000, size=n)
+    la, lb = rng.integers(300, 2000, size=n), rng.integers(300, 2000, size=n)
+    cols = hostops._empty_cols()
+    cols.update(coords=np.stack([xs, xs + la, xs + 50000, xs + 50000 + lb], 1).astype(np.int64), ra=ra, rb=rb, rab=rab,
+                mrabs=rng.uniform(0.5, 5, size=n), mbps=rng.uniform(1e-7, 1e-5, size=n),
+                anc=np.stack([rng.integers(100, 3000, size=n), rng.integers(500, 9000, size=n),
+                              rng.integers(100, 3000, size=n), rng.integers(500, 9000, size=n)], 1).astype(np.float64))
+    for k in ("P2LL", "FDR", "ES", "density", "hyp", "pop", "nbp", "px", "py", "esx", "esy"):
+        cols[k] = np.zeros(n)
+    cols["N"], cols["rpb"] = N, N / float(length)
+    return cols
+
+
+def test_pvalue_worker_processes_give_scipys_values(monkeypatch):
+    """The exact mode evaluates scipy's tails in worker processes (hostops.pvalue_pool; scipy's Boost ufuncs keep the
+    interpreter lock): same bits as evaluating them inline, for cis and trans, through both entry points, and still
+    when the workers have died (the caller then evaluates the chunks itself)."""
+    from scipy.stats import binom, hypergeom, poisson
+    monkeypatch.setenv("CL2_PV_WORKERS", "3")
+    monkeypatch.setattr(hostops, "_pv_pool", None)
+    rng = np.random.default_rng(5)
+    files = [_fake_final(rng, n, N, 50_000_000) for n, N in ((1300, 8_060_000), (700, 4_400_000), (90, 1_500_000), (0, 1000))]
+    try:
+        for cis in (True, False):
+            want = [hostops.scipy_pvalues(dict(f), f["N"], f["rpb"], cis=cis, threads=False) for f in files]
+            f0 = files[0]                      # spot check of the inline path against scipy called as the reference does
+            assert np.array_equal(want[0]["hyp"], np.maximum(1e-300, hypergeom.sf(f0["rab"] - 1.0, f0["N"], f0["ra"], f0["rb"])))
+            assert np.array_equal(want[0]["pop"], np.maximum(1e-300, poisson.sf(f0["rab"] - 1.0, f0["mrabs"])))
+            nn = f0["ra"] * f0["rb"] - f0["rab"] if cis else f0["ra"] * f0["rb"]
+            assert np.array_equal(want[0]["nbp"], np.maximum(1e-300, binom.sf(f0["rab"] - 1.0, nn, f0["mbps"])))
+            got = [dict(f) for f in files]
+            for f in got:
+                hostops.submit_pvalues(f, cis=cis)
+            hostops.wait_pvalues(got)
+            pooled = hostops.scipy_pvalues(dict(files[0]), files[0]["N"], files[0]["rpb"], cis=cis)
+            for g, w in zip(got + [pooled], want + [want[0]]):
+                for k in ("hyp", "pop", "nbp", "px", "py", "esx", "esy"):
+                    assert np.array_equal(g[k], w[k]), (cis, k)
+        pool = hostops.pvalue_pool()
+        assert pool is not None and pool.alive == 3
+        for p in pool.procs:                   # the workers die: results must not change, nothing may hang
+            p.kill()
+        for p in pool.procs:
+            p.wait()
+        got = [dict(f) for f in files]
+        for f in got:
+            hostops.submit_pvalues(f, cis=True)
+        hostops.wait_pvalues(got)
+        want = [hostops.scipy_pvalues(dict(f), f["N"], f["rpb"], cis=True, threads=False) for f in files]
+        for g, w in zip(got, want):
+            for k in ("hyp", "pop", "nbp", "px", "py", "esx", "esy"):
+                assert np.array_equal(g[k], w[k]), k
+    finally:
+        pool = hostops._pv_pool
+        if pool:
+            pool.close()
+        hostops._pv_pool = None
