@@ -60,3 +60,21 @@ def test_reference_arm_is_time_bounded_and_prints_the_contract_line():
     assert d["steps"] >= 1 and d["warmup"] == 1 and d["value"] > 0
     assert d["config"]["workload"].startswith("BASELINE configs[1]")
     assert dt < 240, "reference arm took %.0f s for a 6 s budget" % dt
+
+
+def test_recorded_bench_line_carries_the_contract_keys():
+    """The last default bench line recorded on a B200 (profiles/) has every key the measurement contract names."""
+    d = json.loads(open(os.path.join(ROOT, "profiles", "r2e_bench_1gpu_c2_final.json")).read().strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["metric"] == bench.METRIC and d["unit"] == "PETs/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["config"]["workload"].startswith("BASELINE configs[1]") and d["data"] == "synthetic" and d["dtype"] == "int32"
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(d["e2e"])
+    assert d["e2e"]["h2d_bytes_per_step"] > 16 * 99e6 and d["e2e"]["d2h_bytes_per_step"] > 0      # copies inside the timed region
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(d["roofline"]) and d["roofline"]["bound"] == "hbm"
+    assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-12
+    assert set(("value", "unit", "cores", "kind", "sample")) <= set(d["cpu_baseline"]) and d["cpu_baseline"]["kind"] == "port"
+    assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(d["clocks"]) and d["gpu_launches"] > 0
+    assert d["parity_check"]["status"] == "equal"
+    assert abs(d["value"] - d["job"]["pets"] / (d["ms_per_step"] / 1e3)) / d["value"] < 1e-9
