@@ -44,6 +44,41 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _filter_worker(rank, world, port, q, predir, fout):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank), CL2_PIN="0")
+    shard.init_from_env(backend="gloo")
+    from cloops2_b200.callCisLoops import callCisLoops
+    res = callCisLoops(predir, fout, None, eps=[200], minPts=[5], filter=True)     # must return before any GPU work
+    stats = shard.allreduce_stats(np.array([1], dtype=np.int64))                     # the ranks are still in step
+    q.put((rank, res, stats.tolist()))
+    import torch.distributed as dist
+    dist.destroy_process_group()
+
+
+def test_filter_early_return_is_taken_by_every_rank(tmp_path):
+    """`-filter` with a non-empty OUT_filtered directory (callCisLoops.py:518-524): only rank 0 looks at the directory,
+    but every rank must return -- a rank that carried on into the collectives of the run would hang the job (and, with
+    -trans, pair them with another phase's).  No GPU is touched on that path, so this runs on the CPU ranks of gloo."""
+    import json
+    predir, fout = str(tmp_path / "pre"), str(tmp_path / "out")
+    os.mkdir(predir)
+    json.dump({"Unique PETs": 10, "data": {"cis": {}, "trans": {}}}, open(predir + "/petMeta.json", "w"))
+    os.mkdir(fout + "_filtered")
+    open(fout + "_filtered/leftover.ixy", "w").write("x")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_filter_worker, args=(r, 2, port, q, predir, fout)) for r in range(2)]
+    for p in ps:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert out == [(0, None, [2]), (1, None, [2])]
+
+
 def test_wait_policy_by_core_share():
     """Workers and how they wait, by the host cores a rank can count on (shard.wait_policy): 8 spinning workers from 4
     cores up (16-core single-GPU box, 4 cores per rank on an 8-GPU node), one worker fewer than cores above 8, sleeping
