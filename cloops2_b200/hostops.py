@@ -322,8 +322,16 @@ class _PvPool:
         for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
             env[k] = "1"
         for _ in range(workers):
-            p = subprocess.Popen([sys.executable, "-m", "cloops2_b200.pvalues", "--worker"], stdin=subprocess.PIPE,
-                                 stdout=subprocess.PIPE, env=env, cwd=root)
+            # the worker's own pair of pipes (tasks down, results up); its stdin / stdout stay out of the protocol
+            task_r, task_w = os.pipe()
+            res_r, res_w = os.pipe()
+            try:
+                p = subprocess.Popen([sys.executable, "-m", "cloops2_b200.pvalues", "--worker", str(task_r), str(res_w)],
+                                     stdin=subprocess.DEVNULL, pass_fds=(task_r, res_w), env=env, cwd=root)
+            finally:
+                os.close(task_r)
+                os.close(res_w)
+            p.cl2_tasks, p.cl2_results = os.fdopen(task_w, "wb"), os.fdopen(res_r, "rb")
             self.procs.append(p)
             self.alive += 1
             threading.Thread(target=self._feed, args=(p,), daemon=True).start()
@@ -340,8 +348,8 @@ class _PvPool:
                 if not fut.set_running_or_notify_cancel():
                     continue
                 try:
-                    pvalues.send_msg(p.stdin, (args, cis))
-                    ans = pvalues.recv_msg(p.stdout)
+                    pvalues.send_msg(p.cl2_tasks, (args, cis))
+                    ans = pvalues.recv_msg(p.cl2_results)
                     if ans is None or ans[0] != "ok":
                         raise RuntimeError("p-value worker failed: %r" % (ans,))
                     fut.set_result(ans[1])
@@ -385,7 +393,7 @@ class _PvPool:
             self.q.put(None)
         for p in self.procs:
             try:
-                p.stdin.close()
+                p.cl2_tasks.close()          # the worker leaves its loop at end of file
             except Exception:
                 pass
         self.procs = []

@@ -34,9 +34,10 @@ def tails(rab, ra, rb, Nv, rv, mrabs, mbps, la, lb, a0, a1, a2, a3, cis=True):
 
 
 # ---------------------------------------------------------------------------------------------- worker process
-# `python -m cloops2_b200.pvalues --worker`: length-prefixed pickles on stdin ((args tuple, cis) per task), the
-# float64[n, 7] result of tails() on stdout, until stdin closes.  Started by hostops.pvalue_pool(); a plain child
-# process (fresh interpreter, numpy + scipy only), so nothing of the parent -- its CUDA context, its threads, its
+# `python -m cloops2_b200.pvalues --worker RFD WFD`: length-prefixed pickles on the inherited pipe RFD ((args tuple,
+# cis) per task), the float64[n, 7] result of tails() on the pipe WFD, until RFD closes.  The pipes are the worker's
+# own (not stdin / stdout, which anything in the interpreter may write to).  Started by hostops.pvalue_pool(); a plain
+# child process (fresh interpreter, numpy + scipy only), so nothing of the parent -- its CUDA context, its threads, its
 # __main__ module -- is inherited or re-imported.
 def _read_exact(f, n):
     buf = b""
@@ -67,10 +68,9 @@ def recv_msg(f):
     return None if data is None else pickle.loads(data)
 
 
-def _worker_main():
-    import sys
-    fin, fout = sys.stdin.buffer, sys.stdout.buffer
-    sys.stdout = sys.stderr                  # nothing but results may reach the pipe
+def _worker_main(rfd, wfd):
+    import os
+    fin, fout = os.fdopen(rfd, "rb"), os.fdopen(wfd, "wb")
     while True:
         task = recv_msg(fin)
         if task is None:
@@ -84,5 +84,5 @@ def _worker_main():
 
 if __name__ == "__main__":
     import sys
-    if "--worker" in sys.argv:
-        _worker_main()
+    if len(sys.argv) == 4 and sys.argv[1] == "--worker":
+        _worker_main(int(sys.argv[2]), int(sys.argv[3]))
